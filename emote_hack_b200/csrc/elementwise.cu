@@ -1,0 +1,328 @@
+// HBM-bound gather / layout / sampler kernels (coalesced 16-byte accesses along the channel axis).
+#include "common.cuh"
+#include "emote_b200.h"
+#include "host_utils.h"
+
+namespace emote {
+
+static inline unsigned grid_for(long long n, int threads, long long cap = 148LL * 32) {
+  long long b = (n + threads - 1) / threads;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+// latents [B, Cl, F, H, W] fp32 -> rows [B*F*H*W, 64] bf16; col (ky*3+kx)*Cl + c
+__global__ void latent_im2col_kernel(const float* __restrict__ lat, int B, int Cl, int F, int H, int W, float pre_scale,
+                                     const float* __restrict__ pw_w, const float* __restrict__ pw_b,
+                                     __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)B * F * H * W;
+  const long long plane = (long long)H * W;
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < total;
+       m += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(m % W);
+    const int y = (int)((m / W) % H);
+    const long long bf = m / plane;
+    const int f = (int)(bf % F);
+    const long long b = bf / F;
+    __align__(16) __nv_bfloat16 row[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) row[i] = __float2bfloat16(0.f);
+    for (int ky = 0; ky < 3; ++ky) {
+      for (int kx = 0; kx < 3; ++kx) {
+        const int yy = y + ky - 1, xx = x + kx - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        float v[8];
+        for (int c = 0; c < Cl; ++c)
+          v[c] = lat[(((b * Cl + c) * F + f) * H + yy) * W + xx] * pre_scale;
+        if (pw_w) {
+          float u[8];
+          for (int o = 0; o < Cl; ++o) {
+            float acc = pw_b ? pw_b[o] : 0.f;
+            for (int c = 0; c < Cl; ++c) acc += pw_w[o * Cl + c] * v[c];
+            u[o] = acc;
+          }
+          for (int c = 0; c < Cl; ++c) v[c] = u[c];
+        }
+        for (int c = 0; c < Cl; ++c) row[(ky * 3 + kx) * Cl + c] = __float2bfloat16(v[c]);
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + m * 64);
+    const uint4* r = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = r[i];
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ uint4 load8_as_bf16(const T* p);
+template <>
+__device__ __forceinline__ uint4 load8_as_bf16<float>(const float* p) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  uint4 w;
+  w.x = pack_bf16x2(a.x, a.y); w.y = pack_bf16x2(a.z, a.w);
+  w.z = pack_bf16x2(b.x, b.y); w.w = pack_bf16x2(b.z, b.w);
+  return w;
+}
+template <>
+__device__ __forceinline__ uint4 load8_as_bf16<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+// x [n,H,W,C] -> out [n*Ho*Wo, 9*C] bf16 (3x3, pad 1, given stride)
+template <typename T>
+__global__ void im2col3x3_kernel(const T* __restrict__ x, int n_img, int H, int W, int C, int stride, int Ho, int Wo,
+                                 __nv_bfloat16* __restrict__ out) {
+  const int oct = C >> 3;
+  const long long total = (long long)n_img * Ho * Wo * 9 * oct;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % oct);
+    long long r = i / oct;
+    const int tap = (int)(r % 9);
+    r /= 9;
+    const int xo = (int)(r % Wo);
+    const int yo = (int)((r / Wo) % Ho);
+    const long long img = r / ((long long)Wo * Ho);
+    const int yy = yo * stride + tap / 3 - 1;
+    const int xx = xo * stride + tap % 3 - 1;
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) w = load8_as_bf16<T>(x + ((img * H + yy) * W + xx) * C + c8 * 8);
+    *reinterpret_cast<uint4*>(out + r * 9LL * C + (long long)tap * C + c8 * 8) = w;
+  }
+}
+
+__global__ void upsample2x_kernel(const float* __restrict__ x, int n_img, int H, int W, int C,
+                                  __nv_bfloat16* __restrict__ out) {
+  const int oct = C >> 3;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)n_img * Ho * Wo * oct;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % oct);
+    long long r = i / oct;
+    const int xo = (int)(r % Wo);
+    const int yo = (int)((r / Wo) % Ho);
+    const long long img = r / ((long long)Wo * Ho);
+    const uint4 w = load8_as_bf16<float>(x + ((img * H + (yo >> 1)) * W + (xo >> 1)) * C + c8 * 8);
+    *reinterpret_cast<uint4*>(out + r * C + c8 * 8) = w;
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ x, long long rows, int C_src, int c_offset, int C_total,
+                                 __nv_bfloat16* __restrict__ out) {
+  const int oct = C_src >> 3;
+  const long long total = rows * oct;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / oct;
+    const int c8 = (int)(i - r * oct);
+    *reinterpret_cast<uint4*>(out + r * C_total + c_offset + c8 * 8) = load8_as_bf16<float>(x + r * C_src + c8 * 8);
+  }
+}
+
+__global__ void silu_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16(silu_f(x[i]));
+}
+
+// tok [B,F,HW,C] <-> x [B,C,F,HW]
+__global__ void tokens_to_ncfhw_kernel(const float* __restrict__ tok, int B, int C, int F, int HW,
+                                       float* __restrict__ out) {
+  const long long total = (long long)B * C * F * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const int f = (int)((i / HW) % F);
+    const int c = (int)((i / ((long long)HW * F)) % C);
+    const long long b = i / ((long long)HW * F * C);
+    out[i] = tok[((b * F + f) * HW + p) * C + c];
+  }
+}
+__global__ void ncfhw_to_tokens_kernel(const float* __restrict__ x, int B, int C, int F, int HW,
+                                       float* __restrict__ out) {
+  const long long total = (long long)B * C * F * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int p = (int)((i / C) % HW);
+    const int f = (int)((i / ((long long)C * HW)) % F);
+    const long long b = i / ((long long)C * HW * F);
+    out[i] = x[((b * C + c) * F + f) * HW + p];
+  }
+}
+
+__global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                               long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = a[i] + b[i];
+}
+
+// embeddings.py:28-68 (scale = 1, max_period = 10000): [sin | cos], optionally flipped to [cos | sin]
+__global__ void timestep_embedding_kernel(const float* __restrict__ ts, int B, int dim, int flip, float freq_shift,
+                                          __nv_bfloat16* __restrict__ out) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * dim) return;
+  const int b = i / dim, j = i % dim;
+  float v = 0.f;
+  if (j < 2 * half) {
+    const int k = j % half;
+    const bool second = j >= half;
+    const float e = expf(-logf(10000.0f) * (float)k / ((float)half - freq_shift));
+    const float arg = ts[b] * e;
+    const bool is_sin = flip ? second : !second;
+    v = is_sin ? sinf(arg) : cosf(arg);
+  }
+  out[i] = __float2bfloat16(v);
+}
+
+__global__ void cfg_ddim_kernel(float* __restrict__ lat, const float* __restrict__ np, const float* __restrict__ counter,
+                                long long n, int n_frames, long long inner, float gs, float sa_t, float s1a_t,
+                                float sa_p, float s1a_p) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float cnt = counter ? counter[(i / inner) % n_frames] : 1.f;
+    const float eu = np[i] / cnt;
+    const float ec = np[n + i] / cnt;
+    const float eps = eu + gs * (ec - eu);
+    const float x = lat[i];
+    const float x0 = (x - s1a_t * eps) / sa_t;
+    lat[i] = sa_p * x0 + s1a_p * eps;
+  }
+}
+
+// tok [n, HW, ld>=3] -> [n, 3, HW]
+__global__ void vae_post_kernel(const float* __restrict__ tok, int n_img, int HW, int ld, float* __restrict__ of,
+                                uint8_t* __restrict__ ou) {
+  const long long total = (long long)n_img * 3 * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const int c = (int)((i / HW) % 3);
+    const long long img = i / (3LL * HW);
+    float v = tok[(img * HW + p) * ld + c] * 0.5f + 0.5f;
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    if (of) of[i] = v;
+    if (ou) ou[i] = (uint8_t)(v * 255.0f + 0.5f);
+  }
+}
+
+}  // namespace emote
+
+using namespace emote;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int emote_latent_im2col(const float* latent, int32_t B, int32_t Cl, int32_t F, int32_t H, int32_t W,
+                                   float pre_scale, const float* pw_weight, const float* pw_bias, void* out_bf16,
+                                   void* stream) {
+  if (!latent || !out_bf16 || B <= 0 || F <= 0 || H <= 0 || W <= 0) return set_error("emote_latent_im2col: bad arguments");
+  if (Cl <= 0 || Cl > 7) return set_error("emote_latent_im2col: latent channels must be in [1,7] (9*Cl <= 64)");
+  const long long total = (long long)B * F * H * W;
+  latent_im2col_kernel<<<grid_for(total, 128), 128, 0, STREAM(stream)>>>(
+      latent, B, Cl, F, H, W, pre_scale, pw_weight, pw_bias, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  EMOTE_CHECK_LAUNCH("emote_latent_im2col");
+  return 0;
+}
+
+template <typename T>
+static int im2col_impl(const T* x, int n_img, int H, int W, int C, int stride, void* out, void* stream) {
+  if (!x || !out || n_img <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0) return set_error("emote_im2col3x3: bad arguments");
+  if (stride != 1 && stride != 2) return set_error("emote_im2col3x3: stride must be 1 or 2");
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const long long total = (long long)n_img * Ho * Wo * 9 * (C / 8);
+  im2col3x3_kernel<T><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, n_img, H, W, C, stride, Ho, Wo,
+                                                                       reinterpret_cast<__nv_bfloat16*>(out));
+  EMOTE_CHECK_LAUNCH("emote_im2col3x3");
+  return 0;
+}
+extern "C" int emote_im2col3x3(const float* x, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t stride,
+                               void* out_bf16, void* stream) {
+  return im2col_impl<float>(x, n_img, H, W, C, stride, out_bf16, stream);
+}
+extern "C" int emote_im2col3x3_bf16(const void* x, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t stride,
+                                    void* out_bf16, void* stream) {
+  return im2col_impl<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(x), n_img, H, W, C, stride, out_bf16, stream);
+}
+
+extern "C" int emote_upsample2x(const float* x, int32_t n_img, int32_t H, int32_t W, int32_t C, void* out_bf16,
+                                void* stream) {
+  if (!x || !out_bf16 || n_img <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0) return set_error("emote_upsample2x: bad arguments");
+  const long long total = (long long)n_img * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, n_img, H, W, C,
+                                                                     reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  EMOTE_CHECK_LAUNCH("emote_upsample2x");
+  return 0;
+}
+
+extern "C" int emote_cast_bf16(const float* x, int64_t rows, int32_t C_src, int32_t c_offset, int32_t C_total,
+                               void* out_bf16, void* stream) {
+  if (!x || !out_bf16 || rows <= 0 || C_src <= 0 || C_src % 8 != 0 || c_offset % 8 != 0 || C_total % 8 != 0 ||
+      c_offset + C_src > C_total)
+    return set_error("emote_cast_bf16: bad arguments");
+  cast_bf16_kernel<<<grid_for(rows * (C_src / 8), 256), 256, 0, STREAM(stream)>>>(
+      x, rows, C_src, c_offset, C_total, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  EMOTE_CHECK_LAUNCH("emote_cast_bf16");
+  return 0;
+}
+
+extern "C" int emote_silu_bf16(const float* x, int64_t n, void* out_bf16, void* stream) {
+  if (!x || !out_bf16 || n <= 0) return set_error("emote_silu_bf16: bad arguments");
+  silu_bf16_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(x, n, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  EMOTE_CHECK_LAUNCH("emote_silu_bf16");
+  return 0;
+}
+
+extern "C" int emote_tokens_to_ncfhw(const float* tok, int32_t B, int32_t C, int32_t F, int32_t HW, float* out,
+                                     void* stream) {
+  if (!tok || !out || B <= 0 || C <= 0 || F <= 0 || HW <= 0) return set_error("emote_tokens_to_ncfhw: bad arguments");
+  tokens_to_ncfhw_kernel<<<grid_for((long long)B * C * F * HW, 256), 256, 0, STREAM(stream)>>>(tok, B, C, F, HW, out);
+  EMOTE_CHECK_LAUNCH("emote_tokens_to_ncfhw");
+  return 0;
+}
+extern "C" int emote_ncfhw_to_tokens(const float* x, int32_t B, int32_t C, int32_t F, int32_t HW, float* out,
+                                     void* stream) {
+  if (!x || !out || B <= 0 || C <= 0 || F <= 0 || HW <= 0) return set_error("emote_ncfhw_to_tokens: bad arguments");
+  ncfhw_to_tokens_kernel<<<grid_for((long long)B * C * F * HW, 256), 256, 0, STREAM(stream)>>>(x, B, C, F, HW, out);
+  EMOTE_CHECK_LAUNCH("emote_ncfhw_to_tokens");
+  return 0;
+}
+
+extern "C" int emote_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) {
+  if (!a || !b || !out || n <= 0) return set_error("emote_add_f32: bad arguments");
+  add_f32_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(a, b, out, n);
+  EMOTE_CHECK_LAUNCH("emote_add_f32");
+  return 0;
+}
+
+extern "C" int emote_timestep_embedding(const float* timesteps, int32_t B, int32_t dim, int32_t flip_sin_to_cos,
+                                        float freq_shift, void* out_bf16, void* stream) {
+  if (!timesteps || !out_bf16 || B <= 0 || dim <= 1) return set_error("emote_timestep_embedding: bad arguments");
+  const int n = B * dim;
+  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, STREAM(stream)>>>(timesteps, B, dim, flip_sin_to_cos, freq_shift,
+                                                                         reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  EMOTE_CHECK_LAUNCH("emote_timestep_embedding");
+  return 0;
+}
+
+extern "C" int emote_cfg_ddim_step(float* latents, const float* noise_pred, const float* counter, int64_t n,
+                                   int32_t n_frames, int64_t inner, float guidance_scale, float alpha_t,
+                                   float alpha_prev, void* stream) {
+  if (!latents || !noise_pred || n <= 0) return set_error("emote_cfg_ddim_step: bad arguments");
+  if (counter && (n_frames <= 0 || inner <= 0)) return set_error("emote_cfg_ddim_step: bad counter geometry");
+  if (!(alpha_t > 0.f && alpha_t <= 1.f && alpha_prev > 0.f && alpha_prev <= 1.f))
+    return set_error("emote_cfg_ddim_step: alphas must lie in (0,1]");
+  cfg_ddim_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(
+      latents, noise_pred, counter, n, n_frames > 0 ? n_frames : 1, inner > 0 ? inner : 1, guidance_scale,
+      sqrtf(alpha_t), sqrtf(1.f - alpha_t), sqrtf(alpha_prev), sqrtf(1.f - alpha_prev));
+  EMOTE_CHECK_LAUNCH("emote_cfg_ddim_step");
+  return 0;
+}
+
+extern "C" int emote_vae_postprocess(const float* tok, int32_t n_img, int32_t HW, int32_t ld, float* out_f32,
+                                     uint8_t* out_u8, void* stream) {
+  if (!tok || n_img <= 0 || HW <= 0 || ld < 3 || (!out_f32 && !out_u8)) return set_error("emote_vae_postprocess: bad arguments");
+  vae_post_kernel<<<grid_for((long long)n_img * 3 * HW, 256), 256, 0, STREAM(stream)>>>(tok, n_img, HW, ld, out_f32, out_u8);
+  EMOTE_CHECK_LAUNCH("emote_vae_postprocess");
+  return 0;
+}

@@ -1,0 +1,419 @@
+// Persistent warp-specialised tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   out[M,N] = epilogue( A[M,K] (bf16, K-major)  x  W[N,K]^T (bf16, K-major) )       fp32 accumulate in TMEM
+//
+// * operands staged by TMA (128B swizzle) into a multi-stage smem ring, consumed by tcgen05.mma
+//   (UMMA 128 x BN x 16, cta_group::1) issued from a single thread; accumulators double-buffered in TMEM
+//   so the epilogue of tile i overlaps the main loop of tile i+1.
+// * conv mode: A is an NHWC bf16 image tensor; every 3x3 tap is one 4-D TMA box whose out-of-bounds
+//   rows/columns are zero-filled by the TMA unit (= the conv zero padding), so no im2col is materialised.
+//   Replaces cuDNN conv2d behind InflatedConv3d (reference magicanimate/models/resnet.py:30-38).
+// * fused epilogues: bias, per-sample time-embedding bias (resnet.py:186-189), fp32 residual add and
+//   1/output_scale_factor (resnet.py:202-205), GEGLU (orig_attention.py:817-827), bf16 or fp32 store.
+#include "common.cuh"
+#include "emote_b200.h"
+#include "host_utils.h"
+
+namespace emote {
+
+constexpr int BM = 128;       // UMMA M (rows of the output tile, one TMEM lane per row)
+constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle row
+constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA+TMEM alloc, warps2-5 epilogue
+
+struct GemmDev {
+  int M, N, K;
+  int num_kb;        // K blocks of 64 (over all taps)
+  int kb_per_tap;    // C/64 in conv mode
+  int taps;          // 1 or 9
+  int H, W;          // conv image dims
+  int bw, bh;        // TMA box extents in W and H (bw*bh*bn = 128)
+  int tiles_m, tiles_n;
+  const float* bias;
+  const float* row_bias;
+  int rows_per_group;
+  const float* residual;
+  int ldr;
+  float out_scale;
+  int geglu;
+  int out_bf16;
+  int ldc;
+  void* out;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN <= 128) ? 6 : (BN <= 160 ? 5 : 4);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
+  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmDev p) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled tiles need 1024 B alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bar_base = smem + S::STAGES * S::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + S::STAGES;
+  uint64_t* tmem_full = empty_bar + S::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < S::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, S::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / p.tiles_n;
+        const int tn = tile - tm * p.tiles_n;
+        const int m0 = tm * BM;
+        const int n0 = tn * BN;
+        int img0 = 0, y0 = 0, x0 = 0;
+        if (p.taps > 1) {
+          const int hw = p.H * p.W;
+          img0 = m0 / hw;
+          const int rem = m0 - img0 * hw;
+          y0 = rem / p.W;
+          x0 = rem - y0 * p.W;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          if (p.taps > 1) {
+            const int tap = kb / p.kb_per_tap;
+            const int kc = kb - tap * p.kb_per_tap;
+            const int dy = tap / 3 - 1;
+            const int dx = tap - (tap / 3) * 3 - 1;
+            tma_load_4d(sa, &tmA, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img0);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+          }
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          if (++stage == S::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                     (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == S::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[as]);  // accumulator ready for the epilogue
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (TMEM -> regs -> global)
+    const int lane_grp = warp & 3;  // TMEM lane quarter this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile / p.tiles_n;
+      const int tn = tile - tm * p.tiles_n;
+      const int row = tm * BM + lane_grp * 32 + lane;
+      const int n0 = tn * BN;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(as * BN);
+      const bool row_ok = row < p.M;
+      const float* rb = (p.row_bias != nullptr && row_ok) ? p.row_bias + (size_t)(row / p.rows_per_group) * p.N : nullptr;
+      const float* res = (p.residual != nullptr && row_ok) ? p.residual + (size_t)row * p.ldr : nullptr;
+
+      if (!p.geglu) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c * 16, r);
+          tmem_ld_wait();
+          const int col0 = n0 + c * 16;
+          if (row_ok && col0 < p.N) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+            const bool full = (col0 + 16 <= p.N);
+            if (full) {
+              if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + j);
+                  v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                }
+              }
+              if (rb) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const float4 b = *reinterpret_cast<const float4*>(rb + col0 + j);
+                  v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                }
+              }
+              if (res) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const float4 b = *reinterpret_cast<const float4*>(res + col0 + j);
+                  v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] *= p.out_scale;
+              if (p.out_bf16) {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldc + col0;
+                uint4 w0, w1;
+                w0.x = pack_bf16x2(v[0], v[1]);   w0.y = pack_bf16x2(v[2], v[3]);
+                w0.z = pack_bf16x2(v[4], v[5]);   w0.w = pack_bf16x2(v[6], v[7]);
+                w1.x = pack_bf16x2(v[8], v[9]);   w1.y = pack_bf16x2(v[10], v[11]);
+                w1.z = pack_bf16x2(v[12], v[13]); w1.w = pack_bf16x2(v[14], v[15]);
+                *reinterpret_cast<uint4*>(o) = w0;
+                *reinterpret_cast<uint4*>(o + 8) = w1;
+              } else {
+                float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldc + col0;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              }
+            } else {
+              // ragged N tail: scalar path
+              for (int j = 0; j < 16; ++j) {
+                const int col = col0 + j;
+                if (col >= p.N) break;
+                float x = v[j];
+                if (p.bias) x += p.bias[col];
+                if (rb) x += rb[col];
+                if (res) x += res[col];
+                x *= p.out_scale;
+                if (p.out_bf16)
+                  reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)row * p.ldc + col] = __float2bfloat16(x);
+                else
+                  reinterpret_cast<float*>(p.out)[(size_t)row * p.ldc + col] = x;
+              }
+            }
+          }
+        }
+      } else {
+        // GEGLU: tile columns [0, BN/2) hold the value half, [BN/2, BN) the gate half of the same
+        // BN/2 output features (weights are packed that way); out = value * gelu_erf(gate).
+        constexpr int HALF = BN / 2;
+        const int on0 = tn * HALF;
+        const int n_out = p.N / 2;
+#pragma unroll 1
+        for (int c = 0; c < HALF / 16; ++c) {
+          uint32_t rv[16], rg[16];
+          tmem_ld16(taddr + c * 16, rv);
+          tmem_ld16(taddr + HALF + c * 16, rg);
+          tmem_ld_wait();
+          const int ocol0 = on0 + c * 16;
+          if (row_ok && ocol0 < n_out) {
+            float o16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a = __uint_as_float(rv[j]);
+              float g = __uint_as_float(rg[j]);
+              if (p.bias) {
+                a += p.bias[n0 + c * 16 + j];
+                g += p.bias[n0 + HALF + c * 16 + j];
+              }
+              o16[j] = a * gelu_erf_f(g);
+            }
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldc + ocol0;
+            if (ocol0 + 16 <= n_out) {
+              uint4 w0, w1;
+              w0.x = pack_bf16x2(o16[0], o16[1]);   w0.y = pack_bf16x2(o16[2], o16[3]);
+              w0.z = pack_bf16x2(o16[4], o16[5]);   w0.w = pack_bf16x2(o16[6], o16[7]);
+              w1.x = pack_bf16x2(o16[8], o16[9]);   w1.y = pack_bf16x2(o16[10], o16[11]);
+              w1.z = pack_bf16x2(o16[12], o16[13]); w1.w = pack_bf16x2(o16[14], o16[15]);
+              *reinterpret_cast<uint4*>(o) = w0;
+              *reinterpret_cast<uint4*>(o + 8) = w1;
+            } else {
+              for (int j = 0; j < 16 && ocol0 + j < n_out; ++j) o[j] = __float2bfloat16(o16[j]);
+            }
+          }
+        }
+      }
+      // release the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, S::TMEM_COLS);
+  }
+}
+
+// --------------------------------------------------------------------------- host side
+static int g_num_sms = 0;
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDev& p, cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         S::TOTAL);
+    if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(gemm)", e);
+    configured = true;
+  }
+  p.tiles_m = (p.M + BM - 1) / BM;
+  p.tiles_n = (p.N + BN - 1) / BN;
+  const int tiles = p.tiles_m * p.tiles_n;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error_cuda("gemm launch", e);
+  count_launch();
+  return 0;
+}
+
+}  // namespace emote
+
+using namespace emote;
+
+extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const EmoteGemmArgs* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!A || !Wt || !out || !a) return set_error("emote_gemm_bf16: null pointer");
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error("emote_gemm_bf16: non-positive dims");
+  if (a->K % 8 != 0) return set_error("emote_gemm_bf16: K must be a multiple of 8 (16-byte TMA rows)");
+  const bool conv = a->conv_taps == 9;
+  if (a->conv_taps != 1 && a->conv_taps != 9) return set_error("emote_gemm_bf16: conv_taps must be 1 or 9");
+  const bool geglu = a->epilogue == EMOTE_EPI_GEGLU;
+  if (geglu && (a->N % 2 != 0 || a->out_dtype != EMOTE_DT_BF16 || a->residual || a->row_bias))
+    return set_error("emote_gemm_bf16: GEGLU epilogue needs even N, bf16 output, no residual/row_bias");
+  const int bn = a->block_n ? a->block_n : ((a->N % 160 == 0) ? 160 : 128);
+  if (bn != 128 && bn != 160) return set_error("emote_gemm_bf16: block_n must be 128 or 160");
+  if (geglu && a->N % bn != 0) return set_error("emote_gemm_bf16: GEGLU needs N % block_n == 0");
+  if ((a->out_dtype == EMOTE_DT_BF16 && a->ldc % 8 != 0) || (a->out_dtype == EMOTE_DT_F32 && a->ldc % 4 != 0))
+    return set_error("emote_gemm_bf16: ldc must keep rows 16-byte aligned");
+  if (a->residual && a->ldr % 4 != 0) return set_error("emote_gemm_bf16: ldr must be a multiple of 4");
+
+  GemmDev p{};
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.taps = a->conv_taps;
+  p.bias = a->bias; p.row_bias = a->row_bias;
+  p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
+  p.residual = a->residual; p.ldr = a->ldr;
+  p.out_scale = a->out_scale;
+  p.geglu = geglu ? 1 : 0;
+  p.out_bf16 = a->out_dtype == EMOTE_DT_BF16;
+  p.ldc = a->ldc;
+  p.out = out;
+
+  CUtensorMap tmA, tmB;
+  if (conv) {
+    const int C = a->C, H = a->H, W = a->W, NI = a->n_img;
+    if (C <= 0 || C % 64 != 0) return set_error("emote_gemm_bf16(conv): C must be a multiple of 64");
+    if (a->K != 9 * C) return set_error("emote_gemm_bf16(conv): K must equal 9*C");
+    if ((long long)NI * H * W != a->M) return set_error("emote_gemm_bf16(conv): M must equal n_img*H*W");
+    int bw = W < 128 ? W : 128;
+    if (128 % bw != 0 || W % bw != 0) return set_error("emote_gemm_bf16(conv): W must divide or be a multiple of 128");
+    int bh = 128 / bw;
+    if (bh > H) bh = H;
+    if (H % bh != 0) return set_error("emote_gemm_bf16(conv): H incompatible with the 128-row tile");
+    int bnimg = 128 / (bw * bh);
+    if (bnimg * bw * bh != 128) return set_error("emote_gemm_bf16(conv): H*W must divide or be a multiple of 128");
+    p.H = H; p.W = W; p.bw = bw; p.bh = bh;
+    p.kb_per_tap = C / 64;
+    p.num_kb = 9 * p.kb_per_tap;
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
+    uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnimg};
+    if (int rc = make_tensor_map(&tmA, A, 4, dims, strides, box)) return rc;
+  } else {
+    if (a->lda % 8 != 0 || a->lda < a->K) return set_error("emote_gemm_bf16: lda must be >= K and a multiple of 8");
+    p.kb_per_tap = (a->K + BK - 1) / BK;
+    p.num_kb = p.kb_per_tap;
+    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
+    uint64_t strides[1] = {(uint64_t)a->lda * 2};
+    uint32_t box[2] = {64, 128};
+    if (int rc = make_tensor_map(&tmA, A, 2, dims, strides, box)) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    uint64_t strides[1] = {(uint64_t)a->K * 2};
+    uint32_t box[2] = {64, (uint32_t)bn};
+    if (int rc = make_tensor_map(&tmB, Wt, 2, dims, strides, box)) return rc;
+  }
+  if (bn == 160) return launch_gemm<160>(tmA, tmB, p, stream);
+  return launch_gemm<128>(tmA, tmB, p, stream);
+}

@@ -1,0 +1,281 @@
+// HBM-bound normalisation kernels over tokens-major fp32 activations (coalesced, vectorised):
+//   * GroupNorm statistics (sum / sum of squares per (group batch, group)) with channel-concat support
+//   * GroupNorm apply (+SiLU) -> bf16 GEMM/conv operand (+ optional raw bf16 copy for the shortcut conv)
+//   * LayerNorm (+ additive temporal positional table) -> bf16 GEMM operand
+// Reference ops: nn.GroupNorm resnet.py:180,191 / attention.py:124 / motion_module.py:147 /
+// unet_controlnet.py:476; nn.LayerNorm attention.py:204-232, motion_module.py:208-213.
+#include "common.cuh"
+#include "emote_b200.h"
+#include "host_utils.h"
+
+namespace emote {
+
+constexpr int GN_MAX_PASS = 4;
+constexpr int GN_MAX_GROUPS = 64;
+
+// blockDim = (PX, TY); thread (px, ty) owns channel pairs px + pass*PX and rows ty, ty+TY, ...
+__global__ void gn_stats_kernel(const float* __restrict__ x, int C_src, int c_offset, int cpg, int groups,
+                                long long rows_per_batch, int rows_per_block, int passes, double* __restrict__ sums) {
+  __shared__ float s_acc[GN_MAX_GROUPS * 2];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < groups * 2; i += blockDim.x * blockDim.y) s_acc[i] = 0.f;
+  __syncthreads();
+
+  const int batch = blockIdx.y;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows_per_batch) r1 = rows_per_batch;
+  const float* xb = x + ((long long)batch * rows_per_batch) * C_src;
+
+  float s[GN_MAX_PASS], q[GN_MAX_PASS];
+#pragma unroll
+  for (int i = 0; i < GN_MAX_PASS; ++i) s[i] = q[i] = 0.f;
+
+  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    const float2* row = reinterpret_cast<const float2*>(xb + r * C_src);
+#pragma unroll
+    for (int ps = 0; ps < GN_MAX_PASS; ++ps) {
+      if (ps < passes) {
+        const float2 v = __ldg(row + threadIdx.x + ps * blockDim.x);
+        s[ps] += v.x + v.y;
+        q[ps] += v.x * v.x + v.y * v.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int ps = 0; ps < GN_MAX_PASS; ++ps) {
+    if (ps < passes) {
+      const int c = c_offset + 2 * (threadIdx.x + ps * blockDim.x);
+      const int g = c / cpg;
+      atomicAdd(&s_acc[2 * g], s[ps]);
+      atomicAdd(&s_acc[2 * g + 1], q[ps]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < groups * 2; i += blockDim.x * blockDim.y) {
+    const float v = s_acc[i];
+    if (v != 0.f) atomicAdd(&sums[(long long)batch * groups * 2 + i], (double)v);
+  }
+}
+
+// each thread: 8 consecutive channels of one row
+__global__ void gn_apply_kernel(const float* __restrict__ x, int C_src, int c_offset, int C_total, int cpg,
+                                int groups, long long rows_per_batch, int rows_per_block,
+                                const double* __restrict__ sums, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, int act_silu,
+                                __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ raw_out) {
+  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  const int batch = blockIdx.y;
+  if (threadIdx.x < groups) {
+    const double cnt = (double)rows_per_batch * (double)cpg;
+    const double sm = sums[((long long)batch * groups + threadIdx.x) * 2];
+    const double sq = sums[((long long)batch * groups + threadIdx.x) * 2 + 1];
+    const double mean = sm / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int oct_per_row = C_src >> 3;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long nrows = rows_per_batch - r0;
+  if (nrows > rows_per_block) nrows = rows_per_block;
+  const long long total = nrows * oct_per_row;
+  const long long row_base = (long long)batch * rows_per_batch + r0;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    const long long r = i / oct_per_row;
+    const int c0 = (int)(i - r * oct_per_row) << 3;
+    const float* src = x + (row_base + r) * C_src + c0;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float y[8];
+    const int ct = c_offset + c0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = ct + j;
+      const int g = c / cpg;
+      float t = (v[j] - s_mean[g]) * s_rstd[g] * __ldg(gamma + c) + __ldg(beta + c);
+      y[j] = act_silu ? silu_f(t) : t;
+    }
+    const long long o = (row_base + r) * C_total + ct;
+    uint4 w;
+    w.x = pack_bf16x2(y[0], y[1]); w.y = pack_bf16x2(y[2], y[3]);
+    w.z = pack_bf16x2(y[4], y[5]); w.w = pack_bf16x2(y[6], y[7]);
+    *reinterpret_cast<uint4*>(out + o) = w;
+    if (raw_out) {
+      uint4 u;
+      u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+      u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(raw_out + o) = u;
+    }
+  }
+}
+
+constexpr int LN_MAX_V = 32;  // float2 per lane -> C <= 2048
+
+__global__ void layernorm_kernel(const float* __restrict__ x, long long M, int C, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, const float* __restrict__ pe,
+                                 int pe_rows_per_frame, int pe_frames, __nv_bfloat16* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= M) return;
+  const int nv = C >> 6;  // float2 per lane
+  const float2* xr = reinterpret_cast<const float2*>(x + row * C);
+  float2 v[LN_MAX_V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V; ++i) {
+    if (i < nv) {
+      v[i] = __ldg(xr + lane + i * 32);
+      s += v[i].x + v[i].y;
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V; ++i) {
+    if (i < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean;
+      q += a * a + b * b;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  const float* per = nullptr;
+  if (pe) per = pe + (long long)((row / pe_rows_per_frame) % pe_frames) * C;
+  uint32_t* o = reinterpret_cast<uint32_t*>(out + row * C);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V; ++i) {
+    if (i < nv) {
+      const int c = 2 * (lane + i * 32);
+      const float2 g = __ldg(reinterpret_cast<const float2*>(gamma + c));
+      const float2 b = __ldg(reinterpret_cast<const float2*>(beta + c));
+      float y0 = (v[i].x - mean) * rstd * g.x + b.x;
+      float y1 = (v[i].y - mean) * rstd * g.y + b.y;
+      if (per) {
+        const float2 p2 = __ldg(reinterpret_cast<const float2*>(per + c));
+        y0 += p2.x;
+        y1 += p2.y;
+      }
+      o[lane + i * 32] = pack_bf16x2(y0, y1);
+    }
+  }
+}
+
+__global__ void softmax_rows_kernel(const float* __restrict__ s, int N, float scale, __nv_bfloat16* __restrict__ out) {
+  // one block per row
+  const long long row = blockIdx.x;
+  const float* sr = s + row * N;
+  __shared__ float red[32];
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) m = fmaxf(m, sr[i] * scale);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+    t = warp_max(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  m = red[0];
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sum += __expf(sr[i] * scale - m);
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const float inv = 1.0f / red[0];
+  __nv_bfloat16* o = out + row * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) o[i] = __float2bfloat16(__expf(sr[i] * scale - m) * inv);
+}
+
+}  // namespace emote
+
+using namespace emote;
+
+static int gn_check(int C_src, int c_offset, int C_total, int groups, const char* who) {
+  if (groups <= 0 || groups > GN_MAX_GROUPS || C_total % groups != 0) return set_error(who);
+  const int cpg = C_total / groups;
+  if (cpg % 2 != 0 || c_offset % 8 != 0 || C_src % 8 != 0 || c_offset + C_src > C_total || C_total % 8 != 0)
+    return set_error(who);
+  return 0;
+}
+
+extern "C" int emote_gn_stats(const float* x, int32_t C_src, int32_t c_offset, int32_t C_total, int32_t groups,
+                              int64_t rows_per_batch, int32_t n_batches, double* sums, int32_t zero_first,
+                              void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !sums || rows_per_batch <= 0 || n_batches <= 0) return set_error("emote_gn_stats: bad arguments");
+  if (gn_check(C_src, c_offset, C_total, groups, "emote_gn_stats: unsupported channel/group configuration")) return EMOTE_ERR_INVALID;
+  if (zero_first) {
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups * (size_t)n_batches, stream);
+    if (e != cudaSuccess) return set_error_cuda("emote_gn_stats memset", e);
+  }
+  const int P = C_src / 2;
+  int passes = 1;
+  while (passes <= GN_MAX_PASS && !(P % passes == 0 && P / passes <= 512)) ++passes;
+  if (passes > GN_MAX_PASS) return set_error("emote_gn_stats: C_src too wide");
+  const int PX = P / passes;
+  int TY = 512 / PX;
+  if (TY < 1) TY = 1;
+  int rows_per_block = 64;
+  if (rows_per_block < TY) rows_per_block = TY;
+  const long long chunks = (rows_per_batch + rows_per_block - 1) / rows_per_block;
+  dim3 grid((unsigned)chunks, (unsigned)n_batches), block(PX, TY);
+  gn_stats_kernel<<<grid, block, 0, stream>>>(x, C_src, c_offset, C_total / groups, groups, rows_per_batch,
+                                              rows_per_block, passes, sums);
+  EMOTE_CHECK_LAUNCH("emote_gn_stats");
+  return 0;
+}
+
+extern "C" int emote_gn_apply(const float* x, int32_t C_src, int32_t c_offset, int32_t C_total, int32_t groups,
+                              int64_t rows_per_batch, int32_t n_batches, const double* sums, const float* gamma,
+                              const float* beta, float eps, int32_t act_silu, void* out_bf16, void* raw_out_bf16,
+                              void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !sums || !gamma || !beta || !out_bf16 || rows_per_batch <= 0 || n_batches <= 0)
+    return set_error("emote_gn_apply: bad arguments");
+  if (gn_check(C_src, c_offset, C_total, groups, "emote_gn_apply: unsupported channel/group configuration")) return EMOTE_ERR_INVALID;
+  int rows_per_block = (int)((256LL * 8 * 8) / C_src);  // ~8 octets per thread
+  if (rows_per_block < 1) rows_per_block = 1;
+  const long long chunks = (rows_per_batch + rows_per_block - 1) / rows_per_block;
+  dim3 grid((unsigned)chunks, (unsigned)n_batches);
+  gn_apply_kernel<<<grid, 256, 0, stream>>>(x, C_src, c_offset, C_total, C_total / groups, groups, rows_per_batch,
+                                            rows_per_block, sums, gamma, beta, eps, act_silu,
+                                            reinterpret_cast<__nv_bfloat16*>(out_bf16),
+                                            reinterpret_cast<__nv_bfloat16*>(raw_out_bf16));
+  EMOTE_CHECK_LAUNCH("emote_gn_apply");
+  return 0;
+}
+
+extern "C" int emote_layernorm(const float* x, int64_t M, int32_t C, const float* gamma, const float* beta, float eps,
+                               const float* pe, int32_t pe_rows_per_frame, int32_t pe_frames, void* out_bf16,
+                               void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !gamma || !beta || !out_bf16 || M <= 0) return set_error("emote_layernorm: bad arguments");
+  if (C % 64 != 0 || C > 64 * LN_MAX_V) return set_error("emote_layernorm: C must be a multiple of 64 and <= 2048");
+  if (pe && (pe_rows_per_frame <= 0 || pe_frames <= 0)) return set_error("emote_layernorm: bad positional table dims");
+  const int warps = 8;
+  const long long blocks = (M + warps - 1) / warps;
+  layernorm_kernel<<<(unsigned)blocks, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, pe, pe_rows_per_frame,
+                                                                pe_frames, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  EMOTE_CHECK_LAUNCH("emote_layernorm");
+  return 0;
+}
+
+extern "C" int emote_softmax_rows_bf16(const float* scores, int64_t R, int32_t N, float scale, void* out_bf16,
+                                       void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!scores || !out_bf16 || R <= 0 || N <= 0) return set_error("emote_softmax_rows_bf16: bad arguments");
+  softmax_rows_kernel<<<(unsigned)R, 256, 0, stream>>>(scores, N, scale, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  EMOTE_CHECK_LAUNCH("emote_softmax_rows_bf16");
+  return 0;
+}

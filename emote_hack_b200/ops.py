@@ -1,0 +1,321 @@
+"""Host-side operator layer: torch tensors in, C-ABI kernel launches out.
+
+PyTorch is used here for device memory (allocation, views) and the current CUDA stream only; all arithmetic
+on the hot path runs in libemote_b200.so.  Activations are "tokens-major": a [b, c, f, h, w] tensor stored
+channels-last (torch.channels_last_3d), which is byte-identical to a row-major [(b f h w), c] matrix.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import EmoteAttnArgs, EmoteGemmArgs, check
+
+F32, BF16 = torch.float32, torch.bfloat16
+EPI_LINEAR, EPI_GEGLU = 0, 1
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.EmoteKernelError(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.EmoteKernelError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.EmoteKernelError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def auto_block_n(N: int) -> int:
+    return 160 if N % 160 == 0 else 128
+
+
+# ----------------------------------------------------------------------------------------------- weight packing
+def pack_linear(w: torch.Tensor) -> torch.Tensor:
+    """nn.Linear / 1x1-conv weight [N, K(,1,1)] -> bf16 [N, K] (K-major B operand)."""
+    return w.detach().reshape(w.shape[0], -1).to(BF16).contiguous()
+
+
+def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
+    """conv weight [N, C, 3, 3] -> bf16 [N, 9*C] with column (ky*3+kx)*C + c (tap-major, matches the TMA tap loop)."""
+    n, c = w.shape[0], w.shape[1]
+    return w.detach().permute(0, 2, 3, 1).reshape(n, 9 * c).to(BF16).contiguous()
+
+
+def pack_conv3x3_small(w: torch.Tensor) -> torch.Tensor:
+    """conv weight [N, Cl<=7, 3, 3] -> bf16 [N, 64] matching emote_latent_im2col columns, zero padded."""
+    n, c = w.shape[0], w.shape[1]
+    out = torch.zeros(n, 64, dtype=BF16, device=w.device)
+    out[:, : 9 * c] = w.detach().permute(0, 2, 3, 1).reshape(n, 9 * c).to(BF16)
+    return out
+
+
+def pack_geglu(w: torch.Tensor, b: torch.Tensor):
+    """GEGLU proj [2*inner, K]: rows [0,inner) = value, [inner,2*inner) = gate (orig_attention.py:825-827).
+    Re-ordered per block_n tile as [value rows | gate rows] so one accumulator tile sees both halves."""
+    n2, k = w.shape
+    inner = n2 // 2
+    bn = auto_block_n(n2)
+    half = bn // 2
+    if inner % half != 0:
+        raise _lib.EmoteKernelError(f"GEGLU inner dim {inner} not divisible by {half}")
+    wv, wg = w.detach()[:inner], w.detach()[inner:]
+    wp = torch.stack([wv.reshape(-1, half, k), wg.reshape(-1, half, k)], dim=1).reshape(n2, k)
+    bv, bg = b.detach()[:inner], b.detach()[inner:]
+    bp = torch.stack([bv.reshape(-1, half), bg.reshape(-1, half)], dim=1).reshape(n2)
+    return wp.to(BF16).contiguous(), bp.to(F32).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------- GEMM / conv
+def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, row_bias=None, rows_per_group: int = 0, residual=None,
+         out_scale: float = 1.0, geglu: bool = False, out_dtype=F32, out: Optional[torch.Tensor] = None,
+         conv: Optional[tuple] = None, M: Optional[int] = None) -> torch.Tensor:
+    """out = epilogue(a @ w.T).  a: bf16 [M, K] (or NHWC [n_img, H, W, C] when conv=(n_img, H, W, C)); w: bf16 [N, K]."""
+    _req(a, BF16, "gemm.a"), _req(w, BF16, "gemm.w")
+    N, K = w.shape
+    args = EmoteGemmArgs()
+    if conv is not None:
+        n_img, H, W_, Cc = conv
+        M = n_img * H * W_
+        args.conv_taps, args.n_img, args.H, args.W, args.C = 9, n_img, H, W_, Cc
+        args.lda = Cc
+    else:
+        if M is None:
+            M = a.numel() // K
+        args.conv_taps = 1
+        args.lda = K
+    args.M, args.N, args.K = M, N, K
+    n_out = N // 2 if geglu else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=out_dtype, device=a.device)
+    else:
+        _req(out, out_dtype, "gemm.out")
+    if bias is not None:
+        _req(bias, F32, "gemm.bias")
+    if row_bias is not None:
+        _req(row_bias, F32, "gemm.row_bias")
+    if residual is not None:
+        _req(residual, F32, "gemm.residual")
+    args.bias = _ptr(bias)
+    args.row_bias = _ptr(row_bias)
+    args.rows_per_group = rows_per_group
+    args.residual = _ptr(residual)
+    args.ldr = n_out
+    args.out_scale = out_scale
+    args.epilogue = EPI_GEGLU if geglu else EPI_LINEAR
+    args.out_dtype = 1 if out_dtype == BF16 else 0
+    args.ldc = out.shape[-1]
+    args.block_n = 0
+    check(_lib.load().emote_gemm_bf16(a.data_ptr(), w.data_ptr(), out.data_ptr(), C.byref(args), _stream()),
+          "emote_gemm_bf16")
+    return out
+
+
+def conv_tile_ok(H: int, W: int) -> bool:
+    """Whether the TMA implicit-GEMM tile (128 consecutive pixels as whole rows / whole images) covers H x W."""
+    bw = min(W, 128)
+    if 128 % bw or W % bw:
+        return False
+    bh = min(128 // bw, H)
+    if H % bh:
+        return False
+    return (128 // (bw * bh)) * bw * bh == 128
+
+
+def conv3x3(x_bf16: torch.Tensor, w_packed: torch.Tensor, n_img: int, H: int, W: int, Cc: int, **epi) -> torch.Tensor:
+    """3x3 / stride 1 / pad 1 conv over NHWC bf16.  Implicit GEMM when the tile geometry allows, else explicit im2col."""
+    if conv_tile_ok(H, W) and Cc % 64 == 0:
+        return gemm(x_bf16, w_packed, conv=(n_img, H, W, Cc), **epi)
+    cols = torch.empty((n_img * H * W, 9 * Cc), dtype=BF16, device=x_bf16.device)
+    check(_lib.load().emote_im2col3x3_bf16(x_bf16.data_ptr(), n_img, H, W, Cc, 1, cols.data_ptr(), _stream()),
+          "emote_im2col3x3_bf16")
+    return gemm(cols, w_packed, **epi)
+
+
+def im2col_s2(x: torch.Tensor, n_img: int, H: int, W: int, Cc: int) -> torch.Tensor:
+    _req(x, F32, "im2col_s2.x")
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    cols = torch.empty((n_img * Ho * Wo, 9 * Cc), dtype=BF16, device=x.device)
+    check(_lib.load().emote_im2col3x3(x.data_ptr(), n_img, H, W, Cc, 2, cols.data_ptr(), _stream()), "emote_im2col3x3")
+    return cols
+
+
+def upsample2x(x: torch.Tensor, n_img: int, H: int, W: int, Cc: int) -> torch.Tensor:
+    _req(x, F32, "upsample2x.x")
+    out = torch.empty((n_img * 4 * H * W, Cc), dtype=BF16, device=x.device)
+    check(_lib.load().emote_upsample2x(x.data_ptr(), n_img, H, W, Cc, out.data_ptr(), _stream()), "emote_upsample2x")
+    return out
+
+
+def latent_im2col(lat: torch.Tensor, pre_scale: float = 1.0, pw_weight=None, pw_bias=None) -> torch.Tensor:
+    """lat [B, Cl, F, H, W] fp32 (standard NCFHW contiguous) -> bf16 [B*F*H*W, 64]."""
+    _req(lat, F32, "latent_im2col.lat")
+    B, Cl, F_, H, W = lat.shape
+    out = torch.empty((B * F_ * H * W, 64), dtype=BF16, device=lat.device)
+    check(_lib.load().emote_latent_im2col(lat.data_ptr(), B, Cl, F_, H, W, pre_scale, _ptr(pw_weight), _ptr(pw_bias),
+                                          out.data_ptr(), _stream()), "emote_latent_im2col")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- norms
+def group_norm(sources: Sequence[torch.Tensor], groups: int, rows_per_batch: int, n_batches: int, gamma, beta,
+               eps: float, silu: bool, want_raw: bool = False):
+    """GroupNorm over the channel-concatenation of `sources` (each fp32 [rows, C_i]); returns bf16 [rows, sum C_i]
+    (and the raw bf16 concatenation when want_raw)."""
+    lib = _lib.load()
+    rows = rows_per_batch * n_batches
+    c_total = sum(int(s.shape[-1]) for s in sources)
+    dev = sources[0].device
+    sums = torch.empty((n_batches, groups, 2), dtype=torch.float64, device=dev)
+    out = torch.empty((rows, c_total), dtype=BF16, device=dev)
+    raw = torch.empty((rows, c_total), dtype=BF16, device=dev) if want_raw else None
+    st = _stream()
+    off = 0
+    for i, s in enumerate(sources):
+        _req(s, F32, "group_norm.source")
+        cs = int(s.shape[-1])
+        check(lib.emote_gn_stats(s.data_ptr(), cs, off, c_total, groups, rows_per_batch, n_batches, sums.data_ptr(),
+                                 1 if i == 0 else 0, st), "emote_gn_stats")
+        off += cs
+    off = 0
+    for s in sources:
+        cs = int(s.shape[-1])
+        check(lib.emote_gn_apply(s.data_ptr(), cs, off, c_total, groups, rows_per_batch, n_batches, sums.data_ptr(),
+                                 gamma.data_ptr(), beta.data_ptr(), eps, 1 if silu else 0, out.data_ptr(), _ptr(raw),
+                                 st), "emote_gn_apply")
+        off += cs
+    return out, raw
+
+
+def layer_norm(x: torch.Tensor, gamma, beta, eps: float = 1e-5, pe: Optional[torch.Tensor] = None,
+               rows_per_frame: int = 0, frames: int = 0) -> torch.Tensor:
+    _req(x, F32, "layer_norm.x")
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    out = torch.empty((M, Cc), dtype=BF16, device=x.device)
+    check(_lib.load().emote_layernorm(x.data_ptr(), M, Cc, gamma.data_ptr(), beta.data_ptr(), eps, _ptr(pe),
+                                      rows_per_frame, frames, out.data_ptr(), _stream()), "emote_layernorm")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def attention(q: torch.Tensor, k0: torch.Tensor, v0: torch.Tensor, out: torch.Tensor, *, batch: int, heads: int,
+              head_dim: int, nq: int, n0: int, q_strides, kv0_strides, o_strides, scale: float, kv0_batch_div: int = 1,
+              k1=None, v1=None, n1: int = 0, kv1_strides=(0, 0), kv1_batch_div: int = 1, kv1_first_batch: int = 0):
+    """Strided flash attention; q/k/v/out are bf16 views into (possibly fused) projection outputs.
+    *_strides = (batch_stride, row_stride) in elements."""
+    a = EmoteAttnArgs()
+    a.q, a.k0, a.v0, a.out = q.data_ptr(), k0.data_ptr(), v0.data_ptr(), out.data_ptr()
+    a.k1, a.v1 = _ptr(k1), _ptr(v1)
+    a.batch, a.heads, a.head_dim = batch, heads, head_dim
+    a.nq, a.n0, a.n1 = nq, n0, n1
+    a.q_batch_stride, a.q_row_stride = q_strides
+    a.kv0_batch_stride, a.kv0_row_stride = kv0_strides
+    a.kv1_batch_stride, a.kv1_row_stride = kv1_strides
+    a.o_batch_stride, a.o_row_stride = o_strides
+    a.kv0_batch_div, a.kv1_batch_div, a.kv1_first_batch = kv0_batch_div, kv1_batch_div, kv1_first_batch
+    a.scale = scale
+    check(_lib.load().emote_attention_bf16(C.byref(a), _stream()), "emote_attention_bf16")
+    return out
+
+
+def temporal_attention(qkv: torch.Tensor, B: int, F_: int, HW: int, heads: int, head_dim: int) -> torch.Tensor:
+    _req(qkv, BF16, "temporal_attention.qkv")
+    out = torch.empty((B * F_ * HW, heads * head_dim), dtype=BF16, device=qkv.device)
+    check(_lib.load().emote_temporal_attention_bf16(qkv.data_ptr(), out.data_ptr(), B, F_, HW, heads, head_dim,
+                                                    head_dim ** -0.5, _stream()), "emote_temporal_attention_bf16")
+    return out
+
+
+def softmax_rows(scores: torch.Tensor, scale: float) -> torch.Tensor:
+    _req(scores, F32, "softmax_rows.scores")
+    N = scores.shape[-1]
+    R = scores.numel() // N
+    out = torch.empty(scores.shape, dtype=BF16, device=scores.device)
+    check(_lib.load().emote_softmax_rows_bf16(scores.data_ptr(), R, N, scale, out.data_ptr(), _stream()),
+          "emote_softmax_rows_bf16")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- misc
+def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None, c_offset: int = 0) -> torch.Tensor:
+    _req(x, F32, "cast_bf16.x")
+    cs = x.shape[-1]
+    rows = x.numel() // cs
+    if out is None:
+        out = torch.empty((rows, cs), dtype=BF16, device=x.device)
+    check(_lib.load().emote_cast_bf16(x.data_ptr(), rows, cs, c_offset, out.shape[-1], out.data_ptr(), _stream()),
+          "emote_cast_bf16")
+    return out
+
+
+def silu_bf16(x: torch.Tensor) -> torch.Tensor:
+    _req(x, F32, "silu_bf16.x")
+    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(_lib.load().emote_silu_bf16(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "emote_silu_bf16")
+    return out
+
+
+def tokens_to_ncfhw(tok: torch.Tensor, B: int, Cc: int, F_: int, H: int, W: int, ld: Optional[int] = None):
+    _req(tok, F32, "tokens_to_ncfhw.tok")
+    out = torch.empty((B, Cc, F_, H, W), dtype=F32, device=tok.device)
+    check(_lib.load().emote_tokens_to_ncfhw(tok.data_ptr(), B, Cc, F_, H * W, out.data_ptr(), _stream()),
+          "emote_tokens_to_ncfhw")
+    return out
+
+
+def ncfhw_to_tokens(x: torch.Tensor) -> torch.Tensor:
+    _req(x, F32, "ncfhw_to_tokens.x")
+    B, Cc, F_, H, W = x.shape
+    out = torch.empty((B * F_ * H * W, Cc), dtype=F32, device=x.device)
+    check(_lib.load().emote_ncfhw_to_tokens(x.data_ptr(), B, Cc, F_, H * W, out.data_ptr(), _stream()),
+          "emote_ncfhw_to_tokens")
+    return out
+
+
+def add_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    _req(a, F32, "add.a"), _req(b, F32, "add.b")
+    out = torch.empty_like(a)
+    check(_lib.load().emote_add_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream()), "emote_add_f32")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, flip_sin_to_cos: bool, freq_shift: float) -> torch.Tensor:
+    _req(t, F32, "timestep_embedding.t")
+    out = torch.empty((t.numel(), dim), dtype=BF16, device=t.device)
+    check(_lib.load().emote_timestep_embedding(t.data_ptr(), t.numel(), dim, 1 if flip_sin_to_cos else 0,
+                                               float(freq_shift), out.data_ptr(), _stream()), "emote_timestep_embedding")
+    return out
+
+
+def cfg_ddim_step(latents: torch.Tensor, noise_pred: torch.Tensor, counter: Optional[torch.Tensor], guidance: float,
+                  alpha_t: float, alpha_prev: float) -> torch.Tensor:
+    """latents [1|B, C, F, H, W] fp32 updated in place; noise_pred [2*B, C, F, H, W] (uncond first)."""
+    _req(latents, F32, "cfg_ddim_step.latents"), _req(noise_pred, F32, "cfg_ddim_step.noise_pred")
+    n = latents.numel()
+    n_frames = latents.shape[2]
+    inner = latents.shape[3] * latents.shape[4]
+    check(_lib.load().emote_cfg_ddim_step(latents.data_ptr(), noise_pred.data_ptr(), _ptr(counter), n, n_frames, inner,
+                                          guidance, alpha_t, alpha_prev, _stream()), "emote_cfg_ddim_step")
+    return latents
+
+
+def vae_postprocess(tok: torch.Tensor, n_img: int, H: int, W: int, want_f32: bool = True, want_u8: bool = False):
+    _req(tok, F32, "vae_postprocess.tok")
+    ld = tok.shape[-1]
+    of = torch.empty((n_img, 3, H, W), dtype=F32, device=tok.device) if want_f32 else None
+    ou = torch.empty((n_img, 3, H, W), dtype=torch.uint8, device=tok.device) if want_u8 else None
+    check(_lib.load().emote_vae_postprocess(tok.data_ptr(), n_img, H * W, ld, _ptr(of), _ptr(ou), _stream()),
+          "emote_vae_postprocess")
+    return of, ou

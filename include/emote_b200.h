@@ -1,0 +1,167 @@
+/* emote_b200.h — C ABI of libemote_b200.so (B200 / sm_100a kernels for the Emote-hack denoising hot path).
+ *
+ * The reference (johndpope/Emote-hack) has no FFI: its hot path bottoms out in ATen/cuDNN/cuBLAS library
+ * calls made from Python nn.Modules.  This header is the boundary a maintainer would bind
+ * (ctypes stub in INTEGRATION.md); each entry point names the reference call it replaces (file:line under
+ * the reference checkout).
+ *
+ * Conventions: raw device pointers + explicit sizes, caller-owned buffers, no allocation and no host sync
+ * inside, work is enqueued on `stream` (a cudaStream_t passed as void*).  Every function returns 0 on success,
+ * non-zero on error; emote_last_error() gives the message (thread-local).  "tokens-major" means the
+ * activation tensor [b, c, f, h, w] stored channels-last, i.e. row index = ((b*F + f)*H + y)*W + x, C contiguous.
+ */
+#ifndef EMOTE_B200_H
+#define EMOTE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMOTE_ABI_VERSION 1
+#define EMOTE_ERR_INVALID 1
+#define EMOTE_ERR_CUDA 2
+
+#define EMOTE_DT_F32 0
+#define EMOTE_DT_BF16 1
+
+#define EMOTE_EPI_LINEAR 0
+#define EMOTE_EPI_GEGLU 1
+
+const char* emote_last_error(void);
+long long emote_launch_count(void); /* kernels launched by this library so far (bench.py "gpu_launches") */
+int emote_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------ GEMM / conv
+ * out[M,N] = epilogue(A[M,K] x Wt[N,K]^T), bf16 operands, fp32 accumulation on tcgen05 tensor cores.
+ * conv_taps = 9: A is an NHWC bf16 tensor [n_img,H,W,C]; computes the 3x3 / stride 1 / pad 1 convolution as an
+ * implicit GEMM with Wt packed as [N, (ky*3+kx)*C + c].
+ * Replaces: nn.Linear / nn.Conv2d(1x1) / InflatedConv3d(3x3) — resnet.py:30-38,180-205; attention.py:126-150;
+ * orig_attention.py:606-650,776-781,825-827; motion_module.py:149-159.
+ * Epilogue: v = acc + bias[n] + row_bias[m / rows_per_group, n] + residual[m, n]; out = out_scale * v.
+ * EMOTE_EPI_GEGLU: Wt/bias rows are packed per block_n tile as [value rows | gate rows]; out[M, N/2] bf16 =
+ * (acc_v + b_v) * gelu_erf(acc_g + b_g)   (orig_attention.py:817-827). */
+typedef struct {
+  int32_t M, N, K;
+  int32_t lda;            /* A row pitch in elements (plain GEMM) */
+  int32_t conv_taps;      /* 1 or 9 */
+  int32_t n_img, H, W, C; /* conv mode */
+  const float* bias;      /* [N] or NULL */
+  const float* row_bias;  /* [ceil(M/rows_per_group), N] or NULL */
+  int32_t rows_per_group;
+  const float* residual;  /* [M, ldr] fp32 or NULL; may alias out */
+  int32_t ldr;
+  float out_scale;
+  int32_t epilogue;       /* EMOTE_EPI_* */
+  int32_t out_dtype;      /* EMOTE_DT_* */
+  int32_t ldc;            /* out row pitch in elements */
+  int32_t block_n;        /* 0 = auto (160 if N % 160 == 0 else 128) */
+} EmoteGemmArgs;
+int emote_gemm_bf16(const void* A, const void* Wt, void* out, const EmoteGemmArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ GroupNorm
+ * Two-kernel GroupNorm over tokens-major fp32 activations (nn.GroupNorm at resnet.py:180,191 [5-D: statistics
+ * span all frames of a sample], attention.py:124 and motion_module.py:147 [per frame], unet_controlnet.py:476).
+ * A "group batch" is the set of rows sharing statistics (F*H*W rows for the 5-D norm, H*W for per-frame).
+ * The input may be one of several channel-concatenated sources (torch.cat at unet_3d_blocks.py:629,731):
+ * source channels [0,C_src) map to channels [c_offset, c_offset+C_src) of the C_total-wide normalised tensor.
+ * sums: [n_batches, groups, 2] doubles (sum, sum of squares); zeroed by the call when zero_first != 0. */
+int emote_gn_stats(const float* x, int32_t C_src, int32_t c_offset, int32_t C_total, int32_t groups,
+                   int64_t rows_per_batch, int32_t n_batches, double* sums, int32_t zero_first, void* stream);
+/* y = (x-mean)*rstd*gamma+beta [-> SiLU if act_silu]; written as bf16 into out[row, c_offset + c] (pitch C_total).
+ * raw_out (optional, same layout) receives the un-normalised input rounded to bf16 (shortcut-conv operand). */
+int emote_gn_apply(const float* x, int32_t C_src, int32_t c_offset, int32_t C_total, int32_t groups,
+                   int64_t rows_per_batch, int32_t n_batches, const double* sums, const float* gamma,
+                   const float* beta, float eps, int32_t act_silu, void* out_bf16, void* raw_out_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ LayerNorm
+ * out_bf16[M,C] = LN(x[M,C]) * gamma + beta (+ pe[(row / pe_rows_per_frame) % pe_frames, :]).
+ * nn.LayerNorm at attention.py:204,225,232 and motion_module.py:208,213; the additive table is the temporal
+ * sinusoidal PositionalEncoding applied after the norm (motion_module.py:246-248,283). */
+int emote_layernorm(const float* x, int64_t M, int32_t C, const float* gamma, const float* beta, float eps,
+                    const float* pe, int32_t pe_rows_per_frame, int32_t pe_frames, void* out_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ attention
+ * Flash-style softmax(Q K^T * scale) V on bf16 with fp32 softmax/accumulation (orig_attention.py:655-684).
+ * Keys/values come from up to two segments that are logically concatenated along the key axis
+ * (mutual_self_attention.py:239-241: [self tokens | reference bank]); segment 1 is only visible to batches
+ * b >= kv1_first_batch (the unconditional CFG half must not see the bank, mutual_self_attention.py:244-255).
+ * Row r, head h of batch b lives at base + b_idx*batch_stride + r*row_stride + h*head_dim (elements). */
+typedef struct {
+  const void* q;
+  const void* k0;
+  const void* v0;
+  const void* k1; /* NULL when n1 == 0 */
+  const void* v1;
+  void* out;
+  int32_t batch, heads, head_dim;
+  int32_t nq, n0, n1;
+  int64_t q_batch_stride, q_row_stride;
+  int64_t kv0_batch_stride, kv0_row_stride;
+  int64_t kv1_batch_stride, kv1_row_stride;
+  int64_t o_batch_stride, o_row_stride;
+  int32_t kv0_batch_div; /* kv batch index = b / div (context shared by the frames of a sample) */
+  int32_t kv1_batch_div;
+  int32_t kv1_first_batch;
+  float scale;
+} EmoteAttnArgs;
+int emote_attention_bf16(const EmoteAttnArgs* args, void* stream);
+
+/* Temporal self-attention over the frame axis (VersatileAttention, motion_module.py:275-334): for every
+ * (sample b, pixel p, head h) attends over the F frames.  qkv: tokens-major [B, F, HW, 3*heads*head_dim] bf16
+ * (q | k | v), out: [B, F, HW, heads*head_dim] bf16.  The (b f) d c <-> (b d) f c rearranges
+ * (motion_module.py:280,332) are expressed as strides, never materialised.  F <= 32. */
+int emote_temporal_attention_bf16(const void* qkv, void* out, int32_t B, int32_t F, int32_t HW, int32_t heads,
+                                  int32_t head_dim, float scale, void* stream);
+
+/* row softmax of fp32 scores [R, N] (scaled) -> bf16 probabilities; used by the VAE mid-block attention
+ * (single 512-wide head: orig_attention.py:360-376). */
+int emote_softmax_rows_bf16(const float* scores, int64_t R, int32_t N, float scale, void* out_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ layout / gather
+ * conv_in operand: latents [B, Cl<=7, F, H, W] fp32 -> im2col rows [B*F*H*W, 64] bf16 (cols (ky*3+kx)*Cl + c, rest 0)
+ * after x*pre_scale and an optional pointwise Cl x Cl linear (VAE post_quant_conv).  unet_controlnet.py:411,
+ * EMOAnimationPipeline.py:293-301. */
+int emote_latent_im2col(const float* latent, int32_t B, int32_t Cl, int32_t F, int32_t H, int32_t W, float pre_scale,
+                        const float* pw_weight, const float* pw_bias, void* out_bf16, void* stream);
+/* generic 3x3 pad-1 im2col from tokens-major fp32 [n_img,H,W,C] -> bf16 [n_img*Ho*Wo, 9*C], stride 1 or 2
+ * (Downsample3D, resnet.py:99-110; also the fallback for image sizes the TMA conv tile cannot cover). */
+int emote_im2col3x3(const float* x, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t stride, void* out_bf16,
+                    void* stream);
+/* same gather from a bf16 NHWC source (fallback path of the fused-norm convs) */
+int emote_im2col3x3_bf16(const void* x, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t stride,
+                         void* out_bf16, void* stream);
+/* nearest-neighbour x2 upsample in H and W (Upsample3D, resnet.py:74), fp32 -> bf16 conv operand */
+int emote_upsample2x(const float* x, int32_t n_img, int32_t H, int32_t W, int32_t C, void* out_bf16, void* stream);
+/* out_bf16[row, c_offset + c] = bf16(x[row, c]) (pitch C_total) */
+int emote_cast_bf16(const float* x, int64_t rows, int32_t C_src, int32_t c_offset, int32_t C_total, void* out_bf16,
+                    void* stream);
+/* out_bf16[i] = bf16(silu(x[i]))  (time embedding activation, resnet.py:186) */
+int emote_silu_bf16(const float* x, int64_t n, void* out_bf16, void* stream);
+/* tokens-major [B,F,H,W,C] fp32 <-> [B,C,F,H,W] fp32 */
+int emote_tokens_to_ncfhw(const float* tok, int32_t B, int32_t C, int32_t F, int32_t HW, float* out, void* stream);
+int emote_ncfhw_to_tokens(const float* x, int32_t B, int32_t C, int32_t F, int32_t HW, float* out, void* stream);
+/* out = a + b (ControlNet residual adds, unet_controlnet.py:430-447) */
+int emote_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
+/* sinusoidal timestep embedding -> bf16 [B, dim] (embeddings.py:28-68) */
+int emote_timestep_embedding(const float* timesteps, int32_t B, int32_t dim, int32_t flip_sin_to_cos,
+                             float freq_shift, void* out_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ sampler
+ * Fused window-average + classifier-free guidance + DDIM update (EMOAnimationPipeline.py:790-817, eta = 0):
+ *   eps = eps_u/cnt + g * (eps_c/cnt - eps_u/cnt);  x0 = (x - sqrt(1-a_t) eps)/sqrt(a_t);
+ *   x_prev = sqrt(a_prev) x0 + sqrt(1-a_prev) eps.
+ * noise_pred: [2, n] (uncond, cond) accumulated predictions; counter: [n_frames] visit counts, frame index of
+ * element i = (i / inner) % n_frames; latents updated in place. */
+int emote_cfg_ddim_step(float* latents, const float* noise_pred, const float* counter, int64_t n, int32_t n_frames,
+                        int64_t inner, float guidance_scale, float alpha_t, float alpha_prev, void* stream);
+/* decoded frames: tokens-major [n,H*W,ld>=3] fp32 -> clamp(x/2+0.5,0,1) as fp32 [n,3,H,W] and/or uint8 [n,3,H,W]
+ * (EMOAnimationPipeline.py:304) */
+int emote_vae_postprocess(const float* tok, int32_t n_img, int32_t HW, int32_t ld, float* out_f32, uint8_t* out_u8,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMOTE_B200_H */

@@ -1,0 +1,315 @@
+"""Kernel-level numerics: every CUDA entry point against a plain PyTorch fp32 reference of the same op.
+
+Tolerances: operands are rounded to bf16 before both paths, accumulation is fp32, so the only differences are
+accumulation order and the bf16 rounding of bf16 outputs (rel 2^-9 = 2e-3 per element).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from emote_hack_b200 import ops as o
+    return o
+
+
+def _gen(seed=0):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    return g
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 320, 320), (300, 160, 192), (2, 1280, 320), (154, 640, 768),
+                                   (4096, 960, 320), (1000, 136, 72)])
+def test_gemm_plain(ops, M, N, K):
+    g = _gen(1)
+    a = torch.randn(M, K, device="cuda", generator=g).to(BF16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(BF16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ w.float().t() + bias
+    out = ops.gemm(a, w, bias=bias)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 2e-5
+    out_b = ops.gemm(a, w, bias=bias, out_dtype=BF16)
+    assert rel_l2(out_b, ref) < 4e-3
+
+
+def test_gemm_epilogue_residual_rowbias_scale(ops):
+    g = _gen(2)
+    M, N, K = 512, 320, 640
+    a = torch.randn(M, K, device="cuda", generator=g).to(BF16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(BF16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    rb = torch.randn(4, N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    ref = (a.float() @ w.float().t() + bias + rb.repeat_interleave(128, 0) + res) * 0.5
+    out = ops.gemm(a, w, bias=bias, row_bias=rb, rows_per_group=128, residual=res, out_scale=0.5)
+    assert rel_l2(out, ref) < 2e-5
+    # in-place residual (residual aliases out)
+    res2 = res.clone()
+    ops.gemm(a, w, bias=bias, residual=res2, out=res2)
+    assert rel_l2(res2, a.float() @ w.float().t() + bias + res) < 2e-5
+
+
+@pytest.mark.parametrize("C", [64, 320])
+def test_gemm_geglu(ops, C):
+    g = _gen(3)
+    M, inner = 384, 4 * C
+    a = torch.randn(M, C, device="cuda", generator=g).to(BF16)
+    w = (torch.randn(2 * inner, C, device="cuda", generator=g) / math.sqrt(C)).to(BF16)
+    b = torch.randn(2 * inner, device="cuda", generator=g)
+    h = a.float() @ w.float().t() + b
+    ref = h[:, :inner] * F.gelu(h[:, inner:])
+    wp, bp = ops.pack_geglu(w.float(), b)
+    out = ops.gemm(a, wp, bias=bp, geglu=True, out_dtype=BF16)
+    assert out.shape == (M, inner)
+    assert rel_l2(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize("n_img,H,W,C,N", [(2, 8, 8, 64, 128), (2, 16, 16, 128, 64), (3, 32, 32, 64, 320),
+                                           (2, 64, 64, 320, 320), (1, 128, 128, 128, 128), (1, 256, 256, 64, 3)])
+def test_conv3x3_implicit(ops, n_img, H, W, C, N):
+    g = _gen(4)
+    x = torch.randn(n_img, H, W, C, device="cuda", generator=g).to(BF16)
+    w = (torch.randn(N, C, 3, 3, device="cuda", generator=g) / math.sqrt(9 * C)).to(BF16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    wp = ops.pack_conv3x3(w.float())
+    ld = N if N % 4 == 0 else 4
+    out = torch.zeros(n_img * H * W, ld, device="cuda")
+    ops.conv3x3(x, wp, n_img, H, W, C, bias=bias, out=out)
+    assert rel_l2(out[:, :N], ref) < 2e-5
+
+
+def test_conv3x3_fallback_im2col(ops):
+    g = _gen(5)
+    n_img, H, W, C, N = 2, 12, 12, 64, 128
+    x = torch.randn(n_img, H, W, C, device="cuda", generator=g).to(BF16)
+    w = (torch.randn(N, C, 3, 3, device="cuda", generator=g) / math.sqrt(9 * C)).to(BF16)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    assert not ops.conv_tile_ok(H, W)
+    out = ops.conv3x3(x, ops.pack_conv3x3(w.float()), n_img, H, W, C)
+    assert rel_l2(out, ref) < 2e-5
+
+
+def test_downsample_im2col_s2(ops):
+    g = _gen(6)
+    n_img, H, W, C, N = 2, 16, 16, 64, 128
+    x = torch.randn(n_img, H, W, C, device="cuda", generator=g)
+    w = (torch.randn(N, C, 3, 3, device="cuda", generator=g) / math.sqrt(9 * C)).to(BF16)
+    ref = F.conv2d(x.to(BF16).float().permute(0, 3, 1, 2), w.float(), None, stride=2, padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, N)
+    cols = ops.im2col_s2(x, n_img, H, W, C)
+    out = ops.gemm(cols, ops.pack_conv3x3(w.float()))
+    assert rel_l2(out, ref) < 2e-5
+
+
+def test_upsample2x(ops):
+    g = _gen(7)
+    x = torch.randn(2, 8, 8, 64, device="cuda", generator=g)
+    out = ops.upsample2x(x, 2, 8, 8, 64).view(2, 16, 16, 64)
+    ref = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1).to(BF16)
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("srcs,rows_per_batch,n_batches", [((320,), 1024, 2), ((1280, 640), 256, 2), ((64,), 64, 6),
+                                                          ((640, 320), 512, 2), ((128,), 4096, 1)])
+def test_group_norm(ops, srcs, rows_per_batch, n_batches):
+    g = _gen(8)
+    rows = rows_per_batch * n_batches
+    xs = [torch.randn(rows, c, device="cuda", generator=g) * 2 + 0.5 for c in srcs]
+    ct = sum(srcs)
+    gamma = torch.randn(ct, device="cuda", generator=g)
+    beta = torch.randn(ct, device="cuda", generator=g)
+    out, raw = ops.group_norm(xs, 32, rows_per_batch, n_batches, gamma, beta, 1e-5, True, want_raw=True)
+    xc = torch.cat(xs, dim=1).view(n_batches, rows_per_batch, ct).permute(0, 2, 1)  # [nb, C, rows]
+    ref = F.silu(F.group_norm(xc, 32, gamma, beta, 1e-5)).permute(0, 2, 1).reshape(rows, ct)
+    assert rel_l2(out, ref) < 4e-3
+    assert torch.equal(raw, torch.cat(xs, dim=1).to(BF16))
+    out2, _ = ops.group_norm(xs, 32, rows_per_batch, n_batches, gamma, beta, 1e-6, False)
+    ref2 = F.group_norm(xc, 32, gamma, beta, 1e-6).permute(0, 2, 1).reshape(rows, ct)
+    assert rel_l2(out2, ref2) < 4e-3
+
+
+@pytest.mark.parametrize("C", [64, 320, 1280])
+def test_layer_norm(ops, C):
+    g = _gen(9)
+    F_, HW, B = 4, 16, 2
+    M = B * F_ * HW
+    x = torch.randn(M, C, device="cuda", generator=g) * 3 + 1
+    gamma = torch.randn(C, device="cuda", generator=g)
+    beta = torch.randn(C, device="cuda", generator=g)
+    out = ops.layer_norm(x, gamma, beta)
+    ref = F.layer_norm(x, (C,), gamma, beta, 1e-5)
+    assert rel_l2(out, ref) < 4e-3
+    pe = torch.randn(24, C, device="cuda", generator=g)
+    out2 = ops.layer_norm(x, gamma, beta, pe=pe, rows_per_frame=HW, frames=F_)
+    fidx = (torch.arange(M, device="cuda") // HW) % F_
+    assert rel_l2(out2, ref + pe[fidx]) < 4e-3
+
+
+def _sdpa_ref(q, k, v, scale):
+    s = torch.einsum("bhqd,bhkd->bhqk", q.float(), k.float()) * scale
+    return torch.einsum("bhqk,bhkd->bhqd", s.softmax(-1), v.float())
+
+
+@pytest.mark.parametrize("heads,d,nq,nk", [(8, 40, 256, 256), (8, 80, 64, 64), (8, 160, 64, 64), (4, 16, 64, 64),
+                                           (8, 40, 100, 77), (8, 40, 4096, 4096), (4, 64, 16, 16), (2, 32, 200, 5)])
+def test_flash_attention_fused_qkv(ops, heads, d, nq, nk):
+    g = _gen(10)
+    batch = 3
+    C = heads * d
+    self_attn = nq == nk
+    if self_attn:
+        qkv = torch.randn(batch, nq, 3 * C, device="cuda", generator=g).to(BF16)
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        kvs = (nq * 3 * C, 3 * C)
+        qs = kvs
+    else:
+        qt = torch.randn(batch, nq, C, device="cuda", generator=g).to(BF16)
+        kv = torch.randn(batch, nk, 2 * C, device="cuda", generator=g).to(BF16)
+        q, k, v = qt, kv[..., :C], kv[..., C:]
+        qs, kvs = (nq * C, C), (nk * 2 * C, 2 * C)
+    out = torch.empty(batch, nq, C, device="cuda", dtype=BF16)
+    ops.attention(q, k, v, out, batch=batch, heads=heads, head_dim=d, nq=nq, n0=nk, q_strides=qs, kv0_strides=kvs,
+                  o_strides=(nq * C, C), scale=d ** -0.5)
+    sp = lambda t, n: t.reshape(batch, n, heads, d).permute(0, 2, 1, 3)
+    ref = _sdpa_ref(sp(q, nq), sp(k, nk), sp(v, nk), d ** -0.5).permute(0, 2, 1, 3).reshape(batch, nq, C)
+    assert rel_l2(out, ref) < 6e-3
+
+
+def test_flash_attention_two_segments_cfg(ops):
+    """reference attention: K/V = [self | bank], bank only visible to the conditional half, shared across frames."""
+    g = _gen(11)
+    heads, d, n, F_ = 8, 40, 64, 4
+    C = heads * d
+    batch = 2 * F_
+    qkv = torch.randn(batch, n, 3 * C, device="cuda", generator=g).to(BF16)
+    bank_kv = torch.randn(2, n, 2 * C, device="cuda", generator=g).to(BF16)
+    out = torch.empty(batch, n, C, device="cuda", dtype=BF16)
+    ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], out, batch=batch, heads=heads, head_dim=d, nq=n,
+                  n0=n, q_strides=(n * 3 * C, 3 * C), kv0_strides=(n * 3 * C, 3 * C), o_strides=(n * C, C),
+                  scale=d ** -0.5, k1=bank_kv[..., :C], v1=bank_kv[..., C:], n1=n, kv1_strides=(n * 2 * C, 2 * C),
+                  kv1_batch_div=F_, kv1_first_batch=F_)
+    sp = lambda t, nn_: t.reshape(t.shape[0], nn_, heads, d).permute(0, 2, 1, 3)
+    q, k, v = sp(qkv[..., :C], n), sp(qkv[..., C:2 * C], n), sp(qkv[..., 2 * C:], n)
+    ref_uc = _sdpa_ref(q[:F_], k[:F_], v[:F_], d ** -0.5)
+    bk = sp(bank_kv[1:2, :, :C].expand(F_, -1, -1), n)
+    bv = sp(bank_kv[1:2, :, C:].expand(F_, -1, -1), n)
+    ref_c = _sdpa_ref(q[F_:], torch.cat([k[F_:], bk], 2), torch.cat([v[F_:], bv], 2), d ** -0.5)
+    ref = torch.cat([ref_uc, ref_c]).permute(0, 2, 1, 3).reshape(batch, n, C)
+    assert rel_l2(out, ref) < 6e-3
+
+
+@pytest.mark.parametrize("heads,d,F_,HW", [(8, 40, 16, 64), (8, 160, 16, 16), (4, 16, 8, 64), (8, 80, 24, 16),
+                                           (8, 40, 32, 16), (4, 64, 1, 16)])
+def test_temporal_attention(ops, heads, d, F_, HW):
+    g = _gen(12)
+    B = 2
+    C = heads * d
+    qkv = torch.randn(B, F_, HW, 3 * C, device="cuda", generator=g).to(BF16)
+    out = ops.temporal_attention(qkv.view(-1, 3 * C), B, F_, HW, heads, d).view(B, F_, HW, C)
+    sp = lambda t: t.permute(0, 2, 1, 3).reshape(B * HW, F_, heads, d).permute(0, 2, 1, 3)
+    ref = _sdpa_ref(sp(qkv[..., :C]), sp(qkv[..., C:2 * C]), sp(qkv[..., 2 * C:]), d ** -0.5)
+    ref = ref.permute(0, 2, 1, 3).reshape(B, HW, F_, C).permute(0, 2, 1, 3)
+    assert rel_l2(out, ref) < 6e-3
+
+
+def test_softmax_rows(ops):
+    g = _gen(13)
+    s = torch.randn(300, 4096, device="cuda", generator=g) * 4
+    out = ops.softmax_rows(s, 0.25)
+    assert rel_l2(out, (s * 0.25).softmax(-1)) < 4e-3
+
+
+def test_latent_im2col_and_small_conv(ops):
+    g = _gen(14)
+    B, Cl, F_, H, W, N = 2, 4, 3, 8, 8, 64
+    lat = torch.randn(B, Cl, F_, H, W, device="cuda", generator=g)
+    w = torch.randn(N, Cl, 3, 3, device="cuda", generator=g) * 0.2
+    bias = torch.randn(N, device="cuda", generator=g)
+    cols = ops.latent_im2col(lat)
+    out = ops.gemm(cols, ops.pack_conv3x3_small(w), bias=bias)
+    x2d = lat.permute(0, 2, 1, 3, 4).reshape(B * F_, Cl, H, W)
+    ref = F.conv2d(x2d.to(BF16).float(), w.to(BF16).float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    assert rel_l2(out, ref) < 2e-5
+    # with pre-scale + pointwise linear (VAE post_quant_conv folded in front)
+    pw = torch.randn(Cl, Cl, device="cuda", generator=g)
+    pb = torch.randn(Cl, device="cuda", generator=g)
+    cols2 = ops.latent_im2col(lat, pre_scale=1 / 0.18215, pw_weight=pw, pw_bias=pb)
+    z = F.conv2d(x2d / 0.18215, pw.view(Cl, Cl, 1, 1), pb)
+    ref2 = F.conv2d(z.to(BF16).float(), w.to(BF16).float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    out2 = ops.gemm(cols2, ops.pack_conv3x3_small(w), bias=bias)
+    assert rel_l2(out2, ref2) < 3e-3
+
+
+def test_layout_and_misc(ops):
+    g = _gen(15)
+    B, Cc, F_, H, W = 2, 4, 3, 8, 8
+    x = torch.randn(B, Cc, F_, H, W, device="cuda", generator=g)
+    tok = ops.ncfhw_to_tokens(x)
+    assert torch.equal(tok.view(B, F_, H, W, Cc), x.permute(0, 2, 3, 4, 1))
+    assert torch.equal(ops.tokens_to_ncfhw(tok, B, Cc, F_, H, W), x)
+    y = torch.randn_like(x)
+    assert torch.equal(ops.add_f32(x, y), x + y)
+    assert rel_l2(ops.silu_bf16(x), F.silu(x)) < 4e-3
+    wide = torch.randn(64, 128, device="cuda", generator=g)
+    dst = torch.zeros(64, 256, device="cuda", dtype=BF16)
+    ops.cast_bf16(wide, dst, c_offset=128)
+    assert torch.equal(dst[:, 128:], wide.to(BF16)) and dst[:, :128].abs().sum() == 0
+
+
+def test_timestep_embedding(ops):
+    t = torch.tensor([981.0, 1.0, 500.0], device="cuda")
+    out = ops.timestep_embedding(t, 320, True, 0.0)
+    half = 160
+    e = torch.exp(-math.log(10000.0) * torch.arange(half, device="cuda", dtype=torch.float32) / half)
+    emb = t[:, None] * e[None]
+    ref = torch.cat([torch.cos(emb), torch.sin(emb)], -1)
+    assert (out.float() - ref).abs().max() < 1.5e-2  # bf16 output + large-argument sin/cos
+
+
+def test_cfg_ddim_step(ops):
+    g = _gen(16)
+    lat = torch.randn(1, 4, 6, 8, 8, device="cuda", generator=g)
+    npred = torch.randn(2, 4, 6, 8, 8, device="cuda", generator=g)
+    cnt = torch.tensor([1, 2, 1, 1, 2, 1], device="cuda", dtype=torch.float32)
+    a_t, a_p, gs = 0.37, 0.52, 7.5
+    e = npred / cnt.view(1, 1, 6, 1, 1)
+    eps = e[0:1] + gs * (e[1:2] - e[0:1])
+    x0 = (lat - (1 - a_t) ** 0.5 * eps) / a_t ** 0.5
+    ref = a_p ** 0.5 * x0 + (1 - a_p) ** 0.5 * eps
+    out = ops.cfg_ddim_step(lat.clone(), npred, cnt, gs, a_t, a_p)
+    assert rel_l2(out, ref) < 1e-5
+
+
+def test_vae_postprocess(ops):
+    g = _gen(17)
+    tok = torch.randn(2 * 64, 4, device="cuda", generator=g)
+    of, ou = ops.vae_postprocess(tok, 2, 8, 8, want_f32=True, want_u8=True)
+    ref = (tok[:, :3].view(2, 64, 3).permute(0, 2, 1).reshape(2, 3, 8, 8) / 2 + 0.5).clamp(0, 1)
+    assert torch.allclose(of, ref, atol=1e-6)
+    assert (ou.float() - ref * 255).abs().max() <= 0.5 + 1e-3
+
+
+def test_errors_are_loud(ops):
+    from emote_hack_b200._lib import EmoteKernelError
+    a = torch.zeros(16, 12, device="cuda", dtype=BF16)
+    w = torch.zeros(16, 12, device="cuda", dtype=BF16)
+    with pytest.raises(EmoteKernelError):
+        ops.gemm(a, w)  # K not a multiple of 8
+    with pytest.raises(EmoteKernelError):
+        ops.gemm(a.cpu(), w)

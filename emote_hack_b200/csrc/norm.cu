@@ -16,9 +16,11 @@ constexpr int GN_MAX_GROUPS = 64;
 // blockDim = (PX, TY); thread (px, ty) owns channel pairs px + pass*PX and rows ty, ty+TY, ...
 __global__ void gn_stats_kernel(const float* __restrict__ x, int C_src, int c_offset, int cpg, int groups,
                                 long long rows_per_batch, int rows_per_block, int passes, double* __restrict__ sums) {
-  __shared__ float s_acc[GN_MAX_GROUPS * 2];
+  // fp64 accumulation end to end: E[x^2] - mean^2 cancels badly in fp32 when |mean| >> std, and the atomics'
+  // ordering would otherwise leak ~1e-6 run-to-run noise into every normalised value.
+  __shared__ double s_acc[GN_MAX_GROUPS * 2];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  for (int i = tid; i < groups * 2; i += blockDim.x * blockDim.y) s_acc[i] = 0.f;
+  for (int i = tid; i < groups * 2; i += blockDim.x * blockDim.y) s_acc[i] = 0.0;
   __syncthreads();
 
   const int batch = blockIdx.y;
@@ -27,9 +29,9 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int C_src, int c_of
   if (r1 > rows_per_batch) r1 = rows_per_batch;
   const float* xb = x + ((long long)batch * rows_per_batch) * C_src;
 
-  float s[GN_MAX_PASS], q[GN_MAX_PASS];
+  double s[GN_MAX_PASS], q[GN_MAX_PASS];
 #pragma unroll
-  for (int i = 0; i < GN_MAX_PASS; ++i) s[i] = q[i] = 0.f;
+  for (int i = 0; i < GN_MAX_PASS; ++i) s[i] = q[i] = 0.0;
 
   for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
     const float2* row = reinterpret_cast<const float2*>(xb + r * C_src);
@@ -37,8 +39,9 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int C_src, int c_of
     for (int ps = 0; ps < GN_MAX_PASS; ++ps) {
       if (ps < passes) {
         const float2 v = __ldg(row + threadIdx.x + ps * blockDim.x);
-        s[ps] += v.x + v.y;
-        q[ps] += v.x * v.x + v.y * v.y;
+        const double a = (double)v.x, b = (double)v.y;
+        s[ps] += a + b;
+        q[ps] += a * a + b * b;
       }
     }
   }
@@ -53,8 +56,8 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int C_src, int c_of
   }
   __syncthreads();
   for (int i = tid; i < groups * 2; i += blockDim.x * blockDim.y) {
-    const float v = s_acc[i];
-    if (v != 0.f) atomicAdd(&sums[(long long)batch * groups * 2 + i], (double)v);
+    const double v = s_acc[i];
+    if (v != 0.0) atomicAdd(&sums[(long long)batch * groups * 2 + i], v);
   }
 }
 

@@ -319,3 +319,68 @@ def vae_postprocess(tok: torch.Tensor, n_img: int, H: int, W: int, want_f32: boo
     check(_lib.load().emote_vae_postprocess(tok.data_ptr(), n_img, H * W, ld, _ptr(of), _ptr(ou), _stream()),
           "emote_vae_postprocess")
     return of, ou
+
+
+# ----------------------------------------------------------------------------------------------- profiling
+class KernelProfiler:
+    """Brackets every C-ABI launch with CUDA events on the launching stream (bench.py roofline pass, dev profiling).
+
+    with KernelProfiler() as prof: model(...)
+    prof.summary() -> {entry point: (launches, total ms)};  prof.gemm_flops / prof.gemm_ms for the tcgen05 GEMM.
+    """
+
+    def __init__(self):
+        self.records = []
+        self._orig = {}
+
+    def __enter__(self):
+        lib = _lib.load()
+        for name in _lib.SIGNATURES:
+            fn = getattr(lib, name)
+            self._orig[name] = fn
+
+            def wrapped(*args, _fn=fn, _name=name):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                meta = None
+                if _name == "emote_gemm_bf16":
+                    a = args[3]._obj
+                    meta = (a.M, a.N, a.K, a.conv_taps)
+                e0.record()
+                rc = _fn(*args)
+                e1.record()
+                self.records.append((_name, e0, e1, meta))
+                return rc
+
+            setattr(lib, name, wrapped)
+        return self
+
+    def __exit__(self, *exc):
+        lib = _lib.load()
+        for name, fn in self._orig.items():
+            setattr(lib, name, fn)
+        torch.cuda.synchronize()
+        self.times = [(n, e0.elapsed_time(e1), meta) for n, e0, e1, meta in self.records]
+        return False
+
+    def summary(self):
+        out = {}
+        for n, ms, _ in self.times:
+            c, t = out.get(n, (0, 0.0))
+            out[n] = (c + 1, t + ms)
+        return out
+
+    @property
+    def gemm_ms(self):
+        return sum(ms for n, ms, _ in self.times if n == "emote_gemm_bf16")
+
+    @property
+    def gemm_flops(self):
+        return sum(2.0 * m[0] * m[1] * m[2] for n, _, m in self.times if n == "emote_gemm_bf16")
+
+    def gemm_by_shape(self):
+        out = {}
+        for n, ms, m in self.times:
+            if n == "emote_gemm_bf16":
+                c, t = out.get(m, (0, 0.0))
+                out[m] = (c + 1, t + ms)
+        return out

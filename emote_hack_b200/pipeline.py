@@ -1,0 +1,254 @@
+"""Caller side of the hot path: DDIM scheduler, sliding context windows and the denoise + decode loop of
+`EMOAnimationPipeline.__call__` (reference EMOAnimationPipeline.py:543-840), on the sm_100a kernels.
+
+What is mirrored (same names / argument meaning): `DDIMScheduler.{set_timesteps, timesteps, init_noise_sigma,
+scale_model_input, step(...).prev_sample}` (third-party diffusers class the reference instantiates at
+EMOAnimationPipeline.py:908 / magicanimate/pipelines/animation.py:104), `get_context_scheduler('uniform')`
+(magicanimate/pipelines/context.py:20-42), `EMOAnimationPipeline.{prepare_latents, decode_latents, __call__}`.
+What is deliberately NOT here (out of scope for the path): CLIP text encoding, wav2vec feature
+extraction, the AppearanceEncoder (ReferenceNet writer) and the pose ControlNet — their outputs enter as tensors
+(`text_embeddings` / per-frame audio tokens as `encoder_hidden_states`, `reference_banks`).
+
+Multi-GPU: the unit of independent work is (sample | context window) x CFG branch.  `__call__` shards
+the windows of one timestep across ranks (`global_context[rank::world_size]`, EMOAnimationPipeline.py:757) and — only
+when more than one rank contributes to a step — replaces the reference's gather + broadcast + 2 barriers
+(:796-802, :819-821) with ONE all-reduce of the accumulated noise prediction; every rank then runs the fused
+CFG + DDIM update redundantly.  Decoded frames are sharded by frame and all-gathered once (uint8).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .unet3d import ReferenceAttentionControl
+
+
+# =============================================================================================== scheduler
+@dataclass
+class DDIMSchedulerOutput:
+    prev_sample: torch.Tensor
+    pred_original_sample: Optional[torch.Tensor] = None
+
+
+class DDIMScheduler:
+    """diffusers.DDIMScheduler subset used by the reference (eta = 0, epsilon prediction, 'leading' spacing).
+    Defaults = configs/inference.yaml:23-26 + the steps_offset=1 / clip_sample=False the pipeline forces
+    (EMOAnimationPipeline.py:105-130)."""
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012,
+                 beta_schedule: str = "linear", clip_sample: bool = False, set_alpha_to_one: bool = True,
+                 steps_offset: int = 1, prediction_type: str = "epsilon"):
+        if clip_sample or prediction_type != "epsilon":
+            raise NotImplementedError("DDIMScheduler: only clip_sample=False / epsilon prediction (the reference's settings)")
+        if beta_schedule == "linear":
+            betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        elif beta_schedule == "scaled_linear":
+            betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        else:
+            raise NotImplementedError(beta_schedule)
+        self.betas = betas
+        self.alphas = 1.0 - betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.config = type("Cfg", (), dict(num_train_timesteps=num_train_timesteps, steps_offset=steps_offset,
+                                           clip_sample=clip_sample, beta_start=beta_start, beta_end=beta_end,
+                                           beta_schedule=beta_schedule))()
+        self.init_noise_sigma = 1.0
+        self.num_inference_steps: Optional[int] = None
+        self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        self.num_inference_steps = num_inference_steps
+        ratio = self.config.num_train_timesteps // num_inference_steps
+        ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64) + self.config.steps_offset
+        self.timesteps = torch.from_numpy(ts)  # kept on the host: the loop reads python ints (no device sync)
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def alphas_for(self, timestep: int):
+        prev = timestep - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = float(self.alphas_cumprod[timestep])
+        a_prev = float(self.alphas_cumprod[prev]) if prev >= 0 else float(self.final_alpha_cumprod)
+        return a_t, a_prev
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, eta: float = 0.0, **kwargs):
+        """x_t -> x_{t-1}; the arithmetic runs in emote_cfg_ddim_step (guidance folded out: eps is used as is)."""
+        if eta != 0.0:
+            raise NotImplementedError("DDIMScheduler.step: eta != 0 (stochastic DDIM) is not used by the reference")
+        a_t, a_prev = self.alphas_for(int(timestep))
+        out = sample.float().contiguous().clone()
+        eps = model_output.float().contiguous()
+        # guidance 1.0 with identical halves == plain epsilon
+        ops.cfg_ddim_step(out, torch.cat([eps, eps]), None, 1.0, a_t, a_prev)
+        return DDIMSchedulerOutput(prev_sample=out.to(sample.dtype))
+
+
+# =============================================================================================== context windows
+def _ordered_halving(val: int) -> float:
+    return int(f"{val:064b}"[::-1], 2) / (1 << 64)
+
+
+def uniform(step: int = ..., num_steps: Optional[int] = None, num_frames: int = ..., context_size: Optional[int] = None,
+            context_stride: int = 3, context_overlap: int = 4, closed_loop: bool = True):
+    """magicanimate/pipelines/context.py:20-42 — windows of `context_size` frames every size-overlap frames, wrapping
+    modulo num_frames."""
+    if num_frames <= context_size:
+        yield list(range(num_frames))
+        return
+    context_stride = min(context_stride, int(np.ceil(np.log2(num_frames / context_size))) + 1)
+    for context_step in 1 << np.arange(context_stride):
+        pad = int(round(num_frames * _ordered_halving(step)))
+        for j in range(int(_ordered_halving(step) * context_step) + pad,
+                       num_frames + pad + (0 if closed_loop else -context_overlap),
+                       (context_size * context_step - context_overlap)):
+            yield [e % num_frames for e in range(j, j + context_size * context_step, context_step)]
+
+
+def get_context_scheduler(name: str) -> Callable:
+    if name == "uniform":
+        return uniform
+    raise ValueError(f"Unknown context_overlap policy {name}")
+
+
+# =============================================================================================== pipeline
+@dataclass
+class AnimationPipelineOutput:
+    videos: object
+
+
+class EMOAnimationPipeline:
+    """Denoise + decode loop of the reference pipeline for pre-computed conditioning."""
+
+    def __init__(self, vae, unet, scheduler: DDIMScheduler, rank: int = 0, world_size: int = 1,
+                 process_group=None):
+        self.vae, self.unet, self.scheduler = vae, unet, scheduler
+        self.vae_scale_factor = 8
+        self.rank, self.world_size, self.process_group = rank, world_size, process_group
+
+    # -- EMOAnimationPipeline.py:341-368 ---------------------------------------------------------------------------
+    def prepare_latents(self, batch_size, num_channels_latents, video_length, height, width, dtype, device, generator,
+                        latents=None, clip_length=16):
+        shape = (batch_size, num_channels_latents, clip_length, height // self.vae_scale_factor,
+                 width // self.vae_scale_factor)
+        if latents is None:
+            latents = torch.randn(shape, generator=generator, device=device, dtype=dtype)
+            latents = latents.repeat(1, 1, max(1, video_length // clip_length), 1, 1)
+        else:
+            if latents.shape != shape:
+                raise ValueError(f"Unexpected latents shape, got {latents.shape}, expected {shape}")
+            latents = latents.to(device)
+        return latents * self.scheduler.init_noise_sigma
+
+    # -- EMOAnimationPipeline.py:291-307 ---------------------------------------------------------------------------
+    def decode_latents(self, latents, rank=0, decoder_consistency=None):
+        """-> numpy fp32 [b, 3, f, H, W] in [0, 1] (host copy, like the reference)."""
+        if decoder_consistency is not None:
+            raise NotImplementedError("decoder_consistency is not supported")
+        video, _ = self.decode_latents_device(latents)
+        return video.cpu().float().numpy()
+
+    def decode_latents_device(self, latents, want_u8: bool = False, shard: bool = False):
+        """Device-side decode.  With shard=True each rank decodes frames rank::world_size and the uint8 frames are
+        all-gathered once over NCCL (the single collective of the path)."""
+        if not shard or self.world_size == 1:
+            return self.vae.decode_video(latents, want_u8=want_u8)
+        import torch.distributed as dist
+        b, c, f, h, w = latents.shape
+        per = math.ceil(f / self.world_size)
+        lo, hi = min(f, self.rank * per), min(f, (self.rank + 1) * per)
+        pad = torch.zeros((b, 3, per, 8 * h, 8 * w), dtype=torch.uint8, device=latents.device)
+        if hi > lo:
+            _, u8 = self.vae.decode_video(latents[:, :, lo:hi].contiguous(), want_u8=True)
+            pad[:, :, : hi - lo] = u8
+        gathered = [torch.empty_like(pad) for _ in range(self.world_size)]
+        dist.all_gather(gathered, pad, group=self.process_group)
+        video_u8 = torch.cat(gathered, dim=2)[:, :, :f]
+        return None, video_u8
+
+    # -- EMOAnimationPipeline.py:698-823 ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def denoise(self, latents: torch.Tensor, text_embeddings: torch.Tensor, num_inference_steps: int = 50,
+                guidance_scale: float = 7.5, context_frames: int = 16, context_stride: int = 1, context_overlap: int = 4,
+                context_schedule: str = "uniform", reference_banks: Optional[Dict[str, List[torch.Tensor]]] = None,
+                callback: Optional[Callable] = None) -> torch.Tensor:
+        """latents [1, 4, F_total, h, w] fp32 (updated in place and returned); text_embeddings = cat([uncond, cond])
+        of shape [2, n, d], or per-frame [2*F_total, n, d] audio tokens (uncond frames first)."""
+        do_cfg = guidance_scale > 1.0
+        if not do_cfg:
+            raise NotImplementedError("the fused sampler implements the classifier-free-guidance path the reference runs")
+        if latents.shape[0] != 1:
+            raise ValueError("denoise() handles one sample per call (run samples on different ranks / sequentially)")
+        dev = latents.device
+        latents = latents.float().contiguous()
+        f_total = latents.shape[2]
+        self.scheduler.set_timesteps(num_inference_steps, device=dev)
+        windows = list(get_context_scheduler(context_schedule)(0, num_inference_steps, f_total, context_frames,
+                                                               context_stride, context_overlap))
+        counter = torch.zeros(f_total, dtype=torch.float32)
+        for c in windows:
+            counter[c] += 1
+        counter = counter.to(dev)
+        my_windows = windows[self.rank::self.world_size]
+        need_reduce = self.world_size > 1 and len(windows) > 1
+        per_frame_ctx = text_embeddings.shape[0] == 2 * f_total and f_total > 1
+        reader = None
+        if reference_banks is not None:
+            reader = ReferenceAttentionControl(self.unet, do_classifier_free_guidance=True, mode="read",
+                                               fusion_blocks="midup")
+        single_window = len(windows) == 1 and windows[0] == list(range(f_total))
+        noise_pred = torch.zeros((2,) + tuple(latents.shape[1:]), dtype=torch.float32, device=dev)
+        try:
+            for i, t in enumerate(self.scheduler.timesteps.tolist()):
+                if not single_window:
+                    noise_pred.zero_()
+                for c in my_windows:
+                    lat_in = latents if single_window else latents[:, :, c]
+                    lat_in = lat_in.expand(2, -1, -1, -1, -1) if single_window else lat_in.repeat(2, 1, 1, 1, 1)
+                    if per_frame_ctx:
+                        idx = torch.as_tensor(c, device=dev)
+                        ctx = torch.cat([text_embeddings[:f_total][idx], text_embeddings[f_total:][idx]])
+                    else:
+                        ctx = text_embeddings
+                    if reader is not None:
+                        reader.set_banks(reference_banks)
+                    pred = self.unet(lat_in.contiguous(), t, encoder_hidden_states=ctx, return_dict=False)[0]
+                    if single_window:
+                        noise_pred = pred
+                    else:
+                        noise_pred[:, :, c] += pred
+                if need_reduce:
+                    import torch.distributed as dist
+                    dist.all_reduce(noise_pred, group=self.process_group)
+                a_t, a_prev = self.scheduler.alphas_for(int(t))
+                ops.cfg_ddim_step(latents, noise_pred.contiguous(), counter, guidance_scale, a_t, a_prev)
+                if callback is not None:
+                    callback(i, t, latents)
+        finally:
+            if reader is not None:
+                reader.clear()
+                for blk in reader._blocks(self.unet):
+                    blk._ref_mode = None
+        return latents
+
+    @torch.no_grad()
+    def __call__(self, text_embeddings: torch.Tensor, video_length: int, height: int = 512, width: int = 512,
+                 num_inference_steps: int = 50, guidance_scale: float = 7.5, generator=None, latents=None,
+                 output_type: str = "tensor", return_dict: bool = True, context_frames: int = 16,
+                 context_stride: int = 1, context_overlap: int = 4, context_schedule: str = "uniform",
+                 reference_banks=None, callback=None, **unused):
+        dev = text_embeddings.device
+        lat = self.prepare_latents(1, self.unet.in_channels, video_length, height, width, torch.float32, dev, generator,
+                                   latents, clip_length=min(context_frames, video_length))
+        lat = lat[:, :, :video_length].contiguous()
+        lat = self.denoise(lat, text_embeddings, num_inference_steps, guidance_scale, context_frames, context_stride,
+                           context_overlap, context_schedule, reference_banks, callback)
+        video = self.decode_latents(lat, self.rank)
+        if output_type == "tensor":
+            video = torch.from_numpy(video)
+        return AnimationPipelineOutput(videos=video) if return_dict else video

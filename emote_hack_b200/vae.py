@@ -1,0 +1,264 @@
+"""SD VAE decoder on the sm_100a kernels — the `vae.decode(...)` the reference calls once per frame at
+EMOAnimationPipeline.py:291-307 (`diffusers.AutoencoderKL`, a third-party dependency absent from the reference
+tree; topology restated in oracle/vae_decoder.py).
+
+`AutoencoderKL` here mirrors the diffusers interface the pipeline touches (`decode(z).sample`, `config.scaling_factor`)
+and diffusers' state_dict key names for `post_quant_conv.*` and `decoder.*` (both the legacy
+`query/key/value/proj_attn` and the newer `to_q/to_k/to_v/to_out.0` attention names load).  All frames are decoded
+in one batch instead of a Python loop of single-frame calls; `(x/2+0.5).clamp(0,1)` is fused with the final
+layout change.  Kernel plan per stage: gn_stats/gn_apply(SiLU) -> implicit-GEMM conv (tcgen05) with fused bias /
+residual; the 512-wide single-head mid attention is QK^T GEMM -> row softmax -> PV GEMM (V^T produced directly by
+swapping GEMM operand roles), per frame.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import EmoteKernelError
+from .unet3d import AttrDict, _f32c
+
+F32, BF16 = torch.float32, torch.bfloat16
+
+
+class _Conv(nn.Conv2d):
+    """parameter container + packed-weight cache for a 1x1 / 3x3 conv over NHWC tokens"""
+
+    def __init__(self, cin, cout, k):
+        super().__init__(cin, cout, k, padding=k // 2)
+        self._pk = None
+
+    def _apply(self, fn, *a, **kw):
+        self._pk = None
+        return super()._apply(fn, *a, **kw)
+
+    def packed(self):
+        if self._pk is None or self._pk[2] != self.weight._version:
+            with torch.no_grad():
+                k = self.kernel_size[0]
+                if k == 1:
+                    w = ops.pack_linear(self.weight)
+                elif self.in_channels <= 7:
+                    w = ops.pack_conv3x3_small(self.weight)
+                else:
+                    w = ops.pack_conv3x3(self.weight)
+            self._pk = (w, _f32c(self.bias), self.weight._version)
+        return self._pk[0], self._pk[1]
+
+    def run(self, a_bf16, n_img, h, w, **epi):
+        wp, b = self.packed()
+        if self.kernel_size[0] == 1:
+            return ops.gemm(a_bf16, wp, bias=b, **epi)
+        return ops.conv3x3(a_bf16, wp, n_img, h, w, self.in_channels, bias=b, **epi)
+
+
+class ResnetBlock2D(nn.Module):
+    """diffusers ResnetBlock2D with temb=None (same arithmetic as reference resnet.py:177-207 with one frame):
+    GN -> SiLU -> conv3x3 -> GN -> SiLU -> conv3x3 -> + (1x1 shortcut of) input."""
+
+    def __init__(self, cin, cout, groups=32, eps=1e-6):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, cin, eps=eps)
+        self.conv1 = _Conv(cin, cout, 3)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=eps)
+        self.conv2 = _Conv(cout, cout, 3)
+        self.conv_shortcut = _Conv(cin, cout, 1) if cin != cout else None
+
+    def run(self, tok, n_img, h, w):
+        g1, g2 = self.norm1, self.norm2
+        raw_needed = self.conv_shortcut is not None
+        a1, raw = ops.group_norm([tok], g1.num_groups, h * w, n_img, g1.weight, g1.bias, g1.eps, True, want_raw=raw_needed)
+        h1 = self.conv1.run(a1, n_img, h, w)
+        a2, _ = ops.group_norm([h1], g2.num_groups, h * w, n_img, g2.weight, g2.bias, g2.eps, True)
+        if raw_needed:
+            res = self.conv_shortcut.run(raw, n_img, h, w)
+            return self.conv2.run(a2, n_img, h, w, residual=res, out=res)
+        return self.conv2.run(a2, n_img, h, w, residual=tok)
+
+
+class AttentionBlock(nn.Module):
+    """legacy diffusers AttentionBlock (vendored at reference orig_attention.py:253-385): GroupNorm -> q/k/v Linear
+    (+bias) -> softmax(q k^T / sqrt(C)) v, one head -> proj_attn -> + residual."""
+
+    def __init__(self, channels, groups=32, eps=1e-6):
+        super().__init__()
+        self.channels = channels
+        self.group_norm = nn.GroupNorm(groups, channels, eps=eps)
+        self.query = nn.Linear(channels, channels)
+        self.key = nn.Linear(channels, channels)
+        self.value = nn.Linear(channels, channels)
+        self.proj_attn = nn.Linear(channels, channels)
+        self._pk = None
+        self._register_load_state_dict_pre_hook(self._rename)
+
+    @staticmethod
+    def _rename(state_dict, prefix, *a):
+        for new, old in (("to_q", "query"), ("to_k", "key"), ("to_v", "value"), ("to_out.0", "proj_attn")):
+            for suffix in ("weight", "bias"):
+                k = f"{prefix}{new}.{suffix}"
+                if k in state_dict:
+                    state_dict[f"{prefix}{old}.{suffix}"] = state_dict.pop(k)
+
+    def _apply(self, fn, *a, **kw):
+        self._pk = None
+        return super()._apply(fn, *a, **kw)
+
+    def _packed(self):
+        ver = tuple(m.weight._version for m in (self.query, self.key, self.value, self.proj_attn))
+        if self._pk is None or self._pk["ver"] != ver:
+            with torch.no_grad():
+                self._pk = {
+                    "wqk": ops.pack_linear(torch.cat([self.query.weight, self.key.weight], 0)),
+                    "bqk": _f32c(torch.cat([self.query.bias, self.key.bias], 0)),
+                    "wv": ops.pack_linear(self.value.weight), "bv": _f32c(self.value.bias),
+                    "wo": ops.pack_linear(self.proj_attn.weight), "bo": _f32c(self.proj_attn.bias), "ver": ver}
+        return self._pk
+
+    def run(self, tok, n_img, h, w):
+        c, n = self.channels, h * w
+        g, p = self.group_norm, self._packed()
+        a, _ = ops.group_norm([tok], g.num_groups, n, n_img, g.weight, g.bias, g.eps, False)
+        qk = ops.gemm(a, p["wqk"], bias=p["bqk"], out_dtype=BF16)  # [n_img*n, 2c]
+        q = qk[:, :c].contiguous().view(n_img, n, c)
+        k = qk[:, c:].contiguous().view(n_img, n, c)
+        attn = torch.empty((n_img * n, c), dtype=BF16, device=tok.device)
+        av = a.view(n_img, n, c)
+        for i in range(n_img):
+            # V^T[c, n] = Wv x_i^T : the operand roles are swapped so the PV GEMM gets a K-major B operand;
+            # the value bias is added after PV (softmax rows sum to 1)
+            vt = ops.gemm(p["wv"], av[i], out_dtype=BF16)             # [c, n]
+            s = ops.gemm(q[i], k[i])                                  # [n, n] fp32 scores
+            pr = ops.softmax_rows(s, c ** -0.5)                       # bf16 probabilities
+            ops.gemm(pr, vt, bias=p["bv"], out_dtype=BF16, out=attn[i * n:(i + 1) * n])
+        return ops.gemm(attn, p["wo"], bias=p["bo"], residual=tok)
+
+
+class _Up(nn.Module):
+    def __init__(self, ch):
+        super().__init__()
+        self.conv = _Conv(ch, ch, 3)
+
+
+class _UpBlock(nn.Module):
+    def __init__(self, cin, cout, n_layers, add_upsample, groups, eps):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, groups, eps) for i in range(n_layers)])
+        self.upsamplers = nn.ModuleList([_Up(cout)]) if add_upsample else None
+
+
+class _Mid(nn.Module):
+    def __init__(self, ch, groups, eps):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(ch, ch, groups, eps), ResnetBlock2D(ch, ch, groups, eps)])
+        self.attentions = nn.ModuleList([AttentionBlock(ch, groups, eps)])
+
+
+class Decoder(nn.Module):
+    def __init__(self, latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                 norm_num_groups=32, eps=1e-6):
+        super().__init__()
+        top = block_out_channels[-1]
+        self.conv_in = _Conv(latent_channels, top, 3)
+        self.mid_block = _Mid(top, norm_num_groups, eps)
+        rev = list(reversed(block_out_channels))
+        blocks, cin = [], top
+        for i, cout in enumerate(rev):
+            blocks.append(_UpBlock(cin, cout, layers_per_block + 1, i != len(rev) - 1, norm_num_groups, eps))
+            cin = cout
+        self.up_blocks = nn.ModuleList(blocks)
+        self.conv_norm_out = nn.GroupNorm(norm_num_groups, rev[-1], eps=eps)
+        self.conv_out = _Conv(rev[-1], out_channels, 3)
+
+
+@dataclass
+class DecoderOutput:
+    sample: torch.Tensor
+
+
+class AutoencoderKL(nn.Module):
+    """Decoder half of diffusers.AutoencoderKL (the encoder is upstream of the hot path and not built)."""
+
+    def __init__(self, in_channels=3, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                 latent_channels=4, norm_num_groups=32, scaling_factor=0.18215):
+        super().__init__()
+        self.config = AttrDict(in_channels=in_channels, out_channels=out_channels, block_out_channels=tuple(block_out_channels),
+                               layers_per_block=layers_per_block, latent_channels=latent_channels,
+                               norm_num_groups=norm_num_groups, scaling_factor=scaling_factor)
+        self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
+        self.decoder = Decoder(latent_channels, out_channels, block_out_channels, layers_per_block, norm_num_groups)
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        # encoder / quant_conv weights of a full checkpoint are not part of this path
+        sd = {k: v for k, v in state_dict.items() if k.startswith("decoder.") or k.startswith("post_quant_conv.")}
+        return super().load_state_dict(sd, strict=strict, **kw)
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def _decode_tokens(self, z: torch.Tensor, pre_scale: float):
+        """z [n, 4, h, w] fp32 -> decoder output tokens [n*8h*8w, 4] fp32 (3 valid columns)."""
+        if not z.is_cuda:
+            raise EmoteKernelError("emote_hack_b200 modules run on CUDA only (no CPU fallback)")
+        n, cl, h, w = z.shape
+        d = self.decoder
+        pq = self.post_quant_conv
+        cols = ops.latent_im2col(z.float().contiguous().view(n, cl, 1, h, w), pre_scale,
+                                 _f32c(pq.weight).view(cl, cl), _f32c(pq.bias))
+        wp, b = d.conv_in.packed()
+        x = ops.gemm(cols, wp, bias=b)
+        x = d.mid_block.resnets[0].run(x, n, h, w)
+        x = d.mid_block.attentions[0].run(x, n, h, w)
+        x = d.mid_block.resnets[1].run(x, n, h, w)
+        for blk in d.up_blocks:
+            for r in blk.resnets:
+                x = r.run(x, n, h, w)
+            if blk.upsamplers is not None:
+                c = x.shape[1]
+                up = ops.upsample2x(x, n, h, w, c)
+                h, w = 2 * h, 2 * w
+                x = blk.upsamplers[0].conv.run(up, n, h, w)
+        g = d.conv_norm_out
+        a, _ = ops.group_norm([x], g.num_groups, h * w, n, g.weight, g.bias, g.eps, True)
+        out = torch.empty((n * h * w, 4), dtype=F32, device=x.device)
+        d.conv_out.run(a, n, h, w, out=out)
+        return out, h, w
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, return_dict: bool = True):
+        """diffusers `AutoencoderKL.decode`: latents (already divided by the scaling factor) -> images in [-1, 1]."""
+        tok, h, w = self._decode_tokens(z, 1.0)
+        n = z.shape[0]
+        img = ops.tokens_to_ncfhw(tok[:, :3].contiguous(), n, 3, 1, h, w).view(n, 3, h, w)
+        return DecoderOutput(sample=img) if return_dict else (img,)
+
+    @torch.no_grad()
+    def decode_video(self, latents: torch.Tensor, want_u8: bool = False, frame_chunk: Optional[int] = None):
+        """[b, 4, f, h, w] scaled latents -> ([b, 3, f, 8h, 8w] fp32 in [0,1], optional uint8 copy).
+        Fuses `1/0.18215 *`, the frame batching and `(x/2+0.5).clamp(0,1)` (EMOAnimationPipeline.py:293-304)."""
+        b, c, f, h, w = latents.shape
+        z = latents.float().permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+        chunk = frame_chunk or b * f
+        outs_f, outs_u = [], []
+        for s in range(0, b * f, chunk):
+            zc = z[s:s + chunk].contiguous()
+            tok, ho, wo = self._decode_tokens(zc, 1.0 / self.config.scaling_factor)
+            of, ou = ops.vae_postprocess(tok, zc.shape[0], ho, wo, want_f32=True, want_u8=want_u8)
+            outs_f.append(of)
+            if want_u8:
+                outs_u.append(ou)
+        vf = torch.cat(outs_f) if len(outs_f) > 1 else outs_f[0]
+        video = vf.view(b, f, 3, vf.shape[-2], vf.shape[-1]).permute(0, 2, 1, 3, 4)
+        vu = None
+        if want_u8:
+            vu = torch.cat(outs_u) if len(outs_u) > 1 else outs_u[0]
+            vu = vu.view(b, f, 3, vu.shape[-2], vu.shape[-1]).permute(0, 2, 1, 3, 4)
+        return video, vu

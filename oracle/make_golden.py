@@ -1,0 +1,88 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/* from the UNTOUCHED reference modules (run in the build
+container, where /root/reference exists):   python -m oracle.make_golden
+
+The reference ships no tests / golden vectors, so known answers are produced here by importing the
+reference's own `UNet3DConditionModel`, `ReferenceAttentionControl` and `context.uniform` through
+oracle/ref_shim.py, loading deterministic name-keyed weights (tests/util_models.seeded_unet_state_dict) and recording
+outputs for seeded inputs.  Only inputs' seeds, outputs and key/shape lists are stored (small); weights are
+re-derived from the seeds by the tests.
+"""
+from __future__ import annotations
+
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+from oracle import ref_shim  # noqa: E402
+from util_models import FULL_CFG, TINY_CFG, make_banks, make_inputs, seeded_unet_state_dict  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden"
+
+
+def main():
+    GOLD.mkdir(parents=True, exist_ok=True)
+    U = ref_shim.load_reference_unet_class()
+    RC = ref_shim.load_reference_control_class()
+    uniform = ref_shim.load_reference_context_uniform()
+
+    # ---- key / shape lists (state_dict compatibility contract)
+    m = U(**TINY_CFG).eval()
+    tiny_shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+    (GOLD / "unet3d_tiny_keys.json").write_text(json.dumps(tiny_shapes, indent=0, sort_keys=True))
+    with torch.device("meta"):
+        big = U(**FULL_CFG)
+    full_shapes = {k: list(v.shape) for k, v in big.state_dict().items()}
+    (GOLD / "unet3d_full_keys.json").write_text(json.dumps(full_shapes, indent=0, sort_keys=True))
+
+    # ---- tiny network known answers
+    sd = seeded_unet_state_dict(tiny_shapes, seed=0)
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    out = {}
+    with torch.no_grad():
+        for tag, (b, f, hw) in {"a": (2, 4, 8), "b": (2, 8, 16)}.items():
+            x, ctx = make_inputs(b, f, hw)
+            out[f"plain_{tag}"] = m(x, torch.tensor(481), ctx).sample
+        # per-frame (audio-token) context: batch == b*f, passes through un-repeated (attention.py:118-119)
+        x, ctx = make_inputs(2, 4, 8, ctx_tokens=5, per_frame_ctx=True)
+        out["per_frame_ctx"] = m(x, torch.tensor(21), ctx).sample
+        # reference attention (reader hooks on mid+up blocks, CFG on)
+        reader = RC(m, do_classifier_free_guidance=True, mode="read", fusion_blocks="midup", batch_size=1)
+        x, ctx = make_inputs(2, 4, 16)
+        banks = make_banks(m, 16)
+        mods = dict(m.named_modules())
+        for name, tensors in banks.items():
+            mods[name].bank = [t.clone() for t in tensors]
+        out["with_banks"] = m(x, torch.tensor(301), ctx).sample
+        out["without_banks"] = m(x, torch.tensor(301), ctx).sample  # banks were consumed
+        # single blocks
+        g = torch.Generator().manual_seed(3)
+        h = torch.randn(2, 64, 4, 8, 8, generator=g)
+        emb = torch.randn(2, 256, generator=g)
+        ctx7 = torch.randn(2, 7, 64, generator=g)
+        out["blk_h"], out["blk_emb"], out["blk_ctx"] = h, emb, ctx7
+        out["blk_resnet"] = mods["down_blocks.1.resnets.0"](h, emb)
+        out["blk_motion"] = mods["down_blocks.0.motion_modules.0"](h, None, None)
+    # un-hook transformer blocks for the plain transformer golden (fresh model, same weights)
+    m2 = U(**TINY_CFG).eval()
+    m2.load_state_dict(sd)
+    with torch.no_grad():
+        out["blk_transformer"] = dict(m2.named_modules())["down_blocks.0.attentions.0"](h, encoder_hidden_states=ctx7).sample
+    torch.save({k: v.contiguous() for k, v in out.items()}, GOLD / "unet3d_tiny_outputs.pt")
+
+    # ---- context windows of the reference scheduler
+    wins = {}
+    for nf, cs, stride, ov in [(16, 16, 1, 4), (32, 16, 1, 4), (240, 16, 1, 4), (24, 8, 1, 2), (48, 16, 2, 4), (20, 16, 1, 0)]:
+        wins[f"{nf},{cs},{stride},{ov}"] = [list(map(int, w)) for w in uniform(0, 50, nf, cs, stride, ov)]
+    (GOLD / "context_windows.json").write_text(json.dumps(wins))
+    print("golden written:", sorted(p.name for p in GOLD.iterdir()))
+
+
+if __name__ == "__main__":
+    main()

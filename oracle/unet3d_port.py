@@ -41,8 +41,10 @@ def timestep_embedding(t: Tensor, dim: int, flip_sin_to_cos: bool, freq_shift: f
 class UNet3DOracle:
     """Evaluates the reference network from a reference-format state_dict (same key names) and its config."""
 
-    def __init__(self, state_dict: Dict[str, Tensor], config: dict):
-        self.sd = {k: v.detach().float() for k, v in state_dict.items()}
+    def __init__(self, state_dict: Dict[str, Tensor], config: dict, dtype=torch.float32, device=None):
+        # dtype=float32 is the oracle; bfloat16 is only used to calibrate "what eager PyTorch bf16 would give"
+        self.dtype = dtype
+        self.sd = {k: v.detach().to(device=device or v.device, dtype=dtype) for k, v in state_dict.items()}
         c = dict(config)
         self.groups = c.get("norm_num_groups", 32)
         self.eps = c.get("norm_eps", 1e-5)
@@ -181,13 +183,13 @@ class UNet3DOracle:
     def forward(self, sample: Tensor, timestep, encoder_hidden_states: Tensor, banks: Optional[Dict[str, List[Tensor]]] = None,
                 do_classifier_free_guidance: bool = True, down_block_additional_residuals=None,
                 mid_block_additional_residual=None) -> Tensor:
-        x = sample.float()
-        ctx = encoder_hidden_states.float()
+        x = sample.to(self.dtype)
+        ctx = encoder_hidden_states.to(self.dtype)
         if self.center:
             x = 2 * x - 1.0
         t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep], device=x.device)
         t = t.reshape(-1).to(x.device).expand(x.shape[0])
-        emb = timestep_embedding(t, self.time_dim, self.flip, self.shift)
+        emb = timestep_embedding(t, self.time_dim, self.flip, self.shift).to(self.dtype)
         emb = self._lin("time_embedding.linear_2", F.silu(self._lin("time_embedding.linear_1", emb)))
 
         x = self._conv5("conv_in", x)

@@ -1,0 +1,71 @@
+"""Host-side logic that needs no GPU: scheduler tables, window partitioning, and the world_size-2 reduction that
+replaces the reference's gather + broadcast (gloo on CPU)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_counter_and_partition_cover_all_frames():
+    from emote_hack_b200.pipeline import uniform
+    for nf, cs, ov in [(240, 16, 4), (32, 16, 4), (24, 8, 2)]:
+        wins = list(uniform(0, 50, nf, cs, 1, ov))
+        cnt = torch.zeros(nf)
+        for w in wins:
+            cnt[w] += 1
+        assert cnt.min() >= 1  # every frame is denoised at least once
+        for world in (2, 4, 8):
+            parts = [wins[r::world] for r in range(world)]
+            assert sorted(map(tuple, sum(parts, []))) == sorted(map(tuple, wins))
+    assert len(list(uniform(0, 50, 240, 16, 1, 4))) == 20  # 240 f -> 20 windows
+    assert len(list(uniform(0, 50, 32, 16, 1, 4))) == 3
+
+
+def test_ops_refuse_cpu_tensors():
+    from emote_hack_b200 import ops
+    from emote_hack_b200._lib import EmoteKernelError
+    with pytest.raises(EmoteKernelError):
+        ops.layer_norm(torch.zeros(4, 64), torch.ones(64), torch.zeros(64))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nf, cs, ov, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from emote_hack_b200.pipeline import uniform
+    wins = list(uniform(0, 50, nf, cs, 1, ov))
+    g = torch.Generator().manual_seed(0)
+    table = torch.randn(len(wins), 2, 4, cs, 2, 2, generator=g)  # stand-in per-window predictions
+    acc = torch.zeros(2, 4, nf, 2, 2)
+    for wi in range(rank, len(wins), world):  # == windows[rank::world], EMOAnimationPipeline.py:757
+        acc[:, :, wins[wi]] += table[wi]
+    dist.all_reduce(acc)  # the single per-step collective (replaces gather->rank0 sum->broadcast, :796-821)
+    if rank == 0:
+        full = torch.zeros(2, 4, nf, 2, 2)
+        for wi, w in enumerate(wins):
+            full[:, :, w] += table[wi]
+        ret.put(bool(torch.allclose(acc, full, atol=1e-6)))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_window_sharding_all_reduce_equals_single_process():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 40, 16, 4, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get(timeout=10) is True

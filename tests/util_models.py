@@ -1,0 +1,106 @@
+"""Shared test fixtures: seeded configs / weights / inputs for the UNet3D path (no reference needed)."""
+import torch
+
+MM_KW = dict(num_attention_heads=4, num_transformer_block=1, attention_block_types=["Temporal_Self", "Temporal_Self"],
+             temporal_position_encoding=True, temporal_position_encoding_max_len=24, temporal_attention_dim_div=1)
+
+TINY_CFG = dict(sample_size=8, cross_attention_dim=64, block_out_channels=(64, 128, 128, 128), attention_head_dim=4,
+                norm_num_groups=32, use_motion_module=True, motion_module_resolutions=(1, 2, 4, 8),
+                motion_module_type="Vanilla", motion_module_kwargs=MM_KW, unet_use_cross_frame_attention=False,
+                unet_use_temporal_attention=False)
+
+# SD-1.5 widths + configs/inference.yaml kwargs with motion modules on (BASELINE config #2 network)
+FULL_MM_KW = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=["Temporal_Self", "Temporal_Self"],
+                  temporal_position_encoding=True, temporal_position_encoding_max_len=24, temporal_attention_dim_div=1)
+FULL_CFG = dict(sample_size=64, cross_attention_dim=768, use_motion_module=True, motion_module_resolutions=(1, 2, 4, 8),
+                motion_module_mid_block=False, motion_module_decoder_only=False, motion_module_type="Vanilla",
+                motion_module_kwargs=FULL_MM_KW, unet_use_cross_frame_attention=False, unet_use_temporal_attention=False)
+
+
+def rel_l2(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+def rerandomise_zero_inits(model, seed=1, std=0.05):
+    """temporal_transformer.proj_out is zero-initialised (motion_module.py:79-80): without this the temporal path
+    contributes exactly 0 and temporal bugs are invisible (SURVEY.md §7 hard part 6)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "temporal_transformer.proj_out" in n:
+                p.copy_(torch.randn(p.shape, generator=g) * std)
+    return model
+
+
+def make_inputs(b=2, f=4, hw=8, ctx_tokens=7, ctx_dim=64, seed=1234, per_frame_ctx=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(b, 4, f, hw, hw, generator=g)
+    ctx = torch.randn(b * f if per_frame_ctx else b, ctx_tokens, ctx_dim, generator=g)
+    return x, ctx
+
+
+def reader_block_names(model):
+    """names of the mid+up BasicTransformerBlocks, i.e. the ReferenceAttentionControl(fusion_blocks='midup') readers"""
+    return [n for n, m in model.named_modules()
+            if (n.startswith("mid_block") or n.startswith("up_blocks")) and n.endswith("transformer_blocks.0")
+            and "temporal" not in n]
+
+
+def make_banks(model, latent_hw, seed=7):
+    """synthetic ReferenceNet banks [2, HW_level, C_level] per reader block; seeded per block
+    NAME so the reference model, the oracle port and the CUDA modules get identical banks."""
+    import zlib
+    mods = dict(model.named_modules())
+    banks = {}
+    for name in reader_block_names(model):
+        g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + 104729 * seed) % (2 ** 31))
+        c = mods[name].norm1.normalized_shape[0]
+        if name.startswith("mid_block"):
+            side = latent_hw // 8
+        else:
+            side = latent_hw // (8 >> int(name.split(".")[1]))
+        banks[name] = [torch.randn(2, side * side, c, generator=g)]
+    return banks
+
+
+def seeded_state_dict(shapes, seed=0, keep=None):
+    """Deterministic, name-keyed random weights: the reference (in the build container), the oracle port and the CUDA
+    modules all get IDENTICAL parameters without shipping a checkpoint.  `shapes`: {key: shape}; `keep`: tensors to
+    copy verbatim (deterministic buffers such as the sinusoidal `pos_encoder.pe`)."""
+    import zlib
+    out = {}
+    for name in sorted(shapes):
+        shape = tuple(shapes[name])
+        if keep is not None and name in keep:
+            out[name] = keep[name].clone()
+            continue
+        g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + 7919 * seed) % (2 ** 31))
+        if name.endswith(".pe"):
+            raise KeyError(f"{name}: positional tables must be passed through `keep`")
+        if len(shape) >= 2:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            out[name] = torch.randn(shape, generator=g) * (1.0 / fan_in) ** 0.5
+        elif name.endswith("weight") and ("norm" in name):
+            out[name] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            out[name] = 0.05 * torch.randn(shape, generator=g)
+    return out
+
+
+def sinusoid_pe(max_len, d_model):
+    """motion_module.py:239-244 (deterministic buffer)"""
+    import math
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(1, max_len, d_model)
+    pe[0, :, 0::2] = torch.sin(position * div_term)
+    pe[0, :, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+def seeded_unet_state_dict(shapes, seed=0):
+    keep = {k: sinusoid_pe(s[1], s[2]) for k, s in shapes.items() if k.endswith(".pe")}
+    return seeded_state_dict(shapes, seed, keep)

@@ -51,17 +51,23 @@ struct AttnDev {
   float scale_log2;
 };
 
-constexpr int FA_BQ = 64;
 constexpr int FA_BKV = 64;
 constexpr int FA_THREADS = 128;
 
-// Load `rows` x d bf16 (row stride rs elements) into smem [64][DP+8]; rows >= nvalid and cols >= d are zero.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Load `rows` x d bf16 (row stride rs elements) into smem [rows][DP+8]; rows >= nvalid and cols >= d are zero.
 template <int DP>
-__device__ __forceinline__ void fa_load_tile(__nv_bfloat16* s, const __nv_bfloat16* g, long long rs, int nvalid, int d) {
+__device__ __forceinline__ void fa_load_tile(__nv_bfloat16* s, const __nv_bfloat16* g, long long rs, int rows,
+                                             int nvalid, int d) {
   constexpr int PITCH = DP + 8;
   constexpr int CH = DP / 8;  // 16-byte chunks per padded row
   const int dch = d >> 3;
-  for (int i = threadIdx.x; i < 64 * CH; i += FA_THREADS) {
+  for (int i = threadIdx.x; i < rows * CH; i += FA_THREADS) {
     const int r = i / CH;
     const int c = i - r * CH;
     const bool ok = (r < nvalid) && (c < dch);
@@ -70,20 +76,23 @@ __device__ __forceinline__ void fa_load_tile(__nv_bfloat16* s, const __nv_bfloat
   }
 }
 
-template <int DP>
-__global__ void __launch_bounds__(FA_THREADS, 2) flash_attn_kernel(const AttnDev p) {
+// MT = 16-row m-tiles per warp: 4 warps x MT x 16 query rows per CTA.  With MT = 2 every K / V fragment fetched by
+// ldmatrix feeds two independent MMAs (half the shared-memory traffic per FLOP, twice the MMA-level parallelism).
+template <int DP, int MT>
+__global__ void __launch_bounds__(FA_THREADS, (DP <= 96) ? 2 : 1) flash_attn_kernel(const AttnDev p) {
   constexpr int PITCH = DP + 8;
   constexpr int KS = DP / 16;  // k-steps over the head dim
   constexpr int NT = DP / 8;   // output n-tiles
+  constexpr int BQ = 64 * MT;
   extern __shared__ __align__(16) uint8_t fa_smem[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(fa_smem);
-  __nv_bfloat16* sK = sQ + 64 * PITCH;           // [2][64][PITCH]
+  __nv_bfloat16* sK = sQ + BQ * PITCH;           // [2][64][PITCH]
   __nv_bfloat16* sV = sK + 2 * 64 * PITCH;       // [2][64][PITCH]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z, h = blockIdx.y;
-  const int q0 = blockIdx.x * FA_BQ;
+  const int q0 = blockIdx.x * BQ;
 
   const __nv_bfloat16* qg = p.q + (long long)b * p.q_bs + (long long)q0 * p.q_rs + h * p.d;
   const __nv_bfloat16* k0g = p.k0 + (long long)(b / p.kv0_div) * p.kv0_bs + h * p.d;
@@ -116,24 +125,29 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_attn_kernel(const AttnDev
       nvalid = n1 - t1 * FA_BKV;
     }
     if (nvalid > FA_BKV) nvalid = FA_BKV;
-    fa_load_tile<DP>(sK + buf * 64 * PITCH, kg, rs, nvalid, p.d);
-    fa_load_tile<DP>(sV + buf * 64 * PITCH, vg, rs, nvalid, p.d);
+    fa_load_tile<DP>(sK + buf * 64 * PITCH, kg, rs, 64, nvalid, p.d);
+    fa_load_tile<DP>(sV + buf * 64 * PITCH, vg, rs, 64, nvalid, p.d);
   };
 
   {
     int nvq = p.nq - q0;
-    if (nvq > FA_BQ) nvq = FA_BQ;
-    fa_load_tile<DP>(sQ, qg, p.q_rs, nvq, p.d);
+    if (nvq > BQ) nvq = BQ;
+    fa_load_tile<DP>(sQ, qg, p.q_rs, BQ, nvq, p.d);
   }
   issue_kv(0, 0);
   cp_async_commit();
 
-  float o_acc[NT][4];
+  float o_acc[MT][NT][4];
+  float m_run[MT][2], l_run[MT][2];
 #pragma unroll
-  for (int i = 0; i < NT; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
-  float m_run[2] = {-INFINITY, -INFINITY};
-  float l_run[2] = {0.f, 0.f};
-  uint32_t qf[KS][4];
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int i = 0; i < NT; ++i) o_acc[mt][i][0] = o_acc[mt][i][1] = o_acc[mt][i][2] = o_acc[mt][i][3] = 0.f;
+    m_run[mt][0] = m_run[mt][1] = -INFINITY;
+    l_run[mt][0] = l_run[mt][1] = 0.f;
+  }
+  uint32_t qf[MT][KS][4];
+  const int qrow_w = warp * 16 * MT;  // first query row (within the CTA tile) owned by this warp
 
   for (int tile = 0; tile < ntiles; ++tile) {
     const int buf = tile & 1;
@@ -148,19 +162,23 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_attn_kernel(const AttnDev
     if (tile == 0) {
       // Q fragments stay in registers for the whole kernel
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const int row = warp * 16 + (lane & 15);
-        const int col = ks * 16 + (lane >> 4) * 8;
-        ldsm_x4(smem_u32(sQ + row * PITCH + col), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
-      }
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const int row = qrow_w + mt * 16 + (lane & 15);
+          const int col = ks * 16 + (lane >> 4) * 8;
+          ldsm_x4(smem_u32(sQ + row * PITCH + col), qf[mt][ks][0], qf[mt][ks][1], qf[mt][ks][2], qf[mt][ks][3]);
+        }
     }
     const __nv_bfloat16* sKb = sK + buf * 64 * PITCH;
     const __nv_bfloat16* sVb = sV + buf * 64 * PITCH;
 
-    // ---- S = Q K^T  (16 x 64 per warp)
-    float s_acc[8][4];
+    // ---- S = Q K^T  (MT x 16 x 64 per warp)
+    float s_acc[MT][8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s_acc[i][0] = s_acc[i][1] = s_acc[i][2] = s_acc[i][3] = 0.f;
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_acc[mt][i][0] = s_acc[mt][i][1] = s_acc[mt][i][2] = s_acc[mt][i][3] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
@@ -169,8 +187,11 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_attn_kernel(const AttnDev
         const int row = np * 16 + (lane & 7) + (lane >> 4) * 8;
         const int col = ks * 16 + ((lane >> 3) & 1) * 8;
         ldsm_x4(smem_u32(sKb + row * PITCH + col), b0, b1, b2, b3);
-        mma_bf16_16816(s_acc[2 * np], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b0, b1);
-        mma_bf16_16816(s_acc[2 * np + 1], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b2, b3);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16_16816(s_acc[mt][2 * np], qf[mt][ks][0], qf[mt][ks][1], qf[mt][ks][2], qf[mt][ks][3], b0, b1);
+          mma_bf16_16816(s_acc[mt][2 * np + 1], qf[mt][ks][0], qf[mt][ks][1], qf[mt][ks][2], qf[mt][ks][3], b2, b3);
+        }
       }
     }
     // ---- mask the ragged tail of the segment
@@ -178,57 +199,59 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_attn_kernel(const AttnDev
     if (tile < tiles0) nvalid = p.n0 - tile * FA_BKV; else nvalid = n1 - (tile - tiles0) * FA_BKV;
     if (nvalid < FA_BKV) {
 #pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const int c = nt * 8 + 2 * t;
+          if (c >= nvalid) s_acc[mt][nt][0] = s_acc[mt][nt][2] = -INFINITY;
+          if (c + 1 >= nvalid) s_acc[mt][nt][1] = s_acc[mt][nt][3] = -INFINITY;
+        }
+    }
+    // ---- online softmax (rows g and g+8 of each 16-row m-tile); P packed as A fragments
+    uint32_t pf[MT][4][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        const int c = nt * 8 + 2 * t;
-        if (c >= nvalid) s_acc[nt][0] = s_acc[nt][2] = -INFINITY;
-        if (c + 1 >= nvalid) s_acc[nt][1] = s_acc[nt][3] = -INFINITY;
+        mx[0] = fmaxf(mx[0], fmaxf(s_acc[mt][nt][0], s_acc[mt][nt][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(s_acc[mt][nt][2], s_acc[mt][nt][3]));
       }
-    }
-    // ---- online softmax (rows g and g+8 of this warp's 16)
-    float mx[2] = {-INFINITY, -INFINITY};
+      float corr[2], msc[2];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      mx[0] = fmaxf(mx[0], fmaxf(s_acc[nt][0], s_acc[nt][1]));
-      mx[1] = fmaxf(mx[1], fmaxf(s_acc[nt][2], s_acc[nt][3]));
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-    }
-    float corr[2], msc[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const float m_new = fmaxf(m_run[r], mx[r]);
-      corr[r] = (m_run[r] == -INFINITY) ? 0.f : exp2f((m_run[r] - m_new) * p.scale_log2);
-      msc[r] = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
-      m_run[r] = m_new;
-    }
-    float rs[2] = {0.f, 0.f};
-    uint32_t pf[4][4];  // P as A fragments for the 4 k-steps of 16 kv rows
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = exp2f(s_acc[nt][0] * p.scale_log2 - msc[0]);
-      const float p1 = exp2f(s_acc[nt][1] * p.scale_log2 - msc[0]);
-      const float p2 = exp2f(s_acc[nt][2] * p.scale_log2 - msc[1]);
-      const float p3 = exp2f(s_acc[nt][3] * p.scale_log2 - msc[1]);
-      rs[0] += p0 + p1;
-      rs[1] += p2 + p3;
-      const int kk = nt >> 1;
-      if ((nt & 1) == 0) {
-        pf[kk][0] = pack_bf16x2(p0, p1);
-        pf[kk][1] = pack_bf16x2(p2, p3);
-      } else {
-        pf[kk][2] = pack_bf16x2(p0, p1);
-        pf[kk][3] = pack_bf16x2(p2, p3);
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float m_new = fmaxf(m_run[mt][r], mx[r]);
+        corr[r] = (m_run[mt][r] == -INFINITY) ? 0.f : ex2_approx((m_run[mt][r] - m_new) * p.scale_log2);
+        msc[r] = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+        m_run[mt][r] = m_new;
       }
-    }
+      float rs[2] = {0.f, 0.f};
 #pragma unroll
-    for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
+      for (int nt = 0; nt < 8; ++nt) {
+        const float p0 = ex2_approx(fmaf(s_acc[mt][nt][0], p.scale_log2, -msc[0]));
+        const float p1 = ex2_approx(fmaf(s_acc[mt][nt][1], p.scale_log2, -msc[0]));
+        const float p2 = ex2_approx(fmaf(s_acc[mt][nt][2], p.scale_log2, -msc[1]));
+        const float p3 = ex2_approx(fmaf(s_acc[mt][nt][3], p.scale_log2, -msc[1]));
+        rs[0] += p0 + p1;
+        rs[1] += p2 + p3;
+        const int kk = nt >> 1;
+        if ((nt & 1) == 0) {
+          pf[mt][kk][0] = pack_bf16x2(p0, p1);
+          pf[mt][kk][1] = pack_bf16x2(p2, p3);
+        } else {
+          pf[mt][kk][2] = pack_bf16x2(p0, p1);
+          pf[mt][kk][3] = pack_bf16x2(p2, p3);
+        }
+      }
 #pragma unroll
-    for (int i = 0; i < NT; ++i) {
-      o_acc[i][0] *= corr[0]; o_acc[i][1] *= corr[0];
-      o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
+      for (int r = 0; r < 2; ++r) l_run[mt][r] = l_run[mt][r] * corr[r] + rs[r];
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        o_acc[mt][i][0] *= corr[0]; o_acc[mt][i][1] *= corr[0];
+        o_acc[mt][i][2] *= corr[1]; o_acc[mt][i][3] *= corr[1];
+      }
     }
     // ---- O += P V
 #pragma unroll
@@ -239,36 +262,43 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_attn_kernel(const AttnDev
         const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
         const int col = np * 16 + (lane >> 4) * 8;
         ldsm_x4_t(smem_u32(sVb + row * PITCH + col), b0, b1, b2, b3);
-        mma_bf16_16816(o_acc[2 * np], pf[kk][0], pf[kk][1], pf[kk][2], pf[kk][3], b0, b1);
-        mma_bf16_16816(o_acc[2 * np + 1], pf[kk][0], pf[kk][1], pf[kk][2], pf[kk][3], b2, b3);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16_16816(o_acc[mt][2 * np], pf[mt][kk][0], pf[mt][kk][1], pf[mt][kk][2], pf[mt][kk][3], b0, b1);
+          mma_bf16_16816(o_acc[mt][2 * np + 1], pf[mt][kk][0], pf[mt][kk][1], pf[mt][kk][2], pf[mt][kk][3], b2, b3);
+        }
       }
     }
     __syncthreads();  // everyone done with buf before it is refilled
   }
 
   // ---- finalise: O / l, stage through this warp's Q rows, 16-byte stores
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
-    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
-  }
-  const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
-  const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
-  __nv_bfloat16* sO = sQ + warp * 16 * PITCH;
-#pragma unroll
-  for (int i = 0; i < NT; ++i) {
-    *reinterpret_cast<uint32_t*>(sO + g * PITCH + i * 8 + 2 * t) = pack_bf16x2(o_acc[i][0] * inv0, o_acc[i][1] * inv0);
-    *reinterpret_cast<uint32_t*>(sO + (g + 8) * PITCH + i * 8 + 2 * t) =
-        pack_bf16x2(o_acc[i][2] * inv1, o_acc[i][3] * inv1);
-  }
-  __syncwarp();
   const int dch = p.d >> 3;
   __nv_bfloat16* og = p.out + (long long)b * p.o_bs + h * p.d;
-  for (int i = lane; i < 16 * dch; i += 32) {
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l_run[mt][r] += __shfl_xor_sync(0xffffffffu, l_run[mt][r], 1);
+      l_run[mt][r] += __shfl_xor_sync(0xffffffffu, l_run[mt][r], 2);
+    }
+    const float inv0 = l_run[mt][0] > 0.f ? 1.f / l_run[mt][0] : 0.f;
+    const float inv1 = l_run[mt][1] > 0.f ? 1.f / l_run[mt][1] : 0.f;
+    __nv_bfloat16* sO = sQ + (qrow_w + mt * 16) * PITCH;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      *reinterpret_cast<uint32_t*>(sO + g * PITCH + i * 8 + 2 * t) =
+          pack_bf16x2(o_acc[mt][i][0] * inv0, o_acc[mt][i][1] * inv0);
+      *reinterpret_cast<uint32_t*>(sO + (g + 8) * PITCH + i * 8 + 2 * t) =
+          pack_bf16x2(o_acc[mt][i][2] * inv1, o_acc[mt][i][3] * inv1);
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < 16 * MT * dch; i += 32) {
     const int r = i / dch, c = i - r * dch;
-    const int qrow = q0 + warp * 16 + r;
+    const int qrow = q0 + qrow_w + r;
     if (qrow < p.nq) {
-      const uint4 v = *reinterpret_cast<const uint4*>(sO + r * PITCH + c * 8);
+      const uint4 v = *reinterpret_cast<const uint4*>(sQ + (qrow_w + r) * PITCH + c * 8);
       *reinterpret_cast<uint4*>(og + (long long)qrow * p.o_rs + c * 8) = v;
     }
   }
@@ -416,15 +446,18 @@ __global__ void __launch_bounds__(TA_WARPS * 32) temporal_attn_kernel(const __nv
 
 template <int DP>
 static int launch_flash(const AttnDev& p, int batch, cudaStream_t stream) {
-  constexpr int SMEM = 5 * 64 * (DP + 8) * 2;
+  // 32 query rows per warp while the accumulators still fit the register file, 16 for the widest heads
+  constexpr int MT = (DP <= 80) ? 2 : 1;
+  constexpr int BQ = 64 * MT;
+  constexpr int SMEM = (BQ + 4 * 64) * (DP + 8) * 2;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<DP, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(flash_attn)", e);
     configured = true;
   }
-  dim3 grid((p.nq + FA_BQ - 1) / FA_BQ, p.heads, batch);
-  flash_attn_kernel<DP><<<grid, FA_THREADS, SMEM, stream>>>(p);
+  dim3 grid((p.nq + BQ - 1) / BQ, p.heads, batch);
+  flash_attn_kernel<DP, MT><<<grid, FA_THREADS, SMEM, stream>>>(p);
   EMOTE_CHECK_LAUNCH("emote_attention_bf16");
   return 0;
 }

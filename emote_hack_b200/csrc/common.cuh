@@ -103,6 +103,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x (8 columns x N): mma-style fragment, thread (g = lane/4, t = lane%4) gets
+//   r[4j+0..1] = (row g,   cols 8j+2t, 8j+2t+1),  r[4j+2..3] = (row g+8, same cols)   (cute SM100_TMEM_LOAD_16dp256bNx)
+__device__ __forceinline__ void tmem_ld_16x256b_x1(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor, K-major operand, 128B swizzle, rows of 64 bf16 (=128 B),
@@ -125,6 +139,21 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 // ---------------------------------------------------------------- numerics
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact-GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 output rounding):
+// one MUFU.EX2 + one MUFU.RCP + a 5-term Horner instead of the branchy libdevice erff in the GEGLU epilogue.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float tt, ex;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tt) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-1.4426950408889634f * z * z));
+  float poly = fmaf(1.061405429f, tt, -1.453152027f);
+  poly = fmaf(poly, tt, 1.421413741f);
+  poly = fmaf(poly, tt, -0.284496736f);
+  poly = fmaf(poly, tt, 0.254829592f);
+  // 0.5 x (1 + sign(x) (1 - P)) with P = poly * t * exp(-z^2):  x >= 0 -> x - 0.5 x P,  x < 0 -> 0.5 x P
+  const float hp = 0.5f * x * (poly * tt * ex);
+  return x >= 0.f ? x - hp : hp;
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

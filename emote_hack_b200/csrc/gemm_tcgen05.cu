@@ -18,7 +18,11 @@ namespace emote {
 
 constexpr int BM = 128;       // UMMA M (rows of the output tile, one TMEM lane per row)
 constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle row
-constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA+TMEM alloc, warps2-5 epilogue
+// warp0 = TMA producer, warp1 = MMA issuer + TMEM allocator, then EPI_WARPS epilogue warps.  Two variants:
+//   HAS_ADD (residual and/or per-sample bias): 8 epilogue warps that prefetch their whole fp32 residual span into
+//            registers BEFORE waiting for the accumulator, so ~80 KB/SM of residual reads overlap the main loop;
+//   plain / GEGLU: 16 epilogue warps (4 per TMEM lane quarter) to hide TMEM and issue latency.
+constexpr int gemm_threads(int epi_warps) { return 64 + 32 * epi_warps; }
 
 struct GemmDev {
   int M, N, K;
@@ -51,8 +55,8 @@ struct GemmSmem {
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int EPI_WARPS, bool HAS_ADD>
+__global__ void __launch_bounds__(gemm_threads(EPI_WARPS), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmDev p) {
   using S = GemmSmem<BN>;
@@ -78,7 +82,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[s], EPI_WARPS);  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -173,128 +177,167 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps (TMEM -> regs -> global)
-    const int lane_grp = warp & 3;  // TMEM lane quarter this warp may access
+    // EPI_WARPS warps: warp w may touch TMEM lanes 32*(w%4)..+31; the warps of a lane quarter take the 8-column
+    // chunks of the tile round-robin.  tcgen05.ld.16x256b hands thread (g = lane/4, t = lane%4) the mma-style
+    // fragment rows {g, g+8} x columns {2t, 2t+1}: a quad covers one full 32-byte sector of an fp32 row, so global
+    // reads of the residual and writes of the output are sector-complete.  The loop is software pipelined: the TMEM
+    // loads and the residual / bias loads of chunk i+1 are in flight while chunk i is finished and stored.
+    constexpr int NP = EPI_WARPS / 4;   // warps per lane quarter
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int part = ew >> 2;
+    const int g = lane >> 2, t = lane & 3;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
-      const int row = tm * BM + lane_grp * 32 + lane;
+      const int row0 = tm * BM + quarter * 32 + g;  // this thread's rows: row0 + 8*i, i = 0..3
       const int n0 = tn * BN;
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(as * BN);
-      const bool row_ok = row < p.M;
-      const float* rb = (p.row_bias != nullptr && row_ok) ? p.row_bias + (size_t)(row / p.rows_per_group) * p.N : nullptr;
-      const float* res = (p.residual != nullptr && row_ok) ? p.residual + (size_t)row * p.ldr : nullptr;
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
+      bool rok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rok[i] = (row0 + 8 * i) < p.M;
 
       if (!p.geglu) {
-#pragma unroll 1
-        for (int c = 0; c < BN / 16; ++c) {
-          uint32_t r[16];
-          tmem_ld16(taddr + c * 16, r);
-          tmem_ld_wait();
-          const int col0 = n0 + c * 16;
-          if (row_ok && col0 < p.N) {
-            float v[16];
+        constexpr int NCT = BN / 8;                     // 8-column chunks in the tile
+        constexpr int NCH = NCT / NP;                   // contiguous chunks per warp
+        static_assert(NCT % NP == 0, "tile columns must split evenly over the warps of a lane quarter");
+        const int c_first = part * NCH;
+        size_t ooff[4];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-            const bool full = (col0 + 16 <= p.N);
-            if (full) {
-              if (p.bias) {
+        for (int i = 0; i < 4; ++i) ooff[i] = (size_t)(row0 + 8 * i) * p.ldc;
+        // ---- residual / per-sample bias of this warp's whole column span, issued before the accumulator wait
+        float add[HAS_ADD ? NCH : 1][8];
+        if constexpr (HAS_ADD) {
+          const bool has_res = p.residual != nullptr, has_rb = p.row_bias != nullptr;
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + j);
-                  v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          for (int ci = 0; ci < NCH; ++ci) {
+            const int col = n0 + (c_first + ci) * 8 + 2 * t;
+            const bool c0ok = col < p.N, c1ok = col + 1 < p.N;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = row0 + 8 * i;
+              float v0 = 0.f, v1 = 0.f;
+              if (rok[i]) {
+                if (has_res) {
+                  const float* rp = p.residual + (size_t)row * p.ldr + col;
+                  if (c1ok) { const float2 r2 = *reinterpret_cast<const float2*>(rp); v0 = r2.x; v1 = r2.y; }
+                  else if (c0ok) v0 = rp[0];
+                }
+                if (has_rb) {
+                  const float* bp = p.row_bias + (size_t)(row / p.rows_per_group) * p.N + col;
+                  if (c1ok) { const float2 r2 = *reinterpret_cast<const float2*>(bp); v0 += r2.x; v1 += r2.y; }
+                  else if (c0ok) v0 += bp[0];
                 }
               }
-              if (rb) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  const float4 b = *reinterpret_cast<const float4*>(rb + col0 + j);
-                  v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                }
-              }
-              if (res) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  const float4 b = *reinterpret_cast<const float4*>(res + col0 + j);
-                  v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                }
-              }
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] *= p.out_scale;
-              if (p.out_bf16) {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldc + col0;
-                uint4 w0, w1;
-                w0.x = pack_bf16x2(v[0], v[1]);   w0.y = pack_bf16x2(v[2], v[3]);
-                w0.z = pack_bf16x2(v[4], v[5]);   w0.w = pack_bf16x2(v[6], v[7]);
-                w1.x = pack_bf16x2(v[8], v[9]);   w1.y = pack_bf16x2(v[10], v[11]);
-                w1.z = pack_bf16x2(v[12], v[13]); w1.w = pack_bf16x2(v[14], v[15]);
-                *reinterpret_cast<uint4*>(o) = w0;
-                *reinterpret_cast<uint4*>(o + 8) = w1;
-              } else {
-                float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldc + col0;
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                  *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              }
-            } else {
-              // ragged N tail: scalar path
-              for (int j = 0; j < 16; ++j) {
-                const int col = col0 + j;
-                if (col >= p.N) break;
-                float x = v[j];
-                if (p.bias) x += p.bias[col];
-                if (rb) x += rb[col];
-                if (res) x += res[col];
-                x *= p.out_scale;
-                if (p.out_bf16)
-                  reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)row * p.ldc + col] = __float2bfloat16(x);
-                else
-                  reinterpret_cast<float*>(p.out)[(size_t)row * p.ldc + col] = x;
-              }
+              add[ci][2 * i] = v0;
+              add[ci][2 * i + 1] = v1;
             }
           }
         }
-      } else {
-        // GEGLU: tile columns [0, BN/2) hold the value half, [BN/2, BN) the gate half of the same
-        // BN/2 output features (weights are packed that way); out = value * gelu_erf(gate).
-        constexpr int HALF = BN / 2;
-        const int on0 = tn * HALF;
-        const int n_out = p.N / 2;
-#pragma unroll 1
-        for (int c = 0; c < HALF / 16; ++c) {
-          uint32_t rv[16], rg[16];
-          tmem_ld16(taddr + c * 16, rv);
-          tmem_ld16(taddr + HALF + c * 16, rg);
-          tmem_ld_wait();
-          const int ocol0 = on0 + c * 16;
-          if (row_ok && ocol0 < n_out) {
-            float o16[16];
+        uint32_t acc[2][8];
+        auto issue = [&](int ci, uint32_t (&a)[8]) {
+          const uint32_t col_t = static_cast<uint32_t>((c_first + ci) * 8);
+          uint32_t lo[4], hi[4];
+          tmem_ld_16x256b_x1(tbase + col_t, lo);
+          tmem_ld_16x256b_x1(tbase + (16u << 16) + col_t, hi);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float a = __uint_as_float(rv[j]);
-              float g = __uint_as_float(rg[j]);
-              if (p.bias) {
-                a += p.bias[n0 + c * 16 + j];
-                g += p.bias[n0 + HALF + c * 16 + j];
+          for (int k = 0; k < 4; ++k) { a[k] = lo[k]; a[4 + k] = hi[k]; }
+        };
+        auto finish = [&](int ci, const uint32_t (&a)[8]) {
+          const int col = n0 + (c_first + ci) * 8 + 2 * t;
+          const bool c0ok = col < p.N, c1ok = col + 1 < p.N;
+          float b0 = 0.f, b1 = 0.f;
+          if (p.bias) {
+            if (c0ok) b0 = __ldg(p.bias + col);
+            if (c1ok) b1 = __ldg(p.bias + col + 1);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            // rows g, g+8 come from the low 16-lane load, rows g+16, g+24 from the high one
+            const int ri = (i >> 1) * 4 + (i & 1) * 2;
+            float v0 = __uint_as_float(a[ri]) + b0, v1 = __uint_as_float(a[ri + 1]) + b1;
+            if constexpr (HAS_ADD) { v0 += add[ci][2 * i]; v1 += add[ci][2 * i + 1]; }
+            v0 *= p.out_scale; v1 *= p.out_scale;
+            if (rok[i] && c0ok) {
+              if (p.out_bf16) {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[i] + col;
+                if (c1ok) *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(v0, v1);
+                else o[0] = __float2bfloat16(v0);
+              } else {
+                float* o = reinterpret_cast<float*>(p.out) + ooff[i] + col;
+                if (c1ok) *reinterpret_cast<float2*>(o) = make_float2(v0, v1);
+                else o[0] = v0;
               }
-              o16[j] = a * gelu_erf_f(g);
-            }
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldc + ocol0;
-            if (ocol0 + 16 <= n_out) {
-              uint4 w0, w1;
-              w0.x = pack_bf16x2(o16[0], o16[1]);   w0.y = pack_bf16x2(o16[2], o16[3]);
-              w0.z = pack_bf16x2(o16[4], o16[5]);   w0.w = pack_bf16x2(o16[6], o16[7]);
-              w1.x = pack_bf16x2(o16[8], o16[9]);   w1.y = pack_bf16x2(o16[10], o16[11]);
-              w1.z = pack_bf16x2(o16[12], o16[13]); w1.w = pack_bf16x2(o16[14], o16[15]);
-              *reinterpret_cast<uint4*>(o) = w0;
-              *reinterpret_cast<uint4*>(o + 8) = w1;
-            } else {
-              for (int j = 0; j < 16 && ocol0 + j < n_out; ++j) o[j] = __float2bfloat16(o16[j]);
             }
           }
+        };
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        issue(0, acc[0]);
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          tmem_ld_wait();
+          if (ci + 1 < NCH) issue(ci + 1, acc[(ci + 1) & 1]);
+          finish(ci, acc[ci & 1]);
+        }
+      } else {
+        // GEGLU: tile columns [0, BN/2) hold the value half, [BN/2, BN) the gate half of the same BN/2 output
+        // features (weights are packed that way); out = (value + b_v) * gelu_erf(gate + b_g).
+        constexpr int HALF = BN / 2;
+        constexpr int NCT = HALF / 8;
+        constexpr int NCH = (NCT + NP - 1) / NP;   // round-robin over the warps of the quarter (may be uneven)
+        const int n_out = p.N / 2;
+        size_t ooff[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ooff[i] = (size_t)(row0 + 8 * i) * p.ldc;
+        uint32_t av[2][8], ag[2][8];
+        float bb[2][4];
+        auto issue = [&](int ci, uint32_t (&v)[8], uint32_t (&gt)[8], float (&b)[4]) {
+          const int cc = part + ci * NP;
+          if (cc < NCT) {
+            const uint32_t col_t = static_cast<uint32_t>(cc * 8);
+            uint32_t lo[4], hi[4], glo[4], ghi[4];
+            tmem_ld_16x256b_x1(tbase + col_t, lo);
+            tmem_ld_16x256b_x1(tbase + (16u << 16) + col_t, hi);
+            tmem_ld_16x256b_x1(tbase + HALF + col_t, glo);
+            tmem_ld_16x256b_x1(tbase + (16u << 16) + HALF + col_t, ghi);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { v[k] = lo[k]; v[4 + k] = hi[k]; gt[k] = glo[k]; gt[4 + k] = ghi[k]; }
+            const int tc = cc * 8 + 2 * t;
+            if (p.bias) {
+              b[0] = __ldg(p.bias + n0 + tc); b[1] = __ldg(p.bias + n0 + tc + 1);
+              b[2] = __ldg(p.bias + n0 + HALF + tc); b[3] = __ldg(p.bias + n0 + HALF + tc + 1);
+            } else {
+              b[0] = b[1] = b[2] = b[3] = 0.f;
+            }
+          }
+        };
+        auto finish = [&](int ci, const uint32_t (&v)[8], const uint32_t (&gt)[8], const float (&b)[4]) {
+          const int cc = part + ci * NP;
+          if (cc < NCT) {
+            const int ocol = tn * HALF + cc * 8 + 2 * t;
+            const bool cok = ocol < n_out;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int ri = (i >> 1) * 4 + (i & 1) * 2;
+              const float a0 = __uint_as_float(v[ri]) + b[0], a1 = __uint_as_float(v[ri + 1]) + b[1];
+              const float q0 = __uint_as_float(gt[ri]) + b[2], q1 = __uint_as_float(gt[ri + 1]) + b[3];
+              const uint32_t packed = pack_bf16x2(a0 * gelu_erf_fast(q0), a1 * gelu_erf_fast(q1));
+              if (rok[i] && cok)
+                *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[i] + ocol) = packed;
+            }
+          }
+        };
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        issue(0, av[0], ag[0], bb[0]);
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          tmem_ld_wait();
+          if (ci + 1 < NCH) issue(ci + 1, av[(ci + 1) & 1], ag[(ci + 1) & 1], bb[(ci + 1) & 1]);
+          finish(ci, av[ci & 1], ag[ci & 1], bb[ci & 1]);
         }
       }
       // release the accumulator stage back to the MMA warp
@@ -319,13 +362,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 // --------------------------------------------------------------------------- host side
 static int g_num_sms = 0;
 
-template <int BN>
+template <int BN, int EPI_WARPS, bool HAS_ADD>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDev& p, cudaStream_t stream) {
   using S = GemmSmem<BN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         S::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(gemm)", e);
     configured = true;
   }
@@ -339,11 +382,17 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDev& 
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, p);
+  gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD><<<grid, gemm_threads(EPI_WARPS), S::TOTAL, stream>>>(tmA, tmB, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error_cuda("gemm launch", e);
   count_launch();
   return 0;
+}
+
+template <int BN>
+static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDev& p, cudaStream_t stream) {
+  if (!p.geglu && (p.residual != nullptr || p.row_bias != nullptr)) return launch_gemm<BN, 8, true>(tmA, tmB, p, stream);
+  return launch_gemm<BN, 16, false>(tmA, tmB, p, stream);
 }
 
 }  // namespace emote
@@ -414,6 +463,6 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
     uint32_t box[2] = {64, (uint32_t)bn};
     if (int rc = make_tensor_map(&tmB, Wt, 2, dims, strides, box)) return rc;
   }
-  if (bn == 160) return launch_gemm<160>(tmA, tmB, p, stream);
-  return launch_gemm<128>(tmA, tmB, p, stream);
+  if (bn == 160) return dispatch_gemm<160>(tmA, tmB, p, stream);
+  return dispatch_gemm<128>(tmA, tmB, p, stream);
 }

@@ -33,15 +33,25 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int C_src, int c_of
 #pragma unroll
   for (int i = 0; i < GN_MAX_PASS; ++i) s[i] = q[i] = 0.0;
 
-  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    const float2* row = reinterpret_cast<const float2*>(xb + r * C_src);
+  // 4 rows in flight per thread (independent 8-byte loads); the 8 values are pre-summed in fp32 in a fixed order
+  // (deterministic), everything after that is fp64.
+  const long long stride = blockDim.y;
+  for (long long r = r0 + threadIdx.y; r < r1; r += 4 * stride) {
 #pragma unroll
     for (int ps = 0; ps < GN_MAX_PASS; ++ps) {
       if (ps < passes) {
-        const float2 v = __ldg(row + threadIdx.x + ps * blockDim.x);
-        const double a = (double)v.x, b = (double)v.y;
-        s[ps] += a + b;
-        q[ps] += a * a + b * b;
+        const int cp = threadIdx.x + ps * blockDim.x;
+        float2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long rr = r + u * stride;
+          v[u] = (rr < r1) ? __ldg(reinterpret_cast<const float2*>(xb + rr * C_src) + cp) : make_float2(0.f, 0.f);
+        }
+        const float sf = ((v[0].x + v[0].y) + (v[1].x + v[1].y)) + ((v[2].x + v[2].y) + (v[3].x + v[3].y));
+        const float qf = ((v[0].x * v[0].x + v[0].y * v[0].y) + (v[1].x * v[1].x + v[1].y * v[1].y)) +
+                         ((v[2].x * v[2].x + v[2].y * v[2].y) + (v[3].x * v[3].x + v[3].y * v[3].y));
+        s[ps] += (double)sf;
+        q[ps] += (double)qf;
       }
     }
   }
@@ -61,75 +71,94 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int C_src, int c_of
   }
 }
 
-// each thread: 8 consecutive channels of one row
+// y = x * scale[c] + shift[c] with scale = rstd*gamma, shift = beta - mean*rstd*gamma staged in shared memory per
+// block; blockDim = (octets per pass, rows in parallel): no integer division in the streaming loop.
 __global__ void gn_apply_kernel(const float* __restrict__ x, int C_src, int c_offset, int C_total, int cpg,
                                 int groups, long long rows_per_batch, int rows_per_block,
                                 const double* __restrict__ sums, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int act_silu,
                                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ raw_out) {
-  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  extern __shared__ __align__(16) float gn_smem[];
+  float* s_scale = gn_smem;
+  float* s_shift = gn_smem + C_src;
   const int batch = blockIdx.y;
-  if (threadIdx.x < groups) {
-    const double cnt = (double)rows_per_batch * (double)cpg;
-    const double sm = sums[((long long)batch * groups + threadIdx.x) * 2];
-    const double sq = sums[((long long)batch * groups + threadIdx.x) * 2 + 1];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthr = blockDim.x * blockDim.y;
+  const double cnt = (double)rows_per_batch * (double)cpg;
+  for (int c = tid; c < C_src; c += nthr) {
+    const int ct = c_offset + c;
+    const int g = ct / cpg;
+    const double sm = sums[((long long)batch * groups + g) * 2];
+    const double sq = sums[((long long)batch * groups + g) * 2 + 1];
     const double mean = sm / cnt;
     double var = sq / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = (float)mean;
-    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = rstd * gamma[ct];
+    s_scale[c] = sc;
+    s_shift[c] = beta[ct] - (float)mean * sc;
   }
   __syncthreads();
-  const int oct_per_row = C_src >> 3;
+  const int opr = C_src >> 3;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
-  long long nrows = rows_per_batch - r0;
-  if (nrows > rows_per_block) nrows = rows_per_block;
-  const long long total = nrows * oct_per_row;
-  const long long row_base = (long long)batch * rows_per_batch + r0;
-  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-    const long long r = i / oct_per_row;
-    const int c0 = (int)(i - r * oct_per_row) << 3;
-    const float* src = x + (row_base + r) * C_src + c0;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
-    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    float y[8];
-    const int ct = c_offset + c0;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows_per_batch) r1 = rows_per_batch;
+  const long long row_base = (long long)batch * rows_per_batch;
+  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    const float* xr = x + (row_base + r) * C_src;
+    __nv_bfloat16* orow = out + (row_base + r) * C_total + c_offset;
+    __nv_bfloat16* rrow = raw_out ? raw_out + (row_base + r) * C_total + c_offset : nullptr;
+    for (int o = threadIdx.x; o < opr; o += blockDim.x) {
+      const int c0 = o << 3;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(xr + c0));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(xr + c0 + 4));
+      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      const float4 sa = *reinterpret_cast<const float4*>(s_scale + c0);
+      const float4 sb = *reinterpret_cast<const float4*>(s_scale + c0 + 4);
+      const float4 ha = *reinterpret_cast<const float4*>(s_shift + c0);
+      const float4 hb = *reinterpret_cast<const float4*>(s_shift + c0 + 4);
+      const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+      const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+      float y[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = ct + j;
-      const int g = c / cpg;
-      float t = (v[j] - s_mean[g]) * s_rstd[g] * __ldg(gamma + c) + __ldg(beta + c);
-      y[j] = act_silu ? silu_f(t) : t;
-    }
-    const long long o = (row_base + r) * C_total + ct;
-    uint4 w;
-    w.x = pack_bf16x2(y[0], y[1]); w.y = pack_bf16x2(y[2], y[3]);
-    w.z = pack_bf16x2(y[4], y[5]); w.w = pack_bf16x2(y[6], y[7]);
-    *reinterpret_cast<uint4*>(out + o) = w;
-    if (raw_out) {
-      uint4 u;
-      u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-      u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(raw_out + o) = u;
+      for (int j = 0; j < 8; ++j) {
+        const float tt = fmaf(v[j], sc[j], sh[j]);
+        y[j] = act_silu ? silu_f(tt) : tt;
+      }
+      uint4 w;
+      w.x = pack_bf16x2(y[0], y[1]); w.y = pack_bf16x2(y[2], y[3]);
+      w.z = pack_bf16x2(y[4], y[5]); w.w = pack_bf16x2(y[6], y[7]);
+      *reinterpret_cast<uint4*>(orow + c0) = w;
+      if (rrow) {
+        uint4 u;
+        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+        u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(rrow + c0) = u;
+      }
     }
   }
 }
 
 constexpr int LN_MAX_V = 32;  // float2 per lane -> C <= 2048
 
-__global__ void layernorm_kernel(const float* __restrict__ x, long long M, int C, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, float eps, const float* __restrict__ pe,
-                                 int pe_rows_per_frame, int pe_frames, __nv_bfloat16* __restrict__ out) {
+// One warp per row, NV float2 per lane (C = 64*NV).  NV is a template parameter so the row lives in exactly
+// 2*NV registers (occupancy) and all loads of a row are issued back to back (bytes in flight).
+template <int NV>
+__global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict__ x, long long M, int C_rt,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, const float* __restrict__ pe, int pe_rows_per_frame,
+                                                        int pe_frames, __nv_bfloat16* __restrict__ out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= M) return;
-  const int nv = C >> 6;  // float2 per lane
+  const int nv = (NV > 0) ? NV : (C_rt >> 6);
+  constexpr int CAP = (NV > 0) ? NV : LN_MAX_V;
+  const int C = nv << 6;
   const float2* xr = reinterpret_cast<const float2*>(x + row * C);
-  float2 v[LN_MAX_V];
+  float2 v[CAP];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V; ++i) {
+  for (int i = 0; i < CAP; ++i) {
     if (i < nv) {
       v[i] = __ldg(xr + lane + i * 32);
       s += v[i].x + v[i].y;
@@ -138,7 +167,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long M, int C
   const float mean = warp_sum(s) / (float)C;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V; ++i) {
+  for (int i = 0; i < CAP; ++i) {
     if (i < nv) {
       const float a = v[i].x - mean, b = v[i].y - mean;
       q += a * a + b * b;
@@ -149,7 +178,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long M, int C
   if (pe) per = pe + (long long)((row / pe_rows_per_frame) % pe_frames) * C;
   uint32_t* o = reinterpret_cast<uint32_t*>(out + row * C);
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V; ++i) {
+  for (int i = 0; i < CAP; ++i) {
     if (i < nv) {
       const int c = 2 * (lane + i * 32);
       const float2 g = __ldg(reinterpret_cast<const float2*>(gamma + c));
@@ -229,8 +258,8 @@ extern "C" int emote_gn_stats(const float* x, int32_t C_src, int32_t c_offset, i
   const int PX = P / passes;
   int TY = 512 / PX;
   if (TY < 1) TY = 1;
-  int rows_per_block = 64;
-  if (rows_per_block < TY) rows_per_block = TY;
+  int rows_per_block = 16 * TY;
+  if (rows_per_block < 64) rows_per_block = 64;
   const long long chunks = (rows_per_batch + rows_per_block - 1) / rows_per_block;
   dim3 grid((unsigned)chunks, (unsigned)n_batches), block(PX, TY);
   gn_stats_kernel<<<grid, block, 0, stream>>>(x, C_src, c_offset, C_total / groups, groups, rows_per_batch,
@@ -247,14 +276,20 @@ extern "C" int emote_gn_apply(const float* x, int32_t C_src, int32_t c_offset, i
   if (!x || !sums || !gamma || !beta || !out_bf16 || rows_per_batch <= 0 || n_batches <= 0)
     return set_error("emote_gn_apply: bad arguments");
   if (gn_check(C_src, c_offset, C_total, groups, "emote_gn_apply: unsupported channel/group configuration")) return EMOTE_ERR_INVALID;
-  int rows_per_block = (int)((256LL * 8 * 8) / C_src);  // ~8 octets per thread
-  if (rows_per_block < 1) rows_per_block = 1;
+  const int opr = C_src / 8;
+  int bx = opr < 256 ? opr : 256;
+  while (opr % bx != 0) --bx;  // octets per pass divide the row evenly
+  int by = 256 / bx;
+  if (by < 1) by = 1;
+  int rows_per_block = 8 * by;
+  if (rows_per_block < 16) rows_per_block = 16;
   const long long chunks = (rows_per_batch + rows_per_block - 1) / rows_per_block;
-  dim3 grid((unsigned)chunks, (unsigned)n_batches);
-  gn_apply_kernel<<<grid, 256, 0, stream>>>(x, C_src, c_offset, C_total, C_total / groups, groups, rows_per_batch,
-                                            rows_per_block, sums, gamma, beta, eps, act_silu,
-                                            reinterpret_cast<__nv_bfloat16*>(out_bf16),
-                                            reinterpret_cast<__nv_bfloat16*>(raw_out_bf16));
+  dim3 grid((unsigned)chunks, (unsigned)n_batches), block(bx, by);
+  const size_t smem = 2 * (size_t)C_src * sizeof(float);
+  gn_apply_kernel<<<grid, block, smem, stream>>>(x, C_src, c_offset, C_total, C_total / groups, groups, rows_per_batch,
+                                                 rows_per_block, sums, gamma, beta, eps, act_silu,
+                                                 reinterpret_cast<__nv_bfloat16*>(out_bf16),
+                                                 reinterpret_cast<__nv_bfloat16*>(raw_out_bf16));
   EMOTE_CHECK_LAUNCH("emote_gn_apply");
   return 0;
 }
@@ -266,10 +301,22 @@ extern "C" int emote_layernorm(const float* x, int64_t M, int32_t C, const float
   if (!x || !gamma || !beta || !out_bf16 || M <= 0) return set_error("emote_layernorm: bad arguments");
   if (C % 64 != 0 || C > 64 * LN_MAX_V) return set_error("emote_layernorm: C must be a multiple of 64 and <= 2048");
   if (pe && (pe_rows_per_frame <= 0 || pe_frames <= 0)) return set_error("emote_layernorm: bad positional table dims");
-  const int warps = 8;
+  const int warps = 4;
   const long long blocks = (M + warps - 1) / warps;
-  layernorm_kernel<<<(unsigned)blocks, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, pe, pe_rows_per_frame,
-                                                                pe_frames, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+#define EMOTE_LN(NVV) layernorm_kernel<NVV><<<(unsigned)blocks, warps * 32, 0, stream>>>( \
+      x, M, C, gamma, beta, eps, pe, pe_rows_per_frame, pe_frames, o)
+  switch (C / 64) {
+    case 1: EMOTE_LN(1); break;
+    case 2: EMOTE_LN(2); break;
+    case 4: EMOTE_LN(4); break;
+    case 5: EMOTE_LN(5); break;
+    case 8: EMOTE_LN(8); break;
+    case 10: EMOTE_LN(10); break;
+    case 20: EMOTE_LN(20); break;
+    default: EMOTE_LN(0); break;
+  }
+#undef EMOTE_LN
   EMOTE_CHECK_LAUNCH("emote_layernorm");
   return 0;
 }

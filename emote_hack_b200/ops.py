@@ -345,6 +345,11 @@ class KernelProfiler:
                 if _name == "emote_gemm_bf16":
                     a = args[3]._obj
                     meta = (a.M, a.N, a.K, a.conv_taps)
+                elif _name == "emote_attention_bf16":
+                    a = args[0]._obj
+                    meta = (a.batch, a.heads, a.head_dim, a.nq, a.n0, a.n1)
+                else:
+                    meta = tuple(x for x in args if isinstance(x, int) and x < (1 << 40))[:6]
                 e0.record()
                 rc = _fn(*args)
                 e1.record()
@@ -377,10 +382,10 @@ class KernelProfiler:
     def gemm_flops(self):
         return sum(2.0 * m[0] * m[1] * m[2] for n, _, m in self.times if n == "emote_gemm_bf16")
 
-    def gemm_by_shape(self):
+    def by_shape(self, name="emote_gemm_bf16"):
         out = {}
         for n, ms, m in self.times:
-            if n == "emote_gemm_bf16":
+            if n == name:
                 c, t = out.get(m, (0, 0.0))
                 out[m] = (c + 1, t + ms)
         return out

@@ -1,0 +1,41 @@
+"""Dev tool: time individual GEMM shapes (CUDA events over many back-to-back launches)."""
+import sys
+from pathlib import Path
+import torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from emote_hack_b200 import ops
+BF16 = torch.bfloat16
+shapes = [  # (M, N, K, mode)
+    (131072, 2560, 320, "geglu"), (131072, 320, 320, "res"), (32768, 640, 640, "res"), (8192, 1280, 1280, "res"),
+    (131072, 960, 320, "bf16"), (32768, 5120, 640, "geglu"), (8192, 10240, 1280, "geglu"), (131072, 320, 1280, "res"),
+    (2048, 1280, 1280, "res"), (8192, 8192, 8192, "bf16"),
+]
+only = sys.argv[1:] and [int(a) for a in sys.argv[1:]]
+for i, (M, N, K, mode) in enumerate(shapes):
+    if only and i not in only:
+        continue
+    a = torch.randn(M, K, device="cuda").to(BF16)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(BF16)
+    bias = torch.randn(N, device="cuda")
+    if mode == "geglu":
+        wp, bp = ops.pack_geglu(w.float(), bias)
+        fn = lambda: ops.gemm(a, wp, bias=bp, geglu=True, out_dtype=BF16)
+    elif mode == "res":
+        res = torch.randn(M, N, device="cuda")
+        out = torch.empty(M, N, device="cuda")
+        fn = lambda: ops.gemm(a, w, bias=bias, residual=res, out=out)
+    else:
+        out = torch.empty(M, N, device="cuda", dtype=BF16)
+        fn = lambda: ops.gemm(a, w, bias=bias, out_dtype=BF16, out=out)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    n = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / n * 1e3
+    print(f"{i}: M={M} N={N} K={K} {mode:6s} {us:9.1f} us  {2.0*M*N*K/us/1e6:8.1f} TF/s")

@@ -1,0 +1,401 @@
+// tcgen05 flash attention for the spatial self-attention / reference-attention layers (head_dim 40 and 80), where
+// >80% of the attention time of a UNet call is spent (N = 4096 / 1024 keys per image).
+//
+//   per CTA: 128 query rows of one (image, head).  Per 64-key tile:
+//     S  = Q K^T          tcgen05.mma 128 x 64 x 16 (x KSTEPS), Q/K K-major 128B-swizzled smem, S in TMEM (fp32)
+//     P  = exp2(S*c - m)  4 softmax warps, one thread per query row (TMEM lane == row: no shuffles), P -> smem (bf16)
+//     PV = P V            tcgen05.mma 128 x NPV x 16 (x4), A = P (K-major), B = V consumed MN-major straight from
+//                         its natural [key][d] layout (no transpose), result in TMEM
+//     O  = O*corr + PV    accumulated in registers by the row's thread (no TMEM read-modify-write of O)
+//   warp 0 streams K/V tiles with cp.async into a 3-stage ring (manual 128B swizzle; zero-fills the tail), warp 1
+//   issues the MMAs, warps 2-5 do the softmax.  S and PV are double buffered in TMEM so the softmax of tile j+1
+//   overlaps P V of tile j.  Two CTAs fit per SM (96 KB smem, 256 TMEM columns each) for latency hiding.
+//
+// Same semantics as flash_attn_kernel in attention.cu (two key/value segments, per-batch visibility of segment 1,
+// ragged tails); reference arithmetic: orig_attention.py:655-684, mutual_self_attention.py:239-255.
+#include "common.cuh"
+#include "emote_b200.h"
+#include "host_utils.h"
+
+namespace emote {
+
+struct AttnTcDev {
+  const __nv_bfloat16 *q, *k0, *v0, *k1, *v1;
+  __nv_bfloat16* out;
+  int heads, d;
+  int nq, n0, n1;
+  long long q_bs, q_rs, kv0_bs, kv0_rs, kv1_bs, kv1_rs, o_bs, o_rs;
+  int kv0_div, kv1_div, kv1_first;
+  float scale_log2;
+};
+
+constexpr int TC_BQ = 128;
+constexpr int TC_BKV = 64;
+constexpr int TC_STAGES = 3;   // K/V ring; a tile is published TC_LOOKAHEAD tiles after it was issued
+constexpr int TC_LOOKAHEAD = 1;
+constexpr int TC_THREADS = 192;  // warp0 loader, warp1 MMA, warps 2-5 softmax
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// UMMA smem descriptor, MN-major operand, 128B swizzle: rows = K index (128 B = 64 MN elements each), 8-row groups
+// 1024 B apart (SBO), 64-element MN atoms `lbo_bytes` apart (LBO).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int M, int N) {  // A K-major, B MN-major
+  return umma_idesc_bf16(M, N) | (1u << 16);
+}
+
+// D = head dim (40 or 80).  ATOMS = 64-element swizzle atoms covering D, KSTEPS = 16-wide MMA k-steps over D,
+// NPV = PV accumulator columns (D rounded up to 16).
+template <int D>
+struct TcCfg {
+  static constexpr int ATOMS = (D + 63) / 64;
+  static constexpr int KSTEPS = (D + 15) / 16;
+  static constexpr int NPV = KSTEPS * 16;
+  static constexpr int CH = D / 8;                       // 16-byte chunks per row that carry data
+  static constexpr int Q_BYTES = ATOMS * TC_BQ * 128;
+  static constexpr int KV_TILE = ATOMS * TC_BKV * 128;   // one K or V tile
+  static constexpr int STAGE = 2 * KV_TILE;
+  static constexpr int P_BYTES = TC_BQ * 128;            // 128 rows x 64 keys bf16
+  static constexpr int SMEM = Q_BYTES + TC_STAGES * STAGE + 2 * P_BYTES + 256 + 1024;
+  static constexpr int TMEM_COLS = (2 * TC_BKV + 2 * NPV <= 256) ? 256 : 512;
+  static constexpr int PV_COL0 = 2 * TC_BKV;
+};
+
+template <int D>
+__global__ void __launch_bounds__(TC_THREADS, (D <= 64) ? 2 : 1) flash_attn_tc_kernel(const AttnTcDev p) {
+  using C = TcCfg<D>;
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + C::Q_BYTES;
+  uint8_t* sP = sKV + TC_STAGES * C::STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * C::P_BYTES);
+  uint64_t* kv_full = bars;                  // [STAGES] loader -> MMA (32 arrivals)
+  uint64_t* kv_empty = kv_full + TC_STAGES;  // [STAGES] MMA commit -> loader
+  uint64_t* s_full = kv_empty + TC_STAGES;   // [2] MMA commit -> softmax
+  uint64_t* p_full = s_full + 2;             // [2] softmax (4 warp arrivals) -> MMA
+  uint64_t* o_full = p_full + 2;             // [2] MMA commit -> softmax
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int q0 = blockIdx.x * TC_BQ;
+
+  const int n1 = (p.n1 > 0 && b >= p.kv1_first) ? p.n1 : 0;
+  const int tiles0 = (p.n0 + TC_BKV - 1) / TC_BKV;
+  const int tiles1 = (n1 + TC_BKV - 1) / TC_BKV;
+  const int ntiles = tiles0 + tiles1;
+
+  // ---- one-time setup: zero the operand ring (pad chunks stay zero forever), barriers, TMEM, Q tile
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = (C::Q_BYTES + TC_STAGES * C::STAGE + 2 * C::P_BYTES) / 16;
+    for (int i = threadIdx.x; i < n16; i += TC_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&kv_full[s], 32);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 4);   // one arrival per softmax warp
+      mbar_init(&o_full[s], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  __syncthreads();
+  {
+    // Q tile: rows q0..q0+127, chunks < D/8; atom = chunk/8; physical 16B slot = (chunk%8) ^ (row%8)
+    const __nv_bfloat16* qg = p.q + (long long)b * p.q_bs + (long long)q0 * p.q_rs + h * p.d;
+    const int nvq = p.nq - q0;
+    for (int i = threadIdx.x; i < TC_BQ * C::CH; i += TC_THREADS) {
+      const int r = i / C::CH, c = i - r * C::CH;
+      const uint32_t dst = smem_u32(sQ) + (c >> 3) * (TC_BQ * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4);
+      cp_async16_zfill(dst, qg + (long long)r * p.q_rs + c * 8, r < nvq);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ K/V loader (cp.async, all 32 lanes)
+    const __nv_bfloat16* k0g = p.k0 + (long long)(b / p.kv0_div) * p.kv0_bs + h * p.d;
+    const __nv_bfloat16* v0g = p.v0 + (long long)(b / p.kv0_div) * p.kv0_bs + h * p.d;
+    const __nv_bfloat16* k1g = nullptr;
+    const __nv_bfloat16* v1g = nullptr;
+    if (n1 > 0) {
+      k1g = p.k1 + (long long)(b / p.kv1_div) * p.kv1_bs + h * p.d;
+      v1g = p.v1 + (long long)(b / p.kv1_div) * p.kv1_bs + h * p.d;
+    }
+    for (int j = 0; j < ntiles; ++j) {
+      const int stage = j % TC_STAGES;
+      // slot reuse needs P V of tile j-STAGES; that only needs tiles <= j-STAGES+1 published, which happened at
+      // iteration j-1 at the latest (LOOKAHEAD < STAGES-1): no circular wait with the MMA warp
+      if (j >= TC_STAGES) mbar_wait(&kv_empty[stage], ((j / TC_STAGES) - 1) & 1);
+      const __nv_bfloat16 *kg, *vg;
+      long long rs;
+      int nvalid;
+      if (j < tiles0) {
+        kg = k0g + (long long)j * TC_BKV * p.kv0_rs; vg = v0g + (long long)j * TC_BKV * p.kv0_rs;
+        rs = p.kv0_rs; nvalid = p.n0 - j * TC_BKV;
+      } else {
+        const int t1 = j - tiles0;
+        kg = k1g + (long long)t1 * TC_BKV * p.kv1_rs; vg = v1g + (long long)t1 * TC_BKV * p.kv1_rs;
+        rs = p.kv1_rs; nvalid = n1 - t1 * TC_BKV;
+      }
+      const uint32_t kdst = smem_u32(sKV + stage * C::STAGE);
+      const uint32_t vdst = kdst + C::KV_TILE;
+      for (int i = lane; i < TC_BKV * C::CH; i += 32) {
+        const int r = i / C::CH, c = i - r * C::CH;
+        const uint32_t off = (c >> 3) * (TC_BKV * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4);
+        const bool ok = r < nvalid;
+        cp_async16_zfill(kdst + off, kg + (long long)r * rs + c * 8, ok);
+        cp_async16_zfill(vdst + off, vg + (long long)r * rs + c * 8, ok);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (j >= TC_LOOKAHEAD) {  // tile j-LOOKAHEAD has landed -> publish it to the async proxy / MMA warp
+        asm volatile("cp.async.wait_group %0;" ::"n"(TC_LOOKAHEAD) : "memory");
+        fence_proxy_async();
+        mbar_arrive(&kv_full[(j - TC_LOOKAHEAD) % TC_STAGES]);
+      }
+    }
+    // drain: everything has landed once wait_group 0 returns
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    fence_proxy_async();
+    for (int j = (ntiles > TC_LOOKAHEAD ? ntiles - TC_LOOKAHEAD : 0); j < ntiles; ++j) mbar_arrive(&kv_full[j % TC_STAGES]);
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(TC_BQ, TC_BKV);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16_bmn(TC_BQ, C::NPV);
+      auto issue_s = [&](int j) {
+        const int stage = j % TC_STAGES;
+        mbar_wait(&kv_full[stage], (j / TC_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t ka = smem_u32(sKV + stage * C::STAGE);
+        const uint32_t qa = smem_u32(sQ);
+        const uint32_t d_tmem = tmem_base + (j & 1) * TC_BKV;
+#pragma unroll
+        for (int ks = 0; ks < C::KSTEPS; ++ks) {
+          const uint64_t da = umma_desc_sw128(qa + (ks >> 2) * (TC_BQ * 128)) + static_cast<uint64_t>(2 * (ks & 3));
+          const uint64_t db = umma_desc_sw128(ka + (ks >> 2) * (TC_BKV * 128)) + static_cast<uint64_t>(2 * (ks & 3));
+          umma_f16(d_tmem, da, db, idesc_s, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[j & 1]);
+      };
+      issue_s(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) issue_s(j + 1);  // S buffer (j+1)&1 was released by p_full(j-1), waited last iteration
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        const int stage = j % TC_STAGES;
+        const uint32_t va = smem_u32(sKV + stage * C::STAGE) + C::KV_TILE;
+        const uint32_t pa = smem_u32(sP + (j & 1) * C::P_BYTES);
+        const uint32_t d_tmem = tmem_base + C::PV_COL0 + (j & 1) * C::NPV;
+#pragma unroll
+        for (int ks = 0; ks < TC_BKV / 16; ++ks) {
+          const uint64_t da = umma_desc_sw128(pa) + static_cast<uint64_t>(2 * ks);
+          // MN-major B: 16 keys = 16 rows of 128 B further down the tile
+          const uint64_t db = umma_desc_sw128_mn(va + ks * 16 * 128, TC_BKV * 128);
+          umma_f16(d_tmem, da, db, idesc_pv, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[j & 1]);
+        umma_commit(&kv_empty[stage]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warps: thread == query row
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;          // row inside the CTA tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    float o_acc[C::NPV];
+#pragma unroll
+    for (int i = 0; i < C::NPV; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+    const float sc = p.scale_log2;
+
+    auto accumulate_pv = [&](int j, float corr) {
+      mbar_wait(&o_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ta = tmem_base + lane_addr + C::PV_COL0 + (j & 1) * C::NPV;
+      uint32_t r[C::NPV / 16][16];
+#pragma unroll
+      for (int c = 0; c < C::NPV / 16; ++c) tmem_ld16(ta + c * 16, r[c]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < C::NPV / 16; ++c)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) o_acc[c * 16 + k] = fmaf(o_acc[c * 16 + k], corr, __uint_as_float(r[c][k]));
+    };
+
+    for (int j = 0; j < ntiles; ++j) {
+      int nvalid = (j < tiles0) ? (p.n0 - j * TC_BKV) : (n1 - (j - tiles0) * TC_BKV);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ta = tmem_base + lane_addr + (j & 1) * TC_BKV;
+      uint32_t s0[32], s1[32];
+      tmem_ld32(ta, s0);
+      tmem_ld32(ta + 32, s1);
+      tmem_ld_wait();
+      if (nvalid < TC_BKV) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          if (k >= nvalid) s0[k] = 0xff800000u;        // -inf
+          if (k + 32 >= nvalid) s1[k] = 0xff800000u;
+        }
+      }
+      // row max: 8 independent chains, then a tree (the serial fmax chain was the critical path of this loop)
+      float mxa[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mxa[k] = fmaxf(__uint_as_float(s0[k]), __uint_as_float(s1[k]));
+#pragma unroll
+      for (int k = 8; k < 32; ++k) mxa[k & 7] = fmaxf(mxa[k & 7], fmaxf(__uint_as_float(s0[k]), __uint_as_float(s1[k])));
+      const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
+                             fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = (m_run == -INFINITY) ? 0.f : ex2f((m_run - m_new) * sc);
+      const float msc = m_new * sc;
+      m_run = m_new;
+      float rs[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) rs[k] = 0.f;
+      uint8_t* prow = sP + (j & 1) * C::P_BYTES + row * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys
+        float pv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int idx = c * 8 + k;
+          const float sv = __uint_as_float(idx < 32 ? s0[idx] : s1[idx - 32]);
+          pv[k] = ex2f(fmaf(sv, sc, -msc));
+          rs[k] += pv[k];
+        }
+        uint4 w;
+        w.x = pack_bf16x2(pv[0], pv[1]); w.y = pack_bf16x2(pv[2], pv[3]);
+        w.z = pack_bf16x2(pv[4], pv[5]); w.w = pack_bf16x2(pv[6], pv[7]);
+        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = w;
+      }
+      const float rsum = ((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7]));
+      l_run = l_run * corr + rsum;
+      // publish P (generic-proxy smem writes -> async proxy) and release S[j&1]: one arrival per warp
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+      // fold in the previous tile's P V while the tensor core works on this one
+      if (j > 0) accumulate_pv(j - 1, corr_prev);
+      corr_prev = corr;
+    }
+    accumulate_pv(ntiles - 1, corr_prev);
+
+    const int qrow = q0 + row;
+    if (qrow < p.nq) {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      __nv_bfloat16* og = p.out + (long long)b * p.o_bs + (long long)qrow * p.o_rs + h * p.d;
+#pragma unroll
+      for (int c = 0; c < C::CH; ++c) {
+        uint4 w;
+        w.x = pack_bf16x2(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
+        w.y = pack_bf16x2(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
+        w.z = pack_bf16x2(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
+        w.w = pack_bf16x2(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(og + c * 8) = w;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int D>
+static int launch_tc(const AttnTcDev& p, int batch, cudaStream_t stream) {
+  using C = TcCfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(flash_attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(flash_attn_tc)", e);
+    configured = true;
+  }
+  dim3 grid((p.nq + TC_BQ - 1) / TC_BQ, p.heads, batch);
+  flash_attn_tc_kernel<D><<<grid, TC_THREADS, C::SMEM, stream>>>(p);
+  EMOTE_CHECK_LAUNCH("emote_attention_tc_bf16");
+  return 0;
+}
+
+}  // namespace emote
+
+using namespace emote;
+
+extern "C" int emote_attention_tc_supported(int32_t head_dim) { return (head_dim == 40 || head_dim == 80) ? 1 : 0; }
+
+extern "C" int emote_attention_tc_bf16(const EmoteAttnArgs* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a || !a->q || !a->k0 || !a->v0 || !a->out) return set_error("emote_attention_tc_bf16: null pointer");
+  if (a->batch <= 0 || a->heads <= 0 || a->nq <= 0 || a->n0 <= 0 || a->n1 < 0)
+    return set_error("emote_attention_tc_bf16: bad sizes");
+  if (!emote_attention_tc_supported(a->head_dim)) return set_error("emote_attention_tc_bf16: head_dim must be 40 or 80");
+  if (a->n1 > 0 && (!a->k1 || !a->v1)) return set_error("emote_attention_tc_bf16: segment 1 pointers missing");
+  if (a->batch > 65535 || a->heads > 65535) return set_error("emote_attention_tc_bf16: grid too large");
+  const int64_t strides[] = {a->q_batch_stride, a->q_row_stride, a->kv0_batch_stride, a->kv0_row_stride,
+                             a->kv1_batch_stride, a->kv1_row_stride, a->o_batch_stride, a->o_row_stride};
+  for (int64_t s : strides)
+    if (s % 8 != 0) return set_error("emote_attention_tc_bf16: strides must keep rows 16-byte aligned");
+  AttnTcDev p{};
+  p.q = (const __nv_bfloat16*)a->q; p.k0 = (const __nv_bfloat16*)a->k0; p.v0 = (const __nv_bfloat16*)a->v0;
+  p.k1 = (const __nv_bfloat16*)a->k1; p.v1 = (const __nv_bfloat16*)a->v1; p.out = (__nv_bfloat16*)a->out;
+  p.heads = a->heads; p.d = a->head_dim; p.nq = a->nq; p.n0 = a->n0; p.n1 = a->n1;
+  p.q_bs = a->q_batch_stride; p.q_rs = a->q_row_stride;
+  p.kv0_bs = a->kv0_batch_stride; p.kv0_rs = a->kv0_row_stride;
+  p.kv1_bs = a->kv1_batch_stride; p.kv1_rs = a->kv1_row_stride;
+  p.o_bs = a->o_batch_stride; p.o_rs = a->o_row_stride;
+  p.kv0_div = a->kv0_batch_div > 0 ? a->kv0_batch_div : 1;
+  p.kv1_div = a->kv1_batch_div > 0 ? a->kv1_batch_div : 1;
+  p.kv1_first = a->kv1_first_batch;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  if (a->head_dim == 40) return launch_tc<40>(p, a->batch, stream);
+  return launch_tc<80>(p, a->batch, stream);
+}

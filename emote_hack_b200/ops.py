@@ -212,7 +212,8 @@ def layer_norm(x: torch.Tensor, gamma, beta, eps: float = 1e-5, pe: Optional[tor
 # ----------------------------------------------------------------------------------------------- attention
 def attention(q: torch.Tensor, k0: torch.Tensor, v0: torch.Tensor, out: torch.Tensor, *, batch: int, heads: int,
               head_dim: int, nq: int, n0: int, q_strides, kv0_strides, o_strides, scale: float, kv0_batch_div: int = 1,
-              k1=None, v1=None, n1: int = 0, kv1_strides=(0, 0), kv1_batch_div: int = 1, kv1_first_batch: int = 0):
+              k1=None, v1=None, n1: int = 0, kv1_strides=(0, 0), kv1_batch_div: int = 1, kv1_first_batch: int = 0,
+              impl: str = "auto"):
     """Strided flash attention; q/k/v/out are bf16 views into (possibly fused) projection outputs.
     *_strides = (batch_stride, row_stride) in elements."""
     a = EmoteAttnArgs()
@@ -226,7 +227,14 @@ def attention(q: torch.Tensor, k0: torch.Tensor, v0: torch.Tensor, out: torch.Te
     a.o_batch_stride, a.o_row_stride = o_strides
     a.kv0_batch_div, a.kv1_batch_div, a.kv1_first_batch = kv0_batch_div, kv1_batch_div, kv1_first_batch
     a.scale = scale
-    check(_lib.load().emote_attention_bf16(C.byref(a), _stream()), "emote_attention_bf16")
+    lib = _lib.load()
+    # tcgen05 kernel for the long-sequence self-attention shapes; warp-level mma kernel for short key sets (text /
+    # audio context) and the other head dims
+    use_tc = impl == "tc" or (impl == "auto" and head_dim == 40 and n0 >= 256)
+    if use_tc:
+        check(lib.emote_attention_tc_bf16(C.byref(a), _stream()), "emote_attention_tc_bf16")
+    else:
+        check(lib.emote_attention_bf16(C.byref(a), _stream()), "emote_attention_bf16")
     return out
 
 
@@ -345,7 +353,7 @@ class KernelProfiler:
                 if _name == "emote_gemm_bf16":
                     a = args[3]._obj
                     meta = (a.M, a.N, a.K, a.conv_taps)
-                elif _name == "emote_attention_bf16":
+                elif _name in ("emote_attention_bf16", "emote_attention_tc_bf16"):
                     a = args[0]._obj
                     meta = (a.batch, a.heads, a.head_dim, a.nq, a.n0, a.n1)
                 else:

@@ -25,6 +25,7 @@ import numpy as np
 import torch
 
 from . import ops
+from . import unet3d as _unet3d
 from .unet3d import ReferenceAttentionControl
 
 
@@ -116,6 +117,53 @@ def get_context_scheduler(name: str) -> Callable:
     raise ValueError(f"Unknown context_overlap policy {name}")
 
 
+# =============================================================================================== CUDA graph
+class GraphedUNet:
+    """One UNet3D step (all ~650 kernel launches) captured in a CUDA graph and replayed per (timestep, window):
+    static input buffers (latents, timestep, context, banks), static output.  Removes the per-launch CPU cost
+    (ctypes + tensor-map encoding + allocator) from the 50-step loop."""
+
+    def __init__(self, unet, lat_shape, ctx: torch.Tensor, banks: Optional[Dict[str, List[torch.Tensor]]], dev):
+        self.unet = unet
+        self.lat = torch.zeros(lat_shape, dtype=torch.float32, device=dev)
+        self.t = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.ctx = torch.empty_like(ctx, dtype=torch.float32).copy_(ctx)
+        self.banks = None if banks is None else {k: [t.clone() for t in v] for k, v in banks.items()}
+        self.reader = None
+        if self.banks is not None:
+            self.reader = ReferenceAttentionControl(unet, do_classifier_free_guidance=True, mode="read", fusion_blocks="midup")
+        prev = _unet3d.CTX_KV_CACHE_ENABLED
+        _unet3d.CTX_KV_CACHE_ENABLED = False
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._run()  # warm-up: packs weights, sets kernel attributes (not capturable work)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self._run()
+        finally:
+            _unet3d.CTX_KV_CACHE_ENABLED = prev
+            if self.reader is not None:
+                self.reader.clear()
+                for blk in self.reader._blocks(unet):
+                    blk._ref_mode = None
+
+    def _run(self):
+        if self.reader is not None:
+            self.reader.set_banks(self.banks)
+        return self.unet(self.lat, self.t, encoder_hidden_states=self.ctx, return_dict=False)[0]
+
+    def __call__(self, lat: torch.Tensor, t: int, ctx: Optional[torch.Tensor] = None) -> torch.Tensor:
+        self.lat.copy_(lat)
+        self.t.fill_(float(t))
+        if ctx is not None and ctx is not self.ctx:
+            self.ctx.copy_(ctx)
+        self.graph.replay()
+        return self.out
+
+
 # =============================================================================================== pipeline
 @dataclass
 class AnimationPipelineOutput:
@@ -130,6 +178,7 @@ class EMOAnimationPipeline:
         self.vae, self.unet, self.scheduler = vae, unet, scheduler
         self.vae_scale_factor = 8
         self.rank, self.world_size, self.process_group = rank, world_size, process_group
+        self._graphs: Dict[tuple, GraphedUNet] = {}
 
     # -- EMOAnimationPipeline.py:341-368 ---------------------------------------------------------------------------
     def prepare_latents(self, batch_size, num_channels_latents, video_length, height, width, dtype, device, generator,
@@ -176,7 +225,7 @@ class EMOAnimationPipeline:
     def denoise(self, latents: torch.Tensor, text_embeddings: torch.Tensor, num_inference_steps: int = 50,
                 guidance_scale: float = 7.5, context_frames: int = 16, context_stride: int = 1, context_overlap: int = 4,
                 context_schedule: str = "uniform", reference_banks: Optional[Dict[str, List[torch.Tensor]]] = None,
-                callback: Optional[Callable] = None) -> torch.Tensor:
+                callback: Optional[Callable] = None, use_cuda_graph: bool = True) -> torch.Tensor:
         """latents [1, 4, F_total, h, w] fp32 (updated in place and returned); text_embeddings = cat([uncond, cond])
         of shape [2, n, d], or per-frame [2*F_total, n, d] audio tokens (uncond frames first)."""
         do_cfg = guidance_scale > 1.0
@@ -198,11 +247,28 @@ class EMOAnimationPipeline:
         need_reduce = self.world_size > 1 and len(windows) > 1
         per_frame_ctx = text_embeddings.shape[0] == 2 * f_total and f_total > 1
         reader = None
-        if reference_banks is not None:
-            reader = ReferenceAttentionControl(self.unet, do_classifier_free_guidance=True, mode="read",
-                                               fusion_blocks="midup")
         single_window = len(windows) == 1 and windows[0] == list(range(f_total))
         noise_pred = torch.zeros((2,) + tuple(latents.shape[1:]), dtype=torch.float32, device=dev)
+        graphed = None
+        if use_cuda_graph and not per_frame_ctx and len(my_windows) > 0:
+            wlen = len(my_windows[0])
+            key = (2, latents.shape[1], wlen, latents.shape[3], latents.shape[4], tuple(text_embeddings.shape),
+                   None if reference_banks is None else tuple(sorted((k, tuple(v[0].shape)) for k, v in reference_banks.items())))
+            if all(len(w) == wlen for w in my_windows):
+                graphed = self._graphs.get(key)
+                if graphed is None:
+                    graphed = GraphedUNet(self.unet, (2, latents.shape[1], wlen, latents.shape[3], latents.shape[4]),
+                                          text_embeddings, reference_banks, dev)
+                    self._graphs[key] = graphed
+                else:
+                    graphed.ctx.copy_(text_embeddings)
+                    if reference_banks is not None:
+                        for k, v in reference_banks.items():
+                            for dst, src in zip(graphed.banks[k], v):
+                                dst.copy_(src)
+        if graphed is None and reference_banks is not None:  # eager path: banks are re-armed before every UNet call
+            reader = ReferenceAttentionControl(self.unet, do_classifier_free_guidance=True, mode="read",
+                                               fusion_blocks="midup")
         try:
             for i, t in enumerate(self.scheduler.timesteps.tolist()):
                 if not single_window:
@@ -215,11 +281,14 @@ class EMOAnimationPipeline:
                         ctx = torch.cat([text_embeddings[:f_total][idx], text_embeddings[f_total:][idx]])
                     else:
                         ctx = text_embeddings
-                    if reader is not None:
-                        reader.set_banks(reference_banks)
-                    pred = self.unet(lat_in.contiguous(), t, encoder_hidden_states=ctx, return_dict=False)[0]
+                    if graphed is not None:
+                        pred = graphed(lat_in, t)
+                    else:
+                        if reader is not None:
+                            reader.set_banks(reference_banks)
+                        pred = self.unet(lat_in.contiguous(), t, encoder_hidden_states=ctx, return_dict=False)[0]
                     if single_window:
-                        noise_pred = pred
+                        noise_pred = pred  # (a static graph output: consumed by the fused update below before the next replay)
                     else:
                         noise_pred[:, :, c] += pred
                 if need_reduce:

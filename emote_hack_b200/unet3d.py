@@ -28,6 +28,11 @@ from ._lib import EmoteKernelError
 
 F32, BF16 = torch.float32, torch.bfloat16
 
+# The context K/V projections are cached per context tensor (constant over the denoising steps).  CUDA-graph capture
+# switches the cache off so the projections are part of the captured step and replays stay correct when the static
+# context buffer is refilled (pipeline.GraphedUNet).
+CTX_KV_CACHE_ENABLED = True
+
 
 # =============================================================================================== helpers
 class AttrDict(dict):
@@ -358,13 +363,13 @@ class CrossAttention(_PackedModule):
         # The cache holds a reference to the context tensor itself (identity + version): a data_ptr key would go
         # stale when the allocator hands the same address to a different tensor.
         cc = self._ctx_cache
-        if cc is not None and cc[0] is ctx and cc[1] == ctx._version and self._pk is not None:
+        if CTX_KV_CACHE_ENABLED and cc is not None and cc[0] is ctx and cc[1] == ctx._version and self._pk is not None:
             return cc[2]
         p = self.pk
         flat = ctx.reshape(-1, ctx.shape[-1])
         a = flat if flat.dtype == BF16 and flat.is_contiguous() else ops.cast_bf16(flat.float().contiguous())
         kv = ops.gemm(a, p["wkv"], bias=p.get("bkv"), out_dtype=BF16)
-        self._ctx_cache = (ctx, ctx._version, kv)
+        self._ctx_cache = (ctx, ctx._version, kv) if CTX_KV_CACHE_ENABLED else None
         return kv
 
     def cross_attention(self, a_bf16: torch.Tensor, batch: int, n: int, ctx: torch.Tensor) -> torch.Tensor:

@@ -107,6 +107,10 @@ typedef struct {
   float scale;
 } EmoteAttnArgs;
 int emote_attention_bf16(const EmoteAttnArgs* args, void* stream);
+/* Same contract on the tcgen05 tensor cores (S and P*V accumulate in TMEM, V consumed MN-major): head_dim 40 / 80,
+ * i.e. the 64x64 and 32x32 spatial self-attention / reference-attention layers that dominate the attention time. */
+int emote_attention_tc_bf16(const EmoteAttnArgs* args, void* stream);
+int emote_attention_tc_supported(int32_t head_dim); /* 1 if emote_attention_tc_bf16 handles this head_dim */
 
 /* Temporal self-attention over the frame axis (VersatileAttention, motion_module.py:275-334): for every
  * (sample b, pixel p, head h) attends over the F frames.  qkv: tokens-major [B, F, HW, 3*heads*head_dim] bf16

@@ -313,3 +313,46 @@ def test_errors_are_loud(ops):
         ops.gemm(a, w)  # K not a multiple of 8
     with pytest.raises(EmoteKernelError):
         ops.gemm(a.cpu(), w)
+
+
+@pytest.mark.parametrize("heads,d,nq,nk", [(8, 40, 256, 256), (8, 40, 1024, 1024), (8, 80, 256, 256), (2, 40, 200, 300),
+                                           (8, 40, 4096, 4096), (4, 80, 1024, 1024), (1, 40, 64, 64)])
+def test_flash_attention_tcgen05(ops, heads, d, nq, nk):
+    g = _gen(20)
+    batch = 3
+    C = heads * d
+    if nq == nk:
+        qkv = torch.randn(batch, nq, 3 * C, device="cuda", generator=g).to(BF16)
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        qs = kvs = (nq * 3 * C, 3 * C)
+    else:
+        qt = torch.randn(batch, nq, C, device="cuda", generator=g).to(BF16)
+        kv = torch.randn(batch, nk, 2 * C, device="cuda", generator=g).to(BF16)
+        q, k, v = qt, kv[..., :C], kv[..., C:]
+        qs, kvs = (nq * C, C), (nk * 2 * C, 2 * C)
+    out = torch.zeros(batch, nq, C, device="cuda", dtype=BF16)
+    ops.attention(q, k, v, out, batch=batch, heads=heads, head_dim=d, nq=nq, n0=nk, q_strides=qs, kv0_strides=kvs,
+                  o_strides=(nq * C, C), scale=d ** -0.5, impl="tc")
+    sp = lambda t, n: t.reshape(batch, n, heads, d).permute(0, 2, 1, 3)
+    ref = _sdpa_ref(sp(q, nq), sp(k, nk), sp(v, nk), d ** -0.5).permute(0, 2, 1, 3).reshape(batch, nq, C)
+    e = rel_l2(out, ref)
+    print(f"tc attention heads={heads} d={d} nq={nq} nk={nk}: rel_l2={e:.2e}")
+    assert e < 6e-3
+
+
+def test_flash_attention_tcgen05_two_segments_cfg(ops):
+    g = _gen(21)
+    heads, d, n, F_ = 8, 40, 256, 4
+    C = heads * d
+    batch = 2 * F_
+    qkv = torch.randn(batch, n, 3 * C, device="cuda", generator=g).to(BF16)
+    bank_kv = torch.randn(2, n, 2 * C, device="cuda", generator=g).to(BF16)
+    outs = []
+    for impl in ("tc", "mma"):
+        out = torch.zeros(batch, n, C, device="cuda", dtype=BF16)
+        ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], out, batch=batch, heads=heads, head_dim=d,
+                      nq=n, n0=n, q_strides=(n * 3 * C, 3 * C), kv0_strides=(n * 3 * C, 3 * C), o_strides=(n * C, C),
+                      scale=d ** -0.5, k1=bank_kv[..., :C], v1=bank_kv[..., C:], n1=n, kv1_strides=(n * 2 * C, 2 * C),
+                      kv1_batch_div=F_, kv1_first_batch=F_, impl=impl)
+        outs.append(out)
+    assert rel_l2(outs[0], outs[1]) < 6e-3

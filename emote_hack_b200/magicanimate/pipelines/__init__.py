@@ -1,0 +1,1 @@
+from . import context  # noqa: F401

@@ -123,6 +123,8 @@ class GraphedUNet:
     static input buffers (latents, timestep, context, banks), static output.  Removes the per-launch CPU cost
     (ctypes + tensor-map encoding + allocator) from the 50-step loop."""
 
+    replayed_kernels = 0  # kernels of libemote_b200 launched through graph replays (bench.py "gpu_launches")
+
     def __init__(self, unet, lat_shape, ctx: torch.Tensor, banks: Optional[Dict[str, List[torch.Tensor]]], dev):
         self.unet = unet
         self.lat = torch.zeros(lat_shape, dtype=torch.float32, device=dev)
@@ -140,9 +142,12 @@ class GraphedUNet:
             with torch.cuda.stream(side):
                 self._run()  # warm-up: packs weights, sets kernel attributes (not capturable work)
             torch.cuda.current_stream(dev).wait_stream(side)
+            from . import _lib
+            n0 = _lib.launch_count()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.out = self._run()
+            self.kernels_per_replay = _lib.launch_count() - n0  # kernel nodes of this library inside the graph
         finally:
             _unet3d.CTX_KV_CACHE_ENABLED = prev
             if self.reader is not None:
@@ -161,6 +166,7 @@ class GraphedUNet:
         if ctx is not None and ctx is not self.ctx:
             self.ctx.copy_(ctx)
         self.graph.replay()
+        GraphedUNet.replayed_kernels += self.kernels_per_replay
         return self.out
 
 

@@ -10,6 +10,7 @@ shapes = [  # (M, N, K, mode)
     (131072, 2560, 320, "geglu"), (131072, 320, 320, "res"), (32768, 640, 640, "res"), (8192, 1280, 1280, "res"),
     (131072, 960, 320, "bf16"), (32768, 5120, 640, "geglu"), (8192, 10240, 1280, "geglu"), (131072, 320, 1280, "res"),
     (2048, 1280, 1280, "res"), (8192, 8192, 8192, "bf16"),
+    (131072, 320, 2880, "conv320"), (8192, 1280, 11520, "conv1280"),
 ]
 only = sys.argv[1:] and [int(a) for a in sys.argv[1:]]
 for i, (M, N, K, mode) in enumerate(shapes):
@@ -18,7 +19,16 @@ for i, (M, N, K, mode) in enumerate(shapes):
     a = torch.randn(M, K, device="cuda").to(BF16)
     w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(BF16)
     bias = torch.randn(N, device="cuda")
-    if mode == "geglu":
+    if mode.startswith("conv"):
+        Cc = K // 9
+        hw = {320: 64, 1280: 16}[Cc]
+        n_img = M // (hw * hw)
+        x = torch.randn(n_img, hw, hw, Cc, device="cuda").to(BF16)
+        wc = ops.pack_conv3x3(torch.randn(N, Cc, 3, 3, device="cuda") / K ** 0.5)
+        res = torch.randn(M, N, device="cuda")
+        out = torch.empty(M, N, device="cuda")
+        fn = lambda: ops.conv3x3(x, wc, n_img, hw, hw, Cc, bias=bias, residual=res, out=out)
+    elif mode == "geglu":
         wp, bp = ops.pack_geglu(w.float(), bias)
         fn = lambda: ops.gemm(a, wp, bias=bp, geglu=True, out_dtype=BF16)
     elif mode == "res":

@@ -69,3 +69,29 @@ def test_world_size_2_window_sharding_all_reduce_equals_single_process():
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(timeout=10) is True
+
+
+def test_reference_module_paths_resolve_to_b200_classes():
+    """the reference's import paths, aliased through sys.modules, give the B200 classes."""
+    import importlib
+    import sys
+    import emote_hack_b200.magicanimate as b200
+    from emote_hack_b200 import unet3d
+    saved = {k: v for k, v in sys.modules.items() if k == "magicanimate" or k.startswith("magicanimate.")}
+    try:
+        for k in saved:
+            del sys.modules[k]
+        sys.modules["magicanimate"] = b200
+        sys.modules["magicanimate.models"] = b200.models
+        for name in ("unet_controlnet", "unet_3d_blocks", "resnet", "attention", "motion_module", "mutual_self_attention"):
+            sys.modules[f"magicanimate.models.{name}"] = getattr(b200.models, name)
+        mod = importlib.import_module("magicanimate.models.unet_controlnet")
+        assert mod.UNet3DConditionModel is unet3d.UNet3DConditionModel
+        from magicanimate.models.mutual_self_attention import ReferenceAttentionControl
+        assert ReferenceAttentionControl is unet3d.ReferenceAttentionControl
+        from magicanimate.models.motion_module import get_motion_module
+        assert get_motion_module is unet3d.get_motion_module
+    finally:
+        for k in [k for k in sys.modules if k == "magicanimate" or k.startswith("magicanimate.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

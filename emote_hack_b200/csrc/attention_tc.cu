@@ -7,7 +7,7 @@
 //     PV = P V            tcgen05.mma 128 x NPV x 16 (x4), A = P (K-major), B = V consumed MN-major straight from
 //                         its natural [key][d] layout (no transpose), result in TMEM
 //     O  = O*corr + PV    accumulated in registers by the row's thread (no TMEM read-modify-write of O)
-//   warp 0 streams K/V tiles with cp.async into a 3-stage ring (manual 128B swizzle; zero-fills the tail), warp 1
+//   one thread of warp 0 streams K/V tiles with TMA into a 3-stage ring (128B swizzle; zero-fills the tail), warp 1
 //   issues the MMAs, warps 2-5 do the softmax.  S and PV are double buffered in TMEM so the softmax of tile j+1
 //   overlaps P V of tile j.  Two CTAs fit per SM (96 KB smem, 256 TMEM columns each) for latency hiding.
 //
@@ -31,8 +31,8 @@ struct AttnTcDev {
 
 constexpr int TC_BQ = 128;
 constexpr int TC_BKV = 64;
-constexpr int TC_STAGES = 3;   // K/V ring; a tile is published TC_LOOKAHEAD tiles after it was issued
-constexpr int TC_LOOKAHEAD = 1;
+constexpr int TC_STAGES = 3;   // K/V ring
+
 constexpr int TC_THREADS = 192;  // warp0 loader, warp1 MMA, warps 2-5 softmax
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
@@ -91,7 +91,10 @@ struct TcCfg {
 };
 
 template <int D>
-__global__ void __launch_bounds__(TC_THREADS, (D <= 64) ? 2 : 1) flash_attn_tc_kernel(const AttnTcDev p) {
+__global__ void __launch_bounds__(TC_THREADS, (D <= 64) ? 2 : 1)
+flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
+                     const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
+                     const AttnTcDev p) {
   using C = TcCfg<D>;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(TC_THREADS, (D <= 64) ? 2 : 1) flash_attn_tc_k
   uint8_t* sKV = sQ + C::Q_BYTES;
   uint8_t* sP = sKV + TC_STAGES * C::STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * C::P_BYTES);
-  uint64_t* kv_full = bars;                  // [STAGES] loader -> MMA (32 arrivals)
+  uint64_t* kv_full = bars;                  // [STAGES] TMA (expect_tx) -> MMA
   uint64_t* kv_empty = kv_full + TC_STAGES;  // [STAGES] MMA commit -> loader
   uint64_t* s_full = kv_empty + TC_STAGES;   // [2] MMA commit -> softmax
   uint64_t* p_full = s_full + 2;             // [2] softmax (4 warp arrivals) -> MMA
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(TC_THREADS, (D <= 64) ? 2 : 1) flash_attn_tc_k
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(&kv_full[s], 32);
+      mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -157,51 +160,31 @@ __global__ void __launch_bounds__(TC_THREADS, (D <= 64) ? 2 : 1) flash_attn_tc_k
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ K/V loader (cp.async, all 32 lanes)
-    const __nv_bfloat16* k0g = p.k0 + (long long)(b / p.kv0_div) * p.kv0_bs + h * p.d;
-    const __nv_bfloat16* v0g = p.v0 + (long long)(b / p.kv0_div) * p.kv0_bs + h * p.d;
-    const __nv_bfloat16* k1g = nullptr;
-    const __nv_bfloat16* v1g = nullptr;
-    if (n1 > 0) {
-      k1g = p.k1 + (long long)(b / p.kv1_div) * p.kv1_bs + h * p.d;
-      v1g = p.v1 + (long long)(b / p.kv1_div) * p.kv1_bs + h * p.d;
-    }
-    for (int j = 0; j < ntiles; ++j) {
-      const int stage = j % TC_STAGES;
-      // slot reuse needs P V of tile j-STAGES; that only needs tiles <= j-STAGES+1 published, which happened at
-      // iteration j-1 at the latest (LOOKAHEAD < STAGES-1): no circular wait with the MMA warp
-      if (j >= TC_STAGES) mbar_wait(&kv_empty[stage], ((j / TC_STAGES) - 1) & 1);
-      const __nv_bfloat16 *kg, *vg;
-      long long rs;
-      int nvalid;
-      if (j < tiles0) {
-        kg = k0g + (long long)j * TC_BKV * p.kv0_rs; vg = v0g + (long long)j * TC_BKV * p.kv0_rs;
-        rs = p.kv0_rs; nvalid = p.n0 - j * TC_BKV;
-      } else {
-        const int t1 = j - tiles0;
-        kg = k1g + (long long)t1 * TC_BKV * p.kv1_rs; vg = v1g + (long long)t1 * TC_BKV * p.kv1_rs;
-        rs = p.kv1_rs; nvalid = n1 - t1 * TC_BKV;
-      }
-      const uint32_t kdst = smem_u32(sKV + stage * C::STAGE);
-      const uint32_t vdst = kdst + C::KV_TILE;
-      for (int i = lane; i < TC_BKV * C::CH; i += 32) {
-        const int r = i / C::CH, c = i - r * C::CH;
-        const uint32_t off = (c >> 3) * (TC_BKV * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4);
-        const bool ok = r < nvalid;
-        cp_async16_zfill(kdst + off, kg + (long long)r * rs + c * 8, ok);
-        cp_async16_zfill(vdst + off, vg + (long long)r * rs + c * 8, ok);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (j >= TC_LOOKAHEAD) {  // tile j-LOOKAHEAD has landed -> publish it to the async proxy / MMA warp
-        asm volatile("cp.async.wait_group %0;" ::"n"(TC_LOOKAHEAD) : "memory");
-        fence_proxy_async();
-        mbar_arrive(&kv_full[(j - TC_LOOKAHEAD) % TC_STAGES]);
+    // ------------------------------------------------------------------ K/V loader: one thread, TMA
+    // Each K / V tile is 64 keys x (ATOMS x 64) columns starting at column h*D of the [batch][key][heads*D] view: the
+    // box over-reads up to 64-D%64 columns of the NEXT head (or zero-fill past the row end).  Harmless: the matching Q
+    // columns are zero (QK^T) and the extra P*V columns are never stored.  Rows past the segment end are zero-filled.
+    if (lane == 0) {
+      tma_prefetch_desc(&tmK0);
+      tma_prefetch_desc(&tmV0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int stage = j % TC_STAGES;
+        if (j >= TC_STAGES) mbar_wait(&kv_empty[stage], ((j / TC_STAGES) - 1) & 1);
+        uint8_t* kdst = sKV + stage * C::STAGE;
+        uint8_t* vdst = kdst + C::KV_TILE;
+        mbar_expect_tx(&kv_full[stage], C::STAGE);
+        const bool seg0 = j < tiles0;
+        const CUtensorMap* mk = seg0 ? &tmK0 : &tmK1;
+        const CUtensorMap* mv = seg0 ? &tmV0 : &tmV1;
+        const int row = (seg0 ? j : j - tiles0) * TC_BKV;
+        const int bidx = seg0 ? b / p.kv0_div : b / p.kv1_div;
+#pragma unroll
+        for (int a = 0; a < C::ATOMS; ++a) {
+          tma_load_3d(kdst + a * (TC_BKV * 128), mk, &kv_full[stage], h * D + a * 64, row, bidx);
+          tma_load_3d(vdst + a * (TC_BKV * 128), mv, &kv_full[stage], h * D + a * 64, row, bidx);
+        }
       }
     }
-    // drain: everything has landed once wait_group 0 returns
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    fence_proxy_async();
-    for (int j = (ntiles > TC_LOOKAHEAD ? ntiles - TC_LOOKAHEAD : 0); j < ntiles; ++j) mbar_arrive(&kv_full[j % TC_STAGES]);
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
@@ -351,6 +334,15 @@ __global__ void __launch_bounds__(TC_THREADS, (D <= 64) ? 2 : 1) flash_attn_tc_k
   }
 }
 
+// [batch][key][cols] bf16 view starting at `base` (the k or v pointer, i.e. already offset to its first column)
+static int make_kv_map(CUtensorMap* m, const void* base, int cols, int nkeys, long long row_stride, long long batch_stride,
+                       int nbatch) {
+  uint64_t dims[3] = {(uint64_t)cols, (uint64_t)nkeys, (uint64_t)nbatch};
+  uint64_t strides[2] = {(uint64_t)row_stride * 2, (uint64_t)(nbatch > 1 ? batch_stride : row_stride * nkeys) * 2};
+  uint32_t box[3] = {64, (uint32_t)TC_BKV, 1};
+  return make_tensor_map(m, base, 3, dims, strides, box);
+}
+
 template <int D>
 static int launch_tc(const AttnTcDev& p, int batch, cudaStream_t stream) {
   using C = TcCfg<D>;
@@ -360,8 +352,21 @@ static int launch_tc(const AttnTcDev& p, int batch, cudaStream_t stream) {
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(flash_attn_tc)", e);
     configured = true;
   }
+  const int cols = p.heads * p.d;
+  CUtensorMap mk0, mv0, mk1, mv1;
+  const int nb0 = (batch + p.kv0_div - 1) / p.kv0_div;
+  if (int rc = make_kv_map(&mk0, p.k0, cols, p.n0, p.kv0_rs, p.kv0_bs, nb0)) return rc;
+  if (int rc = make_kv_map(&mv0, p.v0, cols, p.n0, p.kv0_rs, p.kv0_bs, nb0)) return rc;
+  if (p.n1 > 0) {
+    const int nb1 = (batch + p.kv1_div - 1) / p.kv1_div;
+    if (int rc = make_kv_map(&mk1, p.k1, cols, p.n1, p.kv1_rs, p.kv1_bs, nb1)) return rc;
+    if (int rc = make_kv_map(&mv1, p.v1, cols, p.n1, p.kv1_rs, p.kv1_bs, nb1)) return rc;
+  } else {
+    mk1 = mk0;
+    mv1 = mv0;
+  }
   dim3 grid((p.nq + TC_BQ - 1) / TC_BQ, p.heads, batch);
-  flash_attn_tc_kernel<D><<<grid, TC_THREADS, C::SMEM, stream>>>(p);
+  flash_attn_tc_kernel<D><<<grid, TC_THREADS, C::SMEM, stream>>>(mk0, mv0, mk1, mv1, p);
   EMOTE_CHECK_LAUNCH("emote_attention_tc_bf16");
   return 0;
 }

@@ -69,8 +69,10 @@ def test_vae_decode_video_and_state_dict_aliases(tiny_vae):
     ref = oracle.decode_latents(lat)
     vid, u8 = vae.decode_video(lat.cuda(), want_u8=True)
     assert vid.shape == ref.shape == (1, 3, 3, 64, 64)
-    assert (vid.cpu() - ref).abs().max() < 3e-2
-    assert (u8.cpu().float() / 255 - ref).abs().max() < 3e-2 + 1 / 255
+    e, emax = rel_l2(vid, ref), (vid.cpu() - ref).abs().max().item()
+    print(f"vae decode_video rel_l2={e:.2e} max_abs={emax:.2e}")
+    assert e < 2e-2 and emax < 6e-2   # [0,1] images; same bf16-operand budget as test_vae_decode
+    assert (u8.cpu().float() / 255 - vid.cpu()).abs().max() <= 0.5 / 255 + 1e-6   # uint8 copy = rounded fp32 video
     # chunked decode == batched decode; newer diffusers attention key names load
     vid2, _ = vae.decode_video(lat.cuda(), frame_chunk=2)
     assert rel_l2(vid2, vid) < 1e-5

@@ -35,6 +35,7 @@ class EmoteGemmArgs(C.Structure):
         ("out_dtype", C.c_int32),
         ("ldc", C.c_int32),
         ("block_n", C.c_int32),
+        ("pair_mode", C.c_int32),
     ]
 
 

@@ -164,12 +164,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
     // Each K / V tile is 64 keys x (ATOMS x 64) columns starting at column h*D of the [batch][key][heads*D] view: the
     // box over-reads up to 64-D%64 columns of the NEXT head (or zero-fill past the row end).  Harmless: the matching Q
     // columns are zero (QK^T) and the extra P*V columns are never stored.  Rows past the segment end are zero-filled.
-    if (lane == 0) {
-      tma_prefetch_desc(&tmK0);
-      tma_prefetch_desc(&tmV0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int stage = j % TC_STAGES;
-        if (j >= TC_STAGES) mbar_wait(&kv_empty[stage], ((j / TC_STAGES) - 1) & 1);
+    for (int j = 0; j < ntiles; ++j) {  // warp-uniform loop, one elected lane issues
+      const int stage = j % TC_STAGES;
+      if (j >= TC_STAGES) mbar_wait(&kv_empty[stage], ((j / TC_STAGES) - 1) & 1);
+      if (elect_one()) {
         uint8_t* kdst = sKV + stage * C::STAGE;
         uint8_t* vdst = kdst + C::KV_TILE;
         mbar_expect_tx(&kv_full[stage], C::STAGE);
@@ -184,45 +182,52 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
           tma_load_3d(vdst + a * (TC_BKV * 128), mv, &kv_full[stage], h * D + a * 64, row, bidx);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane)
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(TC_BQ, TC_BKV);
       constexpr uint32_t idesc_pv = umma_idesc_bf16_bmn(TC_BQ, C::NPV);
       auto issue_s = [&](int j) {
         const int stage = j % TC_STAGES;
         mbar_wait(&kv_full[stage], (j / TC_STAGES) & 1);
         tc_fence_after();
-        const uint32_t ka = smem_u32(sKV + stage * C::STAGE);
-        const uint32_t qa = smem_u32(sQ);
-        const uint32_t d_tmem = tmem_base + (j & 1) * TC_BKV;
+        if (elect_one()) {
+          const uint32_t ka = smem_u32(sKV + stage * C::STAGE);
+          const uint32_t qa = smem_u32(sQ);
+          const uint32_t d_tmem = tmem_base + (j & 1) * TC_BKV;
 #pragma unroll
-        for (int ks = 0; ks < C::KSTEPS; ++ks) {
-          const uint64_t da = umma_desc_sw128(qa + (ks >> 2) * (TC_BQ * 128)) + static_cast<uint64_t>(2 * (ks & 3));
-          const uint64_t db = umma_desc_sw128(ka + (ks >> 2) * (TC_BKV * 128)) + static_cast<uint64_t>(2 * (ks & 3));
-          umma_f16(d_tmem, da, db, idesc_s, ks != 0 ? 1u : 0u);
+          for (int ks = 0; ks < C::KSTEPS; ++ks) {
+            const uint64_t da = umma_desc_sw128(qa + (ks >> 2) * (TC_BQ * 128)) + static_cast<uint64_t>(2 * (ks & 3));
+            const uint64_t db = umma_desc_sw128(ka + (ks >> 2) * (TC_BKV * 128)) + static_cast<uint64_t>(2 * (ks & 3));
+            umma_f16(d_tmem, da, db, idesc_s, ks != 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[j & 1]);
         }
-        umma_commit(&s_full[j & 1]);
+        __syncwarp();
       };
       issue_s(0);
       for (int j = 0; j < ntiles; ++j) {
         if (j + 1 < ntiles) issue_s(j + 1);  // S buffer (j+1)&1 was released by p_full(j-1), waited last iteration
         mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
-        const int stage = j % TC_STAGES;
-        const uint32_t va = smem_u32(sKV + stage * C::STAGE) + C::KV_TILE;
-        const uint32_t pa = smem_u32(sP + (j & 1) * C::P_BYTES);
-        const uint32_t d_tmem = tmem_base + C::PV_COL0 + (j & 1) * C::NPV;
+        if (elect_one()) {
+          const int stage = j % TC_STAGES;
+          const uint32_t va = smem_u32(sKV + stage * C::STAGE) + C::KV_TILE;
+          const uint32_t pa = smem_u32(sP + (j & 1) * C::P_BYTES);
+          const uint32_t d_tmem = tmem_base + C::PV_COL0 + (j & 1) * C::NPV;
 #pragma unroll
-        for (int ks = 0; ks < TC_BKV / 16; ++ks) {
-          const uint64_t da = umma_desc_sw128(pa) + static_cast<uint64_t>(2 * ks);
-          // MN-major B: 16 keys = 16 rows of 128 B further down the tile
-          const uint64_t db = umma_desc_sw128_mn(va + ks * 16 * 128, TC_BKV * 128);
-          umma_f16(d_tmem, da, db, idesc_pv, ks != 0 ? 1u : 0u);
+          for (int ks = 0; ks < TC_BKV / 16; ++ks) {
+            const uint64_t da = umma_desc_sw128(pa) + static_cast<uint64_t>(2 * ks);
+            // MN-major B: 16 keys = 16 rows of 128 B further down the tile
+            const uint64_t db = umma_desc_sw128_mn(va + ks * 16 * 128, TC_BKV * 128);
+            umma_f16(d_tmem, da, db, idesc_pv, ks != 0 ? 1u : 0u);
+          }
+          umma_commit(&o_full[j & 1]);
+          umma_commit(&kv_empty[stage]);
         }
-        umma_commit(&o_full[j & 1]);
-        umma_commit(&kv_empty[stage]);
+        __syncwarp();
       }
     }
   } else {

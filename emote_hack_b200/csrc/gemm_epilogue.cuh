@@ -1,0 +1,186 @@
+// Shared by the 1-CTA and the CTA-pair GEMM kernels: launch parameters and the per-tile epilogue
+// (TMEM -> registers -> fused bias / residual / GEGLU -> global).
+#pragma once
+#include "common.cuh"
+
+namespace emote {
+
+constexpr int BM = 128;       // rows of the output tile owned by one CTA (one TMEM lane per row)
+constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle row
+
+struct GemmDev {
+  int M, N, K;
+  int num_kb;        // K blocks of 64 (over all taps)
+  int kb_per_tap;    // C/64 in conv mode
+  int taps;          // 1 or 9
+  int H, W;          // conv image dims
+  int bw, bh;        // TMA box extents in W and H (bw*bh*bn = 128)
+  int tiles_m, tiles_n;
+  const float* bias;
+  const float* row_bias;
+  int rows_per_group;
+  const float* residual;
+  int ldr;
+  float out_scale;
+  int geglu;
+  int out_bf16;
+  int ldc;
+  void* out;
+};
+
+
+// One output tile of one CTA.  `tbase` = TMEM address of the accumulator stage for this warp's lane quarter,
+// `row_base` = first global row of the tile, (`n0`, `tn`) = first column / column-tile index.  The caller has NOT yet
+// waited for the accumulator: `wait_full()` is invoked after the residual prefetch has been issued.
+template <int BN, int EPI_WARPS, bool HAS_ADD, class WaitFull>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tbase, int row_base, int n0, int tn,
+                                                   int quarter, int part, int lane, WaitFull wait_full) {
+  constexpr int NP = EPI_WARPS / 4;   // warps per lane quarter
+  const int g = lane >> 2, t = lane & 3;
+  const int row0 = row_base + quarter * 32 + g;  // this thread's rows: row0 + 8*i, i = 0..3
+  bool rok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rok[i] = (row0 + 8 * i) < p.M;
+
+  if (!p.geglu) {
+    constexpr int NCT = BN / 8;                     // 8-column chunks in the tile
+    constexpr int NCH = NCT / NP;                   // contiguous chunks per warp
+    static_assert(NCT % NP == 0, "tile columns must split evenly over the warps of a lane quarter");
+    const int c_first = part * NCH;
+    size_t ooff[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ooff[i] = (size_t)(row0 + 8 * i) * p.ldc;
+    // ---- residual / per-sample bias of this warp's whole column span, issued before the accumulator wait
+    float add[HAS_ADD ? NCH : 1][8];
+    if constexpr (HAS_ADD) {
+      const bool has_res = p.residual != nullptr, has_rb = p.row_bias != nullptr;
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int col = n0 + (c_first + ci) * 8 + 2 * t;
+        const bool c0ok = col < p.N, c1ok = col + 1 < p.N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = row0 + 8 * i;
+          float v0 = 0.f, v1 = 0.f;
+          if (rok[i]) {
+            if (has_res) {
+              const float* rp = p.residual + (size_t)row * p.ldr + col;
+              if (c1ok) { const float2 r2 = *reinterpret_cast<const float2*>(rp); v0 = r2.x; v1 = r2.y; }
+              else if (c0ok) v0 = rp[0];
+            }
+            if (has_rb) {
+              const float* bp = p.row_bias + (size_t)(row / p.rows_per_group) * p.N + col;
+              if (c1ok) { const float2 r2 = *reinterpret_cast<const float2*>(bp); v0 += r2.x; v1 += r2.y; }
+              else if (c0ok) v0 += bp[0];
+            }
+          }
+          add[ci][2 * i] = v0;
+          add[ci][2 * i + 1] = v1;
+        }
+      }
+    }
+    uint32_t acc[2][8];
+    auto issue = [&](int ci, uint32_t (&a)[8]) {
+      const uint32_t col_t = static_cast<uint32_t>((c_first + ci) * 8);
+      uint32_t lo[4], hi[4];
+      tmem_ld_16x256b_x1(tbase + col_t, lo);
+      tmem_ld_16x256b_x1(tbase + (16u << 16) + col_t, hi);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a[k] = lo[k]; a[4 + k] = hi[k]; }
+    };
+    auto finish = [&](int ci, const uint32_t (&a)[8]) {
+      const int col = n0 + (c_first + ci) * 8 + 2 * t;
+      const bool c0ok = col < p.N, c1ok = col + 1 < p.N;
+      float b0 = 0.f, b1 = 0.f;
+      if (p.bias) {
+        if (c0ok) b0 = __ldg(p.bias + col);
+        if (c1ok) b1 = __ldg(p.bias + col + 1);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        // rows g, g+8 come from the low 16-lane load, rows g+16, g+24 from the high one
+        const int ri = (i >> 1) * 4 + (i & 1) * 2;
+        float v0 = __uint_as_float(a[ri]) + b0, v1 = __uint_as_float(a[ri + 1]) + b1;
+        if constexpr (HAS_ADD) { v0 += add[ci][2 * i]; v1 += add[ci][2 * i + 1]; }
+        v0 *= p.out_scale; v1 *= p.out_scale;
+        if (rok[i] && c0ok) {
+          if (p.out_bf16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[i] + col;
+            if (c1ok) *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(v0, v1);
+            else o[0] = __float2bfloat16(v0);
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + ooff[i] + col;
+            if (c1ok) *reinterpret_cast<float2*>(o) = make_float2(v0, v1);
+            else o[0] = v0;
+          }
+        }
+      }
+    };
+    wait_full();
+    issue(0, acc[0]);
+#pragma unroll
+    for (int ci = 0; ci < NCH; ++ci) {
+      tmem_ld_wait();
+      if (ci + 1 < NCH) issue(ci + 1, acc[(ci + 1) & 1]);
+      finish(ci, acc[ci & 1]);
+    }
+  } else {
+    // GEGLU: tile columns [0, BN/2) hold the value half, [BN/2, BN) the gate half of the same BN/2 output
+    // features (weights are packed that way); out = (value + b_v) * gelu_erf(gate + b_g).
+    constexpr int HALF = BN / 2;
+    constexpr int NCT = HALF / 8;
+    constexpr int NCH = (NCT + NP - 1) / NP;   // round-robin over the warps of the quarter (may be uneven)
+    const int n_out = p.N / 2;
+    size_t ooff[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ooff[i] = (size_t)(row0 + 8 * i) * p.ldc;
+    uint32_t av[2][8], ag[2][8];
+    float bb[2][4];
+    auto issue = [&](int ci, uint32_t (&v)[8], uint32_t (&gt)[8], float (&b)[4]) {
+      const int cc = part + ci * NP;
+      if (cc < NCT) {
+        const uint32_t col_t = static_cast<uint32_t>(cc * 8);
+        uint32_t lo[4], hi[4], glo[4], ghi[4];
+        tmem_ld_16x256b_x1(tbase + col_t, lo);
+        tmem_ld_16x256b_x1(tbase + (16u << 16) + col_t, hi);
+        tmem_ld_16x256b_x1(tbase + HALF + col_t, glo);
+        tmem_ld_16x256b_x1(tbase + (16u << 16) + HALF + col_t, ghi);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[k] = lo[k]; v[4 + k] = hi[k]; gt[k] = glo[k]; gt[4 + k] = ghi[k]; }
+        const int tc = cc * 8 + 2 * t;
+        if (p.bias) {
+          b[0] = __ldg(p.bias + n0 + tc); b[1] = __ldg(p.bias + n0 + tc + 1);
+          b[2] = __ldg(p.bias + n0 + HALF + tc); b[3] = __ldg(p.bias + n0 + HALF + tc + 1);
+        } else {
+          b[0] = b[1] = b[2] = b[3] = 0.f;
+        }
+      }
+    };
+    auto finish = [&](int ci, const uint32_t (&v)[8], const uint32_t (&gt)[8], const float (&b)[4]) {
+      const int cc = part + ci * NP;
+      if (cc < NCT) {
+        const int ocol = tn * HALF + cc * 8 + 2 * t;
+        const bool cok = ocol < n_out;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ri = (i >> 1) * 4 + (i & 1) * 2;
+          const float a0 = __uint_as_float(v[ri]) + b[0], a1 = __uint_as_float(v[ri + 1]) + b[1];
+          const float q0 = __uint_as_float(gt[ri]) + b[2], q1 = __uint_as_float(gt[ri + 1]) + b[3];
+          const uint32_t packed = pack_bf16x2(a0 * gelu_erf_fast(q0), a1 * gelu_erf_fast(q1));
+          if (rok[i] && cok)
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[i] + ocol) = packed;
+        }
+      }
+    };
+    wait_full();
+    issue(0, av[0], ag[0], bb[0]);
+#pragma unroll
+    for (int ci = 0; ci < NCH; ++ci) {
+      tmem_ld_wait();
+      if (ci + 1 < NCH) issue(ci + 1, av[(ci + 1) & 1], ag[(ci + 1) & 1], bb[(ci + 1) & 1]);
+      finish(ci, av[ci & 1], ag[ci & 1], bb[ci & 1]);
+    }
+  }
+}
+
+}  // namespace emote

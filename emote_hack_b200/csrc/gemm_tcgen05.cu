@@ -11,38 +11,17 @@
 // * fused epilogues: bias, per-sample time-embedding bias (resnet.py:186-189), fp32 residual add and
 //   1/output_scale_factor (resnet.py:202-205), GEGLU (orig_attention.py:817-827), bf16 or fp32 store.
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 #include "emote_b200.h"
 #include "host_utils.h"
 
 namespace emote {
 
-constexpr int BM = 128;       // UMMA M (rows of the output tile, one TMEM lane per row)
-constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle row
 // warp0 = TMA producer, warp1 = MMA issuer + TMEM allocator, then EPI_WARPS epilogue warps.  Two variants:
 //   HAS_ADD (residual and/or per-sample bias): 8 epilogue warps that prefetch their whole fp32 residual span into
 //            registers BEFORE waiting for the accumulator, so ~80 KB/SM of residual reads overlap the main loop;
 //   plain / GEGLU: 16 epilogue warps (4 per TMEM lane quarter) to hide TMEM and issue latency.
 constexpr int gemm_threads(int epi_warps) { return 64 + 32 * epi_warps; }
-
-struct GemmDev {
-  int M, N, K;
-  int num_kb;        // K blocks of 64 (over all taps)
-  int kb_per_tap;    // C/64 in conv mode
-  int taps;          // 1 or 9
-  int H, W;          // conv image dims
-  int bw, bh;        // TMA box extents in W and H (bw*bh*bn = 128)
-  int tiles_m, tiles_n;
-  const float* bias;
-  const float* row_bias;
-  int rows_per_group;
-  const float* residual;
-  int ldr;
-  float out_scale;
-  int geglu;
-  int out_bf16;
-  int ldc;
-  void* out;
-};
 
 template <int BN>
 struct GemmSmem {
@@ -98,8 +77,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int num_tiles = p.tiles_m * p.tiles_n;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (warp-uniform loop, one
+    // elected lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -117,19 +97,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * S::STAGE_BYTES;
-          uint8_t* sb = sa + S::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-          if (p.taps > 1) {
-            const int tap = kb / p.kb_per_tap;
-            const int kc = kb - tap * p.kb_per_tap;
-            const int dy = tap / 3 - 1;
-            const int dx = tap - (tap / 3) * 3 - 1;
-            tma_load_4d(sa, &tmA, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img0);
-          } else {
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * S::STAGE_BYTES;
+            uint8_t* sb = sa + S::A_BYTES;
+            mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+            if (p.taps > 1) {
+              const int tap = kb / p.kb_per_tap;
+              const int kc = kb - tap * p.kb_per_tap;
+              const int dy = tap / 3 - 1;
+              const int dx = tap - (tap / 3) * 3 - 1;
+              tma_load_4d(sa, &tmA, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img0);
+            } else {
+              tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+            }
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
           }
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          __syncwarp();
           if (++stage == S::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -138,8 +121,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one
+    // elected lane issues)
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -152,23 +136,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint32_t sb = sa + S::A_BYTES;
-          const uint64_t da = umma_desc_sw128(sa);
-          const uint64_t db = umma_desc_sw128(sb);
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+            const uint32_t sb = sa + S::A_BYTES;
+            const uint64_t da = umma_desc_sw128(sa);
+            const uint64_t db = umma_desc_sw128(sb);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                     (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+              umma_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                       (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == S::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[as]);  // accumulator ready for the epilogue
+        if (elect_one()) umma_commit(&tmem_full[as]);  // accumulator ready for the epilogue
+        __syncwarp();
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -182,164 +170,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // fragment rows {g, g+8} x columns {2t, 2t+1}: a quad covers one full 32-byte sector of an fp32 row, so global
     // reads of the residual and writes of the output are sector-complete.  The loop is software pipelined: the TMEM
     // loads and the residual / bias loads of chunk i+1 are in flight while chunk i is finished and stored.
-    constexpr int NP = EPI_WARPS / 4;   // warps per lane quarter
     const int ew = warp - 2;
     const int quarter = warp & 3;
     const int part = ew >> 2;
-    const int g = lane >> 2, t = lane & 3;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
-      const int row0 = tm * BM + quarter * 32 + g;  // this thread's rows: row0 + 8*i, i = 0..3
-      const int n0 = tn * BN;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
-      bool rok[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) rok[i] = (row0 + 8 * i) < p.M;
-
-      if (!p.geglu) {
-        constexpr int NCT = BN / 8;                     // 8-column chunks in the tile
-        constexpr int NCH = NCT / NP;                   // contiguous chunks per warp
-        static_assert(NCT % NP == 0, "tile columns must split evenly over the warps of a lane quarter");
-        const int c_first = part * NCH;
-        size_t ooff[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ooff[i] = (size_t)(row0 + 8 * i) * p.ldc;
-        // ---- residual / per-sample bias of this warp's whole column span, issued before the accumulator wait
-        float add[HAS_ADD ? NCH : 1][8];
-        if constexpr (HAS_ADD) {
-          const bool has_res = p.residual != nullptr, has_rb = p.row_bias != nullptr;
-#pragma unroll
-          for (int ci = 0; ci < NCH; ++ci) {
-            const int col = n0 + (c_first + ci) * 8 + 2 * t;
-            const bool c0ok = col < p.N, c1ok = col + 1 < p.N;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int row = row0 + 8 * i;
-              float v0 = 0.f, v1 = 0.f;
-              if (rok[i]) {
-                if (has_res) {
-                  const float* rp = p.residual + (size_t)row * p.ldr + col;
-                  if (c1ok) { const float2 r2 = *reinterpret_cast<const float2*>(rp); v0 = r2.x; v1 = r2.y; }
-                  else if (c0ok) v0 = rp[0];
-                }
-                if (has_rb) {
-                  const float* bp = p.row_bias + (size_t)(row / p.rows_per_group) * p.N + col;
-                  if (c1ok) { const float2 r2 = *reinterpret_cast<const float2*>(bp); v0 += r2.x; v1 += r2.y; }
-                  else if (c0ok) v0 += bp[0];
-                }
-              }
-              add[ci][2 * i] = v0;
-              add[ci][2 * i + 1] = v1;
-            }
-          }
-        }
-        uint32_t acc[2][8];
-        auto issue = [&](int ci, uint32_t (&a)[8]) {
-          const uint32_t col_t = static_cast<uint32_t>((c_first + ci) * 8);
-          uint32_t lo[4], hi[4];
-          tmem_ld_16x256b_x1(tbase + col_t, lo);
-          tmem_ld_16x256b_x1(tbase + (16u << 16) + col_t, hi);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { a[k] = lo[k]; a[4 + k] = hi[k]; }
-        };
-        auto finish = [&](int ci, const uint32_t (&a)[8]) {
-          const int col = n0 + (c_first + ci) * 8 + 2 * t;
-          const bool c0ok = col < p.N, c1ok = col + 1 < p.N;
-          float b0 = 0.f, b1 = 0.f;
-          if (p.bias) {
-            if (c0ok) b0 = __ldg(p.bias + col);
-            if (c1ok) b1 = __ldg(p.bias + col + 1);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            // rows g, g+8 come from the low 16-lane load, rows g+16, g+24 from the high one
-            const int ri = (i >> 1) * 4 + (i & 1) * 2;
-            float v0 = __uint_as_float(a[ri]) + b0, v1 = __uint_as_float(a[ri + 1]) + b1;
-            if constexpr (HAS_ADD) { v0 += add[ci][2 * i]; v1 += add[ci][2 * i + 1]; }
-            v0 *= p.out_scale; v1 *= p.out_scale;
-            if (rok[i] && c0ok) {
-              if (p.out_bf16) {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[i] + col;
-                if (c1ok) *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(v0, v1);
-                else o[0] = __float2bfloat16(v0);
-              } else {
-                float* o = reinterpret_cast<float*>(p.out) + ooff[i] + col;
-                if (c1ok) *reinterpret_cast<float2*>(o) = make_float2(v0, v1);
-                else o[0] = v0;
-              }
-            }
-          }
-        };
+      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD>(p, tbase, tm * BM, tn * BN, tn, quarter, part, lane, [&]() {
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
-        issue(0, acc[0]);
-#pragma unroll
-        for (int ci = 0; ci < NCH; ++ci) {
-          tmem_ld_wait();
-          if (ci + 1 < NCH) issue(ci + 1, acc[(ci + 1) & 1]);
-          finish(ci, acc[ci & 1]);
-        }
-      } else {
-        // GEGLU: tile columns [0, BN/2) hold the value half, [BN/2, BN) the gate half of the same BN/2 output
-        // features (weights are packed that way); out = (value + b_v) * gelu_erf(gate + b_g).
-        constexpr int HALF = BN / 2;
-        constexpr int NCT = HALF / 8;
-        constexpr int NCH = (NCT + NP - 1) / NP;   // round-robin over the warps of the quarter (may be uneven)
-        const int n_out = p.N / 2;
-        size_t ooff[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ooff[i] = (size_t)(row0 + 8 * i) * p.ldc;
-        uint32_t av[2][8], ag[2][8];
-        float bb[2][4];
-        auto issue = [&](int ci, uint32_t (&v)[8], uint32_t (&gt)[8], float (&b)[4]) {
-          const int cc = part + ci * NP;
-          if (cc < NCT) {
-            const uint32_t col_t = static_cast<uint32_t>(cc * 8);
-            uint32_t lo[4], hi[4], glo[4], ghi[4];
-            tmem_ld_16x256b_x1(tbase + col_t, lo);
-            tmem_ld_16x256b_x1(tbase + (16u << 16) + col_t, hi);
-            tmem_ld_16x256b_x1(tbase + HALF + col_t, glo);
-            tmem_ld_16x256b_x1(tbase + (16u << 16) + HALF + col_t, ghi);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { v[k] = lo[k]; v[4 + k] = hi[k]; gt[k] = glo[k]; gt[4 + k] = ghi[k]; }
-            const int tc = cc * 8 + 2 * t;
-            if (p.bias) {
-              b[0] = __ldg(p.bias + n0 + tc); b[1] = __ldg(p.bias + n0 + tc + 1);
-              b[2] = __ldg(p.bias + n0 + HALF + tc); b[3] = __ldg(p.bias + n0 + HALF + tc + 1);
-            } else {
-              b[0] = b[1] = b[2] = b[3] = 0.f;
-            }
-          }
-        };
-        auto finish = [&](int ci, const uint32_t (&v)[8], const uint32_t (&gt)[8], const float (&b)[4]) {
-          const int cc = part + ci * NP;
-          if (cc < NCT) {
-            const int ocol = tn * HALF + cc * 8 + 2 * t;
-            const bool cok = ocol < n_out;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int ri = (i >> 1) * 4 + (i & 1) * 2;
-              const float a0 = __uint_as_float(v[ri]) + b[0], a1 = __uint_as_float(v[ri + 1]) + b[1];
-              const float q0 = __uint_as_float(gt[ri]) + b[2], q1 = __uint_as_float(gt[ri + 1]) + b[3];
-              const uint32_t packed = pack_bf16x2(a0 * gelu_erf_fast(q0), a1 * gelu_erf_fast(q1));
-              if (rok[i] && cok)
-                *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[i] + ocol) = packed;
-            }
-          }
-        };
-        mbar_wait(&tmem_full[as], aphase);
-        tc_fence_after();
-        issue(0, av[0], ag[0], bb[0]);
-#pragma unroll
-        for (int ci = 0; ci < NCH; ++ci) {
-          tmem_ld_wait();
-          if (ci + 1 < NCH) issue(ci + 1, av[(ci + 1) & 1], ag[(ci + 1) & 1], bb[(ci + 1) & 1]);
-          finish(ci, av[ci & 1], ag[ci & 1], bb[ci & 1]);
-        }
-      }
+      });
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -360,6 +203,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 }
 
 // --------------------------------------------------------------------------- host side
+int launch_gemm_pair(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDev& p, cudaStream_t stream);  // gemm2_tcgen05.cu
 static int g_num_sms = 0;
 
 template <int BN, int EPI_WARPS, bool HAS_ADD>
@@ -457,12 +301,19 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
     uint32_t box[2] = {64, 128};
     if (int rc = make_tensor_map(&tmA, A, 2, dims, strides, box)) return rc;
   }
+  // CTA pairs (cta_group::2, UMMA M = 256, B tile split over the two SMs) for the tensor-bound shapes: the 3x3
+  // convolutions and the large-K GEMMs, when there are enough 256-row tiles to occupy the 74 pairs.
+  const long long pair_tiles = ((long long)(a->M + 255) / 256) * ((a->N + bn - 1) / bn);
+  bool use_pair = (conv || a->K >= 1024) && a->M >= 256 && pair_tiles >= 64;
+  if (a->pair_mode == 1) use_pair = true;
+  if (a->pair_mode == 2) use_pair = false;
   {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t strides[1] = {(uint64_t)a->K * 2};
-    uint32_t box[2] = {64, (uint32_t)bn};
+    uint32_t box[2] = {64, (uint32_t)(use_pair ? bn / 2 : bn)};
     if (int rc = make_tensor_map(&tmB, Wt, 2, dims, strides, box)) return rc;
   }
+  if (use_pair) return launch_gemm_pair(bn, tmA, tmB, p, stream);
   if (bn == 160) return dispatch_gemm<160>(tmA, tmB, p, stream);
   return dispatch_gemm<128>(tmA, tmB, p, stream);
 }

@@ -304,6 +304,151 @@ __global__ void __launch_bounds__(FA_THREADS, (DP <= 96) ? 2 : 1) flash_attn_ker
   }
 }
 
+// --------------------------------------------------------------------------- short-key-set attention
+// Cross-attention to the text (77 tokens) / audio (5 tokens) context: the whole K and V of one (context, head) fit in
+// shared memory, so a CTA loads them ONCE and then streams 64-row query tiles (double buffered) through a single-pass
+// softmax.  The generic flash kernel paid its per-CTA setup (K/V tile loads, pipeline fill) for only 77 keys of work.
+// NK16 = number of 16-key groups covering the key set (keys beyond n0 are zero-filled and masked).
+template <int DP, int NK16>
+__global__ void __launch_bounds__(FA_THREADS) short_kv_attn_kernel(const AttnDev p, int q_tiles_per_cta) {
+  constexpr int PITCH = DP + 8;
+  constexpr int KS = DP / 16;
+  constexpr int NT = DP / 8;
+  constexpr int NKEY = NK16 * 16;
+  constexpr int SNT = NK16 * 2;  // score n-tiles of 8 keys
+  extern __shared__ __align__(16) uint8_t sk_smem[];
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(sk_smem);
+  __nv_bfloat16* sV = sK + NKEY * PITCH;
+  __nv_bfloat16* sQ = sV + NKEY * PITCH;  // [2][64][PITCH]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const __nv_bfloat16* kg = p.k0 + (long long)(b / p.kv0_div) * p.kv0_bs + h * p.d;
+  const __nv_bfloat16* vg = p.v0 + (long long)(b / p.kv0_div) * p.kv0_bs + h * p.d;
+  const __nv_bfloat16* qb = p.q + (long long)b * p.q_bs + h * p.d;
+  __nv_bfloat16* ob = p.out + (long long)b * p.o_bs + h * p.d;
+  const int n_qtiles = (p.nq + 63) / 64;
+  const int qt0 = blockIdx.x * q_tiles_per_cta;
+  int qt1 = qt0 + q_tiles_per_cta;
+  if (qt1 > n_qtiles) qt1 = n_qtiles;
+  if (qt0 >= qt1) return;
+
+  fa_load_tile<DP>(sK, kg, p.kv0_rs, NKEY, p.n0, p.d);
+  fa_load_tile<DP>(sV, vg, p.kv0_rs, NKEY, p.n0, p.d);
+  {
+    int nv = p.nq - qt0 * 64;
+    fa_load_tile<DP>(sQ, qb + (long long)qt0 * 64 * p.q_rs, p.q_rs, 64, nv > 64 ? 64 : nv, p.d);
+  }
+  cp_async_commit();
+  const int dch = p.d >> 3;
+
+  for (int qt = qt0; qt < qt1; ++qt) {
+    const int buf = (qt - qt0) & 1;
+    if (qt + 1 < qt1) {
+      int nv = p.nq - (qt + 1) * 64;
+      fa_load_tile<DP>(sQ + (buf ^ 1) * 64 * PITCH, qb + (long long)(qt + 1) * 64 * p.q_rs, p.q_rs, 64, nv > 64 ? 64 : nv, p.d);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    __nv_bfloat16* sQb = sQ + buf * 64 * PITCH;
+    float s_acc[SNT][4];
+#pragma unroll
+    for (int i = 0; i < SNT; ++i) s_acc[i][0] = s_acc[i][1] = s_acc[i][2] = s_acc[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t a0, a1, a2, a3;
+      ldsm_x4(smem_u32(sQb + (warp * 16 + (lane & 15)) * PITCH + ks * 16 + (lane >> 4) * 8), a0, a1, a2, a3);
+#pragma unroll
+      for (int np = 0; np < NK16; ++np) {
+        uint32_t b0, b1, b2, b3;
+        const int row = np * 16 + (lane & 7) + (lane >> 4) * 8;
+        const int col = ks * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4(smem_u32(sK + row * PITCH + col), b0, b1, b2, b3);
+        mma_bf16_16816(s_acc[2 * np], a0, a1, a2, a3, b0, b1);
+        mma_bf16_16816(s_acc[2 * np + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < SNT; ++nt) {
+      const int c = nt * 8 + 2 * t;
+      if (c >= p.n0) s_acc[nt][0] = s_acc[nt][2] = -INFINITY;
+      if (c + 1 >= p.n0) s_acc[nt][1] = s_acc[nt][3] = -INFINITY;
+      mx[0] = fmaxf(mx[0], fmaxf(s_acc[nt][0], s_acc[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s_acc[nt][2], s_acc[nt][3]));
+    }
+    float sum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      mx[r] *= p.scale_log2;
+    }
+    uint32_t pf[NK16][4];
+#pragma unroll
+    for (int nt = 0; nt < SNT; ++nt) {
+      const float p0 = ex2_approx(fmaf(s_acc[nt][0], p.scale_log2, -mx[0]));
+      const float p1 = ex2_approx(fmaf(s_acc[nt][1], p.scale_log2, -mx[0]));
+      const float p2 = ex2_approx(fmaf(s_acc[nt][2], p.scale_log2, -mx[1]));
+      const float p3 = ex2_approx(fmaf(s_acc[nt][3], p.scale_log2, -mx[1]));
+      sum[0] += p0 + p1;
+      sum[1] += p2 + p3;
+      const int kk = nt >> 1;
+      if ((nt & 1) == 0) {
+        pf[kk][0] = pack_bf16x2(p0, p1);
+        pf[kk][1] = pack_bf16x2(p2, p3);
+      } else {
+        pf[kk][2] = pack_bf16x2(p0, p1);
+        pf[kk][3] = pack_bf16x2(p2, p3);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+    }
+    const float inv0 = 1.f / sum[0], inv1 = 1.f / sum[1];
+    float o_acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NK16; ++kk) {
+#pragma unroll
+      for (int np = 0; np < NT / 2; ++np) {
+        uint32_t b0, b1, b2, b3;
+        const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int col = np * 16 + (lane >> 4) * 8;
+        ldsm_x4_t(smem_u32(sV + row * PITCH + col), b0, b1, b2, b3);
+        mma_bf16_16816(o_acc[2 * np], pf[kk][0], pf[kk][1], pf[kk][2], pf[kk][3], b0, b1);
+        mma_bf16_16816(o_acc[2 * np + 1], pf[kk][0], pf[kk][1], pf[kk][2], pf[kk][3], b2, b3);
+      }
+    }
+    // stage the warp's 16 output rows through its (consumed) Q rows, then 16-byte stores
+    __syncwarp();
+    __nv_bfloat16* sO = sQb + warp * 16 * PITCH;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      *reinterpret_cast<uint32_t*>(sO + g * PITCH + i * 8 + 2 * t) = pack_bf16x2(o_acc[i][0] * inv0, o_acc[i][1] * inv0);
+      *reinterpret_cast<uint32_t*>(sO + (g + 8) * PITCH + i * 8 + 2 * t) =
+          pack_bf16x2(o_acc[i][2] * inv1, o_acc[i][3] * inv1);
+    }
+    __syncwarp();
+    for (int i = lane; i < 16 * dch; i += 32) {
+      const int r = i / dch, c = i - r * dch;
+      const int qrow = qt * 64 + warp * 16 + r;
+      if (qrow < p.nq) {
+        const uint4 v = *reinterpret_cast<const uint4*>(sO + r * PITCH + c * 8);
+        *reinterpret_cast<uint4*>(ob + (long long)qrow * p.o_rs + c * 8) = v;
+      }
+    }
+    __syncthreads();  // Q buffer `buf` is refilled two iterations later; everyone must be done with it
+  }
+}
+
 // --------------------------------------------------------------------------- temporal attention
 constexpr int TA_WARPS = 4;
 
@@ -462,6 +607,36 @@ static int launch_flash(const AttnDev& p, int batch, cudaStream_t stream) {
   return 0;
 }
 
+template <int DP, int NK16>
+static int launch_short_kv(const AttnDev& p, int batch, cudaStream_t stream) {
+  constexpr int SMEM = (2 * NK16 * 16 + 2 * 64) * (DP + 8) * 2;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(short_kv_attn_kernel<DP, NK16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(short_kv_attn)", e);
+    configured = true;
+  }
+  const int n_qtiles = (p.nq + 63) / 64;
+  // ~4 CTAs per SM worth of work items, each streaming several query tiles over one resident K/V
+  int per_cta = (int)(((long long)n_qtiles * p.heads * batch + 148 * 4 - 1) / (148 * 4));
+  if (per_cta < 1) per_cta = 1;
+  if (per_cta > n_qtiles) per_cta = n_qtiles;
+  dim3 grid((n_qtiles + per_cta - 1) / per_cta, p.heads, batch);
+  short_kv_attn_kernel<DP, NK16><<<grid, FA_THREADS, SMEM, stream>>>(p, per_cta);
+  EMOTE_CHECK_LAUNCH("emote_attention_bf16");
+  return 0;
+}
+
+template <int DP>
+static int dispatch_short_kv(const AttnDev& p, int batch, cudaStream_t stream) {
+  const int nk16 = (p.n0 + 15) / 16;
+  if (nk16 <= 1) return launch_short_kv<DP, 1>(p, batch, stream);
+  if (nk16 <= 2) return launch_short_kv<DP, 2>(p, batch, stream);
+  if (nk16 <= 5) return launch_short_kv<DP, 5>(p, batch, stream);
+  return launch_short_kv<DP, 8>(p, batch, stream);
+}
+
 template <int DP, int FP>
 static int launch_temporal(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int F, int HW, int heads, int d,
                            float scale_log2, cudaStream_t stream) {
@@ -529,6 +704,9 @@ extern "C" int emote_attention_bf16(const EmoteAttnArgs* a, void* stream_) {
   p.kv1_first = a->kv1_first_batch;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   const int dp = padded_head_dim(a->head_dim);
+  if (a->n1 == 0 && a->n0 <= 128 && a->nq >= 256) {  // text / audio context: K/V resident in smem, queries streamed
+    EMOTE_DP_DISPATCH(dp, return dispatch_short_kv<DPV>(p, a->batch, stream));
+  }
   EMOTE_DP_DISPATCH(dp, return launch_flash<DPV>(p, a->batch, stream));
   return 0;
 }

@@ -18,10 +18,7 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int C_src, int c_of
                                 long long rows_per_batch, int rows_per_block, int passes, double* __restrict__ sums) {
   // fp64 accumulation end to end: E[x^2] - mean^2 cancels badly in fp32 when |mean| >> std, and the atomics'
   // ordering would otherwise leak ~1e-6 run-to-run noise into every normalised value.
-  __shared__ double s_acc[GN_MAX_GROUPS * 2];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  for (int i = tid; i < groups * 2; i += blockDim.x * blockDim.y) s_acc[i] = 0.0;
-  __syncthreads();
 
   const int batch = blockIdx.y;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
@@ -58,19 +55,29 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int C_src, int c_of
       }
     }
   }
+  // block reduction without shared-memory fp64 atomics (those are CAS loops and dominated the kernel): every thread
+  // parks its partials, then one thread per (group, statistic) sums the <= cpg/2 * blockDim.y slots of its group
+  __shared__ double part[2][GN_MAX_PASS][512];
 #pragma unroll
   for (int ps = 0; ps < GN_MAX_PASS; ++ps) {
     if (ps < passes) {
-      const int c = c_offset + 2 * (threadIdx.x + ps * blockDim.x);
-      const int g = c / cpg;
-      atomicAdd(&s_acc[2 * g], s[ps]);
-      atomicAdd(&s_acc[2 * g + 1], q[ps]);
+      part[0][ps][tid] = s[ps];
+      part[1][ps][tid] = q[ps];
     }
   }
   __syncthreads();
-  for (int i = tid; i < groups * 2; i += blockDim.x * blockDim.y) {
-    const double v = s_acc[i];
-    if (v != 0.0) atomicAdd(&sums[(long long)batch * groups * 2 + i], v);
+  if (tid < groups * 2) {
+    const int g = tid >> 1, which = tid & 1;
+    int c_lo = g * cpg, c_hi = c_lo + cpg;            // channel range of the group in the concatenated tensor
+    if (c_lo < c_offset) c_lo = c_offset;
+    if (c_hi > c_offset + C_src) c_hi = c_offset + C_src;
+    double acc = 0.0;
+    for (int c = c_lo; c < c_hi; c += 2) {
+      const int cp = (c - c_offset) >> 1;
+      const int ps = cp / (int)blockDim.x, tx = cp - ps * (int)blockDim.x;
+      for (int ty = 0; ty < (int)blockDim.y; ++ty) acc += part[which][ps][ty * blockDim.x + tx];
+    }
+    if (c_lo < c_hi) atomicAdd(&sums[(long long)batch * groups * 2 + tid], acc);
   }
 }
 

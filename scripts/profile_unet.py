@@ -42,7 +42,7 @@ for m, (c, v) in sorted(prof.by_shape("emote_attention_bf16").items(), key=lambd
     print(f"  {str(m):34s} n={c:3d} {v:8.3f} ms  {fl/v/1e9:8.1f} TF/s")
 for nm in ("emote_layernorm", "emote_gn_stats", "emote_gn_apply", "emote_temporal_attention_bf16"):
     print(nm)
-    for m, (c, v) in sorted(prof.by_shape(nm).items(), key=lambda kv: -kv[1][1])[:6]:
+    for m, (c, v) in sorted(prof.by_shape(nm).items(), key=lambda kv: -kv[1][1])[:10]:
         print(f"  {str(m):40s} n={c:3d} {v:8.3f} ms")
 lat = torch.randn(1, 4, 16, 64, 64, device=dev) * 0.18215
 vae.decode_video(lat); torch.cuda.synchronize()

@@ -167,7 +167,10 @@ def _sdpa_ref(q, k, v, scale):
 
 
 @pytest.mark.parametrize("heads,d,nq,nk", [(8, 40, 256, 256), (8, 80, 64, 64), (8, 160, 64, 64), (4, 16, 64, 64),
-                                           (8, 40, 100, 77), (8, 40, 4096, 4096), (4, 64, 16, 16), (2, 32, 200, 5)])
+                                           (8, 40, 100, 77), (8, 40, 4096, 4096), (4, 64, 16, 16), (2, 32, 200, 5),
+                                           # short key sets with many queries -> resident-K/V streaming kernel
+                                           (8, 40, 4096, 77), (8, 80, 1024, 77), (8, 160, 256, 5), (4, 64, 300, 128),
+                                           (8, 40, 1000, 16), (2, 16, 257, 33)])
 def test_flash_attention_fused_qkv(ops, heads, d, nq, nk):
     g = _gen(10)
     batch = 3

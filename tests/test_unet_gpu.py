@@ -183,3 +183,43 @@ def test_unet_full_width_one_frame_pair():
     e = rel_l2(out, ref)
     print(f"unet full width 1x2f 64x64: rel_l2={e:.2e}")
     assert e < 2e-2
+
+
+def test_unet_non_tileable_latent_size_uses_im2col_path(tiny):
+    """BASELINE config #4 geometry class (96x96 latents): image rows that do not pack into 128-pixel TMA boxes take the
+    explicit im2col + GEMM path (ops.conv3x3) — still the CUDA kernels, same numerics."""
+    from emote_hack_b200 import ops
+    m, o, _ = tiny
+    assert not ops.conv_tile_ok(24, 24) and not ops.conv_tile_ok(12, 12)
+    x, ctx = make_inputs(2, 2, 24)
+    ref = o(x, 201, ctx)
+    out = m(x.cuda(), 201, ctx.cuda()).sample
+    e = rel_l2(out, ref)
+    print(f"unet tiny 24x24 latent (im2col conv path): rel_l2={e:.2e}")
+    assert e < 2e-2
+
+
+def test_unet_32_frame_window_audio_tokens_and_banks():
+    """BASELINE config #3 features together: one 32-frame window (needs temporal_position_encoding_max_len >= 32, the
+    shipped 24 crashes in the reference too: motion_module.py:247), per-frame audio tokens as context, reference banks."""
+    import copy
+    from emote_hack_b200.unet3d import ReferenceAttentionControl, UNet3DConditionModel
+    from oracle.unet3d_port import UNet3DOracle
+    cfg = copy.deepcopy(TINY_CFG)
+    cfg["motion_module_kwargs"]["temporal_position_encoding_max_len"] = 32
+    torch.manual_seed(2)
+    m = rerandomise_zero_inits(UNet3DConditionModel(**cfg).eval())
+    o = UNet3DOracle(m.state_dict(), dict(m.config))
+    m = m.cuda()
+    x, ctx = make_inputs(2, 32, 8, ctx_tokens=5, per_frame_ctx=True)
+    banks = make_banks(m, 8)
+    ref = o(x, 641, ctx, banks=banks)
+    reader = ReferenceAttentionControl(m, do_classifier_free_guidance=True, mode="read", fusion_blocks="midup")
+    reader.set_banks({k: [v.cuda() for v in vs] for k, vs in banks.items()})
+    out = m(x.cuda(), 641, ctx.cuda()).sample
+    e = rel_l2(out, ref)
+    print(f"unet tiny F=32 + audio ctx + banks: rel_l2={e:.2e}")
+    assert e < 2e-2
+    with pytest.raises(ValueError):  # 24-entry table, 32 frames
+        m24 = rerandomise_zero_inits(UNet3DConditionModel(**TINY_CFG).eval()).cuda()
+        m24(x.cuda(), 641, ctx.cuda())

@@ -36,6 +36,7 @@ class EmoteGemmArgs(C.Structure):
         ("ldc", C.c_int32),
         ("block_n", C.c_int32),
         ("pair_mode", C.c_int32),
+        ("tma_store", C.c_int32),
     ]
 
 

@@ -32,9 +32,12 @@ struct GemmDev {
 // One output tile of one CTA.  `tbase` = TMEM address of the accumulator stage for this warp's lane quarter,
 // `row_base` = first global row of the tile, (`n0`, `tn`) = first column / column-tile index.  The caller has NOT yet
 // waited for the accumulator: `wait_full()` is invoked after the residual prefetch has been issued.
-template <int BN, int EPI_WARPS, bool HAS_ADD, class WaitFull>
+// TMA_OUT: bf16 results are staged in shared memory (`stage`, dense [128][BN or BN/2] bf16) for one bulk tensor store
+// per tile issued by the caller — full-line L2 writes instead of 16-byte partial-sector stores.
+template <int BN, int EPI_WARPS, bool HAS_ADD, bool TMA_OUT, class WaitFull>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tbase, int row_base, int n0, int tn,
-                                                   int quarter, int part, int lane, WaitFull wait_full) {
+                                                   int quarter, int part, int lane, __nv_bfloat16* stage,
+                                                   WaitFull wait_full) {
   constexpr int NP = EPI_WARPS / 4;   // warps per lane quarter
   const int g = lane >> 2, t = lane & 3;
   const int row0 = row_base + quarter * 32 + g;  // this thread's rows: row0 + 8*i, i = 0..3
@@ -103,7 +106,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
         float v0 = __uint_as_float(a[ri]) + b0, v1 = __uint_as_float(a[ri + 1]) + b1;
         if constexpr (HAS_ADD) { v0 += add[ci][2 * i]; v1 += add[ci][2 * i + 1]; }
         v0 *= p.out_scale; v1 *= p.out_scale;
-        if (rok[i] && c0ok) {
+        if constexpr (TMA_OUT) {
+          const int lr = quarter * 32 + g + 8 * i, lc = (c_first + ci) * 8 + 2 * t;
+          *reinterpret_cast<uint32_t*>(stage + lr * BN + lc) = pack_bf16x2(v0, v1);
+        } else if (rok[i] && c0ok) {
           if (p.out_bf16) {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[i] + col;
             if (c1ok) *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(v0, v1);
@@ -167,7 +173,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
           const float a0 = __uint_as_float(v[ri]) + b[0], a1 = __uint_as_float(v[ri + 1]) + b[1];
           const float q0 = __uint_as_float(gt[ri]) + b[2], q1 = __uint_as_float(gt[ri + 1]) + b[3];
           const uint32_t packed = pack_bf16x2(a0 * gelu_erf_fast(q0), a1 * gelu_erf_fast(q1));
-          if (rok[i] && cok)
+          if constexpr (TMA_OUT) {
+            const int lr = quarter * 32 + g + 8 * i, lc = cc * 8 + 2 * t;
+            *reinterpret_cast<uint32_t*>(stage + lr * HALF + lc) = packed;
+          } else if (rok[i] && cok)
             *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[i] + ocol) = packed;
         }
       }

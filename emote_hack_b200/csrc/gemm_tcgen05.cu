@@ -23,26 +23,28 @@ namespace emote {
 //   plain / GEGLU: 16 epilogue warps (4 per TMEM lane quarter) to hide TMEM and issue latency.
 constexpr int gemm_threads(int epi_warps) { return 64 + 32 * epi_warps; }
 
-template <int BN>
+template <int BN, bool TMA_OUT = false>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN <= 128) ? 6 : (BN <= 160 ? 5 : 4);
+  static constexpr int OUT_BYTES = TMA_OUT ? BM * BN * 2 : 0;   // bf16 output tile staged for the TMA store
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024 /*align slack*/;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
 };
 
-template <int BN, int EPI_WARPS, bool HAS_ADD>
+template <int BN, int EPI_WARPS, bool HAS_ADD, bool TMA_OUT>
 __global__ void __launch_bounds__(gemm_threads(EPI_WARPS), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmDev p) {
-  using S = GemmSmem<BN>;
+                         const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
+  using S = GemmSmem<BN, TMA_OUT>;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024 B alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bar_base = smem + S::STAGES * S::STAGE_BYTES;
+  __nv_bfloat16* stage_out = reinterpret_cast<__nv_bfloat16*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint8_t* bar_base = smem + S::STAGES * S::STAGE_BYTES + S::OUT_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + S::STAGES;
   uint64_t* tmem_full = empty_bar + S::STAGES;
@@ -175,22 +177,42 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int part = ew >> 2;
     int as = 0;
     uint32_t aphase = 0;
+    bool first_tile = true;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
-      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD>(p, tbase, tm * BM, tn * BN, tn, quarter, part, lane, [&]() {
-        mbar_wait(&tmem_full[as], aphase);
-        tc_fence_after();
-      });
+      if constexpr (TMA_OUT) {
+        if (!first_tile) {  // the previous tile's bulk store must have read the staging buffer before it is rewritten
+          if (threadIdx.x == 64) bulk_wait_read0();
+          named_bar_sync(2, EPI_WARPS * 32);
+        }
+        first_tile = false;
+      }
+      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, TMA_OUT>(p, tbase, tm * BM, tn * BN, tn, quarter, part, lane, stage_out,
+                                                          [&]() {
+                                                            mbar_wait(&tmem_full[as], aphase);
+                                                            tc_fence_after();
+                                                          });
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if constexpr (TMA_OUT) {
+        fence_proxy_async_smem();                 // staging writes -> visible to the TMA (async proxy)
+        named_bar_sync(1, EPI_WARPS * 32);
+        if (threadIdx.x == 64) {
+          tma_store_2d(&tmC, stage_out, p.geglu ? tn * (BN / 2) : tn * BN, tm * BM);  // clips rows >= M / cols >= N
+          bulk_commit();
+        }
+      }
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
       }
+    }
+    if constexpr (TMA_OUT) {
+      if (threadIdx.x == 64) bulk_wait0();
     }
   }
 
@@ -203,15 +225,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 }
 
 // --------------------------------------------------------------------------- host side
-int launch_gemm_pair(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDev& p, cudaStream_t stream);  // gemm2_tcgen05.cu
+int launch_gemm_pair(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, bool tma_out,
+                     GemmDev& p, cudaStream_t stream);  // gemm2_tcgen05.cu
 static int g_num_sms = 0;
 
-template <int BN, int EPI_WARPS, bool HAS_ADD>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDev& p, cudaStream_t stream) {
-  using S = GemmSmem<BN>;
+template <int BN, int EPI_WARPS, bool HAS_ADD, bool TMA_OUT>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmDev& p,
+                       cudaStream_t stream) {
+  using S = GemmSmem<BN, TMA_OUT>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, TMA_OUT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(gemm)", e);
     configured = true;
@@ -226,7 +250,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDev& 
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD><<<grid, gemm_threads(EPI_WARPS), S::TOTAL, stream>>>(tmA, tmB, p);
+  gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, TMA_OUT>
+      <<<grid, gemm_threads(EPI_WARPS), S::TOTAL, stream>>>(tmA, tmB, tmC, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error_cuda("gemm launch", e);
   count_launch();
@@ -234,9 +259,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDev& 
 }
 
 template <int BN>
-static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDev& p, cudaStream_t stream) {
-  if (!p.geglu && (p.residual != nullptr || p.row_bias != nullptr)) return launch_gemm<BN, 8, true>(tmA, tmB, p, stream);
-  return launch_gemm<BN, 16, false>(tmA, tmB, p, stream);
+static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, bool tma_out, GemmDev& p,
+                         cudaStream_t stream) {
+  if (!p.geglu && (p.residual != nullptr || p.row_bias != nullptr))
+    return launch_gemm<BN, 8, true, false>(tmA, tmB, tmC, p, stream);
+  if (tma_out) return launch_gemm<BN, 16, false, true>(tmA, tmB, tmC, p, stream);
+  return launch_gemm<BN, 16, false, false>(tmA, tmB, tmC, p, stream);
 }
 
 }  // namespace emote
@@ -313,7 +341,17 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
     uint32_t box[2] = {64, (uint32_t)(use_pair ? bn / 2 : bn)};
     if (int rc = make_tensor_map(&tmB, Wt, 2, dims, strides, box)) return rc;
   }
-  if (use_pair) return launch_gemm_pair(bn, tmA, tmB, p, stream);
-  if (bn == 160) return dispatch_gemm<160>(tmA, tmB, p, stream);
-  return dispatch_gemm<128>(tmA, tmB, p, stream);
+  // bf16 outputs without residual adds (QKV / q projections, GEGLU) leave through a staged TMA bulk store
+  CUtensorMap tmC = tmB;
+  const bool tma_out = p.out_bf16 && !(p.residual || p.row_bias) && a->tma_store != 2;
+  if (tma_out) {
+    const int n_out = geglu ? a->N / 2 : a->N;
+    uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)a->M};
+    uint64_t strides[1] = {(uint64_t)a->ldc * 2};
+    uint32_t box[2] = {(uint32_t)(geglu ? bn / 2 : bn), 128};
+    if (int rc = make_tensor_map(&tmC, out, 2, dims, strides, box, /*swizzle128=*/false)) return rc;
+  }
+  if (use_pair) return launch_gemm_pair(bn, tmA, tmB, tmC, tma_out, p, stream);
+  if (bn == 160) return dispatch_gemm<160>(tmA, tmB, tmC, tma_out, p, stream);
+  return dispatch_gemm<128>(tmA, tmB, tmC, tma_out, p, stream);
 }

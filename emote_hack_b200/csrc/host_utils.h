@@ -15,7 +15,7 @@ void count_launch(int n = 1);
 // rank-2..5 bf16 tensor map, 128B swizzle, zero OOB fill. dims/box innermost-first;
 // strides (bytes) for dims 1..rank-1.
 int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box);
+                    const uint32_t* box, bool swizzle128 = true);
 
 #define EMOTE_CHECK_LAUNCH(name)                                   \
   do {                                                             \

@@ -80,7 +80,7 @@ def pack_geglu(w: torch.Tensor, b: torch.Tensor):
 # ----------------------------------------------------------------------------------------------- GEMM / conv
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, row_bias=None, rows_per_group: int = 0, residual=None,
          out_scale: float = 1.0, geglu: bool = False, out_dtype=F32, out: Optional[torch.Tensor] = None,
-         conv: Optional[tuple] = None, M: Optional[int] = None, pair_mode: int = 0) -> torch.Tensor:
+         conv: Optional[tuple] = None, M: Optional[int] = None, pair_mode: int = 0, tma_store: int = 0) -> torch.Tensor:
     """out = epilogue(a @ w.T).  a: bf16 [M, K] (or NHWC [n_img, H, W, C] when conv=(n_img, H, W, C)); w: bf16 [N, K]."""
     _req(a, BF16, "gemm.a"), _req(w, BF16, "gemm.w")
     N, K = w.shape
@@ -118,6 +118,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, row_bias=None, rows_per
     args.ldc = out.shape[-1]
     args.block_n = 0
     args.pair_mode = pair_mode
+    args.tma_store = tma_store
     check(_lib.load().emote_gemm_bf16(a.data_ptr(), w.data_ptr(), out.data_ptr(), C.byref(args), _stream()),
           "emote_gemm_bf16")
     return out

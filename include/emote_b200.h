@@ -58,6 +58,7 @@ typedef struct {
   int32_t ldc;            /* out row pitch in elements */
   int32_t block_n;        /* 0 = auto (160 if N % 160 == 0 else 128) */
   int32_t pair_mode;      /* 0 = auto, 1 = force CTA pairs (cta_group::2, 256-row tiles), 2 = force single CTA */
+  int32_t tma_store;      /* 0 = auto (bf16 outputs without residual leave through a staged TMA store), 2 = never */
 } EmoteGemmArgs;
 int emote_gemm_bf16(const void* A, const void* Wt, void* out, const EmoteGemmArgs* args, void* stream);
 

@@ -81,26 +81,29 @@ __device__ __forceinline__ void tma2_load_4d(void* smem_dst, const void* desc, u
       : "memory");
 }
 
-template <int BN, bool TMA_OUT = false>
+template <int BN, int OUT_MODE = 0>
 struct Gemm2Smem {
   static constexpr int A_BYTES = BM * BK * 2;            // 16 KB: this CTA's 128 rows
   static constexpr int B_BYTES = (BN / 2) * BK * 2;      // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = TMA_OUT ? ((BN <= 128) ? 7 : 6) : ((BN <= 128) ? 8 : 7);
-  static constexpr int OUT_BYTES = TMA_OUT ? BM * BN * 2 : 0;
+  static constexpr int STAGES = ((BN <= 128) ? 8 : 7) - (OUT_MODE == 1 ? 1 : (OUT_MODE == 2 ? ((BN <= 128) ? 2 : 2) : 0));
+  static constexpr int OUT_BYTES = OUT_MODE == 1 ? BM * BN * 2 : (OUT_MODE == 2 ? BM * BN * 4 : 0);
   static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + 256 + 1024;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
 };
 
-template <int BN, int EPI_WARPS, bool HAS_ADD, bool TMA_OUT>
+template <int BN, int EPI_WARPS, bool HAS_ADD, int OUT_MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                          const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
-  using S = Gemm2Smem<BN, TMA_OUT>;
+                          const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                          const GemmDev p) {
+  using S = Gemm2Smem<BN, OUT_MODE>;
+  constexpr bool TMA_OUT = OUT_MODE != 0;
   extern __shared__ uint8_t smem_raw2[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
-  __nv_bfloat16* stage_out = reinterpret_cast<__nv_bfloat16*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint8_t* stage_out = smem + S::STAGES * S::STAGE_BYTES;
   uint8_t* bar_base = smem + S::STAGES * S::STAGE_BYTES + S::OUT_BYTES;
+  uint64_t* res_full = reinterpret_cast<uint64_t*>(bar_base + 192);  // per CTA: residual boxes landed (mode 2)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);   // used in the leader: bytes of BOTH CTAs
   uint64_t* empty_bar = full_bar + S::STAGES;                    // per CTA, multicast commit
   uint64_t* tmem_full = empty_bar + S::STAGES;                   // per CTA, multicast commit
@@ -123,6 +126,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 2 * EPI_WARPS);
     }
+    mbar_init(res_full, 1);
     mbar_fence_init();
   }
   cluster_sync_all();  // barriers of both CTAs are initialised before anyone signals across the pair
@@ -232,23 +236,40 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     int as = 0;
     uint32_t aphase = 0;
     bool first_tile = true;
+    // mode 2 with a residual: see gemm_tcgen05.cu (each CTA of the pair stages the residual of its own 128 rows)
+    const bool res_tma = OUT_MODE == 2 && p.residual != nullptr;
+    uint32_t rphase = 0;
+    constexpr int NBOX = BN / 32;
+    auto load_residual = [&](int tile) {
+      const int tm = tile / p.tiles_n;
+      const int tn = tile - tm * p.tiles_n;
+      const int rb = tm * (2 * BM) + static_cast<int>(rank) * BM;
+      int nb = 0;
+      for (int b = 0; b < NBOX; ++b) nb += (tn * BN + b * 32 < p.N) ? 1 : 0;
+      mbar_expect_tx(res_full, static_cast<uint32_t>(nb) * (BM * 128));
+      for (int b = 0; b < nb; ++b) tma_load_2d(stage_out + b * (BM * 128), &tmR, res_full, tn * BN + b * 32, rb);
+    };
+    if (res_tma && threadIdx.x == 64 && pair < num_tiles) load_residual(pair);
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
       const int row_base = tm * (2 * BM) + static_cast<int>(rank) * BM;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
       if constexpr (TMA_OUT) {
-        if (!first_tile) {
+        if (res_tma) {
+          mbar_wait(res_full, rphase);
+          rphase ^= 1;
+        } else if (!first_tile) {
           if (threadIdx.x == 64) bulk_wait_read0();
           named_bar_sync(2, EPI_WARPS * 32);
         }
         first_tile = false;
       }
-      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, TMA_OUT>(p, tbase, row_base, tn * BN, tn, quarter, part, lane, stage_out,
-                                                          [&]() {
-                                                            mbar_wait(&tmem_full[as], aphase);
-                                                            tc_fence_after();
-                                                          });
+      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, OUT_MODE>(p, tbase, row_base, tn * BN, tn, quarter, part, lane, stage_out,
+                                                           [&]() {
+                                                             mbar_wait(&tmem_full[as], aphase);
+                                                             tc_fence_after();
+                                                           });
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(&tmem_empty[as], 0));
@@ -256,8 +277,19 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         fence_proxy_async_smem();
         named_bar_sync(1, EPI_WARPS * 32);
         if (threadIdx.x == 64) {
-          tma_store_2d(&tmC, stage_out, p.geglu ? tn * (BN / 2) : tn * BN, row_base);
+          if (row_base < p.M) {   // the second CTA of the last pair may own no valid rows
+            if constexpr (OUT_MODE == 1) {
+              tma_store_2d(&tmC, stage_out, p.geglu ? tn * (BN / 2) : tn * BN, row_base);
+            } else {
+              for (int b = 0; b < NBOX; ++b)
+                if (tn * BN + b * 32 < p.N) tma_store_2d(&tmC, stage_out + b * (BM * 128), tn * BN + b * 32, row_base);
+            }
+          }
           bulk_commit();
+          if (res_tma && tile + num_pairs < num_tiles) {
+            bulk_wait_read0();
+            load_residual(tile + num_pairs);
+          }
         }
       }
       if (++as == 2) {
@@ -280,13 +312,13 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 
 static int g2_num_sms = 0;
 
-template <int BN, int EPI_WARPS, bool HAS_ADD, bool TMA_OUT>
-static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmDev& p,
-                        cudaStream_t stream) {
-  using S = Gemm2Smem<BN, TMA_OUT>;
+template <int BN, int EPI_WARPS, bool HAS_ADD, int OUT_MODE>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                        GemmDev& p, cudaStream_t stream) {
+  using S = Gemm2Smem<BN, OUT_MODE>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, TMA_OUT>,
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, OUT_MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(gemm2)", e);
     configured = true;
@@ -302,8 +334,8 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   }
   const int max_pairs = g2_num_sms / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  gemm2_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, TMA_OUT>
-      <<<2 * pairs, 64 + 32 * EPI_WARPS, S::TOTAL, stream>>>(tmA, tmB, tmC, p);
+  gemm2_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, OUT_MODE>
+      <<<2 * pairs, 64 + 32 * EPI_WARPS, S::TOTAL, stream>>>(tmA, tmB, tmC, tmR, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error_cuda("gemm2 launch", e);
   count_launch();
@@ -311,17 +343,19 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
 }
 
 // entry used by emote_gemm_bf16 (gemm_tcgen05.cu) for the shapes routed to CTA pairs
-int launch_gemm_pair(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, bool tma_out,
-                     GemmDev& p, cudaStream_t stream) {
+int launch_gemm_pair(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                     int out_mode, GemmDev& p, cudaStream_t stream) {
   const bool has_add = !p.geglu && (p.residual != nullptr || p.row_bias != nullptr);
   if (bn == 160) {
-    if (has_add) return launch_gemm2<160, 8, true, false>(tmA, tmB, tmC, p, stream);
-    if (tma_out) return launch_gemm2<160, 16, false, true>(tmA, tmB, tmC, p, stream);
-    return launch_gemm2<160, 16, false, false>(tmA, tmB, tmC, p, stream);
+    if (out_mode == 2) return launch_gemm2<160, 16, false, 2>(tmA, tmB, tmC, tmR, p, stream);
+    if (has_add) return launch_gemm2<160, 8, true, 0>(tmA, tmB, tmC, tmR, p, stream);
+    if (out_mode == 1) return launch_gemm2<160, 16, false, 1>(tmA, tmB, tmC, tmR, p, stream);
+    return launch_gemm2<160, 16, false, 0>(tmA, tmB, tmC, tmR, p, stream);
   }
-  if (has_add) return launch_gemm2<128, 8, true, false>(tmA, tmB, tmC, p, stream);
-  if (tma_out) return launch_gemm2<128, 16, false, true>(tmA, tmB, tmC, p, stream);
-  return launch_gemm2<128, 16, false, false>(tmA, tmB, tmC, p, stream);
+  if (out_mode == 2) return launch_gemm2<128, 16, false, 2>(tmA, tmB, tmC, tmR, p, stream);
+  if (has_add) return launch_gemm2<128, 8, true, 0>(tmA, tmB, tmC, tmR, p, stream);
+  if (out_mode == 1) return launch_gemm2<128, 16, false, 1>(tmA, tmB, tmC, tmR, p, stream);
+  return launch_gemm2<128, 16, false, 0>(tmA, tmB, tmC, tmR, p, stream);
 }
 
 }  // namespace emote

@@ -32,12 +32,17 @@ struct GemmDev {
 // One output tile of one CTA.  `tbase` = TMEM address of the accumulator stage for this warp's lane quarter,
 // `row_base` = first global row of the tile, (`n0`, `tn`) = first column / column-tile index.  The caller has NOT yet
 // waited for the accumulator: `wait_full()` is invoked after the residual prefetch has been issued.
-// TMA_OUT: bf16 results are staged in shared memory (`stage`, dense [128][BN or BN/2] bf16) for one bulk tensor store
-// per tile issued by the caller — full-line L2 writes instead of 16-byte partial-sector stores.
-template <int BN, int EPI_WARPS, bool HAS_ADD, bool TMA_OUT, class WaitFull>
+// OUT_MODE 0: results go straight to global memory (8-byte / 4-byte stores).
+// OUT_MODE 1: bf16 results are staged in shared memory (`stage`, dense [128][BN or BN/2] bf16) for one bulk tensor store
+//             per tile issued by the caller — full-line L2 writes instead of 16-byte partial-sector stores.
+// OUT_MODE 2: fp32 results; `stage` holds BN/32 boxes of [128 rows][32 floats] in the TMA 128-byte swizzle.  When
+//             p.residual is set the caller has TMA-loaded the fp32 residual tile into the same boxes: the epilogue
+//             adds in place and the caller bulk-stores the boxes (the residual stream never touches the LSU path).
+template <int BN, int EPI_WARPS, bool HAS_ADD, int OUT_MODE, class WaitFull>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tbase, int row_base, int n0, int tn,
-                                                   int quarter, int part, int lane, __nv_bfloat16* stage,
-                                                   WaitFull wait_full) {
+                                                   int quarter, int part, int lane, void* stage_, WaitFull wait_full) {
+  constexpr bool TMA_OUT = OUT_MODE == 1;
+  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(stage_);
   constexpr int NP = EPI_WARPS / 4;   // warps per lane quarter
   const int g = lane >> 2, t = lane & 3;
   const int row0 = row_base + quarter * 32 + g;  // this thread's rows: row0 + 8*i, i = 0..3
@@ -99,12 +104,30 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
         if (c0ok) b0 = __ldg(p.bias + col);
         if (c1ok) b1 = __ldg(p.bias + col + 1);
       }
+      if constexpr (OUT_MODE == 2) {
+        if (p.row_bias) {  // host guarantees the 128 rows of a tile share one group (rows_per_group % 128 == 0)
+          const float* rb = p.row_bias + (size_t)(row_base / p.rows_per_group) * p.N + col;
+          if (c0ok) b0 += __ldg(rb);
+          if (c1ok) b1 += __ldg(rb + 1);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         // rows g, g+8 come from the low 16-lane load, rows g+16, g+24 from the high one
         const int ri = (i >> 1) * 4 + (i & 1) * 2;
         float v0 = __uint_as_float(a[ri]) + b0, v1 = __uint_as_float(a[ri + 1]) + b1;
         if constexpr (HAS_ADD) { v0 += add[ci][2 * i]; v1 += add[ci][2 * i + 1]; }
+        if constexpr (OUT_MODE == 2) {
+          const int lr = quarter * 32 + g + 8 * i, lc = (c_first + ci) * 8 + 2 * t;
+          float* sp = reinterpret_cast<float*>(stage_) + (lc >> 5) * (BM * 32) + lr * 32 +
+                      ((((lc & 31) >> 2) ^ (lr & 7)) << 2) + (lc & 3);
+          if (p.residual) {
+            const float2 r2 = *reinterpret_cast<const float2*>(sp);
+            v0 += r2.x; v1 += r2.y;
+          }
+          *reinterpret_cast<float2*>(sp) = make_float2(v0 * p.out_scale, v1 * p.out_scale);
+          continue;
+        }
         v0 *= p.out_scale; v1 *= p.out_scale;
         if constexpr (TMA_OUT) {
           const int lr = quarter * 32 + g + 8 * i, lc = (c_first + ci) * 8 + 2 * t;

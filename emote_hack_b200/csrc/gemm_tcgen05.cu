@@ -23,33 +23,37 @@ namespace emote {
 //   plain / GEGLU: 16 epilogue warps (4 per TMEM lane quarter) to hide TMEM and issue latency.
 constexpr int gemm_threads(int epi_warps) { return 64 + 32 * epi_warps; }
 
-template <int BN, bool TMA_OUT = false>
+template <int BN, int OUT_MODE = 0>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN <= 128) ? 6 : (BN <= 160 ? 5 : 4);
-  static constexpr int OUT_BYTES = TMA_OUT ? BM * BN * 2 : 0;   // bf16 output tile staged for the TMA store
+  static constexpr int STAGES = ((BN <= 128) ? 6 : (BN <= 160 ? 5 : 4)) - (OUT_MODE == 2 ? 1 : 0);
+  // output tile staged for the TMA store: bf16 (mode 1) or fp32 residual-in / result-out boxes (mode 2)
+  static constexpr int OUT_BYTES = OUT_MODE == 1 ? BM * BN * 2 : (OUT_MODE == 2 ? BM * BN * 4 : 0);
   static constexpr int BAR_BYTES = 256;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024 /*align slack*/;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
 };
 
-template <int BN, int EPI_WARPS, bool HAS_ADD, bool TMA_OUT>
+template <int BN, int EPI_WARPS, bool HAS_ADD, int OUT_MODE>
 __global__ void __launch_bounds__(gemm_threads(EPI_WARPS), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
-  using S = GemmSmem<BN, TMA_OUT>;
+                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                         const GemmDev p) {
+  using S = GemmSmem<BN, OUT_MODE>;
+  constexpr bool TMA_OUT = OUT_MODE != 0;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024 B alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __nv_bfloat16* stage_out = reinterpret_cast<__nv_bfloat16*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint8_t* stage_out = smem + S::STAGES * S::STAGE_BYTES;
   uint8_t* bar_base = smem + S::STAGES * S::STAGE_BYTES + S::OUT_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + S::STAGES;
   uint64_t* tmem_full = empty_bar + S::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = reinterpret_cast<uint64_t*>(bar_base + 192);  // mode 2: residual boxes landed in the staging buffer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -65,6 +69,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], EPI_WARPS);  // one arrive per epilogue warp
     }
+    mbar_init(res_full, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -178,22 +183,39 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     int as = 0;
     uint32_t aphase = 0;
     bool first_tile = true;
+    // mode 2 with a residual: thread 64 TMA-loads the fp32 residual tile of the NEXT tile into the staging boxes as soon
+    // as the bulk store of the current tile has read them; the epilogue warps wait on res_full before touching them.
+    const bool res_tma = OUT_MODE == 2 && p.residual != nullptr;
+    uint32_t rphase = 0;
+    constexpr int NBOX = BN / 32;
+    auto load_residual = [&](int tile) {
+      const int tm = tile / p.tiles_n;
+      const int tn = tile - tm * p.tiles_n;
+      int nb = 0;
+      for (int b = 0; b < NBOX; ++b) nb += (tn * BN + b * 32 < p.N) ? 1 : 0;
+      mbar_expect_tx(res_full, static_cast<uint32_t>(nb) * (BM * 128));
+      for (int b = 0; b < nb; ++b) tma_load_2d(stage_out + b * (BM * 128), &tmR, res_full, tn * BN + b * 32, tm * BM);
+    };
+    if (res_tma && threadIdx.x == 64 && static_cast<int>(blockIdx.x) < num_tiles) load_residual(blockIdx.x);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
       if constexpr (TMA_OUT) {
-        if (!first_tile) {  // the previous tile's bulk store must have read the staging buffer before it is rewritten
+        if (res_tma) {
+          mbar_wait(res_full, rphase);
+          rphase ^= 1;
+        } else if (!first_tile) {  // the previous tile's bulk store must have read the staging buffer before it is rewritten
           if (threadIdx.x == 64) bulk_wait_read0();
           named_bar_sync(2, EPI_WARPS * 32);
         }
         first_tile = false;
       }
-      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, TMA_OUT>(p, tbase, tm * BM, tn * BN, tn, quarter, part, lane, stage_out,
-                                                          [&]() {
-                                                            mbar_wait(&tmem_full[as], aphase);
-                                                            tc_fence_after();
-                                                          });
+      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, OUT_MODE>(p, tbase, tm * BM, tn * BN, tn, quarter, part, lane, stage_out,
+                                                           [&]() {
+                                                             mbar_wait(&tmem_full[as], aphase);
+                                                             tc_fence_after();
+                                                           });
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -202,8 +224,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         fence_proxy_async_smem();                 // staging writes -> visible to the TMA (async proxy)
         named_bar_sync(1, EPI_WARPS * 32);
         if (threadIdx.x == 64) {
-          tma_store_2d(&tmC, stage_out, p.geglu ? tn * (BN / 2) : tn * BN, tm * BM);  // clips rows >= M / cols >= N
+          if constexpr (OUT_MODE == 1) {
+            tma_store_2d(&tmC, stage_out, p.geglu ? tn * (BN / 2) : tn * BN, tm * BM);  // clips rows >= M / cols >= N
+          } else {
+            for (int b = 0; b < NBOX; ++b)
+              if (tn * BN + b * 32 < p.N) tma_store_2d(&tmC, stage_out + b * (BM * 128), tn * BN + b * 32, tm * BM);
+          }
           bulk_commit();
+          if (res_tma && tile + static_cast<int>(gridDim.x) < num_tiles) {
+            bulk_wait_read0();
+            load_residual(tile + gridDim.x);
+          }
         }
       }
       if (++as == 2) {
@@ -225,17 +256,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 }
 
 // --------------------------------------------------------------------------- host side
-int launch_gemm_pair(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, bool tma_out,
-                     GemmDev& p, cudaStream_t stream);  // gemm2_tcgen05.cu
+int launch_gemm_pair(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                     int out_mode, GemmDev& p, cudaStream_t stream);  // gemm2_tcgen05.cu
 static int g_num_sms = 0;
 
-template <int BN, int EPI_WARPS, bool HAS_ADD, bool TMA_OUT>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmDev& p,
-                       cudaStream_t stream) {
-  using S = GemmSmem<BN, TMA_OUT>;
+template <int BN, int EPI_WARPS, bool HAS_ADD, int OUT_MODE>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                       GemmDev& p, cudaStream_t stream) {
+  using S = GemmSmem<BN, OUT_MODE>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, TMA_OUT>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, OUT_MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(gemm)", e);
     configured = true;
@@ -250,8 +281,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, TMA_OUT>
-      <<<grid, gemm_threads(EPI_WARPS), S::TOTAL, stream>>>(tmA, tmB, tmC, p);
+  gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, OUT_MODE>
+      <<<grid, gemm_threads(EPI_WARPS), S::TOTAL, stream>>>(tmA, tmB, tmC, tmR, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error_cuda("gemm launch", e);
   count_launch();
@@ -259,12 +290,13 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 }
 
 template <int BN>
-static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, bool tma_out, GemmDev& p,
-                         cudaStream_t stream) {
+static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                         int out_mode, GemmDev& p, cudaStream_t stream) {
+  if (out_mode == 2) return launch_gemm<BN, 16, false, 2>(tmA, tmB, tmC, tmR, p, stream);
   if (!p.geglu && (p.residual != nullptr || p.row_bias != nullptr))
-    return launch_gemm<BN, 8, true, false>(tmA, tmB, tmC, p, stream);
-  if (tma_out) return launch_gemm<BN, 16, false, true>(tmA, tmB, tmC, p, stream);
-  return launch_gemm<BN, 16, false, false>(tmA, tmB, tmC, p, stream);
+    return launch_gemm<BN, 8, true, 0>(tmA, tmB, tmC, tmR, p, stream);
+  if (out_mode == 1) return launch_gemm<BN, 16, false, 1>(tmA, tmB, tmC, tmR, p, stream);
+  return launch_gemm<BN, 16, false, 0>(tmA, tmB, tmC, tmR, p, stream);
 }
 
 }  // namespace emote
@@ -341,17 +373,39 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
     uint32_t box[2] = {64, (uint32_t)(use_pair ? bn / 2 : bn)};
     if (int rc = make_tensor_map(&tmB, Wt, 2, dims, strides, box)) return rc;
   }
-  // bf16 outputs without residual adds (QKV / q projections, GEGLU) leave through a staged TMA bulk store
-  CUtensorMap tmC = tmB;
-  const bool tma_out = p.out_bf16 && !(p.residual || p.row_bias) && a->tma_store != 2;
-  if (tma_out) {
+  // Staged TMA epilogues (tma_store != 2):
+  //   mode 1: bf16 outputs without residual adds (QKV / q projections, GEGLU) leave through one bulk tensor store;
+  //   mode 2: fp32 outputs of the HBM/epilogue-bound shapes (K <= 4096; the deep-K convolutions keep their full operand
+  //           ring): the fp32 residual tile is TMA-loaded into swizzled staging boxes, added in place and bulk-stored
+  //           (per-sample row_bias is folded into the column bias when a tile never straddles a group).
+  CUtensorMap tmC = tmB, tmR = tmB;
+  int out_mode = 0;
+  if (a->tma_store != 2) {
+    if (p.out_bf16 && !(p.residual || p.row_bias)) {
+      out_mode = 1;
+    } else if (!p.out_bf16 && !geglu && a->K <= 4096 && (!p.row_bias || p.rows_per_group % 128 == 0) &&
+               (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) {
+      out_mode = 2;
+    }
+  }
+  if (out_mode == 1) {
     const int n_out = geglu ? a->N / 2 : a->N;
     uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)a->M};
     uint64_t strides[1] = {(uint64_t)a->ldc * 2};
     uint32_t box[2] = {(uint32_t)(geglu ? bn / 2 : bn), 128};
     if (int rc = make_tensor_map(&tmC, out, 2, dims, strides, box, /*swizzle128=*/false)) return rc;
+  } else if (out_mode == 2) {
+    uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M};
+    uint64_t strides[1] = {(uint64_t)a->ldc * 4};
+    uint32_t box[2] = {32, 128};
+    if (int rc = make_tensor_map(&tmC, out, 2, dims, strides, box, true, 4)) return rc;
+    tmR = tmC;
+    if (p.residual) {
+      strides[0] = (uint64_t)a->ldr * 4;
+      if (int rc = make_tensor_map(&tmR, p.residual, 2, dims, strides, box, true, 4)) return rc;
+    }
   }
-  if (use_pair) return launch_gemm_pair(bn, tmA, tmB, tmC, tma_out, p, stream);
-  if (bn == 160) return dispatch_gemm<160>(tmA, tmB, tmC, tma_out, p, stream);
-  return dispatch_gemm<128>(tmA, tmB, tmC, tma_out, p, stream);
+  if (use_pair) return launch_gemm_pair(bn, tmA, tmB, tmC, tmR, out_mode, p, stream);
+  if (bn == 160) return dispatch_gemm<160>(tmA, tmB, tmC, tmR, out_mode, p, stream);
+  return dispatch_gemm<128>(tmA, tmB, tmC, tmR, out_mode, p, stream);
 }

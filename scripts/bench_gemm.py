@@ -8,6 +8,7 @@ sys.path.insert(0, str(ROOT))
 from emote_hack_b200 import ops
 BF16 = torch.bfloat16
 TS = int(os.environ.get('TMA_STORE', '0'))
+PM = int(os.environ.get('PAIR', '0'))
 shapes = [  # (M, N, K, mode)
     (131072, 2560, 320, "geglu"), (131072, 320, 320, "res"), (32768, 640, 640, "res"), (8192, 1280, 1280, "res"),
     (131072, 960, 320, "bf16"), (32768, 5120, 640, "geglu"), (8192, 10240, 1280, "geglu"), (131072, 320, 1280, "res"),
@@ -29,17 +30,17 @@ for i, (M, N, K, mode) in enumerate(shapes):
         wc = ops.pack_conv3x3(torch.randn(N, Cc, 3, 3, device="cuda") / K ** 0.5)
         res = torch.randn(M, N, device="cuda")
         out = torch.empty(M, N, device="cuda")
-        fn = lambda: ops.conv3x3(x, wc, n_img, hw, hw, Cc, bias=bias, residual=res, out=out)
+        fn = lambda: ops.conv3x3(x, wc, n_img, hw, hw, Cc, bias=bias, residual=res, out=out, tma_store=TS, pair_mode=PM)
     elif mode == "geglu":
         wp, bp = ops.pack_geglu(w.float(), bias)
-        fn = lambda: ops.gemm(a, wp, bias=bp, geglu=True, out_dtype=BF16, tma_store=TS)
+        fn = lambda: ops.gemm(a, wp, bias=bp, geglu=True, out_dtype=BF16, tma_store=TS, pair_mode=PM)
     elif mode == "res":
         res = torch.randn(M, N, device="cuda")
         out = torch.empty(M, N, device="cuda")
-        fn = lambda: ops.gemm(a, w, bias=bias, residual=res, out=out)
+        fn = lambda: ops.gemm(a, w, bias=bias, residual=res, out=out, pair_mode=PM, tma_store=TS)
     else:
         out = torch.empty(M, N, device="cuda", dtype=BF16)
-        fn = lambda: ops.gemm(a, w, bias=bias, out_dtype=BF16, out=out, tma_store=TS)
+        fn = lambda: ops.gemm(a, w, bias=bias, out_dtype=BF16, out=out, tma_store=TS, pair_mode=PM)
     for _ in range(3):
         fn()
     torch.cuda.synchronize()

@@ -14,56 +14,56 @@ constexpr int GN_MAX_PASS = 4;
 constexpr int GN_MAX_GROUPS = 64;
 
 // blockDim = (PX, TY); thread (px, ty) owns channel pairs px + pass*PX and rows ty, ty+TY, ...
-__global__ void gn_stats_kernel(const float* __restrict__ x, int C_src, int c_offset, int cpg, int groups,
-                                long long rows_per_batch, int rows_per_block, int passes, double* __restrict__ sums) {
+// Blocks walk the tensor BACKWARDS (last rows first): the producer (a GEMM epilogue) wrote the rows in ascending order,
+// so the tail is what is still resident in L2; gn_apply then walks forwards over the rows this kernel touched last.
+template <int PASSES>
+__global__ void __launch_bounds__(512) gn_stats_kernel(const float* __restrict__ x, int C_src, int c_offset, int cpg,
+                                                       int groups, long long rows_per_batch, int rows_per_block,
+                                                       double* __restrict__ sums) {
   // fp64 accumulation end to end: E[x^2] - mean^2 cancels badly in fp32 when |mean| >> std, and the atomics'
   // ordering would otherwise leak ~1e-6 run-to-run noise into every normalised value.
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
 
-  const int batch = blockIdx.y;
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const int batch = gridDim.y - 1 - blockIdx.y;
+  const long long r0 = (long long)(gridDim.x - 1 - blockIdx.x) * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows_per_batch) r1 = rows_per_batch;
   const float* xb = x + ((long long)batch * rows_per_batch) * C_src;
 
-  double s[GN_MAX_PASS], q[GN_MAX_PASS];
+  double s[PASSES], q[PASSES];
 #pragma unroll
-  for (int i = 0; i < GN_MAX_PASS; ++i) s[i] = q[i] = 0.0;
+  for (int i = 0; i < PASSES; ++i) s[i] = q[i] = 0.0;
 
-  // 8 rows in flight per thread (independent 8-byte loads: ~60 KB outstanding per SM); the 16 values are pre-summed
-  // in fp32 in a fixed order (deterministic), everything after that is fp64.
+  // 8 rows in flight per thread and pass (independent 8-byte loads); the 16 values are pre-summed in fp32 in a fixed
+  // order (deterministic), everything after that is fp64.
   const long long stride = blockDim.y;
   for (long long r = r0 + threadIdx.y; r < r1; r += 8 * stride) {
 #pragma unroll
-    for (int ps = 0; ps < GN_MAX_PASS; ++ps) {
-      if (ps < passes) {
-        const int cp = threadIdx.x + ps * blockDim.x;
-        float2 v[8];
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int cp = threadIdx.x + ps * blockDim.x;
+      float2 v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const long long rr = r + u * stride;
-          v[u] = (rr < r1) ? __ldg(reinterpret_cast<const float2*>(xb + rr * C_src) + cp) : make_float2(0.f, 0.f);
-        }
-        float sf = 0.f, qf = 0.f;
-#pragma unroll
-        for (int u = 0; u < 8; u += 2) {
-          sf += (v[u].x + v[u].y) + (v[u + 1].x + v[u + 1].y);
-          qf += (v[u].x * v[u].x + v[u].y * v[u].y) + (v[u + 1].x * v[u + 1].x + v[u + 1].y * v[u + 1].y);
-        }
-        s[ps] += (double)sf;
-        q[ps] += (double)qf;
+      for (int u = 0; u < 8; ++u) {
+        const long long rr = r + u * stride;
+        v[u] = (rr < r1) ? __ldg(reinterpret_cast<const float2*>(xb + rr * C_src) + cp) : make_float2(0.f, 0.f);
       }
+      float sf = 0.f, qf = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) {
+        sf += (v[u].x + v[u].y) + (v[u + 1].x + v[u + 1].y);
+        qf += (v[u].x * v[u].x + v[u].y * v[u].y) + (v[u + 1].x * v[u + 1].x + v[u + 1].y * v[u + 1].y);
+      }
+      s[ps] += (double)sf;
+      q[ps] += (double)qf;
     }
   }
   // block reduction without shared-memory fp64 atomics (those are CAS loops and dominated the kernel): every thread
   // parks its partials, then one thread per (group, statistic) sums the <= cpg/2 * blockDim.y slots of its group
-  __shared__ double part[2][GN_MAX_PASS][512];
+  __shared__ double part[2][PASSES][512];
 #pragma unroll
-  for (int ps = 0; ps < GN_MAX_PASS; ++ps) {
-    if (ps < passes) {
-      part[0][ps][tid] = s[ps];
-      part[1][ps][tid] = q[ps];
-    }
+  for (int ps = 0; ps < PASSES; ++ps) {
+    part[0][ps][tid] = s[ps];
+    part[1][ps][tid] = q[ps];
   }
   __syncthreads();
   if (tid < groups * 2) {
@@ -82,68 +82,84 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int C_src, int c_of
 }
 
 // y = x * scale[c] + shift[c] with scale = rstd*gamma, shift = beta - mean*rstd*gamma staged in shared memory per
-// block; blockDim = (octets per pass, rows in parallel): no integer division in the streaming loop.
-__global__ void gn_apply_kernel(const float* __restrict__ x, int C_src, int c_offset, int C_total, int cpg,
-                                int groups, long long rows_per_batch, int rows_per_block,
-                                const double* __restrict__ sums, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, float eps, int act_silu,
-                                __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ raw_out) {
+// block; blockDim = (octets per pass, rows in parallel); GN_APPLY_U rows per thread are in flight per batch.
+constexpr int GN_APPLY_U = 4;  // rows per thread in flight
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, int C_src, int c_offset, int C_total,
+                                                       int cpg, int groups, long long rows_per_batch, int rows_per_block,
+                                                       const double* __restrict__ sums, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps, int act_silu,
+                                                       __nv_bfloat16* __restrict__ out,
+                                                       __nv_bfloat16* __restrict__ raw_out) {
   extern __shared__ __align__(16) float gn_smem[];
   float* s_scale = gn_smem;
   float* s_shift = gn_smem + C_src;
   const int batch = blockIdx.y;
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const int nthr = blockDim.x * blockDim.y;
-  const double cnt = (double)rows_per_batch * (double)cpg;
-  for (int c = tid; c < C_src; c += nthr) {
-    const int ct = c_offset + c;
-    const int g = ct / cpg;
-    const double sm = sums[((long long)batch * groups + g) * 2];
-    const double sq = sums[((long long)batch * groups + g) * 2 + 1];
-    const double mean = sm / cnt;
-    double var = sq / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float sc = rstd * gamma[ct];
-    s_scale[c] = sc;
-    s_shift[c] = beta[ct] - (float)mean * sc;
+  {
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nthr = blockDim.x * blockDim.y;
+    const double cnt = (double)rows_per_batch * (double)cpg;
+    for (int c = tid; c < C_src; c += nthr) {
+      const int ct = c_offset + c;
+      const int g = ct / cpg;
+      const double sm = sums[((long long)batch * groups + g) * 2];
+      const double sq = sums[((long long)batch * groups + g) * 2 + 1];
+      const double mean = sm / cnt;
+      double var = sq / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float sc = rstd * gamma[ct];
+      s_scale[c] = sc;
+      s_shift[c] = beta[ct] - (float)mean * sc;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   const int opr = C_src >> 3;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows_per_batch) r1 = rows_per_batch;
   const long long row_base = (long long)batch * rows_per_batch;
-  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    const float* xr = x + (row_base + r) * C_src;
-    __nv_bfloat16* orow = out + (row_base + r) * C_total + c_offset;
-    __nv_bfloat16* rrow = raw_out ? raw_out + (row_base + r) * C_total + c_offset : nullptr;
+  const long long stride = blockDim.y;
+  for (long long r = r0 + threadIdx.y; r < r1; r += GN_APPLY_U * stride) {
     for (int o = threadIdx.x; o < opr; o += blockDim.x) {
       const int c0 = o << 3;
-      const float4 a = __ldg(reinterpret_cast<const float4*>(xr + c0));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(xr + c0 + 4));
-      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      float4 a[GN_APPLY_U], b[GN_APPLY_U];
+#pragma unroll
+      for (int u = 0; u < GN_APPLY_U; ++u) {   // all loads of the batch are in flight before the first store
+        const long long rr = r + u * stride;
+        if (rr < r1) {
+          const float* xr = x + (row_base + rr) * C_src + c0;
+          a[u] = __ldg(reinterpret_cast<const float4*>(xr));
+          b[u] = __ldg(reinterpret_cast<const float4*>(xr + 4));
+        }
+      }
       const float4 sa = *reinterpret_cast<const float4*>(s_scale + c0);
       const float4 sb = *reinterpret_cast<const float4*>(s_scale + c0 + 4);
       const float4 ha = *reinterpret_cast<const float4*>(s_shift + c0);
       const float4 hb = *reinterpret_cast<const float4*>(s_shift + c0 + 4);
       const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
       const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-      float y[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float tt = fmaf(v[j], sc[j], sh[j]);
-        y[j] = act_silu ? silu_f(tt) : tt;
-      }
-      uint4 w;
-      w.x = pack_bf16x2(y[0], y[1]); w.y = pack_bf16x2(y[2], y[3]);
-      w.z = pack_bf16x2(y[4], y[5]); w.w = pack_bf16x2(y[6], y[7]);
-      *reinterpret_cast<uint4*>(orow + c0) = w;
-      if (rrow) {
-        uint4 u;
-        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-        u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(rrow + c0) = u;
+      for (int u = 0; u < GN_APPLY_U; ++u) {
+        const long long rr = r + u * stride;
+        if (rr < r1) {
+          const float v[8] = {a[u].x, a[u].y, a[u].z, a[u].w, b[u].x, b[u].y, b[u].z, b[u].w};
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float tt = fmaf(v[j], sc[j], sh[j]);
+            y[j] = act_silu ? silu_f(tt) : tt;
+          }
+          uint4 w;
+          w.x = pack_bf16x2(y[0], y[1]); w.y = pack_bf16x2(y[2], y[3]);
+          w.z = pack_bf16x2(y[4], y[5]); w.w = pack_bf16x2(y[6], y[7]);
+          *reinterpret_cast<uint4*>(out + (row_base + rr) * C_total + c_offset + c0) = w;
+          if (raw_out) {
+            uint4 q;
+            q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
+            q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(raw_out + (row_base + rr) * C_total + c_offset + c0) = q;
+          }
+        }
       }
     }
   }
@@ -159,8 +175,10 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
                                                         float eps, const float* __restrict__ pe, int pe_rows_per_frame,
                                                         int pe_frames, __nv_bfloat16* __restrict__ out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (row >= M) return;
+  // rows are visited last-to-first: the producing GEMM wrote them in ascending order, so the tail is still in L2, and
+  // the rows written here last (the head) are the first ones the consuming GEMM loads.
+  const long long row = M - 1 - ((long long)blockIdx.x * (blockDim.x >> 5) + warp);
+  if (row < 0) return;
   const int nv = (NV > 0) ? NV : (C_rt >> 6);
   constexpr int CAP = (NV > 0) ? NV : LN_MAX_V;
   const int C = nv << 6;
@@ -268,12 +286,22 @@ extern "C" int emote_gn_stats(const float* x, int32_t C_src, int32_t c_offset, i
   const int PX = P / passes;
   int TY = 512 / PX;
   if (TY < 1) TY = 1;
-  int rows_per_block = 32 * TY;
-  if (rows_per_block < 64) rows_per_block = 64;
+  // one batch of loads covers 8*TY rows; small tensors get one batch per block (more blocks than SMs), large ones up
+  // to 4 batches per block to amortise the block reduction and its atomics
+  const long long total_rows = rows_per_batch * (long long)n_batches;
+  long long k = total_rows / (8LL * TY * 1184);
+  if (k < 1) k = 1;
+  if (k > 4) k = 4;
+  const int rows_per_block = (int)(8 * TY * k);
   const long long chunks = (rows_per_batch + rows_per_block - 1) / rows_per_block;
   dim3 grid((unsigned)chunks, (unsigned)n_batches), block(PX, TY);
-  gn_stats_kernel<<<grid, block, 0, stream>>>(x, C_src, c_offset, C_total / groups, groups, rows_per_batch,
-                                              rows_per_block, passes, sums);
+  const int cpg = C_total / groups;
+  switch (passes) {
+    case 1: gn_stats_kernel<1><<<grid, block, 0, stream>>>(x, C_src, c_offset, cpg, groups, rows_per_batch, rows_per_block, sums); break;
+    case 2: gn_stats_kernel<2><<<grid, block, 0, stream>>>(x, C_src, c_offset, cpg, groups, rows_per_batch, rows_per_block, sums); break;
+    case 3: gn_stats_kernel<3><<<grid, block, 0, stream>>>(x, C_src, c_offset, cpg, groups, rows_per_batch, rows_per_block, sums); break;
+    default: gn_stats_kernel<4><<<grid, block, 0, stream>>>(x, C_src, c_offset, cpg, groups, rows_per_batch, rows_per_block, sums); break;
+  }
   EMOTE_CHECK_LAUNCH("emote_gn_stats");
   return 0;
 }
@@ -291,8 +319,11 @@ extern "C" int emote_gn_apply(const float* x, int32_t C_src, int32_t c_offset, i
   while (opr % bx != 0) --bx;  // octets per pass divide the row evenly
   int by = 256 / bx;
   if (by < 1) by = 1;
-  int rows_per_block = 8 * by;
-  if (rows_per_block < 16) rows_per_block = 16;
+  const long long total_rows = rows_per_batch * (long long)n_batches;
+  long long k = total_rows / ((long long)GN_APPLY_U * by * 2368);
+  if (k < 1) k = 1;
+  if (k > 4) k = 4;
+  const int rows_per_block = (int)(GN_APPLY_U * by * k);
   const long long chunks = (rows_per_batch + rows_per_block - 1) / rows_per_block;
   dim3 grid((unsigned)chunks, (unsigned)n_batches), block(bx, by);
   const size_t smem = 2 * (size_t)C_src * sizeof(float);

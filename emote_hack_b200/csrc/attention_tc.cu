@@ -45,6 +45,34 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32x2 FMA (FFMA2): {d.x, d.y} = {a.x, a.y} * {b, b} + {c, c}
+__device__ __forceinline__ void ffma2_bcast(float& d0, float& d1, float a0, float a1, float b, float c) {
+  unsigned long long aa, bb, cc, dd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dd) : "l"(aa), "l"(bb), "l"(cc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dd));
+}
+// {d.x, d.y} = {a.x, a.y} * {b, b} + {c.x, c.y}
+__device__ __forceinline__ void ffma2_acc(float& d0, float& d1, float a0, float a1, float b, float c0, float c1) {
+  unsigned long long aa, bb, cc, dd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(c0), "f"(c1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dd) : "l"(aa), "l"(bb), "l"(cc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dd));
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -85,9 +113,11 @@ struct TcCfg {
   static constexpr int KV_TILE = ATOMS * TC_BKV * 128;   // one K or V tile
   static constexpr int STAGE = 2 * KV_TILE;
   static constexpr int P_BYTES = TC_BQ * 128;            // 128 rows x 64 keys bf16
-  static constexpr int SMEM = Q_BYTES + TC_STAGES * STAGE + 2 * P_BYTES + 256 + 1024;
-  static constexpr int TMEM_COLS = (2 * TC_BKV + 2 * NPV <= 256) ? 256 : 512;
+  static constexpr int ONES_BYTES = 16 * 128;            // 16 x 64 bf16 ones: B operand of the row-sum MMA
+  static constexpr int SMEM = Q_BYTES + TC_STAGES * STAGE + 2 * P_BYTES + ONES_BYTES + 256 + 1024;
+  static constexpr int TMEM_COLS = (2 * TC_BKV + 2 * NPV + 32 <= 256) ? 256 : 512;
   static constexpr int PV_COL0 = 2 * TC_BKV;
+  static constexpr int SUM_COL0 = PV_COL0 + 2 * NPV;     // 2 x 16 columns: l = P x ones (every column holds the row sum)
 };
 
 template <int D>
@@ -101,7 +131,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + C::Q_BYTES;
   uint8_t* sP = sKV + TC_STAGES * C::STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * C::P_BYTES);
+  uint8_t* sOnes = sP + 2 * C::P_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + C::ONES_BYTES);
   uint64_t* kv_full = bars;                  // [STAGES] TMA (expect_tx) -> MMA
   uint64_t* kv_empty = kv_full + TC_STAGES;  // [STAGES] MMA commit -> loader
   uint64_t* s_full = kv_empty + TC_STAGES;   // [2] MMA commit -> softmax
@@ -123,6 +154,9 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
     uint4* z = reinterpret_cast<uint4*>(smem);
     const int n16 = (C::Q_BYTES + TC_STAGES * C::STAGE + 2 * C::P_BYTES) / 16;
     for (int i = threadIdx.x; i < n16; i += TC_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    uint4* o = reinterpret_cast<uint4*>(sOnes);
+    for (int i = threadIdx.x; i < C::ONES_BYTES / 16; i += TC_THREADS)
+      o[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0 pairs
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -189,6 +223,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
     {
       constexpr uint32_t idesc_s = umma_idesc_bf16(TC_BQ, TC_BKV);
       constexpr uint32_t idesc_pv = umma_idesc_bf16_bmn(TC_BQ, C::NPV);
+      constexpr uint32_t idesc_sum = umma_idesc_bf16(TC_BQ, 16);
       auto issue_s = [&](int j) {
         const int stage = j % TC_STAGES;
         mbar_wait(&kv_full[stage], (j / TC_STAGES) & 1);
@@ -224,6 +259,13 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
             const uint64_t db = umma_desc_sw128_mn(va + ks * 16 * 128, TC_BKV * 128);
             umma_f16(d_tmem, da, db, idesc_pv, ks != 0 ? 1u : 0u);
           }
+          // row sums of the bf16 P actually multiplied into V: P x ones (K-major 16 x 64 tile of 1.0)
+          const uint32_t oa = smem_u32(sOnes);
+          const uint32_t s_tmem = tmem_base + C::SUM_COL0 + (j & 1) * 16;
+#pragma unroll
+          for (int ks = 0; ks < TC_BKV / 16; ++ks)
+            umma_f16(s_tmem, umma_desc_sw128(pa) + static_cast<uint64_t>(2 * ks),
+                     umma_desc_sw128(oa) + static_cast<uint64_t>(2 * ks), idesc_sum, ks != 0 ? 1u : 0u);
           umma_commit(&o_full[j & 1]);
           umma_commit(&kv_empty[stage]);
         }
@@ -248,11 +290,15 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
       uint32_t r[C::NPV / 16][16];
 #pragma unroll
       for (int c = 0; c < C::NPV / 16; ++c) tmem_ld16(ta + c * 16, r[c]);
+      const uint32_t rsum = tmem_ld1(tmem_base + lane_addr + C::SUM_COL0 + (j & 1) * 16);
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < C::NPV / 16; ++c)
 #pragma unroll
-        for (int k = 0; k < 16; ++k) o_acc[c * 16 + k] = fmaf(o_acc[c * 16 + k], corr, __uint_as_float(r[c][k]));
+        for (int k = 0; k < 16; k += 2)
+          ffma2_acc(o_acc[c * 16 + k], o_acc[c * 16 + k + 1], o_acc[c * 16 + k], o_acc[c * 16 + k + 1], corr,
+                    __uint_as_float(r[c][k]), __uint_as_float(r[c][k + 1]));
+      l_run = fmaf(l_run, corr, __uint_as_float(rsum));
     };
 
     for (int j = 0; j < ntiles; ++j) {
@@ -271,39 +317,36 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
           if (k + 32 >= nvalid) s1[k] = 0xff800000u;
         }
       }
-      // row max: 8 independent chains, then a tree (the serial fmax chain was the critical path of this loop)
+      // row max: 8 independent chains of 3-input max, then a tree
       float mxa[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) mxa[k] = fmaxf(__uint_as_float(s0[k]), __uint_as_float(s1[k]));
 #pragma unroll
-      for (int k = 8; k < 32; ++k) mxa[k & 7] = fmaxf(mxa[k & 7], fmaxf(__uint_as_float(s0[k]), __uint_as_float(s1[k])));
-      const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
-                             fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+      for (int k = 8; k < 32; ++k) mxa[k & 7] = fmax3(mxa[k & 7], __uint_as_float(s0[k]), __uint_as_float(s1[k]));
+      const float mx = fmaxf(fmax3(mxa[0], mxa[1], mxa[2]), fmax3(fmax3(mxa[3], mxa[4], mxa[5]), mxa[6], mxa[7]));
       const float m_new = fmaxf(m_run, mx);
       const float corr = (m_run == -INFINITY) ? 0.f : ex2f((m_run - m_new) * sc);
-      const float msc = m_new * sc;
+      const float nmsc = -(m_new * sc);
       m_run = m_new;
-      float rs[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) rs[k] = 0.f;
       uint8_t* prow = sP + (j & 1) * C::P_BYTES + row * 128;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys
+      for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys; the row sum comes back from the tensor core (P x ones)
         float pv[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 8; k += 2) {
           const int idx = c * 8 + k;
-          const float sv = __uint_as_float(idx < 32 ? s0[idx] : s1[idx - 32]);
-          pv[k] = ex2f(fmaf(sv, sc, -msc));
-          rs[k] += pv[k];
+          const float sa = __uint_as_float(idx < 32 ? s0[idx] : s1[idx - 32]);
+          const float sb = __uint_as_float(idx < 32 ? s0[idx + 1] : s1[idx - 31]);
+          float x0, x1;
+          ffma2_bcast(x0, x1, sa, sb, sc, nmsc);
+          pv[k] = ex2f(x0);
+          pv[k + 1] = ex2f(x1);
         }
         uint4 w;
         w.x = pack_bf16x2(pv[0], pv[1]); w.y = pack_bf16x2(pv[2], pv[3]);
         w.z = pack_bf16x2(pv[4], pv[5]); w.w = pack_bf16x2(pv[6], pv[7]);
         *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = w;
       }
-      const float rsum = ((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7]));
-      l_run = l_run * corr + rsum;
       // publish P (generic-proxy smem writes -> async proxy) and release S[j&1]: one arrival per warp
       fence_proxy_async();
       tc_fence_before();

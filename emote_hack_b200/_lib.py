@@ -37,6 +37,8 @@ class EmoteGemmArgs(C.Structure):
         ("block_n", C.c_int32),
         ("pair_mode", C.c_int32),
         ("tma_store", C.c_int32),
+        ("colstats", C.c_void_p),
+        ("stats_rows", C.c_int32),
     ]
 
 
@@ -62,6 +64,7 @@ _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
     "emote_gemm_bf16": [_vp, _vp, _vp, C.POINTER(EmoteGemmArgs), _vp],
     "emote_gn_stats": [_vp, _i32, _i32, _i32, _i32, _i64, _i32, _vp, _i32, _vp],
+    "emote_gn_colstats_reduce": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "emote_gn_apply": [_vp, _i32, _i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _f32, _i32, _vp, _vp, _vp],
     "emote_layernorm": [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _i32, _i32, _vp, _vp],
     "emote_attention_bf16": [C.POINTER(EmoteAttnArgs), _vp],

@@ -26,6 +26,8 @@ struct GemmDev {
   int out_bf16;
   int ldc;
   void* out;
+  double* colstats;  // optional [M / stats_rows][N][2] per-column (sum, sum of squares) of the fp32 output, else null
+  int stats_rows;    // rows per statistics batch (multiple of 128: a tile never straddles two batches)
 };
 
 
@@ -111,25 +113,32 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
           if (c1ok) b1 += __ldg(rb + 1);
         }
       }
+      const bool stats = p.colstats != nullptr;   // fused GroupNorm statistics of the values being written
+      float cs0 = 0.f, cq0 = 0.f, cs1 = 0.f, cq1 = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         // rows g, g+8 come from the low 16-lane load, rows g+16, g+24 from the high one
         const int ri = (i >> 1) * 4 + (i & 1) * 2;
         float v0 = __uint_as_float(a[ri]) + b0, v1 = __uint_as_float(a[ri + 1]) + b1;
         if constexpr (HAS_ADD) { v0 += add[ci][2 * i]; v1 += add[ci][2 * i + 1]; }
+        float* sp = nullptr;
         if constexpr (OUT_MODE == 2) {
           const int lr = quarter * 32 + g + 8 * i, lc = (c_first + ci) * 8 + 2 * t;
-          float* sp = reinterpret_cast<float*>(stage_) + (lc >> 5) * (BM * 32) + lr * 32 +
-                      ((((lc & 31) >> 2) ^ (lr & 7)) << 2) + (lc & 3);
+          sp = reinterpret_cast<float*>(stage_) + (lc >> 5) * (BM * 32) + lr * 32 +
+               ((((lc & 31) >> 2) ^ (lr & 7)) << 2) + (lc & 3);
           if (p.residual) {
             const float2 r2 = *reinterpret_cast<const float2*>(sp);
             v0 += r2.x; v1 += r2.y;
           }
-          *reinterpret_cast<float2*>(sp) = make_float2(v0 * p.out_scale, v1 * p.out_scale);
-          continue;
         }
         v0 *= p.out_scale; v1 *= p.out_scale;
-        if constexpr (TMA_OUT) {
+        if (stats && rok[i]) {
+          cs0 += v0; cq0 = fmaf(v0, v0, cq0);
+          cs1 += v1; cq1 = fmaf(v1, v1, cq1);
+        }
+        if constexpr (OUT_MODE == 2) {
+          *reinterpret_cast<float2*>(sp) = make_float2(v0, v1);
+        } else if constexpr (TMA_OUT) {
           const int lr = quarter * 32 + g + 8 * i, lc = (c_first + ci) * 8 + 2 * t;
           *reinterpret_cast<uint32_t*>(stage + lr * BN + lc) = pack_bf16x2(v0, v1);
         } else if (rok[i] && c0ok) {
@@ -142,6 +151,23 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
             if (c1ok) *reinterpret_cast<float2*>(o) = make_float2(v0, v1);
             else o[0] = v0;
           }
+        }
+      }
+      if (stats) {
+        // this thread summed its 4 rows; fold the 8 row groups of the warp (lanes differing in g), then one lane per
+        // column pair sends the 32-row partial to the fp64 accumulators of the tile's statistics batch (fire-and-forget
+        // reductions: no shared-memory stage, no extra barrier)
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+          cs0 += __shfl_xor_sync(0xffffffffu, cs0, off);
+          cq0 += __shfl_xor_sync(0xffffffffu, cq0, off);
+          cs1 += __shfl_xor_sync(0xffffffffu, cs1, off);
+          cq1 += __shfl_xor_sync(0xffffffffu, cq1, off);
+        }
+        if (g == 0 && row_base < p.M) {
+          double* cs = p.colstats + ((size_t)(row_base / p.stats_rows) * p.N + col) * 2;
+          if (c0ok) { atomicAdd(cs, (double)cs0); atomicAdd(cs + 1, (double)cq0); }
+          if (c1ok) { atomicAdd(cs + 2, (double)cs1); atomicAdd(cs + 3, (double)cq1); }
         }
       }
     };

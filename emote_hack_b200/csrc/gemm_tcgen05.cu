@@ -331,6 +331,13 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   p.out_bf16 = a->out_dtype == EMOTE_DT_BF16;
   p.ldc = a->ldc;
   p.out = out;
+  if (a->colstats) {
+    if (p.out_bf16 || geglu) return set_error("emote_gemm_bf16: colstats needs a plain fp32 output");
+    if (a->stats_rows <= 0 || a->stats_rows % 128 != 0 || a->M % a->stats_rows != 0)
+      return set_error("emote_gemm_bf16: stats_rows must be a multiple of 128 that divides M");
+    p.colstats = a->colstats;
+    p.stats_rows = a->stats_rows;
+  }
 
   CUtensorMap tmA, tmB;
   if (conv) {

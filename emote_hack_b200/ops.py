@@ -80,8 +80,13 @@ def pack_geglu(w: torch.Tensor, b: torch.Tensor):
 # ----------------------------------------------------------------------------------------------- GEMM / conv
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, row_bias=None, rows_per_group: int = 0, residual=None,
          out_scale: float = 1.0, geglu: bool = False, out_dtype=F32, out: Optional[torch.Tensor] = None,
-         conv: Optional[tuple] = None, M: Optional[int] = None, pair_mode: int = 0, tma_store: int = 0) -> torch.Tensor:
-    """out = epilogue(a @ w.T).  a: bf16 [M, K] (or NHWC [n_img, H, W, C] when conv=(n_img, H, W, C)); w: bf16 [N, K]."""
+         conv: Optional[tuple] = None, M: Optional[int] = None, pair_mode: int = 0, tma_store: int = 0,
+         stats_rows: int = 0) -> torch.Tensor:
+    """out = epilogue(a @ w.T).  a: bf16 [M, K] (or NHWC [n_img, H, W, C] when conv=(n_img, H, W, C)); w: bf16 [N, K].
+
+    stats_rows > 0 (fp32 outputs): the epilogue also accumulates per-column (sum, sum of squares) of the output per
+    block of `stats_rows` rows; they ride on the returned tensor (`_emote_colstats`) and let group_norm() skip its
+    statistics pass over that tensor."""
     _req(a, BF16, "gemm.a"), _req(w, BF16, "gemm.w")
     N, K = w.shape
     args = EmoteGemmArgs()
@@ -119,9 +124,30 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, row_bias=None, rows_per
     args.block_n = 0
     args.pair_mode = pair_mode
     args.tma_store = tma_store
+    colstats = None
+    if (stats_rows > 0 and FUSED_GN_STATS and out_dtype == F32 and not geglu and stats_rows % 128 == 0
+            and M % stats_rows == 0):
+        colstats = torch.zeros((M // stats_rows, n_out, 2), dtype=torch.float64, device=a.device)
+        args.colstats, args.stats_rows = colstats.data_ptr(), stats_rows
     check(_lib.load().emote_gemm_bf16(a.data_ptr(), w.data_ptr(), out.data_ptr(), C.byref(args), _stream()),
           "emote_gemm_bf16")
+    if colstats is not None:
+        out._emote_colstats = (colstats, stats_rows, out._version)
+    elif getattr(out, "_emote_colstats", None) is not None:
+        out._emote_colstats = None   # overwritten in place: statistics of the old contents no longer apply
     return out
+
+
+FUSED_GN_STATS = True   # GEMM epilogues that feed a GroupNorm also produce its statistics
+
+
+def stats_rows_for(rows_per_frame: int, rows_per_sample: int) -> int:
+    """Finest statistics granularity a 128-row GEMM tile never straddles: per frame, else per sample, else none (0)."""
+    if rows_per_frame % 128 == 0:
+        return rows_per_frame
+    if rows_per_sample % 128 == 0:
+        return rows_per_sample
+    return 0
 
 
 def conv_tile_ok(H: int, W: int) -> bool:
@@ -187,8 +213,16 @@ def group_norm(sources: Sequence[torch.Tensor], groups: int, rows_per_batch: int
     for i, s in enumerate(sources):
         _req(s, F32, "group_norm.source")
         cs = int(s.shape[-1])
-        check(lib.emote_gn_stats(s.data_ptr(), cs, off, c_total, groups, rows_per_batch, n_batches, sums.data_ptr(),
-                                 1 if i == 0 else 0, st), "emote_gn_stats")
+        info = getattr(s, "_emote_colstats", None)
+        if (info is not None and FUSED_GN_STATS and info[2] == s._version and rows_per_batch % info[1] == 0
+                and info[0].shape[0] * info[1] == rows and info[0].shape[1] == cs):
+            # statistics were accumulated by the GEMM epilogue that wrote this source
+            check(lib.emote_gn_colstats_reduce(info[0].data_ptr(), cs, off, c_total, groups, rows_per_batch // info[1],
+                                               n_batches, sums.data_ptr(), 1 if i == 0 else 0, st),
+                  "emote_gn_colstats_reduce")
+        else:
+            check(lib.emote_gn_stats(s.data_ptr(), cs, off, c_total, groups, rows_per_batch, n_batches, sums.data_ptr(),
+                                     1 if i == 0 else 0, st), "emote_gn_stats")
         off += cs
     off = 0
     for s in sources:

@@ -52,6 +52,9 @@ def _tokens(x: torch.Tensor) -> Tuple[torch.Tensor, Tuple[int, int, int, int, in
     if not x.is_cuda:
         raise EmoteKernelError("emote_hack_b200 modules run on CUDA only (no CPU fallback)")
     b, c, f, h, w = x.shape
+    rec = getattr(x, "_emote_tok", None)
+    if rec is not None and rec[0]._version == rec[1] and x.dtype == F32 and rec[0].shape == (b * f * h * w, c):
+        return rec[0], (b, c, f, h, w)   # the token tensor a previous module produced (keeps its fused GN statistics)
     if x.dtype != F32:
         x = x.float()
     xt = x.permute(0, 2, 3, 4, 1)
@@ -62,7 +65,9 @@ def _tokens(x: torch.Tensor) -> Tuple[torch.Tensor, Tuple[int, int, int, int, in
 
 def _untokens(tok: torch.Tensor, b: int, c: int, f: int, h: int, w: int) -> torch.Tensor:
     """tokens [(b f h w), c] -> [b, c, f, h, w] view with channels-last strides."""
-    return tok.view(b, f, h, w, c).permute(0, 4, 1, 2, 3)
+    v = tok.view(b, f, h, w, c).permute(0, 4, 1, 2, 3)
+    v._emote_tok = (tok, tok._version)
+    return v
 
 
 class _PackedModule(nn.Module):
@@ -139,14 +144,16 @@ class InflatedConv3d(nn.Conv2d):
                 raise EmoteKernelError("emote_hack_b200 modules run on CUDA only (no CPU fallback)")
             b, c, f, h, w = x.shape
             wp, bias = self.packed()
-            out = ops.gemm(ops.latent_im2col(x.float().contiguous()), wp, bias=bias)
+            out = ops.gemm(ops.latent_im2col(x.float().contiguous()), wp, bias=bias,
+                           stats_rows=ops.stats_rows_for(h * w, f * h * w))
             return _untokens(out, b, self.out_channels, f, h, w)
         tok, (b, c, f, h, w) = _tokens(x)
         wp, bias = self.packed()
         if self.kernel_size[0] == 3 and self.stride[0] == 2:
             cols = ops.im2col_s2(tok, b * f, h, w, c)
             ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-            return _untokens(ops.gemm(cols, wp, bias=bias), b, self.out_channels, f, ho, wo)
+            return _untokens(ops.gemm(cols, wp, bias=bias, stats_rows=ops.stats_rows_for(ho * wo, f * ho * wo)),
+                             b, self.out_channels, f, ho, wo)
         out = self.forward_tokens(ops.cast_bf16(tok), b * f, h, w)
         return _untokens(out, b, self.out_channels, f, h, w)
 
@@ -169,7 +176,7 @@ class Upsample3D(nn.Module):
             raise NotImplementedError("Upsample3D: forced output_size is not supported (inputs must be multiples of 8)")
         tok, (b, c, f, h, w) = _tokens(hidden_states)
         up = ops.upsample2x(tok, b * f, h, w, c)
-        out = self.conv.forward_tokens(up, b * f, 2 * h, 2 * w)
+        out = self.conv.forward_tokens(up, b * f, 2 * h, 2 * w, stats_rows=ops.stats_rows_for(4 * h * w, 4 * f * h * w))
         return _untokens(out, b, self.out_channels, f, 2 * h, 2 * w)
 
 
@@ -253,14 +260,15 @@ class ResnetBlock3D(nn.Module):
                 act = ops.silu_bf16(temb.float().contiguous())
             wt, bt = self._temb_packed()
             row_bias = ops.gemm(act, wt, bias=bt)  # [b, cout] fp32
-        h1 = self.conv1.forward_tokens(a1, n_img, h, w, row_bias=row_bias, rows_per_group=rows_pb)
+        h1 = self.conv1.forward_tokens(a1, n_img, h, w, row_bias=row_bias, rows_per_group=rows_pb,
+                                       stats_rows=rows_pb if rows_pb % 128 == 0 else 0)  # feeds norm2 (5-D)
         a2, _ = ops.group_norm([h1], g2.num_groups, rows_pb, b, g2.weight, g2.bias, g2.eps, True)
         if need_raw:
             res = self.conv_shortcut.forward_tokens(raw, n_img, h, w)
         else:
             res = toks[0]
         out = self.conv2.forward_tokens(a2, n_img, h, w, residual=res, out_scale=1.0 / self.output_scale_factor,
-                                        out=res if need_raw else None)
+                                        out=res if need_raw else None, stats_rows=ops.stats_rows_for(h * w, rows_pb))
         return _untokens(out, b, self.out_channels, f, h, w)
 
 
@@ -529,7 +537,8 @@ class Transformer3DModel(nn.Module):
             # context is NOT repeated per frame (attention.py:118-119): the attention kernel indexes it by b = img // f
             x = block(x, encoder_hidden_states=encoder_hidden_states, timestep=timestep, video_length=f)
         inner = x.shape[-1]
-        out = ops.gemm(ops.cast_bf16(x.reshape(-1, inner)), p["wo"], bias=p["bo"], residual=tok)
+        out = ops.gemm(ops.cast_bf16(x.reshape(-1, inner)), p["wo"], bias=p["bo"], residual=tok,
+                       stats_rows=ops.stats_rows_for(h * w, f * h * w))
         out = _untokens(out, b, c, f, h, w)
         return Transformer3DModelOutput(sample=out) if return_dict else (out,)
 
@@ -682,7 +691,7 @@ class TemporalTransformer3DModel(nn.Module):
         nblk = len(self.transformer_blocks)
         for i, block in enumerate(self.transformer_blocks):
             x = block.run(x, b, f, h * w, last_bf16=(i == nblk - 1))  # last FF epilogue emits the proj_out operand
-        out = ops.gemm(x, p["wo"], bias=p["bo"], residual=tok)
+        out = ops.gemm(x, p["wo"], bias=p["bo"], residual=tok, stats_rows=ops.stats_rows_for(h * w, f * h * w))
         return _untokens(out, b, c, f, h, w)
 
 

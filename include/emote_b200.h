@@ -58,7 +58,10 @@ typedef struct {
   int32_t ldc;            /* out row pitch in elements */
   int32_t block_n;        /* 0 = auto (160 if N % 160 == 0 else 128) */
   int32_t pair_mode;      /* 0 = auto, 1 = force CTA pairs (cta_group::2, 256-row tiles), 2 = force single CTA */
-  int32_t tma_store;      /* 0 = auto (bf16 outputs without residual leave through a staged TMA store), 2 = never */
+  int32_t tma_store;      /* 0 = auto (staged TMA-store epilogues where they apply), 2 = never */
+  double* colstats;       /* optional fused GroupNorm statistics of the fp32 output: [M / stats_rows][N][2] fp64
+                             (sum, sum of squares per column and statistics batch), ACCUMULATED into (caller zeroes) */
+  int32_t stats_rows;     /* rows per statistics batch; multiple of 128 that divides M */
 } EmoteGemmArgs;
 int emote_gemm_bf16(const void* A, const void* Wt, void* out, const EmoteGemmArgs* args, void* stream);
 
@@ -71,6 +74,15 @@ int emote_gemm_bf16(const void* A, const void* Wt, void* out, const EmoteGemmArg
  * sums: [n_batches, groups, 2] doubles (sum, sum of squares); zeroed by the call when zero_first != 0. */
 int emote_gn_stats(const float* x, int32_t C_src, int32_t c_offset, int32_t C_total, int32_t groups,
                    int64_t rows_per_batch, int32_t n_batches, double* sums, int32_t zero_first, void* stream);
+/* GroupNorm statistics from the per-column statistics accumulated by emote_gemm_bf16 (EmoteGemmArgs.colstats) while it
+ * wrote the tensor being normalised: replaces the emote_gn_stats pass over that source (same `sums` layout and
+ * concat semantics: c_offset / C_total; zero_first = overwrite instead of accumulate).  `stat_batches_per_batch`
+ * consecutive statistics batches of colstats [n][C_src][2] form one GroupNorm batch (e.g. the f frames of a sample for
+ * the 5-D GroupNorm of resnet.py:180 when the GEMM kept per-frame statistics). */
+int emote_gn_colstats_reduce(const double* colstats, int32_t C_src, int32_t c_offset, int32_t C_total, int32_t groups,
+                             int32_t stat_batches_per_batch, int32_t n_batches, double* sums, int32_t zero_first,
+                             void* stream);
+
 /* y = (x-mean)*rstd*gamma+beta [-> SiLU if act_silu]; written as bf16 into out[row, c_offset + c] (pitch C_total).
  * raw_out (optional, same layout) receives the un-normalised input rounded to bf16 (shortcut-conv operand). */
 int emote_gn_apply(const float* x, int32_t C_src, int32_t c_offset, int32_t C_total, int32_t groups,

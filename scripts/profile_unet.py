@@ -9,6 +9,8 @@ from emote_hack_b200 import ops  # noqa: E402
 from emote_hack_b200.unet3d import UNet3DConditionModel  # noqa: E402
 from emote_hack_b200.vae import AutoencoderKL  # noqa: E402
 
+import os
+ops.FUSED_GN_STATS = os.environ.get('FUSED', '1') != '0'
 dev = torch.device("cuda")
 torch.manual_seed(0)
 with torch.device(dev):

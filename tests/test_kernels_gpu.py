@@ -144,6 +144,66 @@ def test_group_norm(ops, srcs, rows_per_batch, n_batches):
     assert rel_l2(out2, ref2) < 4e-3
 
 
+def _check_colstats(out, stats_rows):
+    cs, sr, ver = out._emote_colstats
+    assert sr == stats_rows and ver == out._version
+    o = out.double().view(-1, stats_rows, out.shape[1])
+    ref = torch.stack([o.sum(1), (o * o).sum(1)], dim=-1)
+    torch.testing.assert_close(cs, ref, rtol=2e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("M,N,K,sr,mode", [(1024, 320, 320, 256, "res"), (1024, 320, 320, 128, "plain"),
+                                           (512, 136, 72, 256, "res"), (2048, 640, 640, 1024, "rowbias"),
+                                           (1024, 320, 4608, 512, "res"), (1024, 320, 4608, 512, "plain"),
+                                           (896, 1280, 5120, 128, "res")])
+def test_gemm_fused_gn_statistics(ops, M, N, K, sr, mode):
+    """EmoteGemmArgs.colstats: per-column sum / sum of squares of the fp32 output, per block of stats_rows rows —
+    staged-TMA epilogue (K <= 4096), register epilogues (K > 4096), single-CTA and CTA-pair kernels."""
+    g = _gen(21)
+    a = torch.randn(M, K, device="cuda", generator=g).to(BF16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(BF16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g) * 2 + 1 if mode == "res" else None
+    rb = torch.randn(M // sr, N, device="cuda", generator=g) if mode == "rowbias" else None
+    ref = a.float() @ w.float().t() + bias
+    if res is not None:
+        ref = ref + res
+    if rb is not None:
+        ref = ref + rb.repeat_interleave(sr, 0)
+    for pair_mode in (1, 2):
+        out = ops.gemm(a, w, bias=bias, residual=res, row_bias=rb, rows_per_group=sr if rb is not None else 0,
+                       stats_rows=sr, pair_mode=pair_mode)
+        assert rel_l2(out, ref) < 2e-5
+        _check_colstats(out, sr)
+
+
+def test_group_norm_from_fused_statistics(ops):
+    """group_norm() consumes the statistics a conv epilogue accumulated (per frame) for a per-sample GroupNorm and for
+    a concatenation with a second source that has none; results match the unfused path."""
+    g = _gen(22)
+    n_img, H, W, C, N = 8, 16, 16, 64, 320   # 2 samples x 4 frames, 256 rows per frame
+    x = torch.randn(n_img, H, W, C, device="cuda", generator=g).to(BF16)
+    wp = ops.pack_conv3x3(torch.randn(N, C, 3, 3, device="cuda", generator=g) / math.sqrt(9 * C))
+    bias = torch.randn(N, device="cuda", generator=g)
+    skip = torch.randn(n_img * H * W, 320, device="cuda", generator=g)
+    gamma = torch.randn(640, device="cuda", generator=g)
+    beta = torch.randn(640, device="cuda", generator=g)
+    fused = ops.conv3x3(x, wp, n_img, H, W, C, bias=bias, stats_rows=H * W)
+    _check_colstats(fused, H * W)
+    plain = fused.clone()
+    assert getattr(plain, "_emote_colstats", None) is None
+    for rows_pb, nb in ((4 * H * W, 2), (H * W, n_img)):
+        a, _ = ops.group_norm([fused], 32, rows_pb, nb, gamma[:320], beta[:320], 1e-6, True)
+        b, _ = ops.group_norm([plain], 32, rows_pb, nb, gamma[:320], beta[:320], 1e-6, True)
+        assert rel_l2(a, b) < 1e-3 and (a.float() - b.float()).abs().max() < 0.07
+        a, _ = ops.group_norm([fused, skip], 32, rows_pb, nb, gamma, beta, 1e-6, True)
+        b, _ = ops.group_norm([plain, skip], 32, rows_pb, nb, gamma, beta, 1e-6, True)
+        assert rel_l2(a, b) < 1e-3
+        a, _ = ops.group_norm([skip, fused], 32, rows_pb, nb, gamma, beta, 1e-6, False)
+        b, _ = ops.group_norm([skip, plain], 32, rows_pb, nb, gamma, beta, 1e-6, False)
+        assert rel_l2(a, b) < 1e-3
+
+
 @pytest.mark.parametrize("C", [64, 320, 1280])
 def test_layer_norm(ops, C):
     g = _gen(9)

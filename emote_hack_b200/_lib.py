@@ -89,6 +89,7 @@ INTROSPECTION = {
     "emote_last_error": (C.c_char_p, []),
     "emote_launch_count": (C.c_longlong, []),
     "emote_abi_version": (C.c_int, []),
+    "emote_set_pdl": (None, [C.c_int]),
 }
 
 _lib = None

@@ -80,6 +80,7 @@ __device__ __forceinline__ void fa_load_tile(__nv_bfloat16* s, const __nv_bfloat
 // ldmatrix feeds two independent MMAs (half the shared-memory traffic per FLOP, twice the MMA-level parallelism).
 template <int DP, int MT>
 __global__ void __launch_bounds__(FA_THREADS, (DP <= 96) ? 2 : 1) flash_attn_kernel(const AttnDev p) {
+  pdl_prologue();
   constexpr int PITCH = DP + 8;
   constexpr int KS = DP / 16;  // k-steps over the head dim
   constexpr int NT = DP / 8;   // output n-tiles
@@ -311,6 +312,7 @@ __global__ void __launch_bounds__(FA_THREADS, (DP <= 96) ? 2 : 1) flash_attn_ker
 // NK16 = number of 16-key groups covering the key set (keys beyond n0 are zero-filled and masked).
 template <int DP, int NK16>
 __global__ void __launch_bounds__(FA_THREADS) short_kv_attn_kernel(const AttnDev p, int q_tiles_per_cta) {
+  pdl_prologue();
   constexpr int PITCH = DP + 8;
   constexpr int KS = DP / 16;
   constexpr int NT = DP / 8;
@@ -456,6 +458,7 @@ template <int DP, int FP>
 __global__ void __launch_bounds__(TA_WARPS * 32) temporal_attn_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                         __nv_bfloat16* __restrict__ out, int F, int HW,
                                                                         int heads, int d, float scale_log2) {
+  pdl_prologue();
   constexpr int PITCH = DP + 8;
   constexpr int KS = DP / 16;
   constexpr int NT = DP / 8;
@@ -602,7 +605,7 @@ static int launch_flash(const AttnDev& p, int batch, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid((p.nq + BQ - 1) / BQ, p.heads, batch);
-  flash_attn_kernel<DP, MT><<<grid, FA_THREADS, SMEM, stream>>>(p);
+  launch_kernel(flash_attn_kernel<DP, MT>, dim3(grid), dim3(FA_THREADS), SMEM, stream, p);
   EMOTE_CHECK_LAUNCH("emote_attention_bf16");
   return 0;
 }
@@ -623,7 +626,7 @@ static int launch_short_kv(const AttnDev& p, int batch, cudaStream_t stream) {
   if (per_cta < 1) per_cta = 1;
   if (per_cta > n_qtiles) per_cta = n_qtiles;
   dim3 grid((n_qtiles + per_cta - 1) / per_cta, p.heads, batch);
-  short_kv_attn_kernel<DP, NK16><<<grid, FA_THREADS, SMEM, stream>>>(p, per_cta);
+  launch_kernel(short_kv_attn_kernel<DP, NK16>, dim3(grid), dim3(FA_THREADS), SMEM, stream, p, per_cta);
   EMOTE_CHECK_LAUNCH("emote_attention_bf16");
   return 0;
 }
@@ -650,7 +653,7 @@ static int launch_temporal(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, 
   }
   const int hgroups = (heads + TA_WARPS - 1) / TA_WARPS;
   const long long blocks = (long long)B * HW * hgroups;
-  temporal_attn_kernel<DP, FP><<<(unsigned)blocks, TA_WARPS * 32, SMEM, stream>>>(qkv, out, F, HW, heads, d, scale_log2);
+  launch_kernel(temporal_attn_kernel<DP, FP>, dim3((unsigned)blocks), dim3(TA_WARPS * 32), SMEM, stream, qkv, out, F, HW, heads, d, scale_log2);
   EMOTE_CHECK_LAUNCH("emote_temporal_attention_bf16");
   return 0;
 }

@@ -126,6 +126,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
                      const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
                      const AttnTcDev p) {
   using C = TcCfg<D>;
+  pdl_launch_dependents();
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -175,6 +176,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
     tmem_relinquish();
   }
   __syncthreads();
+  pdl_wait();  // smem / barriers / TMEM are ready; q, k, v of earlier kernels may be read from here on
   {
     // Q tile: rows q0..q0+127, chunks < D/8; atom = chunk/8; physical 16B slot = (chunk%8) ^ (row%8)
     const __nv_bfloat16* qg = p.q + (long long)b * p.q_bs + (long long)q0 * p.q_rs + h * p.d;
@@ -414,7 +416,7 @@ static int launch_tc(const AttnTcDev& p, int batch, cudaStream_t stream) {
     mv1 = mv0;
   }
   dim3 grid((p.nq + TC_BQ - 1) / TC_BQ, p.heads, batch);
-  flash_attn_tc_kernel<D><<<grid, TC_THREADS, C::SMEM, stream>>>(mk0, mv0, mk1, mv1, p);
+  launch_kernel(flash_attn_tc_kernel<D>, dim3(grid), dim3(TC_THREADS), C::SMEM, stream, mk0, mv0, mk1, mv1, p);
   EMOTE_CHECK_LAUNCH("emote_attention_tc_bf16");
   return 0;
 }

@@ -14,6 +14,17 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 // one lane of a fully converged warp (CUTLASS `elect_one_sync`): keeps the surrounding control flow warp-uniform, so
 // the single-thread tcgen05 / TMA instructions are not wrapped in per-thread election loops by the compiler
+// Programmatic dependent launch (launch attribute set in host_utils.h: launch_kernel).  Every kernel of the library
+// calls pdl_launch_dependents() first (the next kernel's CTAs may start their prologue as SM resources free up) and
+// pdl_wait() before its first access to global memory produced or consumed by earlier kernels (blocks until the
+// preceding grid has completed and its writes are visible).  Both are no-ops for launches without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));

@@ -16,6 +16,7 @@ static inline unsigned grid_for(long long n, int threads, long long cap = 148LL 
 __global__ void latent_im2col_kernel(const float* __restrict__ lat, int B, int Cl, int F, int H, int W, float pre_scale,
                                      const float* __restrict__ pw_w, const float* __restrict__ pw_b,
                                      __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   const long long total = (long long)B * F * H * W;
   const long long plane = (long long)H * W;
   for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < total;
@@ -74,6 +75,7 @@ __device__ __forceinline__ uint4 load8_as_bf16<__nv_bfloat16>(const __nv_bfloat1
 template <typename T>
 __global__ void im2col3x3_kernel(const T* __restrict__ x, int n_img, int H, int W, int C, int stride, int Ho, int Wo,
                                  __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   const int oct = C >> 3;
   const long long total = (long long)n_img * Ho * Wo * 9 * oct;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -95,6 +97,7 @@ __global__ void im2col3x3_kernel(const T* __restrict__ x, int n_img, int H, int 
 
 __global__ void upsample2x_kernel(const float* __restrict__ x, int n_img, int H, int W, int C,
                                   __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   const int oct = C >> 3;
   const int Ho = 2 * H, Wo = 2 * W;
   const long long total = (long long)n_img * Ho * Wo * oct;
@@ -112,6 +115,7 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, int n_img, int H,
 
 __global__ void cast_bf16_kernel(const float* __restrict__ x, long long rows, int C_src, int c_offset, int C_total,
                                  __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   const int oct = C_src >> 3;
   const long long total = rows * oct;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -123,6 +127,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, long long rows, in
 }
 
 __global__ void silu_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16(silu_f(x[i]));
 }
@@ -130,6 +135,7 @@ __global__ void silu_bf16_kernel(const float* __restrict__ x, long long n, __nv_
 // tok [B,F,HW,C] <-> x [B,C,F,HW]
 __global__ void tokens_to_ncfhw_kernel(const float* __restrict__ tok, int B, int C, int F, int HW,
                                        float* __restrict__ out) {
+  pdl_prologue();
   const long long total = (long long)B * C * F * HW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -142,6 +148,7 @@ __global__ void tokens_to_ncfhw_kernel(const float* __restrict__ tok, int B, int
 }
 __global__ void ncfhw_to_tokens_kernel(const float* __restrict__ x, int B, int C, int F, int HW,
                                        float* __restrict__ out) {
+  pdl_prologue();
   const long long total = (long long)B * C * F * HW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -155,6 +162,7 @@ __global__ void ncfhw_to_tokens_kernel(const float* __restrict__ x, int B, int C
 
 __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                                long long n) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = a[i] + b[i];
 }
@@ -162,6 +170,7 @@ __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restr
 // embeddings.py:28-68 (scale = 1, max_period = 10000): [sin | cos], optionally flipped to [cos | sin]
 __global__ void timestep_embedding_kernel(const float* __restrict__ ts, int B, int dim, int flip, float freq_shift,
                                           __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * dim) return;
@@ -181,6 +190,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ ts, int B, i
 __global__ void cfg_ddim_kernel(float* __restrict__ lat, const float* __restrict__ np, const float* __restrict__ counter,
                                 long long n, int n_frames, long long inner, float gs, float sa_t, float s1a_t,
                                 float sa_p, float s1a_p) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float cnt = counter ? counter[(i / inner) % n_frames] : 1.f;
     const float eu = np[i] / cnt;
@@ -195,6 +205,7 @@ __global__ void cfg_ddim_kernel(float* __restrict__ lat, const float* __restrict
 // tok [n, HW, ld>=3] -> [n, 3, HW]
 __global__ void vae_post_kernel(const float* __restrict__ tok, int n_img, int HW, int ld, float* __restrict__ of,
                                 uint8_t* __restrict__ ou) {
+  pdl_prologue();
   const long long total = (long long)n_img * 3 * HW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -219,8 +230,7 @@ extern "C" int emote_latent_im2col(const float* latent, int32_t B, int32_t Cl, i
   if (!latent || !out_bf16 || B <= 0 || F <= 0 || H <= 0 || W <= 0) return set_error("emote_latent_im2col: bad arguments");
   if (Cl <= 0 || Cl > 7) return set_error("emote_latent_im2col: latent channels must be in [1,7] (9*Cl <= 64)");
   const long long total = (long long)B * F * H * W;
-  latent_im2col_kernel<<<grid_for(total, 128), 128, 0, STREAM(stream)>>>(
-      latent, B, Cl, F, H, W, pre_scale, pw_weight, pw_bias, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  launch_kernel(latent_im2col_kernel, dim3(grid_for(total, 128)), dim3(128), 0, STREAM(stream), latent, B, Cl, F, H, W, pre_scale, pw_weight, pw_bias, reinterpret_cast<__nv_bfloat16*>(out_bf16));
   EMOTE_CHECK_LAUNCH("emote_latent_im2col");
   return 0;
 }
@@ -231,7 +241,7 @@ static int im2col_impl(const T* x, int n_img, int H, int W, int C, int stride, v
   if (stride != 1 && stride != 2) return set_error("emote_im2col3x3: stride must be 1 or 2");
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const long long total = (long long)n_img * Ho * Wo * 9 * (C / 8);
-  im2col3x3_kernel<T><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, n_img, H, W, C, stride, Ho, Wo,
+  launch_kernel(im2col3x3_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, STREAM(stream), x, n_img, H, W, C, stride, Ho, Wo,
                                                                        reinterpret_cast<__nv_bfloat16*>(out));
   EMOTE_CHECK_LAUNCH("emote_im2col3x3");
   return 0;
@@ -249,7 +259,7 @@ extern "C" int emote_upsample2x(const float* x, int32_t n_img, int32_t H, int32_
                                 void* stream) {
   if (!x || !out_bf16 || n_img <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0) return set_error("emote_upsample2x: bad arguments");
   const long long total = (long long)n_img * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, n_img, H, W, C,
+  launch_kernel(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM(stream), x, n_img, H, W, C,
                                                                      reinterpret_cast<__nv_bfloat16*>(out_bf16));
   EMOTE_CHECK_LAUNCH("emote_upsample2x");
   return 0;
@@ -260,15 +270,14 @@ extern "C" int emote_cast_bf16(const float* x, int64_t rows, int32_t C_src, int3
   if (!x || !out_bf16 || rows <= 0 || C_src <= 0 || C_src % 8 != 0 || c_offset % 8 != 0 || C_total % 8 != 0 ||
       c_offset + C_src > C_total)
     return set_error("emote_cast_bf16: bad arguments");
-  cast_bf16_kernel<<<grid_for(rows * (C_src / 8), 256), 256, 0, STREAM(stream)>>>(
-      x, rows, C_src, c_offset, C_total, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  launch_kernel(cast_bf16_kernel, dim3(grid_for(rows * (C_src / 8), 256)), dim3(256), 0, STREAM(stream), x, rows, C_src, c_offset, C_total, reinterpret_cast<__nv_bfloat16*>(out_bf16));
   EMOTE_CHECK_LAUNCH("emote_cast_bf16");
   return 0;
 }
 
 extern "C" int emote_silu_bf16(const float* x, int64_t n, void* out_bf16, void* stream) {
   if (!x || !out_bf16 || n <= 0) return set_error("emote_silu_bf16: bad arguments");
-  silu_bf16_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(x, n, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  launch_kernel(silu_bf16_kernel, dim3(grid_for(n, 256)), dim3(256), 0, STREAM(stream), x, n, reinterpret_cast<__nv_bfloat16*>(out_bf16));
   EMOTE_CHECK_LAUNCH("emote_silu_bf16");
   return 0;
 }
@@ -276,21 +285,21 @@ extern "C" int emote_silu_bf16(const float* x, int64_t n, void* out_bf16, void* 
 extern "C" int emote_tokens_to_ncfhw(const float* tok, int32_t B, int32_t C, int32_t F, int32_t HW, float* out,
                                      void* stream) {
   if (!tok || !out || B <= 0 || C <= 0 || F <= 0 || HW <= 0) return set_error("emote_tokens_to_ncfhw: bad arguments");
-  tokens_to_ncfhw_kernel<<<grid_for((long long)B * C * F * HW, 256), 256, 0, STREAM(stream)>>>(tok, B, C, F, HW, out);
+  launch_kernel(tokens_to_ncfhw_kernel, dim3(grid_for((long long)B * C * F * HW, 256)), dim3(256), 0, STREAM(stream), tok, B, C, F, HW, out);
   EMOTE_CHECK_LAUNCH("emote_tokens_to_ncfhw");
   return 0;
 }
 extern "C" int emote_ncfhw_to_tokens(const float* x, int32_t B, int32_t C, int32_t F, int32_t HW, float* out,
                                      void* stream) {
   if (!x || !out || B <= 0 || C <= 0 || F <= 0 || HW <= 0) return set_error("emote_ncfhw_to_tokens: bad arguments");
-  ncfhw_to_tokens_kernel<<<grid_for((long long)B * C * F * HW, 256), 256, 0, STREAM(stream)>>>(x, B, C, F, HW, out);
+  launch_kernel(ncfhw_to_tokens_kernel, dim3(grid_for((long long)B * C * F * HW, 256)), dim3(256), 0, STREAM(stream), x, B, C, F, HW, out);
   EMOTE_CHECK_LAUNCH("emote_ncfhw_to_tokens");
   return 0;
 }
 
 extern "C" int emote_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) {
   if (!a || !b || !out || n <= 0) return set_error("emote_add_f32: bad arguments");
-  add_f32_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(a, b, out, n);
+  launch_kernel(add_f32_kernel, dim3(grid_for(n, 256)), dim3(256), 0, STREAM(stream), a, b, out, n);
   EMOTE_CHECK_LAUNCH("emote_add_f32");
   return 0;
 }
@@ -299,7 +308,7 @@ extern "C" int emote_timestep_embedding(const float* timesteps, int32_t B, int32
                                         float freq_shift, void* out_bf16, void* stream) {
   if (!timesteps || !out_bf16 || B <= 0 || dim <= 1) return set_error("emote_timestep_embedding: bad arguments");
   const int n = B * dim;
-  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, STREAM(stream)>>>(timesteps, B, dim, flip_sin_to_cos, freq_shift,
+  launch_kernel(timestep_embedding_kernel, dim3((n + 127) / 128), dim3(128), 0, STREAM(stream), timesteps, B, dim, flip_sin_to_cos, freq_shift,
                                                                          reinterpret_cast<__nv_bfloat16*>(out_bf16));
   EMOTE_CHECK_LAUNCH("emote_timestep_embedding");
   return 0;
@@ -312,8 +321,7 @@ extern "C" int emote_cfg_ddim_step(float* latents, const float* noise_pred, cons
   if (counter && (n_frames <= 0 || inner <= 0)) return set_error("emote_cfg_ddim_step: bad counter geometry");
   if (!(alpha_t > 0.f && alpha_t <= 1.f && alpha_prev > 0.f && alpha_prev <= 1.f))
     return set_error("emote_cfg_ddim_step: alphas must lie in (0,1]");
-  cfg_ddim_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(
-      latents, noise_pred, counter, n, n_frames > 0 ? n_frames : 1, inner > 0 ? inner : 1, guidance_scale,
+  launch_kernel(cfg_ddim_kernel, dim3(grid_for(n, 256)), dim3(256), 0, STREAM(stream), latents, noise_pred, counter, n, n_frames > 0 ? n_frames : 1, inner > 0 ? inner : 1, guidance_scale,
       sqrtf(alpha_t), sqrtf(1.f - alpha_t), sqrtf(alpha_prev), sqrtf(1.f - alpha_prev));
   EMOTE_CHECK_LAUNCH("emote_cfg_ddim_step");
   return 0;
@@ -322,7 +330,7 @@ extern "C" int emote_cfg_ddim_step(float* latents, const float* noise_pred, cons
 extern "C" int emote_vae_postprocess(const float* tok, int32_t n_img, int32_t HW, int32_t ld, float* out_f32,
                                      uint8_t* out_u8, void* stream) {
   if (!tok || n_img <= 0 || HW <= 0 || ld < 3 || (!out_f32 && !out_u8)) return set_error("emote_vae_postprocess: bad arguments");
-  vae_post_kernel<<<grid_for((long long)n_img * 3 * HW, 256), 256, 0, STREAM(stream)>>>(tok, n_img, HW, ld, out_f32, out_u8);
+  launch_kernel(vae_post_kernel, dim3(grid_for((long long)n_img * 3 * HW, 256)), dim3(256), 0, STREAM(stream), tok, n_img, HW, ld, out_f32, out_u8);
   EMOTE_CHECK_LAUNCH("emote_vae_postprocess");
   return 0;
 }

@@ -99,6 +99,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                           const GemmDev p) {
   using S = Gemm2Smem<BN, OUT_MODE>;
   constexpr bool TMA_OUT = OUT_MODE != 0;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw2[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_out = smem + S::STAGES * S::STAGE_BYTES;
@@ -138,6 +139,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // set-up done; operands of earlier kernels may be read from here on
 
   const int num_tiles = p.tiles_m * p.tiles_n;   // tiles_m counts 256-row pair tiles
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
@@ -334,8 +336,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   }
   const int max_pairs = g2_num_sms / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  gemm2_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, OUT_MODE>
-      <<<2 * pairs, 64 + 32 * EPI_WARPS, S::TOTAL, stream>>>(tmA, tmB, tmC, tmR, p);
+  launch_kernel(gemm2_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, OUT_MODE>, dim3(2 * pairs), dim3(64 + 32 * EPI_WARPS), S::TOTAL, stream, tmA, tmB, tmC, tmR, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error_cuda("gemm2 launch", e);
   count_launch();

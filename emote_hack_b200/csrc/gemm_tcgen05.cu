@@ -43,6 +43,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                          const GemmDev p) {
   using S = GemmSmem<BN, OUT_MODE>;
   constexpr bool TMA_OUT = OUT_MODE != 0;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024 B alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -80,6 +81,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // barriers, TMEM and descriptors are set up; operands of earlier kernels may be read from here on
 
   const int num_tiles = p.tiles_m * p.tiles_n;
 
@@ -281,8 +283,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, OUT_MODE>
-      <<<grid, gemm_threads(EPI_WARPS), S::TOTAL, stream>>>(tmA, tmB, tmC, tmR, p);
+  launch_kernel(gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, OUT_MODE>, dim3(grid), dim3(gemm_threads(EPI_WARPS)), S::TOTAL, stream, tmA, tmB, tmC, tmR, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error_cuda("gemm launch", e);
   count_launch();

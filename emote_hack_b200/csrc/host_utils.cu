@@ -2,6 +2,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -12,6 +13,7 @@ namespace emote {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
+void set_pdl(int enabled);
 int set_error(const char* msg) {
   std::snprintf(g_err, sizeof(g_err), "%s", msg);
   return EMOTE_ERR_INVALID;
@@ -21,6 +23,18 @@ int set_error_cuda(const char* what, cudaError_t e) {
   return EMOTE_ERR_CUDA;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = std::getenv("EMOTE_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured 2-3 % SLOWER on the UNet step graph (B200, driver 580)
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+void set_pdl(int enabled) { g_pdl.store(enabled ? 1 : 0, std::memory_order_relaxed); }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -71,3 +85,4 @@ int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t
 extern "C" const char* emote_last_error(void) { return emote::g_err; }
 extern "C" long long emote_launch_count(void) { return emote::g_launches.load(std::memory_order_relaxed); }
 extern "C" int emote_abi_version(void) { return EMOTE_ABI_VERSION; }
+extern "C" void emote_set_pdl(int enabled) { emote::set_pdl(enabled); }

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 namespace emote {
 
 int set_error(const char* msg);
@@ -16,6 +18,26 @@ void count_launch(int n = 1);
 // strides (bytes) for dims 1..rank-1.
 int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, bool swizzle128 = true, int elem_bytes = 2);
+
+// All kernels are launched through here: cudaLaunchKernelEx, with programmatic stream serialization (PDL) when
+// enabled (EMOTE_PDL=1 or emote_set_pdl(1); off by default — it measured slower on the UNet step graph); the kernels
+// gate their global-memory accesses with griddepcontrol.wait, a no-op for ordinary launches.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 #define EMOTE_CHECK_LAUNCH(name)                                   \
   do {                                                             \

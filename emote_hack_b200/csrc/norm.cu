@@ -20,6 +20,7 @@ template <int PASSES>
 __global__ void __launch_bounds__(512) gn_stats_kernel(const float* __restrict__ x, int C_src, int c_offset, int cpg,
                                                        int groups, long long rows_per_batch, int rows_per_block,
                                                        double* __restrict__ sums) {
+  pdl_prologue();
   // fp64 accumulation end to end: E[x^2] - mean^2 cancels badly in fp32 when |mean| >> std, and the atomics'
   // ordering would otherwise leak ~1e-6 run-to-run noise into every normalised value.
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const float* __restrict__
 // (batch, group) sums the group's columns over the `fpb` consecutive statistics batches that form one GN batch.
 __global__ void gn_colstats_reduce_kernel(const double* __restrict__ colstats, int C_src, int c_offset, int cpg, int groups,
                                           int fpb, int n_batches, double* __restrict__ sums, int overwrite) {
+  pdl_prologue();
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= n_batches * groups) return;
   const int batch = wid / groups, g = wid - batch * groups;
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ beta, float eps, int act_silu,
                                                        __nv_bfloat16* __restrict__ out,
                                                        __nv_bfloat16* __restrict__ raw_out) {
+  pdl_prologue();
   extern __shared__ __align__(16) float gn_smem[];
   float* s_scale = gn_smem;
   float* s_shift = gn_smem + C_src;
@@ -208,6 +211,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, const float* __restrict__ pe, int pe_rows_per_frame,
                                                         int pe_frames, __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // rows are visited last-to-first: the producing GEMM wrote them in ascending order, so the tail is still in L2, and
   // the rows written here last (the head) are the first ones the consuming GEMM loads.
@@ -258,6 +262,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
 }
 
 __global__ void softmax_rows_kernel(const float* __restrict__ s, int N, float scale, __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   // one block per row
   const long long row = blockIdx.x;
   const float* sr = s + row * N;
@@ -331,10 +336,10 @@ extern "C" int emote_gn_stats(const float* x, int32_t C_src, int32_t c_offset, i
   dim3 grid((unsigned)chunks, (unsigned)n_batches), block(PX, TY);
   const int cpg = C_total / groups;
   switch (passes) {
-    case 1: gn_stats_kernel<1><<<grid, block, 0, stream>>>(x, C_src, c_offset, cpg, groups, rows_per_batch, rows_per_block, sums); break;
-    case 2: gn_stats_kernel<2><<<grid, block, 0, stream>>>(x, C_src, c_offset, cpg, groups, rows_per_batch, rows_per_block, sums); break;
-    case 3: gn_stats_kernel<3><<<grid, block, 0, stream>>>(x, C_src, c_offset, cpg, groups, rows_per_batch, rows_per_block, sums); break;
-    default: gn_stats_kernel<4><<<grid, block, 0, stream>>>(x, C_src, c_offset, cpg, groups, rows_per_batch, rows_per_block, sums); break;
+    case 1: launch_kernel(gn_stats_kernel<1>, dim3(grid), dim3(block), 0, stream, x, C_src, c_offset, cpg, groups, rows_per_batch, rows_per_block, sums); break;
+    case 2: launch_kernel(gn_stats_kernel<2>, dim3(grid), dim3(block), 0, stream, x, C_src, c_offset, cpg, groups, rows_per_batch, rows_per_block, sums); break;
+    case 3: launch_kernel(gn_stats_kernel<3>, dim3(grid), dim3(block), 0, stream, x, C_src, c_offset, cpg, groups, rows_per_batch, rows_per_block, sums); break;
+    default: launch_kernel(gn_stats_kernel<4>, dim3(grid), dim3(block), 0, stream, x, C_src, c_offset, cpg, groups, rows_per_batch, rows_per_block, sums); break;
   }
   EMOTE_CHECK_LAUNCH("emote_gn_stats");
   return 0;
@@ -349,7 +354,7 @@ extern "C" int emote_gn_colstats_reduce(const double* colstats, int32_t C_src, i
   if (gn_check(C_src, c_offset, C_total, groups, "emote_gn_colstats_reduce: unsupported channel/group configuration"))
     return EMOTE_ERR_INVALID;
   const int warps = n_batches * groups;
-  gn_colstats_reduce_kernel<<<(warps + 3) / 4, 128, 0, stream>>>(colstats, C_src, c_offset, C_total / groups, groups,
+  launch_kernel(gn_colstats_reduce_kernel, dim3((warps + 3) / 4), dim3(128), 0, stream, colstats, C_src, c_offset, C_total / groups, groups,
                                                                stat_batches_per_batch, n_batches, sums, zero_first);
   EMOTE_CHECK_LAUNCH("emote_gn_colstats_reduce");
   return 0;
@@ -376,7 +381,7 @@ extern "C" int emote_gn_apply(const float* x, int32_t C_src, int32_t c_offset, i
   const long long chunks = (rows_per_batch + rows_per_block - 1) / rows_per_block;
   dim3 grid((unsigned)chunks, (unsigned)n_batches), block(bx, by);
   const size_t smem = 2 * (size_t)C_src * sizeof(float);
-  gn_apply_kernel<<<grid, block, smem, stream>>>(x, C_src, c_offset, C_total, C_total / groups, groups, rows_per_batch,
+  launch_kernel(gn_apply_kernel, dim3(grid), dim3(block), smem, stream, x, C_src, c_offset, C_total, C_total / groups, groups, rows_per_batch,
                                                  rows_per_block, sums, gamma, beta, eps, act_silu,
                                                  reinterpret_cast<__nv_bfloat16*>(out_bf16),
                                                  reinterpret_cast<__nv_bfloat16*>(raw_out_bf16));
@@ -394,7 +399,7 @@ extern "C" int emote_layernorm(const float* x, int64_t M, int32_t C, const float
   const int warps = 4;
   const long long blocks = (M + warps - 1) / warps;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-#define EMOTE_LN(NVV) layernorm_kernel<NVV><<<(unsigned)blocks, warps * 32, 0, stream>>>( \
+#define EMOTE_LN(NVV) launch_kernel(layernorm_kernel<NVV>, dim3((unsigned)blocks), dim3(warps * 32), 0, stream, \
       x, M, C, gamma, beta, eps, pe, pe_rows_per_frame, pe_frames, o)
   switch (C / 64) {
     case 1: EMOTE_LN(1); break;
@@ -415,7 +420,7 @@ extern "C" int emote_softmax_rows_bf16(const float* scores, int64_t R, int32_t N
                                        void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!scores || !out_bf16 || R <= 0 || N <= 0) return set_error("emote_softmax_rows_bf16: bad arguments");
-  softmax_rows_kernel<<<(unsigned)R, 256, 0, stream>>>(scores, N, scale, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  launch_kernel(softmax_rows_kernel, dim3((unsigned)R), dim3(256), 0, stream, scores, N, scale, reinterpret_cast<__nv_bfloat16*>(out_bf16));
   EMOTE_CHECK_LAUNCH("emote_softmax_rows_bf16");
   return 0;
 }

@@ -141,6 +141,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, row_bias=None, rows_per
 FUSED_GN_STATS = True   # GEMM epilogues that feed a GroupNorm also produce its statistics
 
 
+def set_pdl(enabled: bool) -> None:
+    """Programmatic dependent launch of the library's kernels (default off; also EMOTE_PDL=1)."""
+    _lib.load().emote_set_pdl(1 if enabled else 0)
+
+
 def stats_rows_for(rows_per_frame: int, rows_per_sample: int) -> int:
     """Finest statistics granularity a 128-row GEMM tile never straddles: per frame, else per sample, else none (0)."""
     if rows_per_frame % 128 == 0:

@@ -32,6 +32,9 @@ extern "C" {
 const char* emote_last_error(void);
 long long emote_launch_count(void); /* kernels launched by this library so far (bench.py "gpu_launches") */
 int emote_abi_version(void);
+/* Programmatic dependent launch of the library's kernels (default off; EMOTE_PDL=1 in the environment enables it):
+ * each kernel's set-up may overlap the tail of the previous one; results are unaffected. */
+void emote_set_pdl(int enabled);
 
 /* ------------------------------------------------------------------------------------------------ GEMM / conv
  * out[M,N] = epilogue(A[M,K] x Wt[N,K]^T), bf16 operands, fp32 accumulation on tcgen05 tensor cores.

@@ -457,7 +457,10 @@ class BasicTransformerBlock(nn.Module):
         self._ref_mode: Optional[str] = None
         self._ref_cfg = False
 
-    def forward(self, hidden_states, encoder_hidden_states=None, timestep=None, attention_mask=None, video_length=None):
+    def forward(self, hidden_states, encoder_hidden_states=None, timestep=None, attention_mask=None, video_length=None,
+                _emit_bf16: bool = False):
+        """`_emit_bf16` (internal, used by Transformer3DModel for its last block): the feed-forward epilogue writes the
+        block output directly as the bf16 operand of proj_out instead of fp32 (no separate cast pass)."""
         if attention_mask is not None:
             raise NotImplementedError("BasicTransformerBlock: attention_mask is not supported by the CUDA path")
         if not hidden_states.is_cuda:
@@ -484,6 +487,8 @@ class BasicTransformerBlock(nn.Module):
             x = self.attn2.out_proj(o, x, out=x)
         ln = self.norm3
         a = ops.layer_norm(x, ln.weight, ln.bias, ln.eps)
+        if _emit_bf16:
+            return self.ff.run(a, x, out_dtype=BF16).view(bf, n, c)
         x = self.ff.run(a, x, out=x)
         return x.view(bf, n, c)
 
@@ -533,11 +538,14 @@ class Transformer3DModel(nn.Module):
         p, g = self._packed(), self.norm
         a, _ = ops.group_norm([tok], g.num_groups, h * w, b * f, g.weight, g.bias, g.eps, False)  # per frame
         x = ops.gemm(a, p["wi"], bias=p["bi"]).view(b * f, h * w, -1)
-        for block in self.transformer_blocks:
+        nblk = len(self.transformer_blocks)
+        for i, block in enumerate(self.transformer_blocks):
             # context is NOT repeated per frame (attention.py:118-119): the attention kernel indexes it by b = img // f
-            x = block(x, encoder_hidden_states=encoder_hidden_states, timestep=timestep, video_length=f)
+            x = block(x, encoder_hidden_states=encoder_hidden_states, timestep=timestep, video_length=f,
+                      _emit_bf16=(i == nblk - 1))  # last FF epilogue emits the proj_out operand
         inner = x.shape[-1]
-        out = ops.gemm(ops.cast_bf16(x.reshape(-1, inner)), p["wo"], bias=p["bo"], residual=tok,
+        xa = x.reshape(-1, inner)
+        out = ops.gemm(xa if xa.dtype == BF16 else ops.cast_bf16(xa), p["wo"], bias=p["bo"], residual=tok,
                        stats_rows=ops.stats_rows_for(h * w, f * h * w))
         out = _untokens(out, b, c, f, h, w)
         return Transformer3DModelOutput(sample=out) if return_dict else (out,)

@@ -28,9 +28,11 @@ struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = ((BN <= 128) ? 6 : (BN <= 160 ? 5 : 4)) - (OUT_MODE == 2 ? 1 : 0);
+  static constexpr int STAGES = OUT_MODE == 3 ? 3 : ((BN <= 128) ? 6 : (BN <= 160 ? 5 : 4)) - (OUT_MODE == 2 ? 1 : 0);
   // output tile staged for the TMA store: bf16 (mode 1) or fp32 residual-in / result-out boxes (mode 2)
-  static constexpr int OUT_BYTES = OUT_MODE == 1 ? BM * BN * 2 : (OUT_MODE == 2 ? BM * BN * 4 : 0);
+  // mode 3 = mode 2 with TWO staging buffers (residual of tile i+1 lands while tile i is finished and stored)
+  static constexpr int OUT_BUF = OUT_MODE == 1 ? BM * BN * 2 : (OUT_MODE >= 2 ? BM * BN * 4 : 0);
+  static constexpr int OUT_BYTES = OUT_BUF * (OUT_MODE == 3 ? 2 : 1);
   static constexpr int BAR_BYTES = 256;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024 /*align slack*/;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
@@ -43,6 +45,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                          const GemmDev p) {
   using S = GemmSmem<BN, OUT_MODE>;
   constexpr bool TMA_OUT = OUT_MODE != 0;
+  constexpr int EMODE = OUT_MODE == 3 ? 2 : OUT_MODE;   // epilogue flavour
+  constexpr int NBUF = OUT_MODE == 3 ? 2 : 1;           // staging buffers
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024 B alignment.
@@ -54,7 +58,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* tmem_full = empty_bar + S::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint64_t* res_full = reinterpret_cast<uint64_t*>(bar_base + 192);  // mode 2: residual boxes landed in the staging buffer
+  uint64_t* res_full = reinterpret_cast<uint64_t*>(bar_base + 192);  // [2] modes 2/3: residual boxes landed in staging buffer i
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -70,7 +74,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], EPI_WARPS);  // one arrive per epilogue warp
     }
-    mbar_init(res_full, 1);
+    mbar_init(&res_full[0], 1);
+    mbar_init(&res_full[1], 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -185,39 +190,48 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     int as = 0;
     uint32_t aphase = 0;
     bool first_tile = true;
-    // mode 2 with a residual: thread 64 TMA-loads the fp32 residual tile of the NEXT tile into the staging boxes as soon
-    // as the bulk store of the current tile has read them; the epilogue warps wait on res_full before touching them.
-    const bool res_tma = OUT_MODE == 2 && p.residual != nullptr;
-    uint32_t rphase = 0;
+    // modes 2/3 with a residual: thread 64 TMA-loads the fp32 residual tile of an upcoming tile into the staging boxes
+    // as soon as the bulk store that last used them has been read; the epilogue warps wait on res_full[buf] before
+    // touching them.  Mode 2 has one buffer (load of tile i+1 after the store of tile i); mode 3 has two (the load of
+    // tile i+2 follows the store of tile i, so the residual of tile i+1 is already resident when its epilogue starts).
+    const bool res_tma = EMODE == 2 && p.residual != nullptr;
+    uint32_t rphase[2] = {0, 0};
     constexpr int NBOX = BN / 32;
-    auto load_residual = [&](int tile) {
+    auto load_residual = [&](int tile, int buf) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
       int nb = 0;
       for (int b = 0; b < NBOX; ++b) nb += (tn * BN + b * 32 < p.N) ? 1 : 0;
-      mbar_expect_tx(res_full, static_cast<uint32_t>(nb) * (BM * 128));
-      for (int b = 0; b < nb; ++b) tma_load_2d(stage_out + b * (BM * 128), &tmR, res_full, tn * BN + b * 32, tm * BM);
+      mbar_expect_tx(&res_full[buf], static_cast<uint32_t>(nb) * (BM * 128));
+      for (int b = 0; b < nb; ++b)
+        tma_load_2d(stage_out + buf * S::OUT_BUF + b * (BM * 128), &tmR, &res_full[buf], tn * BN + b * 32, tm * BM);
     };
-    if (res_tma && threadIdx.x == 64 && static_cast<int>(blockIdx.x) < num_tiles) load_residual(blockIdx.x);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    if (res_tma && threadIdx.x == 64) {
+      for (int k = 0; k < NBUF; ++k)
+        if (static_cast<int>(blockIdx.x + k * gridDim.x) < num_tiles) load_residual(blockIdx.x + k * gridDim.x, k);
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
+      const int buf = (NBUF == 2) ? (it & 1) : 0;
+      uint8_t* stage_buf = stage_out + buf * S::OUT_BUF;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
       if constexpr (TMA_OUT) {
         if (res_tma) {
-          mbar_wait(res_full, rphase);
-          rphase ^= 1;
+          mbar_wait(&res_full[buf], rphase[buf]);
+          rphase[buf] ^= 1;
         } else if (!first_tile) {  // the previous tile's bulk store must have read the staging buffer before it is rewritten
           if (threadIdx.x == 64) bulk_wait_read0();
           named_bar_sync(2, EPI_WARPS * 32);
         }
         first_tile = false;
       }
-      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, OUT_MODE>(p, tbase, tm * BM, tn * BN, tn, quarter, part, lane, stage_out,
-                                                           [&]() {
-                                                             mbar_wait(&tmem_full[as], aphase);
-                                                             tc_fence_after();
-                                                           });
+      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, EMODE>(p, tbase, tm * BM, tn * BN, tn, quarter, part, lane, stage_buf,
+                                                        [&]() {
+                                                          mbar_wait(&tmem_full[as], aphase);
+                                                          tc_fence_after();
+                                                        });
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -226,16 +240,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         fence_proxy_async_smem();                 // staging writes -> visible to the TMA (async proxy)
         named_bar_sync(1, EPI_WARPS * 32);
         if (threadIdx.x == 64) {
-          if constexpr (OUT_MODE == 1) {
-            tma_store_2d(&tmC, stage_out, p.geglu ? tn * (BN / 2) : tn * BN, tm * BM);  // clips rows >= M / cols >= N
+          if constexpr (EMODE == 1) {
+            tma_store_2d(&tmC, stage_buf, p.geglu ? tn * (BN / 2) : tn * BN, tm * BM);  // clips rows >= M / cols >= N
           } else {
             for (int b = 0; b < NBOX; ++b)
-              if (tn * BN + b * 32 < p.N) tma_store_2d(&tmC, stage_out + b * (BM * 128), tn * BN + b * 32, tm * BM);
+              if (tn * BN + b * 32 < p.N) tma_store_2d(&tmC, stage_buf + b * (BM * 128), tn * BN + b * 32, tm * BM);
           }
           bulk_commit();
-          if (res_tma && tile + static_cast<int>(gridDim.x) < num_tiles) {
+          const int nxt = tile + NBUF * static_cast<int>(gridDim.x);
+          if (res_tma && nxt < num_tiles) {
             bulk_wait_read0();
-            load_residual(tile + gridDim.x);
+            load_residual(nxt, buf);
           }
         }
       }
@@ -293,7 +308,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 template <int BN>
 static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                          int out_mode, GemmDev& p, cudaStream_t stream) {
-  if (out_mode == 2) return launch_gemm<BN, 16, false, 2>(tmA, tmB, tmC, tmR, p, stream);
+  if constexpr (BN == 128) {
+    if (out_mode == 3) return launch_gemm<BN, 16, false, 3>(tmA, tmB, tmC, tmR, p, stream);
+  }
+  if (out_mode >= 2) return launch_gemm<BN, 16, false, 2>(tmA, tmB, tmC, tmR, p, stream);
   if (!p.geglu && (p.residual != nullptr || p.row_bias != nullptr))
     return launch_gemm<BN, 8, true, 0>(tmA, tmB, tmC, tmR, p, stream);
   if (out_mode == 1) return launch_gemm<BN, 16, false, 1>(tmA, tmB, tmC, tmR, p, stream);
@@ -314,7 +332,14 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   const bool geglu = a->epilogue == EMOTE_EPI_GEGLU;
   if (geglu && (a->N % 2 != 0 || a->out_dtype != EMOTE_DT_BF16 || a->residual || a->row_bias))
     return set_error("emote_gemm_bf16: GEGLU epilogue needs even N, bf16 output, no residual/row_bias");
-  const int bn = a->block_n ? a->block_n : ((a->N % 160 == 0) ? 160 : 128);
+  // Double-buffered residual staging (mode 3, 128-column tiles, single CTA): the HBM-bound 1x1 GEMMs with an fp32
+  // residual at the 320-channel level (K <= 320: 97 -> 79 us; slower than mode 2 from K = 640 on; tma_store == 4 forces it).
+  const bool mode2_ok = a->tma_store != 2 && a->out_dtype == EMOTE_DT_F32 && !geglu &&
+                        (!a->row_bias || (a->rows_per_group > 0 && a->rows_per_group % 128 == 0)) &&
+                        (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0;
+  const bool want3 = mode2_ok && !conv && a->residual && a->pair_mode != 1 && a->block_n != 160 && a->tma_store != 3 &&
+                     (a->K <= 320 || a->tma_store == 4);
+  const int bn = want3 ? 128 : (a->block_n ? a->block_n : ((a->N % 160 == 0) ? 160 : 128));
   if (bn != 128 && bn != 160) return set_error("emote_gemm_bf16: block_n must be 128 or 160");
   if (geglu && a->N % bn != 0) return set_error("emote_gemm_bf16: GEGLU needs N % block_n == 0");
   if ((a->out_dtype == EMOTE_DT_BF16 && a->ldc % 8 != 0) || (a->out_dtype == EMOTE_DT_F32 && a->ldc % 4 != 0))
@@ -374,7 +399,7 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   const long long pair_tiles = ((long long)(a->M + 255) / 256) * ((a->N + bn - 1) / bn);
   bool use_pair = (conv || a->K >= 1024) && a->M >= 256 && pair_tiles >= 64;
   if (a->pair_mode == 1) use_pair = true;
-  if (a->pair_mode == 2) use_pair = false;
+  if (a->pair_mode == 2 || want3) use_pair = false;
   {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t strides[1] = {(uint64_t)a->K * 2};
@@ -391,9 +416,8 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   if (a->tma_store != 2) {
     if (p.out_bf16 && !(p.residual || p.row_bias)) {
       out_mode = 1;
-    } else if (!p.out_bf16 && !geglu && a->K <= 4096 && (!p.row_bias || p.rows_per_group % 128 == 0) &&
-               (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) {
-      out_mode = 2;
+    } else if (mode2_ok && (a->K <= 4096 || want3)) {
+      out_mode = want3 ? 3 : 2;
     }
   }
   if (out_mode == 1) {
@@ -402,7 +426,7 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
     uint64_t strides[1] = {(uint64_t)a->ldc * 2};
     uint32_t box[2] = {(uint32_t)(geglu ? bn / 2 : bn), 128};
     if (int rc = make_tensor_map(&tmC, out, 2, dims, strides, box, /*swizzle128=*/false)) return rc;
-  } else if (out_mode == 2) {
+  } else if (out_mode >= 2) {
     uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M};
     uint64_t strides[1] = {(uint64_t)a->ldc * 4};
     uint32_t box[2] = {32, 128};

@@ -90,6 +90,12 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* desc, ui
 }
 
 // TMA store (shared::cta -> global through a tensor map), bulk async-group completion
+// pull a tensor-map box into L2 ahead of the TMA load that will need it
+__device__ __forceinline__ void tma_prefetch_2d(const void* desc, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(desc)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(desc)),

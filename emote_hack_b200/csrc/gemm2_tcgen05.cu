@@ -259,6 +259,12 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
       if constexpr (TMA_OUT) {
         if (res_tma) {
+          if (threadIdx.x == 64 && tile + num_pairs < num_tiles) {  // next tile's residual -> L2 (see gemm_tcgen05.cu)
+            const int nt = tile + num_pairs, ntm = nt / p.tiles_n, ntn = nt - ntm * p.tiles_n;
+            const int nrb = ntm * (2 * BM) + static_cast<int>(rank) * BM;
+            for (int b = 0; b < NBOX; ++b)
+              if (ntn * BN + b * 32 < p.N) tma_prefetch_2d(&tmR, ntn * BN + b * 32, nrb);
+          }
           mbar_wait(res_full, rphase);
           rphase ^= 1;
         } else if (!first_tile) {

@@ -219,6 +219,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
       if constexpr (TMA_OUT) {
         if (res_tma) {
+          if (NBUF == 1 && threadIdx.x == 64 && tile + static_cast<int>(gridDim.x) < num_tiles) {
+            // single staging buffer: the next tile's residual can only be loaded after this tile's store; have it
+            // waiting in L2 by then
+            const int nt = tile + gridDim.x, ntm = nt / p.tiles_n, ntn = nt - ntm * p.tiles_n;
+            for (int b = 0; b < NBOX; ++b)
+              if (ntn * BN + b * 32 < p.N) tma_prefetch_2d(&tmR, ntn * BN + b * 32, ntm * BM);
+          }
           mbar_wait(&res_full[buf], rphase[buf]);
           rphase[buf] ^= 1;
         } else if (!first_tile) {  // the previous tile's bulk store must have read the staging buffer before it is rewritten

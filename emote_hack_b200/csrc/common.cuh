@@ -185,7 +185,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 }
 
 // ---------------------------------------------------------------- numerics
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// silu(x) = x * sigmoid(x) = 0.5 x (1 + tanh(x / 2)): one MUFU op (tanh.approx, |rel err| < 2^-10.9, below bf16
+// resolution) instead of ex2 + a full-precision divide; the GroupNorm apply kernel was MUFU-limited with the latter.
+__device__ __forceinline__ float silu_f(float x) {
+  float t;
+  const float h = 0.5f * x;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 // exact-GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 output rounding):
 // one MUFU.EX2 + one MUFU.RCP + a 5-term Horner instead of the branchy libdevice erff in the GEGLU epilogue.

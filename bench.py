@@ -29,6 +29,8 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 METRIC = "denoised frames/sec at 512x512x16f, 50-step DDIM"
+WORKLOAD = ("512x512 ref, 16-frame window, 50 DDIM steps, CFG pair [2,4,16,64,64], SD-1.5-width UNet3D (1276.7 M params, "
+            "motion modules on), text ctx [2,77,768], VAE decode to 16x3x512x512 (BASELINE.json configs[1]); one clip per GPU")
 UNIT = "frames/s"
 FRAMES, LAT, DDIM_STEPS, GUIDANCE = 16, 64, 50, 7.5
 # algorithmic FLOPs of one UNet call on [2,4,16,64,64] (FlopCounterMode on the reference)
@@ -176,8 +178,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * FRAMES / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "512x512 ref, 16-frame window, 50 DDIM steps, CFG pair, SD-1.5-width UNet3D + motion "
-                               "modules, VAE decode (BASELINE.json configs[1])"},
+        "config": {"workload": WORKLOAD},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "oracle port (fp32 restatement of the reference, validated against it): 1 UNet "
                                    f"frame-evaluation [1,4,1,64,64] ({sample['t_frame_eval_s']:.2f} s) + 1 VAE frame "
@@ -320,9 +321,7 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "512x512 ref, 16-frame window, 50 DDIM steps, CFG pair [2,4,16,64,64], SD-1.5-width "
-                                   "UNet3D (1276.7 M params, motion modules on), text ctx [2,77,768], VAE decode to "
-                                   "16x3x512x512 (BASELINE.json configs[1]); one clip per GPU",
+            "config": {"workload": WORKLOAD,
                        "precision": "bf16 tensor-core operands, fp32 accumulate / residual stream / statistics",
                        "l2": "per-step working set (2.6 GB packed weights + >5 GB activations) >> 126 MB L2; no flush needed",
                        "unet_tflop_per_call": UNET_TFLOP_PER_CALL},

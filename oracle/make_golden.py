@@ -23,6 +23,8 @@ from oracle import ref_shim  # noqa: E402
 from util_models import FULL_CFG, TINY_CFG, make_banks, make_inputs, seeded_unet_state_dict  # noqa: E402
 
 GOLD = ROOT / "tests" / "golden"
+# tag -> (block_out_channels, frames, latent size, weight seed); tests/test_oracle.py re-derives weights and inputs
+VAE_CASES = {"tiny": ((32, 32, 64, 64), 2, 8, 1), "mid": ((64, 128, 128, 128), 1, 16, 2)}
 
 
 def main():
@@ -81,6 +83,15 @@ def main():
     for nf, cs, stride, ov in [(16, 16, 1, 4), (32, 16, 1, 4), (240, 16, 1, 4), (24, 8, 1, 2), (48, 16, 2, 4), (20, 16, 1, 0)]:
         wins[f"{nf},{cs},{stride},{ov}"] = [list(map(int, w)) for w in uniform(0, 50, nf, cs, stride, ov)]
     (GOLD / "context_windows.json").write_text(json.dumps(wins))
+    # ---- VAE decoder: the reference's own leaf modules wired in the published SD-VAE decoder order
+    from oracle.vae_decoder import random_vae_decoder_state_dict
+    vae_out = {}
+    for tag, (widths, n, hw, seed) in VAE_CASES.items():
+        vsd = random_vae_decoder_state_dict(block_out_channels=widths, seed=seed)
+        dec = ref_shim.build_reference_vae_decoder(vsd, block_out_channels=widths)
+        z = torch.randn(n, 4, hw, hw, generator=torch.Generator().manual_seed(100 + seed))
+        vae_out[tag] = dec(z[:, :, None])[:, :, 0].contiguous()
+    torch.save(vae_out, GOLD / "vae_decoder_outputs.pt")
     print("golden written:", sorted(p.name for p in GOLD.iterdir()))
 
 

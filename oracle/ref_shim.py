@@ -186,3 +186,73 @@ def load_reference_context_uniform():
     from magicanimate.pipelines.context import uniform
 
     return uniform
+
+
+def build_reference_vae_decoder(state_dict, block_out_channels=(128, 256, 512, 512), layers_per_block: int = 2,
+                                groups: int = 32, eps: float = 1e-6):
+    """SD-VAE decoder wired out of the reference's OWN leaf modules (no arithmetic here, topology only).
+
+    `diffusers.AutoencoderKL` is absent, but every arithmetic leaf of its decoder has a twin inside /root/reference:
+    the 2-D resnet is `ResnetBlock3D` with one frame and no time embedding (resnet.py:114-207), the mid-block attention
+    is the legacy `AttentionBlock` (orig_attention.py:253-385), the upsampler is `Upsample3D` (resnet.py:42-84) and
+    the plain convs are `InflatedConv3d` (resnet.py:30-39).  Composing them in the published decoder order gives a
+    decoder whose every multiply-add is executed by untouched reference code; `oracle/vae_decoder.py` is pinned
+    against it (tests/golden/vae_decoder_outputs.pt).  What remains anchored only on the public definition is the
+    ORDER of the blocks.  Input / output: [n, 4, 1, h, w] -> [n, 3, 1, 8h, 8w].
+    """
+    install()
+    from magicanimate.models.orig_attention import AttentionBlock
+    from magicanimate.models.resnet import InflatedConv3d, ResnetBlock3D, Upsample3D
+
+    def res(cin, cout):
+        return ResnetBlock3D(in_channels=cin, out_channels=cout, temb_channels=None, groups=groups, eps=eps)
+
+    class _Attn5D(nn.Module):
+        """[n, c, 1, h, w] view around the reference's 4-D AttentionBlock (a reshape, no arithmetic)."""
+
+        def __init__(self, c):
+            super().__init__()
+            self.inner = AttentionBlock(c, None, groups, 1.0, eps)
+
+        def forward(self, x):
+            return self.inner(x[:, :, 0])[:, :, None]
+
+    top = block_out_channels[-1]
+    mods = OrderedDict()
+    mods["post_quant_conv"] = InflatedConv3d(4, 4, 1)
+    mods["decoder.conv_in"] = InflatedConv3d(4, top, 3, padding=1)
+    mods["decoder.mid_block.resnets.0"] = res(top, top)
+    mods["decoder.mid_block.attentions.0"] = _Attn5D(top)
+    mods["decoder.mid_block.resnets.1"] = res(top, top)
+    rev = list(reversed(block_out_channels))
+    cin = top
+    for bi, cout in enumerate(rev):
+        for li in range(layers_per_block + 1):
+            mods[f"decoder.up_blocks.{bi}.resnets.{li}"] = res(cin, cout)
+            cin = cout
+        if bi != len(rev) - 1:
+            mods[f"decoder.up_blocks.{bi}.upsamplers.0"] = Upsample3D(cout, use_conv=True)
+    mods["decoder.conv_norm_out"] = nn.GroupNorm(groups, rev[-1], eps=eps)
+    mods["decoder.conv_out"] = InflatedConv3d(rev[-1], 3, 3, padding=1)
+
+    for name, m in mods.items():
+        sd = {}
+        target = m.inner if isinstance(m, _Attn5D) else m
+        for k in target.state_dict():
+            sd[k] = state_dict[f"{name}.{k}"]
+        target.load_state_dict(sd, strict=True)
+        m.eval()
+
+    def decode(z5):
+        x = z5
+        with torch.no_grad():
+            for name, m in mods.items():
+                if isinstance(m, ResnetBlock3D):
+                    x = m(x, None)
+                elif name == "decoder.conv_norm_out":
+                    x = torch.nn.functional.silu(m(x))
+                else:
+                    x = m(x)
+        return x
+
+    return decode

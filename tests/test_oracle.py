@@ -120,6 +120,34 @@ def test_ddim_restatement():
         assert rel_l2(back, x) < 1e-5
 
 
+VAE_CASES = {"tiny": ((32, 32, 64, 64), 2, 8, 1), "mid": ((64, 128, 128, 128), 1, 16, 2)}  # = oracle/make_golden.py
+
+
+def test_vae_oracle_matches_reference_leaf_golden():
+    """oracle/vae_decoder.py against the decoder wired out of the reference's own ResnetBlock3D / AttentionBlock /
+    Upsample3D / InflatedConv3d (oracle/ref_shim.build_reference_vae_decoder), recorded in tests/golden/."""
+    from oracle.vae_decoder import VAEDecoderOracle, random_vae_decoder_state_dict
+    gold = torch.load(GOLD / "vae_decoder_outputs.pt")
+    for tag, (widths, n, hw, seed) in VAE_CASES.items():
+        sd = random_vae_decoder_state_dict(block_out_channels=widths, seed=seed)
+        z = torch.randn(n, 4, hw, hw, generator=torch.Generator().manual_seed(100 + seed))
+        got = VAEDecoderOracle(sd).decode(z)
+        assert got.shape == gold[tag].shape == (n, 3, 8 * hw, 8 * hw)
+        assert rel_l2(got, gold[tag]) < 1e-5
+
+
+def test_vae_oracle_against_live_reference_leaves():
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("/root/reference only exists in the build container")
+    from oracle.vae_decoder import VAEDecoderOracle, random_vae_decoder_state_dict
+    widths = (32, 64, 64, 96)
+    sd = random_vae_decoder_state_dict(block_out_channels=widths, seed=9)
+    z = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(9))
+    ref = ref_shim.build_reference_vae_decoder(sd, block_out_channels=widths)(z[:, :, None])[:, :, 0]
+    assert rel_l2(VAEDecoderOracle(sd).decode(z), ref) < 1e-5
+
+
 def test_vae_oracle_shapes():
     from oracle.vae_decoder import VAEDecoderOracle, random_vae_decoder_state_dict
     sd = random_vae_decoder_state_dict(block_out_channels=(32, 32, 64, 64), seed=1)

@@ -11,7 +11,8 @@ import subprocess
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "lib" / "libemote_b200.so"
+# EMOTE_B200_LIB: dev override (same-box A/B of two builds of the library); the default is the in-tree build
+LIB_PATH = Path(os.environ.get("EMOTE_B200_LIB") or (_HERE / "lib" / "libemote_b200.so"))
 CSRC = _HERE / "csrc"
 
 

@@ -287,7 +287,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         if (threadIdx.x == 64) {
           if (row_base < p.M) {   // the second CTA of the last pair may own no valid rows
             if constexpr (OUT_MODE == 1) {
-              tma_store_2d(&tmC, stage_out, p.geglu ? tn * (BN / 2) : tn * BN, row_base);
+              store_bf16_boxes<BN>(&tmC, stage_out, p, tn, row_base);
             } else {
               for (int b = 0; b < NBOX; ++b)
                 if (tn * BN + b * 32 < p.N) tma_store_2d(&tmC, stage_out + b * (BM * 128), tn * BN + b * 32, row_base);

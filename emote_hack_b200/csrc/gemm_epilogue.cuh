@@ -31,12 +31,21 @@ struct GemmDev {
 };
 
 
+// OUT_MODE 1: bulk-store the staged bf16 tile (issued by one thread; TMA clips rows >= M and columns >= N).
+template <int BN>
+__device__ __forceinline__ void store_bf16_boxes(const CUtensorMap* tmC, const uint8_t* stage, const GemmDev& p, int tn,
+                                                 int row_base) {
+  tma_store_2d(tmC, stage, p.geglu ? tn * (BN / 2) : tn * BN, row_base);
+}
+
 // One output tile of one CTA.  `tbase` = TMEM address of the accumulator stage for this warp's lane quarter,
 // `row_base` = first global row of the tile, (`n0`, `tn`) = first column / column-tile index.  The caller has NOT yet
 // waited for the accumulator: `wait_full()` is invoked after the residual prefetch has been issued.
 // OUT_MODE 0: results go straight to global memory (8-byte / 4-byte stores).
 // OUT_MODE 1: bf16 results are staged in shared memory (`stage`, dense [128][BN or BN/2] bf16) for one bulk tensor store
-//             per tile issued by the caller — full-line L2 writes instead of 16-byte partial-sector stores.
+//             per tile issued by the caller — full-line L2 writes instead of 16-byte partial-sector stores.  (Narrow
+//             swizzled boxes — 32 columns / 64B swizzle, 16 / 32B — remove the 4-way bank conflicts of the dense layout
+//             but measured slower: GEGLU K=320 241 -> 315 us; the bulk store prefers one wide box.)
 // OUT_MODE 2: fp32 results; `stage` holds BN/32 boxes of [128 rows][32 floats] in the TMA 128-byte swizzle.  When
 //             p.residual is set the caller has TMA-loaded the fp32 residual tile into the same boxes: the epilogue
 //             adds in place and the caller bulk-stores the boxes (the residual stream never touches the LSU path).
@@ -44,7 +53,6 @@ template <int BN, int EPI_WARPS, bool HAS_ADD, int OUT_MODE, class WaitFull>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tbase, int row_base, int n0, int tn,
                                                    int quarter, int part, int lane, void* stage_, WaitFull wait_full) {
   constexpr bool TMA_OUT = OUT_MODE == 1;
-  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(stage_);
   constexpr int NP = EPI_WARPS / 4;   // warps per lane quarter
   const int g = lane >> 2, t = lane & 3;
   const int row0 = row_base + quarter * 32 + g;  // this thread's rows: row0 + 8*i, i = 0..3
@@ -89,16 +97,11 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
         }
       }
     }
-    uint32_t acc[2][8];
-    auto issue = [&](int ci, uint32_t (&a)[8]) {
-      const uint32_t col_t = static_cast<uint32_t>((c_first + ci) * 8);
-      uint32_t lo[4], hi[4];
-      tmem_ld_16x256b_x1(tbase + col_t, lo);
-      tmem_ld_16x256b_x1(tbase + (16u << 16) + col_t, hi);
+    // ---- column bias (+ the tile's per-sample bias in mode 2) of this warp's span: loaded here, before the accumulator
+    // wait, so the global-load latency is off the per-chunk critical path (it used to be paid once per 8-column chunk)
+    float bia[NCH][2];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { a[k] = lo[k]; a[4 + k] = hi[k]; }
-    };
-    auto finish = [&](int ci, const uint32_t (&a)[8]) {
+    for (int ci = 0; ci < NCH; ++ci) {
       const int col = n0 + (c_first + ci) * 8 + 2 * t;
       const bool c0ok = col < p.N, c1ok = col + 1 < p.N;
       float b0 = 0.f, b1 = 0.f;
@@ -113,6 +116,22 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
           if (c1ok) b1 += __ldg(rb + 1);
         }
       }
+      bia[ci][0] = b0;
+      bia[ci][1] = b1;
+    }
+    uint32_t acc[2][8];
+    auto issue = [&](int ci, uint32_t (&a)[8]) {
+      const uint32_t col_t = static_cast<uint32_t>((c_first + ci) * 8);
+      uint32_t lo[4], hi[4];
+      tmem_ld_16x256b_x1(tbase + col_t, lo);
+      tmem_ld_16x256b_x1(tbase + (16u << 16) + col_t, hi);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a[k] = lo[k]; a[4 + k] = hi[k]; }
+    };
+    auto finish = [&](int ci, const uint32_t (&a)[8]) {
+      const int col = n0 + (c_first + ci) * 8 + 2 * t;
+      const bool c0ok = col < p.N, c1ok = col + 1 < p.N;
+      const float b0 = bia[ci][0], b1 = bia[ci][1];
       const bool stats = p.colstats != nullptr;   // fused GroupNorm statistics of the values being written
       float cs0 = 0.f, cq0 = 0.f, cs1 = 0.f, cq1 = 0.f;
 #pragma unroll
@@ -140,7 +159,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
           *reinterpret_cast<float2*>(sp) = make_float2(v0, v1);
         } else if constexpr (TMA_OUT) {
           const int lr = quarter * 32 + g + 8 * i, lc = (c_first + ci) * 8 + 2 * t;
-          *reinterpret_cast<uint32_t*>(stage + lr * BN + lc) = pack_bf16x2(v0, v1);
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(stage_) + lr * BN + lc) = pack_bf16x2(v0, v1);
         } else if (rok[i] && c0ok) {
           if (p.out_bf16) {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[i] + col;
@@ -190,8 +209,18 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
 #pragma unroll
     for (int i = 0; i < 4; ++i) ooff[i] = (size_t)(row0 + 8 * i) * p.ldc;
     uint32_t av[2][8], ag[2][8];
-    float bb[2][4];
-    auto issue = [&](int ci, uint32_t (&v)[8], uint32_t (&gt)[8], float (&b)[4]) {
+    float bb[NCH][4];   // value / gate biases of this warp's chunks, loaded before the accumulator wait
+#pragma unroll
+    for (int ci = 0; ci < NCH; ++ci) {
+      const int cc = part + ci * NP;
+      bb[ci][0] = bb[ci][1] = bb[ci][2] = bb[ci][3] = 0.f;
+      if (cc < NCT && p.bias) {
+        const int tc = cc * 8 + 2 * t;
+        bb[ci][0] = __ldg(p.bias + n0 + tc); bb[ci][1] = __ldg(p.bias + n0 + tc + 1);
+        bb[ci][2] = __ldg(p.bias + n0 + HALF + tc); bb[ci][3] = __ldg(p.bias + n0 + HALF + tc + 1);
+      }
+    }
+    auto issue = [&](int ci, uint32_t (&v)[8], uint32_t (&gt)[8]) {
       const int cc = part + ci * NP;
       if (cc < NCT) {
         const uint32_t col_t = static_cast<uint32_t>(cc * 8);
@@ -202,13 +231,6 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
         tmem_ld_16x256b_x1(tbase + (16u << 16) + HALF + col_t, ghi);
 #pragma unroll
         for (int k = 0; k < 4; ++k) { v[k] = lo[k]; v[4 + k] = hi[k]; gt[k] = glo[k]; gt[4 + k] = ghi[k]; }
-        const int tc = cc * 8 + 2 * t;
-        if (p.bias) {
-          b[0] = __ldg(p.bias + n0 + tc); b[1] = __ldg(p.bias + n0 + tc + 1);
-          b[2] = __ldg(p.bias + n0 + HALF + tc); b[3] = __ldg(p.bias + n0 + HALF + tc + 1);
-        } else {
-          b[0] = b[1] = b[2] = b[3] = 0.f;
-        }
       }
     };
     auto finish = [&](int ci, const uint32_t (&v)[8], const uint32_t (&gt)[8], const float (&b)[4]) {
@@ -221,22 +243,22 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
           const int ri = (i >> 1) * 4 + (i & 1) * 2;
           const float a0 = __uint_as_float(v[ri]) + b[0], a1 = __uint_as_float(v[ri + 1]) + b[1];
           const float q0 = __uint_as_float(gt[ri]) + b[2], q1 = __uint_as_float(gt[ri + 1]) + b[3];
-          const uint32_t packed = pack_bf16x2(a0 * gelu_erf_fast(q0), a1 * gelu_erf_fast(q1));
+          const uint32_t packed = pack_bf16x2(a0 * gelu_sig(q0), a1 * gelu_sig(q1));
           if constexpr (TMA_OUT) {
             const int lr = quarter * 32 + g + 8 * i, lc = cc * 8 + 2 * t;
-            *reinterpret_cast<uint32_t*>(stage + lr * HALF + lc) = packed;
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(stage_) + lr * HALF + lc) = packed;
           } else if (rok[i] && cok)
             *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[i] + ocol) = packed;
         }
       }
     };
     wait_full();
-    issue(0, av[0], ag[0], bb[0]);
+    issue(0, av[0], ag[0]);
 #pragma unroll
     for (int ci = 0; ci < NCH; ++ci) {
       tmem_ld_wait();
-      if (ci + 1 < NCH) issue(ci + 1, av[(ci + 1) & 1], ag[(ci + 1) & 1], bb[(ci + 1) & 1]);
-      finish(ci, av[ci & 1], ag[ci & 1], bb[ci & 1]);
+      if (ci + 1 < NCH) issue(ci + 1, av[(ci + 1) & 1], ag[(ci + 1) & 1]);
+      finish(ci, av[ci & 1], ag[ci & 1], bb[ci]);
     }
   }
 }

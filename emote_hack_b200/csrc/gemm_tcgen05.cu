@@ -248,7 +248,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         named_bar_sync(1, EPI_WARPS * 32);
         if (threadIdx.x == 64) {
           if constexpr (EMODE == 1) {
-            tma_store_2d(&tmC, stage_buf, p.geglu ? tn * (BN / 2) : tn * BN, tm * BM);  // clips rows >= M / cols >= N
+            store_bf16_boxes<BN>(&tmC, stage_buf, p, tn, tm * BM);
           } else {
             for (int b = 0; b < NBOX; ++b)
               if (tn * BN + b * 32 < p.N) tma_store_2d(&tmC, stage_buf + b * (BM * 128), tn * BN + b * 32, tm * BM);
@@ -282,7 +282,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 // --------------------------------------------------------------------------- host side
 int launch_gemm_pair(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                      int out_mode, GemmDev& p, cudaStream_t stream);  // gemm2_tcgen05.cu
+bool gemm_bres_applicable(int M, int N, int K, int bn, int num_sms);                                   // gemm_bres_tcgen05.cu
+int launch_gemm_bres(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmDev& p, int num_sms,
+                     cudaStream_t stream);
 static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
 
 template <int BN, int EPI_WARPS, bool HAS_ADD, int OUT_MODE>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
@@ -298,13 +310,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   p.tiles_m = (p.M + BM - 1) / BM;
   p.tiles_n = (p.N + BN - 1) / BN;
   const int tiles = p.tiles_m * p.tiles_n;
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
   launch_kernel(gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, OUT_MODE>, dim3(grid), dim3(gemm_threads(EPI_WARPS)), S::TOTAL, stream, tmA, tmB, tmC, tmR, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error_cuda("gemm launch", e);
@@ -432,7 +438,7 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
     uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)a->M};
     uint64_t strides[1] = {(uint64_t)a->ldc * 2};
     uint32_t box[2] = {(uint32_t)(geglu ? bn / 2 : bn), 128};
-    if (int rc = make_tensor_map(&tmC, out, 2, dims, strides, box, /*swizzle128=*/false)) return rc;
+    if (int rc = make_tensor_map(&tmC, out, 2, dims, strides, box, /*swizzle=*/0)) return rc;
   } else if (out_mode >= 2) {
     uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M};
     uint64_t strides[1] = {(uint64_t)a->ldc * 4};
@@ -445,6 +451,10 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
     }
   }
   if (use_pair) return launch_gemm_pair(bn, tmA, tmB, tmC, tmR, out_mode, p, stream);
+  // Weight-stationary kernel for the small-K, many-row bf16-output GEMMs (QKV / q / GEGLU at the 320-channel level),
+  // which are L2 -> SM delivery bound in the streaming kernel (pair_mode == 3 disables it).
+  if (!conv && out_mode == 1 && a->pair_mode != 3 && gemm_bres_applicable(a->M, a->N, a->K, bn, num_sms()))
+    return launch_gemm_bres(tmA, tmB, tmC, p, num_sms(), stream);
   if (bn == 160) return dispatch_gemm<160>(tmA, tmB, tmC, tmR, out_mode, p, stream);
   return dispatch_gemm<128>(tmA, tmB, tmC, tmR, out_mode, p, stream);
 }

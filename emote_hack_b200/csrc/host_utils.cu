@@ -50,7 +50,7 @@ static void resolve_encode() {
 }
 
 int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, bool swizzle128, int elem_bytes) {
+                    const uint32_t* box, int swizzle, int elem_bytes) {
   std::call_once(g_encode_once, resolve_encode);
   if (!g_encode) return set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error("TMA base pointer must be 16-byte aligned");
@@ -70,7 +70,8 @@ int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t
   }
   CUresult r = g_encode(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr,
                         gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        swizzle == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                        : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[128];

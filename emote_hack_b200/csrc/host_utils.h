@@ -14,10 +14,10 @@ int set_error(const char* msg);
 int set_error_cuda(const char* what, cudaError_t e);
 void count_launch(int n = 1);
 
-// rank-2..5 bf16 (elem_bytes 2) or fp32 (elem_bytes 4) tensor map, 128B swizzle by default, zero OOB fill. dims/box innermost-first;
-// strides (bytes) for dims 1..rank-1.
+// rank-2..5 bf16 (elem_bytes 2) or fp32 (elem_bytes 4) tensor map, zero OOB fill. dims/box innermost-first; strides (bytes)
+// for dims 1..rank-1.  swizzle: 0 = none, 32 / 64 / 128 = that TMA swizzle span in bytes (1 is accepted as 128).
 int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, bool swizzle128 = true, int elem_bytes = 2);
+                    const uint32_t* box, int swizzle = 128, int elem_bytes = 2);
 
 // All kernels are launched through here: cudaLaunchKernelEx, with programmatic stream serialization (PDL) when
 // enabled (EMOTE_PDL=1 or emote_set_pdl(1); off by default — it measured slower on the UNet step graph); the kernels

@@ -121,7 +121,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, row_bias=None, rows_per
     args.epilogue = EPI_GEGLU if geglu else EPI_LINEAR
     args.out_dtype = 1 if out_dtype == BF16 else 0
     args.ldc = out.shape[-1]
-    args.block_n = 0
+    args.block_n = FORCE_BLOCK_N
     args.pair_mode = pair_mode
     args.tma_store = tma_store
     colstats = None
@@ -138,6 +138,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, row_bias=None, rows_per
     return out
 
 
+FORCE_BLOCK_N = 0       # dev knob (scripts/bench_gemm.py): 0 = library default, else 128 / 160
 FUSED_GN_STATS = True   # GEMM epilogues that feed a GroupNorm also produce its statistics
 
 

@@ -60,7 +60,8 @@ typedef struct {
   int32_t out_dtype;      /* EMOTE_DT_* */
   int32_t ldc;            /* out row pitch in elements */
   int32_t block_n;        /* 0 = auto (160 if N % 160 == 0 else 128) */
-  int32_t pair_mode;      /* 0 = auto, 1 = force CTA pairs (cta_group::2, 256-row tiles), 2 = force single CTA */
+  int32_t pair_mode;      /* 0 = auto, 1 = force CTA pairs (cta_group::2, 256-row tiles), 2 = force single CTA,
+                             3 = auto without the weight-stationary kernel (small-K bf16-output shapes) */
   int32_t tma_store;      /* 0 = auto (staged TMA-store epilogues where they apply), 2 = never, 3 = never the
                              double-buffered residual variant, 4 = double-buffered residual variant for any K */
   double* colstats;       /* optional fused GroupNorm statistics of the fp32 output: [M / stats_rows][N][2] fp64

@@ -46,6 +46,27 @@ def test_gemm_plain(ops, M, N, K):
     assert rel_l2(out_b, ref) < 4e-3
 
 
+@pytest.mark.parametrize("M,N,K,geglu", [(12500, 960, 320, False), (37900, 320, 320, False), (12500, 960, 192, False),
+                                         (5000, 2560, 320, True), (4700, 2560, 64, True)])
+def test_gemm_weight_stationary(ops, M, N, K, geglu):
+    """Shapes routed to gemm_bres_tcgen05_kernel (K <= 320, bf16 staged-store epilogue, many row tiles per CTA),
+    ragged M included; pair_mode=3 runs the same problem through the streaming kernel: results must be identical."""
+    g = _gen(11)
+    a = torch.randn(M, K, device="cuda", generator=g).to(BF16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(BF16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    h = a.float() @ w.float().t() + bias
+    if geglu:
+        ref = h[:, : N // 2] * F.gelu(h[:, N // 2:])
+        wp, bp = ops.pack_geglu(w.float(), bias)
+    else:
+        ref, wp, bp = h, w, bias
+    out = ops.gemm(a, wp, bias=bp, geglu=geglu, out_dtype=BF16)
+    assert rel_l2(out, ref) < 4e-3
+    stream = ops.gemm(a, wp, bias=bp, geglu=geglu, out_dtype=BF16, pair_mode=3)
+    assert torch.equal(out, stream)
+
+
 def test_gemm_epilogue_residual_rowbias_scale(ops):
     g = _gen(2)
     M, N, K = 512, 320, 640

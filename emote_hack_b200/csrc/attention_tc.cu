@@ -17,6 +17,8 @@
 #include "emote_b200.h"
 #include "host_utils.h"
 
+#include <cstdlib>
+
 namespace emote {
 
 struct AttnTcDev {
@@ -62,6 +64,33 @@ __device__ __forceinline__ void ffma2_acc(float& d0, float& d1, float a0, float 
   asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(c0), "f"(c1));
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dd) : "l"(aa), "l"(bb), "l"(cc));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dd));
+}
+// {d.x, d.y} = {a.x, a.y} * {b.x, b.y} + {c, c}
+__device__ __forceinline__ void ffma2_vvb(float& d0, float& d1, float a0, float a1, float b0, float b1, float c) {
+  unsigned long long aa, bb, cc, dd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dd) : "l"(aa), "l"(bb), "l"(cc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dd));
+}
+// 2^x for a pair on the FMA / ALU pipes instead of MUFU.EX2 (the softmax loop is MUFU-bound at head_dim 40: 160 FLOP
+// per exponential).  Cody-Waite: n = round(x) through the 1.5 * 2^23 magic add, f = x - n in [-0.5, 0.5], 2^f by a
+// degree-3 minimax polynomial (max rel. error 7.5e-5, 26x below the bf16 rounding of P), exponent spliced in with one
+// shift-add.  x is clamped at -126 (masked keys arrive as -inf and leave as 2^-126 ~ 0).
+__device__ __forceinline__ void exp2_poly2(float& r0, float& r1, float x0, float x1) {
+  constexpr float MAGIC = 12582912.f;  // 1.5 * 2^23: low mantissa bits of (x + MAGIC) hold round(x)
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  float xf0, xf1, n0, n1, f0, f1, p0, p1;
+  ffma2_bcast(xf0, xf1, x0, x1, 1.0f, MAGIC);
+  ffma2_bcast(n0, n1, xf0, xf1, 1.0f, -MAGIC);
+  ffma2_acc(f0, f1, n0, n1, -1.0f, x0, x1);
+  ffma2_bcast(p0, p1, f0, f1, 0.055171505f, 0.24261077f);
+  ffma2_vvb(p0, p1, p0, p1, f0, f1, 0.69326097f);
+  ffma2_vvb(p0, p1, p0, p1, f0, f1, 0.99992812f);
+  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(xf0) << 23));
+  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(xf1) << 23));
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
@@ -120,7 +149,8 @@ struct TcCfg {
   static constexpr int SUM_COL0 = PV_COL0 + 2 * NPV;     // 2 x 16 columns: l = P x ones (every column holds the row sum)
 };
 
-template <int D>
+// EMU = pairs (of the 4 in every 8-key chunk) whose exponentials run on the FMA pipe (exp2_poly2) instead of MUFU.EX2
+template <int D, int EMU>
 __global__ void __launch_bounds__(TC_THREADS, (D <= 64) ? 2 : 1)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
                      const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
@@ -341,8 +371,12 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
           const float sb = __uint_as_float(idx < 32 ? s0[idx + 1] : s1[idx - 31]);
           float x0, x1;
           ffma2_bcast(x0, x1, sa, sb, sc, nmsc);
-          pv[k] = ex2f(x0);
-          pv[k + 1] = ex2f(x1);
+          if (k >= 8 - 2 * EMU) {   // compile-time after unrolling
+            exp2_poly2(pv[k], pv[k + 1], x0, x1);
+          } else {
+            pv[k] = ex2f(x0);
+            pv[k + 1] = ex2f(x1);
+          }
         }
         uint4 w;
         w.x = pack_bf16x2(pv[0], pv[1]); w.y = pack_bf16x2(pv[2], pv[3]);
@@ -393,12 +427,12 @@ static int make_kv_map(CUtensorMap* m, const void* base, int cols, int nkeys, lo
   return make_tensor_map(m, base, 3, dims, strides, box);
 }
 
-template <int D>
+template <int D, int EMU>
 static int launch_tc(const AttnTcDev& p, int batch, cudaStream_t stream) {
   using C = TcCfg<D>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(flash_attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(flash_attn_tc_kernel<D, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(flash_attn_tc)", e);
     configured = true;
   }
@@ -416,7 +450,7 @@ static int launch_tc(const AttnTcDev& p, int batch, cudaStream_t stream) {
     mv1 = mv0;
   }
   dim3 grid((p.nq + TC_BQ - 1) / TC_BQ, p.heads, batch);
-  launch_kernel(flash_attn_tc_kernel<D>, dim3(grid), dim3(TC_THREADS), C::SMEM, stream, mk0, mv0, mk1, mv1, p);
+  launch_kernel(flash_attn_tc_kernel<D, EMU>, dim3(grid), dim3(TC_THREADS), C::SMEM, stream, mk0, mv0, mk1, mv1, p);
   EMOTE_CHECK_LAUNCH("emote_attention_tc_bf16");
   return 0;
 }
@@ -451,6 +485,17 @@ extern "C" int emote_attention_tc_bf16(const EmoteAttnArgs* a, void* stream_) {
   p.kv1_div = a->kv1_batch_div > 0 ? a->kv1_batch_div : 1;
   p.kv1_first = a->kv1_first_batch;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  if (a->head_dim == 40) return launch_tc<40>(p, a->batch, stream);
-  return launch_tc<80>(p, a->batch, stream);
+  // share of the exponentials moved from MUFU.EX2 to the FMA pipe: 0, 1/4 or 1/2 (EMOTE_ATTN_EMU = 0 / 1 / 2, dev knob)
+  static const int emu = [] {
+    const char* e = std::getenv("EMOTE_ATTN_EMU");
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }();
+  if (a->head_dim == 40) {
+    if (emu == 0) return launch_tc<40, 0>(p, a->batch, stream);
+    if (emu == 2) return launch_tc<40, 2>(p, a->batch, stream);
+    return launch_tc<40, 1>(p, a->batch, stream);
+  }
+  if (emu == 0) return launch_tc<80, 0>(p, a->batch, stream);
+  if (emu == 2) return launch_tc<80, 2>(p, a->batch, stream);
+  return launch_tc<80, 1>(p, a->batch, stream);
 }

@@ -285,6 +285,8 @@ int launch_gemm_pair(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, con
 bool gemm_bres_applicable(int M, int N, int K, int bn, int num_sms);                                   // gemm_bres_tcgen05.cu
 int launch_gemm_bres(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmDev& p, int num_sms,
                      cudaStream_t stream);
+bool gemm_skinny_applicable(const EmoteGemmArgs* a);                                                    // gemm_skinny.cu
+int launch_gemm_skinny(const void* A, const void* Wt, void* out, const EmoteGemmArgs* a, cudaStream_t stream);
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -358,6 +360,8 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   if ((a->out_dtype == EMOTE_DT_BF16 && a->ldc % 8 != 0) || (a->out_dtype == EMOTE_DT_F32 && a->ldc % 4 != 0))
     return set_error("emote_gemm_bf16: ldc must keep rows 16-byte aligned");
   if (a->residual && a->ldr % 4 != 0) return set_error("emote_gemm_bf16: ldr must be a multiple of 4");
+  // M <= 8 (time-embedding products): weight-streaming GEMV instead of a 128-row tensor-core tile
+  if (gemm_skinny_applicable(a)) return launch_gemm_skinny(A, Wt, out, a, stream);
 
   GemmDev p{};
   p.M = a->M; p.N = a->N; p.K = a->K;

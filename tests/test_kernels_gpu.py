@@ -67,6 +67,22 @@ def test_gemm_weight_stationary(ops, M, N, K, geglu):
     assert torch.equal(out, stream)
 
 
+@pytest.mark.parametrize("M,N,K", [(2, 1280, 1280), (1, 320, 1280), (8, 1000, 320), (2, 1280, 320), (3, 64, 2560)])
+def test_gemm_skinny_rows(ops, M, N, K):
+    """M <= 8 goes to the weight-streaming GEMV kernel (time-embedding products); pair_mode=2 forces the tile kernel."""
+    g = _gen(12)
+    a = torch.randn(M, K, device="cuda", generator=g).to(BF16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(BF16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ w.float().t() + bias
+    out = ops.gemm(a, w, bias=bias)
+    assert rel_l2(out, ref) < 2e-5
+    assert rel_l2(ops.gemm(a, w, bias=bias, pair_mode=2), out) < 2e-5
+    if N % 8 == 0:
+        assert rel_l2(ops.gemm(a, w, bias=bias, out_dtype=BF16), ref) < 4e-3
+    assert rel_l2(ops.gemm(a, w), ref - bias) < 2e-5
+
+
 def test_gemm_epilogue_residual_rowbias_scale(ops):
     g = _gen(2)
     M, N, K = 512, 320, 640

@@ -472,6 +472,11 @@ class BasicTransformerBlock(nn.Module):
         bank_kv, bank_n, bank_first = None, 0, 0
         if self._ref_mode == "write":
             self.bank.append(a.view(bf, n, c).float())
+        if self.attn1 is None:
+            # writer tail (appearance_encoder.py:613-621): the block was cut down to its norm1, whose output feeds the bank
+            return hidden_states
+        if self._ref_mode == "write":
+            pass
         elif self._ref_mode == "read" and len(self.bank) > 0:
             bank = self.bank[0] if len(self.bank) == 1 else torch.cat(list(self.bank), dim=1)
             bank_kv, bank_n = self.attn1.project_kv(bank), bank.shape[1]
@@ -526,10 +531,12 @@ class Transformer3DModel(nn.Module):
         return super()._apply(fn, *a, **k)
 
     def _packed(self):
-        ver = (self.proj_in.weight._version, self.proj_out.weight._version)
+        tail = self.proj_out is None   # AppearanceEncoderModel's last transformer: GroupNorm -> proj_in -> norm1 only
+        ver = (self.proj_in.weight._version, None if tail else self.proj_out.weight._version)
         if self._pk is None or self._pk["ver"] != ver:
             self._pk = {"wi": ops.pack_linear(self.proj_in.weight), "bi": _f32c(self.proj_in.bias),
-                        "wo": ops.pack_linear(self.proj_out.weight), "bo": _f32c(self.proj_out.bias), "ver": ver}
+                        "wo": None if tail else ops.pack_linear(self.proj_out.weight),
+                        "bo": None if tail else _f32c(self.proj_out.bias), "ver": ver}
         return self._pk
 
     def forward(self, hidden_states, encoder_hidden_states=None, timestep=None, return_dict: bool = True):
@@ -538,6 +545,9 @@ class Transformer3DModel(nn.Module):
         p, g = self._packed(), self.norm
         a, _ = ops.group_norm([tok], g.num_groups, h * w, b * f, g.weight, g.bias, g.eps, False)  # per frame
         x = ops.gemm(a, p["wi"], bias=p["bi"]).view(b * f, h * w, -1)
+        if self.proj_out is None:
+            self.transformer_blocks[0](x, encoder_hidden_states=encoder_hidden_states, timestep=timestep, video_length=f)
+            return Transformer3DModelOutput(sample=hidden_states) if return_dict else (hidden_states,)
         nblk = len(self.transformer_blocks)
         for i, block in enumerate(self.transformer_blocks):
             # context is NOT repeated per frame (attention.py:118-119): the attention kernel indexes it by b = img // f

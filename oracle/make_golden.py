@@ -20,7 +20,8 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 from oracle import ref_shim  # noqa: E402
-from util_models import FULL_CFG, TINY_CFG, make_banks, make_inputs, seeded_unet_state_dict  # noqa: E402
+from util_models import (FULL_CFG, TINY_CFG, make_banks, make_inputs, reader_block_names, seeded_unet_state_dict,  # noqa: E402
+                         writer_cfg, writer_inputs)
 
 GOLD = ROOT / "tests" / "golden"
 # tag -> (block_out_channels, frames, latent size, weight seed); tests/test_oracle.py re-derives weights and inputs
@@ -83,6 +84,20 @@ def main():
     for nf, cs, stride, ov in [(16, 16, 1, 4), (32, 16, 1, 4), (240, 16, 1, 4), (24, 8, 1, 2), (48, 16, 2, 4), (20, 16, 1, 0)]:
         wins[f"{nf},{cs},{stride},{ov}"] = [list(map(int, w)) for w in uniform(0, 50, nf, cs, stride, ov)]
     (GOLD / "context_windows.json").write_text(json.dumps(wins))
+    # ---- ReferenceNet writer: the reference's own ReferenceAttentionControl(mode="write") on the reference UNet3D with one
+    # frame and no motion modules (= the 2-D SD UNet the AppearanceEncoderModel is, unet_controlnet.py:485-525)
+    wcfg = writer_cfg()
+    mw = U(**wcfg).eval()
+    wshapes = {k: list(v.shape) for k, v in mw.state_dict().items()}
+    (GOLD / "writer_tiny_keys.json").write_text(json.dumps(wshapes, indent=0, sort_keys=True))
+    mw.load_state_dict(seeded_unet_state_dict(wshapes, seed=3))
+    RC(mw, do_classifier_free_guidance=True, mode="write", fusion_blocks="midup", batch_size=1)
+    xw, ctxw = writer_inputs()
+    with torch.no_grad():
+        mw(xw[:, :, None], torch.tensor(441), ctxw)
+    wmods = dict(mw.named_modules())
+    torch.save({n: wmods[n].bank[0].contiguous() for n in reader_block_names(mw)}, GOLD / "writer_tiny_banks.pt")
+
     # ---- VAE decoder: the reference's own leaf modules wired in the published SD-VAE decoder order
     from oracle.vae_decoder import random_vae_decoder_state_dict
     vae_out = {}

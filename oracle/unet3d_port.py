@@ -58,6 +58,7 @@ class UNet3DOracle:
         self.mid_scale = c.get("mid_block_scale_factor", 1)
         self.center = c.get("center_input_sample", False)
         self.n_down = n_blocks
+        self._collect = None
 
     # ------------------------------------------------------------------ primitives
     def _has(self, key: str) -> bool:
@@ -106,6 +107,11 @@ class UNet3DOracle:
     def _basic_block(self, p: str, x: Tensor, ctx: Tensor, heads: int, bank: Optional[Sequence[Tensor]], frames: int,
                      cfg: bool) -> Tensor:
         n1 = self._ln(p + ".norm1", x)
+        if self._collect is not None:
+            # writer hook (mutual_self_attention.py:226-232): the block's LayerNorm1 output is appended to its bank
+            self._collect.setdefault(p, []).append(n1.clone())
+        if not self._has(p + ".attn1.to_q.weight"):
+            return x  # AppearanceEncoderModel's last block keeps only norm1 (appearance_encoder.py:613-621)
         if bank:
             # reader hook (mutual_self_attention.py:237-258): keys/values = [self | bank]; the unconditional first
             # half of the CFG batch is recomputed without the bank
@@ -139,6 +145,8 @@ class UNet3DOracle:
             bp = f"{p}.transformer_blocks.{i}"
             t = self._basic_block(bp, t, ctx, heads, (banks or {}).get(bp), f, cfg)
             i += 1
+        if not self._has(p + ".proj_out.weight"):
+            return x  # trimmed writer tail: nothing downstream of the bank is computed
         wo = self.sd[p + ".proj_out.weight"]
         if wo.dim() == 4:
             t = F.conv2d(t.reshape(b * f, h, w, -1).permute(0, 3, 1, 2), wo, self.sd[p + ".proj_out.bias"])
@@ -182,7 +190,18 @@ class UNet3DOracle:
     @torch.no_grad()
     def forward(self, sample: Tensor, timestep, encoder_hidden_states: Tensor, banks: Optional[Dict[str, List[Tensor]]] = None,
                 do_classifier_free_guidance: bool = True, down_block_additional_residuals=None,
-                mid_block_additional_residual=None) -> Tensor:
+                mid_block_additional_residual=None, collect_banks: Optional[Dict[str, List[Tensor]]] = None) -> Tensor:
+        """`collect_banks` (a dict, filled in place): run as a ReferenceNet WRITER — every BasicTransformerBlock appends
+        its LayerNorm1 output under its module name (the caller keeps the mid / up entries, fusion_blocks='midup')."""
+        self._collect = collect_banks
+        try:
+            return self._forward(sample, timestep, encoder_hidden_states, banks, do_classifier_free_guidance,
+                                 down_block_additional_residuals, mid_block_additional_residual)
+        finally:
+            self._collect = None
+
+    def _forward(self, sample, timestep, encoder_hidden_states, banks, do_classifier_free_guidance,
+                 down_block_additional_residuals, mid_block_additional_residual) -> Tensor:
         x = sample.to(self.dtype)
         ctx = encoder_hidden_states.to(self.dtype)
         if self.center:
@@ -234,6 +253,8 @@ class UNet3DOracle:
                 x = F.interpolate(x, scale_factor=(1.0, 2.0, 2.0), mode="nearest")  # resnet.py:74
                 x = self._conv5(f"{p}.upsamplers.0.conv", x)
 
+        if not self._has("conv_out.weight"):
+            return x  # AppearanceEncoderModel has no output head
         x = F.silu(self._gn("conv_norm_out", x, self.eps))
         return self._conv5("conv_out", x)
 

@@ -120,6 +120,41 @@ def test_ddim_restatement():
         assert rel_l2(back, x) < 1e-5
 
 
+def test_oracle_writer_banks_match_reference_golden():
+    """ReferenceNet writer: oracle run with collect_banks against banks recorded from the reference's own
+    ReferenceAttentionControl(mode="write") on its UNet3D (one frame, no motion modules)."""
+    from oracle.unet3d_port import UNet3DOracle
+    from util_models import APPEARANCE_TRIMMED, reader_block_names, writer_cfg, writer_inputs
+    shapes = json.loads((GOLD / "writer_tiny_keys.json").read_text())
+    gold_banks = torch.load(GOLD / "writer_tiny_banks.pt")
+    sd = seeded_unet_state_dict(shapes, 3)
+    x, ctx = writer_inputs()
+    for trimmed in (False, True):   # full 2-D UNet weights, and the AppearanceEncoderModel subset of them
+        use = {k: v for k, v in sd.items() if not (trimmed and k.startswith(APPEARANCE_TRIMMED))}
+        banks = {}
+        UNet3DOracle(use, writer_cfg())(x[:, :, None], 441, ctx, collect_banks=banks)
+        assert len(gold_banks) == 10
+        for name, want in gold_banks.items():
+            assert len(banks[name]) == 1 and rel_l2(banks[name][0], want) < 1e-5, name
+
+
+def test_appearance_encoder_state_dict_contract():
+    """AppearanceEncoderModel keys == the 2-D SD UNet keys (reference UNet3D without motion modules) minus the tail the
+    reference strips (appearance_encoder.py:613-621 and the missing conv_norm_out / conv_out)."""
+    from emote_hack_b200.appearance_encoder import AppearanceEncoderModel
+    from util_models import APPEARANCE_TRIMMED, appearance_cfg
+    shapes = json.loads((GOLD / "writer_tiny_keys.json").read_text())
+    want = {k: v for k, v in shapes.items() if not k.startswith(APPEARANCE_TRIMMED)}
+    with torch.device("meta"):
+        ours = AppearanceEncoderModel(**appearance_cfg())
+    got = {k: list(v.shape) for k, v in ours.state_dict().items()}
+    assert got == want and len(shapes) - len(want) == 24
+    with pytest.raises(NotImplementedError):
+        AppearanceEncoderModel(addition_embed_type="text", **appearance_cfg())
+    with pytest.raises(TypeError):
+        AppearanceEncoderModel(not_an_option=1, **appearance_cfg())
+
+
 VAE_CASES = {"tiny": ((32, 32, 64, 64), 2, 8, 1), "mid": ((64, 128, 128, 128), 1, 16, 2)}  # = oracle/make_golden.py
 
 

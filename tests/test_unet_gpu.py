@@ -135,6 +135,55 @@ def test_unet_tiny_reference_attention(tiny):
             blk._ref_mode = None
 
 
+def test_appearance_encoder_writer_banks_and_reader_update(tiny):
+    """ReferenceNet writer (AppearanceEncoderModel, appearance_encoder.py) on CUDA: banks against the oracle run as a
+    writer, then ReferenceAttentionControl.update() hands them to the UNet3D reader (EMOAnimationPipeline.py:711-788)."""
+    import json
+    from pathlib import Path
+    from emote_hack_b200.appearance_encoder import AppearanceEncoderModel
+    from emote_hack_b200.unet3d import ReferenceAttentionControl
+    from oracle.unet3d_port import UNet3DOracle
+    from util_models import (APPEARANCE_TRIMMED, appearance_cfg, reader_block_names, seeded_unet_state_dict, writer_cfg,
+                             writer_inputs)
+    shapes = json.loads((Path(__file__).parent / "golden" / "writer_tiny_keys.json").read_text())
+    sd = {k: v for k, v in seeded_unet_state_dict(shapes, 3).items() if not k.startswith(APPEARANCE_TRIMMED)}
+    enc = AppearanceEncoderModel(**appearance_cfg()).eval()
+    missing, unexpected = enc.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    enc = enc.cuda()
+    x, ctx = writer_inputs()
+    want = {}
+    UNet3DOracle(sd, writer_cfg())(x[:, :, None], 441, ctx, collect_banks=want)
+    writer = ReferenceAttentionControl(enc, do_classifier_free_guidance=True, mode="write", fusion_blocks="midup")
+    out = enc(x.cuda(), 441, ctx.cuda()).sample
+    assert out.shape == (2, 64, 16, 16) and torch.isfinite(out).all()
+    names = reader_block_names(enc)
+    mods = dict(enc.named_modules())
+    assert len(names) == 10
+    for n in names:
+        assert len(mods[n].bank) == 1
+        e = rel_l2(mods[n].bank[0], want[n][0])
+        assert e < 2e-2, (n, e)   # a LayerNorm1 output deep inside the bf16-operand network: whole-network budget (2e-2)
+    # hand the banks to the video UNet's reader blocks and compare with the oracle fed the oracle's banks
+    m, o, _ = tiny
+    reader = ReferenceAttentionControl(m, do_classifier_free_guidance=True, mode="read", fusion_blocks="midup")
+    try:
+        reader.update(writer)
+        writer.clear()
+        assert all(len(mods[n].bank) == 0 for n in names)
+        xs, cs = make_inputs(2, 4, 16)
+        out = m(xs.cuda(), 301, cs.cuda()).sample
+        ref = o(xs, 301, cs, banks={n: want[n] for n in names})
+        e = rel_l2(out, ref)
+        print(f"writer -> reader end to end: rel_l2={e:.2e}")
+        assert e < 2e-2
+    finally:
+        for blk in reader._blocks(m):
+            blk._ref_mode = None
+        for blk in writer._blocks(enc):
+            blk._ref_mode = None
+
+
 def test_unet_controlnet_residuals(tiny):
     m, o, _ = tiny
     x, ctx = make_inputs(2, 2, 8)

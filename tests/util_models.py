@@ -104,3 +104,28 @@ def sinusoid_pe(max_len, d_model):
 def seeded_unet_state_dict(shapes, seed=0):
     keep = {k: sinusoid_pe(s[1], s[2]) for k, s in shapes.items() if k.endswith(".pe")}
     return seeded_state_dict(shapes, seed, keep)
+
+
+def writer_cfg():
+    """tiny ReferenceNet writer = TINY_CFG without motion modules (a 2-D SD UNet run as a one-frame UNet3D)"""
+    cfg = dict(TINY_CFG)
+    cfg.update(use_motion_module=False, motion_module_type=None, motion_module_kwargs={})
+    return cfg
+
+
+def writer_inputs(hw=16, seed=5):
+    """reference-image latents [2, 4, hw, hw] (CFG pair) and text context for the writer fixtures"""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(2, 4, hw, hw, generator=g), torch.randn(2, 7, 64, generator=g)
+
+
+APPEARANCE_TRIMMED = ("conv_norm_out.", "conv_out.", "up_blocks.3.attentions.2.proj_out.",
+                      "up_blocks.3.attentions.2.transformer_blocks.0.attn1.", "up_blocks.3.attentions.2.transformer_blocks.0.attn2.",
+                      "up_blocks.3.attentions.2.transformer_blocks.0.norm2.", "up_blocks.3.attentions.2.transformer_blocks.0.norm3.",
+                      "up_blocks.3.attentions.2.transformer_blocks.0.ff.")
+
+
+def appearance_cfg():
+    """AppearanceEncoderModel kwargs matching writer_cfg()"""
+    return dict(sample_size=8, cross_attention_dim=64, block_out_channels=(64, 128, 128, 128), attention_head_dim=4,
+                norm_num_groups=32)

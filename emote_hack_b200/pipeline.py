@@ -5,9 +5,12 @@ What is mirrored (same names / argument meaning): `DDIMScheduler.{set_timesteps,
 scale_model_input, step(...).prev_sample}` (third-party diffusers class the reference instantiates at
 EMOAnimationPipeline.py:908 / magicanimate/pipelines/animation.py:104), `get_context_scheduler('uniform')`
 (magicanimate/pipelines/context.py:20-42), `EMOAnimationPipeline.{prepare_latents, decode_latents, __call__}`.
-What is deliberately NOT here (out of scope for the path): CLIP text encoding, wav2vec feature
-extraction, the AppearanceEncoder (ReferenceNet writer) and the pose ControlNet — their outputs enter as tensors
-(`text_embeddings` / per-frame audio tokens as `encoder_hidden_states`, `reference_banks`).
+The ReferenceNet writer (`AppearanceEncoderModel`) is optional: pass `appearance_encoder` +
+`ref_image_latents` and it runs once per timestep like the reference (:711-716), its banks feeding the reader blocks
+through persistent device buffers (no per-window clone / cast / cat); or pass pre-computed `reference_banks`.
+What is deliberately NOT here (out of scope for the path): CLIP text encoding, wav2vec feature extraction and the
+pose ControlNet — their outputs enter as tensors (`text_embeddings` / per-frame audio tokens as
+`encoder_hidden_states`, `down_block_additional_residuals`).
 
 Multi-GPU: the unit of independent work is (sample | context window) x CFG branch.  `__call__` shards
 the windows of one timestep across ranks (`global_context[rank::world_size]`, EMOAnimationPipeline.py:757) and — only
@@ -125,12 +128,14 @@ class GraphedUNet:
 
     replayed_kernels = 0  # kernels of libemote_b200 launched through graph replays (bench.py "gpu_launches")
 
-    def __init__(self, unet, lat_shape, ctx: torch.Tensor, banks: Optional[Dict[str, List[torch.Tensor]]], dev):
+    def __init__(self, unet, lat_shape, ctx: torch.Tensor, banks: Optional[Dict[str, List[torch.Tensor]]], dev,
+                 alias_banks: bool = False):
+        """alias_banks: read the given bank tensors in place (static outputs of a GraphedWriter) instead of private copies."""
         self.unet = unet
         self.lat = torch.zeros(lat_shape, dtype=torch.float32, device=dev)
         self.t = torch.zeros(1, dtype=torch.float32, device=dev)
         self.ctx = torch.empty_like(ctx, dtype=torch.float32).copy_(ctx)
-        self.banks = None if banks is None else {k: [t.clone() for t in v] for k, v in banks.items()}
+        self.banks = None if banks is None else {k: [t if alias_banks else t.clone() for t in v] for k, v in banks.items()}
         self.reader = None
         if self.banks is not None:
             self.reader = ReferenceAttentionControl(unet, do_classifier_free_guidance=True, mode="read", fusion_blocks="midup")
@@ -168,6 +173,57 @@ class GraphedUNet:
         self.graph.replay()
         GraphedUNet.replayed_kernels += self.kernels_per_replay
         return self.out
+
+
+def _writer_reader_pairs(unet, encoder):
+    """(reader block name, writer block) pairs in the reference's order: both sides sorted by descending norm1 width
+    (mutual_self_attention.py:585-588)."""
+    reader = ReferenceAttentionControl.__new__(ReferenceAttentionControl)
+    reader.fusion_blocks = "midup"
+    names = {id(m): n for n, m in unet.named_modules()}
+    return [(names[id(r)], w) for r, w in zip(reader._blocks(unet), reader._blocks(encoder))]
+
+
+class GraphedWriter:
+    """One ReferenceNet (AppearanceEncoderModel) pass captured in a CUDA graph: static reference latents / timestep /
+    context in, the ten LayerNorm1 banks out at fixed addresses (`reader_banks`: UNet3D reader block name -> [bank]) that
+    a GraphedUNet built with alias_banks=True reads in place — replaces the reference's per-window clone + cast + cat
+    (`ReferenceAttentionControl.update`, mutual_self_attention.py:577-617)."""
+
+    def __init__(self, encoder, unet, ref_latents: torch.Tensor, ctx: torch.Tensor, dev):
+        self.encoder = encoder
+        self.lat = ref_latents.float().contiguous().clone()
+        self.t = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.ctx = torch.empty_like(ctx, dtype=torch.float32).copy_(ctx)
+        self.control = ReferenceAttentionControl(encoder, do_classifier_free_guidance=True, mode="write", fusion_blocks="midup")
+        pairs = _writer_reader_pairs(unet, encoder)
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._run()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            from . import _lib
+            n0 = _lib.launch_count()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._run()
+                self.reader_banks = {name: [w.bank[0]] for name, w in pairs}
+            self.kernels_per_replay = _lib.launch_count() - n0
+        finally:
+            self.control.clear()
+            for blk in self.control._blocks(encoder):
+                blk._ref_mode = None
+
+    def _run(self):
+        self.control.clear()
+        self.encoder(self.lat, self.t, encoder_hidden_states=self.ctx, return_dict=False)
+
+    def __call__(self, t: int):
+        self.t.fill_(float(t))
+        self.graph.replay()
+        GraphedUNet.replayed_kernels += self.kernels_per_replay
+        return self.reader_banks
 
 
 # =============================================================================================== pipeline
@@ -231,9 +287,23 @@ class EMOAnimationPipeline:
     def denoise(self, latents: torch.Tensor, text_embeddings: torch.Tensor, num_inference_steps: int = 50,
                 guidance_scale: float = 7.5, context_frames: int = 16, context_stride: int = 1, context_overlap: int = 4,
                 context_schedule: str = "uniform", reference_banks: Optional[Dict[str, List[torch.Tensor]]] = None,
-                callback: Optional[Callable] = None, use_cuda_graph: bool = True) -> torch.Tensor:
+                callback: Optional[Callable] = None, use_cuda_graph: bool = True, appearance_encoder=None,
+                ref_image_latents: Optional[torch.Tensor] = None,
+                appearance_context: Optional[torch.Tensor] = None) -> torch.Tensor:
         """latents [1, 4, F_total, h, w] fp32 (updated in place and returned); text_embeddings = cat([uncond, cond])
-        of shape [2, n, d], or per-frame [2*F_total, n, d] audio tokens (uncond frames first)."""
+        of shape [2, n, d], or per-frame [2*F_total, n, d] audio tokens (uncond frames first).
+        appearance_encoder + ref_image_latents [1, 4, h, w]: run the ReferenceNet writer once per timestep on the
+        reference-image latents repeated over the CFG pair (EMOAnimationPipeline.py:711-716) and feed its banks to the
+        reader blocks; its context is `appearance_context` [2, n, d] (default: text_embeddings when that is a CFG pair)."""
+        writer_ctx = None
+        if appearance_encoder is not None:
+            if reference_banks is not None:
+                raise ValueError("pass either reference_banks or appearance_encoder, not both")
+            if ref_image_latents is None or ref_image_latents.dim() != 4 or ref_image_latents.shape[0] != 1:
+                raise ValueError("appearance_encoder needs ref_image_latents of shape [1, 4, h, w]")
+            writer_ctx = text_embeddings if appearance_context is None else appearance_context
+            if writer_ctx.shape[0] != 2:
+                raise ValueError("the ReferenceNet writer needs a [2, n, d] context (pass appearance_context)")
         do_cfg = guidance_scale > 1.0
         if not do_cfg:
             raise NotImplementedError("the fused sampler implements the classifier-free-guidance path the reference runs")
@@ -255,30 +325,52 @@ class EMOAnimationPipeline:
         reader = None
         single_window = len(windows) == 1 and windows[0] == list(range(f_total))
         noise_pred = torch.zeros((2,) + tuple(latents.shape[1:]), dtype=torch.float32, device=dev)
-        graphed = None
+        graphed, gwriter, writer, ref_lat2 = None, None, None, None
+        if appearance_encoder is not None:
+            ref_lat2 = ref_image_latents.to(dev).float().repeat(2, 1, 1, 1).contiguous()
+            if use_cuda_graph and not per_frame_ctx and len(my_windows) > 0:
+                wkey = ("writer", id(appearance_encoder), tuple(ref_lat2.shape), tuple(writer_ctx.shape))
+                gwriter = self._graphs.get(wkey)
+                if gwriter is None:
+                    gwriter = GraphedWriter(appearance_encoder, self.unet, ref_lat2, writer_ctx, dev)
+                    self._graphs[wkey] = gwriter
+                else:
+                    gwriter.lat.copy_(ref_lat2)
+                    gwriter.ctx.copy_(writer_ctx)
+                reference_banks = gwriter.reader_banks
+            else:
+                writer = ReferenceAttentionControl(appearance_encoder, do_classifier_free_guidance=True, mode="write",
+                                                   fusion_blocks="midup")
         if use_cuda_graph and not per_frame_ctx and len(my_windows) > 0:
             wlen = len(my_windows[0])
             key = (2, latents.shape[1], wlen, latents.shape[3], latents.shape[4], tuple(text_embeddings.shape),
-                   None if reference_banks is None else tuple(sorted((k, tuple(v[0].shape)) for k, v in reference_banks.items())))
+                   None if reference_banks is None else tuple(sorted((k, tuple(v[0].shape)) for k, v in reference_banks.items())),
+                   None if gwriter is None else id(gwriter))
             if all(len(w) == wlen for w in my_windows):
                 graphed = self._graphs.get(key)
                 if graphed is None:
                     graphed = GraphedUNet(self.unet, (2, latents.shape[1], wlen, latents.shape[3], latents.shape[4]),
-                                          text_embeddings, reference_banks, dev)
+                                          text_embeddings, reference_banks, dev, alias_banks=gwriter is not None)
                     self._graphs[key] = graphed
                 else:
                     graphed.ctx.copy_(text_embeddings)
                     if reference_banks is not None:
                         for k, v in reference_banks.items():
                             for dst, src in zip(graphed.banks[k], v):
-                                dst.copy_(src)
-        if graphed is None and reference_banks is not None:  # eager path: banks are re-armed before every UNet call
+                                if dst is not src:
+                                    dst.copy_(src)
+        if graphed is None and (reference_banks is not None or writer is not None):  # eager path: banks are re-armed before every UNet call
             reader = ReferenceAttentionControl(self.unet, do_classifier_free_guidance=True, mode="read",
                                                fusion_blocks="midup")
         try:
             for i, t in enumerate(self.scheduler.timesteps.tolist()):
                 if not single_window:
                     noise_pred.zero_()
+                if gwriter is not None:
+                    gwriter(t)                                   # banks of this timestep land in the UNet graph's inputs
+                elif writer is not None:
+                    writer.clear()
+                    appearance_encoder(ref_lat2, t, encoder_hidden_states=writer_ctx, return_dict=False)
                 for c in my_windows:
                     lat_in = latents if single_window else latents[:, :, c]
                     lat_in = lat_in.expand(2, -1, -1, -1, -1) if single_window else lat_in.repeat(2, 1, 1, 1, 1)
@@ -290,7 +382,9 @@ class EMOAnimationPipeline:
                     if graphed is not None:
                         pred = graphed(lat_in, t)
                     else:
-                        if reader is not None:
+                        if reader is not None and writer is not None:
+                            reader.update(writer)            # EMOAnimationPipeline.py:774
+                        elif reader is not None:
                             reader.set_banks(reference_banks)
                         pred = self.unet(lat_in.contiguous(), t, encoder_hidden_states=ctx, return_dict=False)[0]
                     if single_window:
@@ -309,6 +403,10 @@ class EMOAnimationPipeline:
                 reader.clear()
                 for blk in reader._blocks(self.unet):
                     blk._ref_mode = None
+            if writer is not None:
+                writer.clear()                                   # EMOAnimationPipeline.py:823
+                for blk in writer._blocks(appearance_encoder):
+                    blk._ref_mode = None
         return latents
 
     @torch.no_grad()
@@ -316,13 +414,16 @@ class EMOAnimationPipeline:
                  num_inference_steps: int = 50, guidance_scale: float = 7.5, generator=None, latents=None,
                  output_type: str = "tensor", return_dict: bool = True, context_frames: int = 16,
                  context_stride: int = 1, context_overlap: int = 4, context_schedule: str = "uniform",
-                 reference_banks=None, callback=None, **unused):
+                 reference_banks=None, callback=None, appearance_encoder=None, ref_image_latents=None,
+                 appearance_context=None, **unused):
         dev = text_embeddings.device
         lat = self.prepare_latents(1, self.unet.in_channels, video_length, height, width, torch.float32, dev, generator,
                                    latents, clip_length=min(context_frames, video_length))
         lat = lat[:, :, :video_length].contiguous()
         lat = self.denoise(lat, text_embeddings, num_inference_steps, guidance_scale, context_frames, context_stride,
-                           context_overlap, context_schedule, reference_banks, callback)
+                           context_overlap, context_schedule, reference_banks, callback,
+                           appearance_encoder=appearance_encoder, ref_image_latents=ref_image_latents,
+                           appearance_context=appearance_context)
         video = self.decode_latents(lat, self.rank)
         if output_type == "tensor":
             video = torch.from_numpy(video)

@@ -156,6 +156,58 @@ def test_denoise_sliding_windows_with_overlap_and_banks(tiny_pipe):
     assert e < 3e-2
 
 
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_denoise_with_appearance_encoder(tiny_pipe, use_graph):
+    """ReferenceNet writer inside the loop (EMOAnimationPipeline.py:711-716, 774, 788, 823): the writer runs once per
+    timestep on the reference-image latents, its banks condition every window of that step; checked against the same
+    loop on the oracle (writer banks from the oracle's writer mode).  Graph path = GraphedWriter + aliased banks."""
+    import json
+    from pathlib import Path
+    from emote_hack_b200.appearance_encoder import AppearanceEncoderModel
+    from emote_hack_b200.pipeline import uniform
+    from oracle.ddim import DDIMOracle, cfg_combine
+    from oracle.unet3d_port import UNet3DOracle
+    from util_models import (APPEARANCE_TRIMMED, appearance_cfg, reader_block_names, seeded_unet_state_dict, writer_cfg)
+    o, pipe = tiny_pipe
+    shapes = json.loads((Path(__file__).parent / "golden" / "writer_tiny_keys.json").read_text())
+    sd = {k: v for k, v in seeded_unet_state_dict(shapes, 3).items() if not k.startswith(APPEARANCE_TRIMMED)}
+    enc = AppearanceEncoderModel(**appearance_cfg()).eval()
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.cuda()
+    wo = UNet3DOracle(sd, writer_cfg())
+    g = torch.Generator().manual_seed(21)
+    lat = torch.randn(1, 4, 12, 8, 8, generator=g)
+    ctx = torch.randn(2, 7, 64, generator=g)
+    ref_lat = torch.randn(1, 4, 8, 8, generator=g)
+    wins = list(uniform(0, 2, 12, 8, 1, 2))
+    names = reader_block_names(pipe.unet)
+    # oracle loop
+    sch = DDIMOracle()
+    ref = lat.clone()
+    for t in sch.set_timesteps(2).tolist():
+        banks = {}
+        wo(ref_lat.repeat(2, 1, 1, 1)[:, :, None], t, ctx, collect_banks=banks)
+        banks = {n: banks[n] for n in names}
+        acc = torch.zeros(2, *ref.shape[1:])
+        cnt = torch.zeros(1, 1, 12, 1, 1)
+        for c in wins:
+            acc[:, :, c] += o(ref[:, :, c].repeat(2, 1, 1, 1, 1), t, ctx, banks=banks)
+            cnt[:, :, c] += 1
+        ref = sch.step(cfg_combine(acc, cnt, 7.5), t, ref)
+    out = pipe.denoise(lat.cuda(), ctx.cuda(), num_inference_steps=2, guidance_scale=7.5, context_frames=8,
+                       context_overlap=2, appearance_encoder=enc, ref_image_latents=ref_lat.cuda(),
+                       use_cuda_graph=use_graph)
+    e = rel_l2(out, ref)
+    print(f"denoise with ReferenceNet writer (graph={use_graph}) rel_l2={e:.2e}")
+    assert e < 3e-2
+    # banks matter (otherwise this test could not see a broken hand-over)
+    plain = pipe.denoise(lat.cuda(), ctx.cuda(), num_inference_steps=2, guidance_scale=7.5, context_frames=8,
+                         context_overlap=2, use_cuda_graph=use_graph)
+    assert rel_l2(plain, ref) > 2 * e
+    with pytest.raises(ValueError):
+        pipe.denoise(lat.cuda(), ctx.cuda(), num_inference_steps=1, appearance_encoder=enc)
+
+
 def test_denoise_per_frame_audio_context(tiny_pipe):
     o, pipe = tiny_pipe
     g = torch.Generator().manual_seed(13)

@@ -64,6 +64,16 @@ def host_cores() -> int:
     return n
 
 
+def gemm_dram_traffic_per_launch():
+    """DRAM bytes per launch of the dominant (GEMM / implicit-GEMM conv) kernels, from the committed ncu capture of one
+    eager UNet call (scripts/one_unet_call.py + scripts/summarize_traffic.py); None when the capture is absent."""
+    try:
+        d = json.loads((ROOT / "profiles" / "r01_unet_call_dram_traffic.json").read_text())
+        return round(float(d["all_gemm_kernels"]["dram_bytes_per_launch"]))
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -284,6 +294,36 @@ def run_ours(args):
     h2d = host_lat.numel() * 4 + host_ctx.numel() * 4
     d2h = host_out.numel()
 
+    # ---- secondary measurement (N=1, rank 0): the same clip with the ReferenceNet on — AppearanceEncoderModel writer once
+    # per timestep + reference attention in the 10 mid/up reader blocks; not part of `value`
+    variants = None
+    if rank == 0 and world == 1 and not args.no_variants:
+        from emote_hack_b200.appearance_encoder import AppearanceEncoderModel
+        torch.manual_seed(1)
+        with torch.device(dev):
+            enc = AppearanceEncoderModel(sample_size=64, cross_attention_dim=768).eval()
+        ref_lat = torch.randn(1, 4, LAT, LAT, generator=torch.Generator().manual_seed(7)).to(dev)
+
+        def ref_clip(lat):
+            lat = pipe.denoise(lat, ctx_dev, num_inference_steps=DDIM_STEPS, guidance_scale=GUIDANCE,
+                               context_frames=FRAMES, appearance_encoder=enc, ref_image_latents=ref_lat)
+            return vae.decode_video(lat, want_u8=True)[1]
+
+        ref_clip(lat_dev.clone())
+        torch.cuda.synchronize()
+        n_var = 2
+        e0.record()
+        for _ in range(n_var):
+            ref_clip(lat_dev.clone())
+        e1.record()
+        torch.cuda.synchronize()
+        variants = {"reference_net_on": {"value": round(FRAMES * n_var / (e0.elapsed_time(e1) / 1000.0), 4), "unit": UNIT,
+                                         "clips": n_var, "what": "config #2 + AppearanceEncoderModel (2-D SD UNet, 859.5 M "
+                                         "params) run once per DDIM step on the reference-image latents [2,4,64,64]; its 10 "
+                                         "LayerNorm1 banks extend the keys of the mid/up spatial self-attention (cond half)"}}
+        del enc
+        torch.cuda.empty_cache()
+
     # ---- roofline pass (untimed): every launch of one UNet call bracketed by CUDA events on the launching stream
     roof = None
     breakdown = None
@@ -296,7 +336,9 @@ def run_ours(args):
         n_gemm = sum(1 for n, _, _ in prof.times if n == "emote_gemm_bf16")
         roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": round(achieved, 1),
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": round(achieved / peaks["bf16_tflops"], 4),
-                "traffic": None, "peak_source": peaks["source"],
+                "traffic": gemm_dram_traffic_per_launch(), "traffic_unit": "bytes/launch (dram__bytes_read.sum + "
+                "dram__bytes_write.sum, mean over the GEMM launches of one UNet call; profiles/r01_unet_call_dram_traffic.json)",
+                "peak_source": peaks["source"],
                 "note": f"{tf:.2f} algorithmic TFLOP (2*M*N*K of the reference's conv/linear ops) in {n_gemm} launches "
                         f"of one UNet call, {prof.gemm_ms:.2f} ms total"}
         total = sum(ms_ for _, ms_, _ in prof.times)
@@ -331,6 +373,7 @@ def run_ours(args):
             "roofline": roof,
             "cpu_baseline": cpu,
             "kernel_breakdown_one_unet_call": breakdown,
+            "variants": variants,
             "model_tflops_per_s": round((DDIM_STEPS * UNET_TFLOP_PER_CALL + FRAMES * VAE_TFLOP_PER_FRAME) * args.steps
                                         / (ms_max / 1000.0), 1),
         }
@@ -365,6 +408,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the secondary ReferenceNet-on measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

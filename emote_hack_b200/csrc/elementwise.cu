@@ -74,7 +74,7 @@ __device__ __forceinline__ uint4 load8_as_bf16<__nv_bfloat16>(const __nv_bfloat1
 // x [n,H,W,C] -> out [n*Ho*Wo, 9*C] bf16 (3x3, pad 1, given stride)
 template <typename T>
 __global__ void im2col3x3_kernel(const T* __restrict__ x, int n_img, int H, int W, int C, int stride, int Ho, int Wo,
-                                 __nv_bfloat16* __restrict__ out) {
+                                 __nv_bfloat16* __restrict__ out, int pad_lo) {
   pdl_prologue();
   const int oct = C >> 3;
   const long long total = (long long)n_img * Ho * Wo * 9 * oct;
@@ -87,8 +87,8 @@ __global__ void im2col3x3_kernel(const T* __restrict__ x, int n_img, int H, int 
     const int xo = (int)(r % Wo);
     const int yo = (int)((r / Wo) % Ho);
     const long long img = r / ((long long)Wo * Ho);
-    const int yy = yo * stride + tap / 3 - 1;
-    const int xx = xo * stride + tap % 3 - 1;
+    const int yy = yo * stride + tap / 3 - pad_lo;
+    const int xx = xo * stride + tap % 3 - pad_lo;
     uint4 w = make_uint4(0u, 0u, 0u, 0u);
     if (yy >= 0 && yy < H && xx >= 0 && xx < W) w = load8_as_bf16<T>(x + ((img * H + yy) * W + xx) * C + c8 * 8);
     *reinterpret_cast<uint4*>(out + r * 9LL * C + (long long)tap * C + c8 * 8) = w;
@@ -242,13 +242,24 @@ static int im2col_impl(const T* x, int n_img, int H, int W, int C, int stride, v
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const long long total = (long long)n_img * Ho * Wo * 9 * (C / 8);
   launch_kernel(im2col3x3_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, STREAM(stream), x, n_img, H, W, C, stride, Ho, Wo,
-                                                                       reinterpret_cast<__nv_bfloat16*>(out));
+                                                                       reinterpret_cast<__nv_bfloat16*>(out), 1);
   EMOTE_CHECK_LAUNCH("emote_im2col3x3");
   return 0;
 }
 extern "C" int emote_im2col3x3(const float* x, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t stride,
                                void* out_bf16, void* stream) {
   return im2col_impl<float>(x, n_img, H, W, C, stride, out_bf16, stream);
+}
+extern "C" int emote_im2col3x3_s2_pad01(const float* x, int32_t n_img, int32_t H, int32_t W, int32_t C, void* out_bf16,
+                                        void* stream) {
+  if (!x || !out_bf16 || n_img <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0 || H % 2 != 0 || W % 2 != 0)
+    return set_error("emote_im2col3x3_s2_pad01: bad arguments (C % 8 == 0, even H and W)");
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)n_img * Ho * Wo * 9 * (C / 8);
+  launch_kernel(im2col3x3_kernel<float>, dim3(grid_for(total, 256)), dim3(256), 0, STREAM(stream), x, n_img, H, W, C, 2, Ho, Wo,
+                reinterpret_cast<__nv_bfloat16*>(out_bf16), 0);
+  EMOTE_CHECK_LAUNCH("emote_im2col3x3_s2_pad01");
+  return 0;
 }
 extern "C" int emote_im2col3x3_bf16(const void* x, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t stride,
                                     void* out_bf16, void* stream) {

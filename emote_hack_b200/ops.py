@@ -185,6 +185,15 @@ def im2col_s2(x: torch.Tensor, n_img: int, H: int, W: int, Cc: int) -> torch.Ten
     return cols
 
 
+def im2col_s2_pad01(x: torch.Tensor, n_img: int, H: int, W: int, Cc: int) -> torch.Tensor:
+    """stride-2 3x3 operand with (0, 1) padding (VAE encoder downsample) -> bf16 [n_img*(H/2)*(W/2), 9*Cc]"""
+    _req(x, F32, "im2col_s2_pad01.x")
+    cols = torch.empty((n_img * (H // 2) * (W // 2), 9 * Cc), dtype=BF16, device=x.device)
+    check(_lib.load().emote_im2col3x3_s2_pad01(x.data_ptr(), n_img, H, W, Cc, cols.data_ptr(), _stream()),
+          "emote_im2col3x3_s2_pad01")
+    return cols
+
+
 def upsample2x(x: torch.Tensor, n_img: int, H: int, W: int, Cc: int) -> torch.Tensor:
     _req(x, F32, "upsample2x.x")
     out = torch.empty((n_img * 4 * H * W, Cc), dtype=BF16, device=x.device)

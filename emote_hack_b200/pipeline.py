@@ -256,6 +256,18 @@ class EMOAnimationPipeline:
             latents = latents.to(device)
         return latents * self.scheduler.init_noise_sigma
 
+    # -- EMOAnimationPipeline.py:402-414 ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def images2latents(self, images, dtype=torch.float32):
+        """RGB frames [f, h, w, 3] (uint8 numpy / tensor) -> scaled VAE latents [f, 4, h/8, w/8] on the VAE's device: the
+        reference-image latents the ReferenceNet writer consumes.  All frames are encoded in one batch instead of the
+        reference's per-frame loop."""
+        images = torch.as_tensor(images)
+        dev = self.vae.device
+        x = (images.to(dev).float() / 127.5 - 1).permute(0, 3, 1, 2).contiguous()
+        mean = self.vae.encode(x)["latent_dist"].mean
+        return (mean * self.vae.config.scaling_factor).to(dtype)
+
     # -- EMOAnimationPipeline.py:291-307 ---------------------------------------------------------------------------
     def decode_latents(self, latents, rank=0, decoder_consistency=None):
         """-> numpy fp32 [b, 3, f, H, W] in [0, 1] (host copy, like the reference)."""

@@ -1,6 +1,7 @@
-"""SD VAE decoder on the sm_100a kernels — the `vae.decode(...)` the reference calls once per frame at
-EMOAnimationPipeline.py:291-307 (`diffusers.AutoencoderKL`, a third-party dependency absent from the reference
-tree; topology restated in oracle/vae_decoder.py).
+"""SD VAE on the sm_100a kernels — the `vae.decode(...)` the reference calls once per frame at
+EMOAnimationPipeline.py:291-307 and the `vae.encode(...)` of `images2latents` (:402-414) that turns the reference image
+into ReferenceNet latents (`diffusers.AutoencoderKL`, a third-party dependency absent from the reference tree; topology
+restated in oracle/vae_decoder.py).
 
 `AutoencoderKL` here mirrors the diffusers interface the pipeline touches (`decode(z).sample`, `config.scaling_factor`)
 and diffusers' state_dict key names for `post_quant_conv.*` and `decoder.*` (both the legacy
@@ -174,13 +175,68 @@ class Decoder(nn.Module):
         self.conv_out = _Conv(rev[-1], out_channels, 3)
 
 
+class _Down(nn.Module):
+    def __init__(self, ch):
+        super().__init__()
+        self.conv = _Conv(ch, ch, 3)   # applied with stride 2 and (0, 1) padding (diffusers Downsample2D(padding=0))
+
+
+class _DownBlock(nn.Module):
+    def __init__(self, cin, cout, n_layers, add_downsample, groups, eps):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, groups, eps) for i in range(n_layers)])
+        self.downsamplers = nn.ModuleList([_Down(cout)]) if add_downsample else None
+
+
+class Encoder(nn.Module):
+    """diffusers `Encoder` (SD VAE): conv_in -> 4 down blocks of `layers_per_block` resnets (stride-2 conv after the
+    first three) -> mid (resnet, single-head attention, resnet) -> GroupNorm -> SiLU -> conv_out to 2 x latent channels."""
+
+    def __init__(self, in_channels=3, latent_channels=4, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                 norm_num_groups=32, eps=1e-6):
+        super().__init__()
+        self.conv_in = _Conv(in_channels, block_out_channels[0], 3)
+        blocks, cin = [], block_out_channels[0]
+        for i, cout in enumerate(block_out_channels):
+            blocks.append(_DownBlock(cin, cout, layers_per_block, i != len(block_out_channels) - 1, norm_num_groups, eps))
+            cin = cout
+        self.down_blocks = nn.ModuleList(blocks)
+        self.mid_block = _Mid(cin, norm_num_groups, eps)
+        self.conv_norm_out = nn.GroupNorm(norm_num_groups, cin, eps=eps)
+        self.conv_out = _Conv(cin, 2 * latent_channels, 3)
+
+
+class DiagonalGaussianDistribution:
+    """diffusers' posterior object as far as the reference touches it (`.mean`, EMOAnimationPipeline.py:412)."""
+
+    def __init__(self, moments: torch.Tensor):
+        self.mean, self.logvar = torch.chunk(moments, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+
+    def mode(self):
+        return self.mean
+
+    def sample(self, generator=None):
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
+
+
+class AutoencoderKLOutput(dict):
+    """supports both `.latent_dist` and `['latent_dist']` (the reference indexes it, EMOAnimationPipeline.py:412)"""
+
+    def __init__(self, latent_dist):
+        super().__init__(latent_dist=latent_dist)
+        self.latent_dist = latent_dist
+
+
 @dataclass
 class DecoderOutput:
     sample: torch.Tensor
 
 
 class AutoencoderKL(nn.Module):
-    """Decoder half of diffusers.AutoencoderKL (the encoder is upstream of the hot path and not built)."""
+    """diffusers.AutoencoderKL: `decode` (hot path) and `encode` (reference image -> ReferenceNet latents)."""
 
     def __init__(self, in_channels=3, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
                  latent_channels=4, norm_num_groups=32, scaling_factor=0.18215):
@@ -188,13 +244,17 @@ class AutoencoderKL(nn.Module):
         self.config = AttrDict(in_channels=in_channels, out_channels=out_channels, block_out_channels=tuple(block_out_channels),
                                layers_per_block=layers_per_block, latent_channels=latent_channels,
                                norm_num_groups=norm_num_groups, scaling_factor=scaling_factor)
+        self.encoder = Encoder(in_channels, latent_channels, block_out_channels, layers_per_block, norm_num_groups)
+        self.quant_conv = _Conv(2 * latent_channels, 2 * latent_channels, 1)
         self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
         self.decoder = Decoder(latent_channels, out_channels, block_out_channels, layers_per_block, norm_num_groups)
 
     def load_state_dict(self, state_dict, strict=True, **kw):
-        # encoder / quant_conv weights of a full checkpoint are not part of this path
-        sd = {k: v for k, v in state_dict.items() if k.startswith("decoder.") or k.startswith("post_quant_conv.")}
-        return super().load_state_dict(sd, strict=strict, **kw)
+        # a decoder-only state dict (decoder.* + post_quant_conv.*) stays loadable: the encoder keeps its own weights
+        if strict and not any(k.startswith("encoder.") for k in state_dict):
+            own = super().state_dict()
+            state_dict = {**{k: v for k, v in own.items() if k.startswith(("encoder.", "quant_conv."))}, **state_dict}
+        return super().load_state_dict(state_dict, strict=strict, **kw)
 
     @property
     def dtype(self):
@@ -231,6 +291,41 @@ class AutoencoderKL(nn.Module):
         out = torch.empty((n * h * w, 4), dtype=F32, device=x.device)
         d.conv_out.run(a, n, h, w, out=out)
         return out, h, w
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, return_dict: bool = True):
+        """diffusers `AutoencoderKL.encode`: images [n, 3, H, W] in [-1, 1] (H, W multiples of 8) -> posterior over
+        [n, 4, H/8, W/8] latents (`.latent_dist.mean`; the caller applies the 0.18215 scaling)."""
+        if not x.is_cuda:
+            raise EmoteKernelError("emote_hack_b200 modules run on CUDA only (no CPU fallback)")
+        n, ci, h, w = x.shape
+        e = self.encoder
+        n_down = sum(1 for b in e.down_blocks if b.downsamplers is not None)
+        if h % (2 ** n_down) or w % (2 ** n_down):
+            raise ValueError(f"image height/width must be multiples of {2 ** n_down}")
+        cols = ops.latent_im2col(x.float().contiguous().view(n, ci, 1, h, w))
+        wp, b = e.conv_in.packed()
+        t = ops.gemm(cols, wp, bias=b)
+        for blk in e.down_blocks:
+            for r in blk.resnets:
+                t = r.run(t, n, h, w)
+            if blk.downsamplers is not None:
+                conv = blk.downsamplers[0].conv
+                c = t.shape[1]
+                wp, b = conv.packed()
+                t = ops.gemm(ops.im2col_s2_pad01(t, n, h, w, c), wp, bias=b)
+                h, w = h // 2, w // 2
+        t = e.mid_block.resnets[0].run(t, n, h, w)
+        t = e.mid_block.attentions[0].run(t, n, h, w)
+        t = e.mid_block.resnets[1].run(t, n, h, w)
+        g = e.conv_norm_out
+        a, _ = ops.group_norm([t], g.num_groups, h * w, n, g.weight, g.bias, g.eps, True)
+        m = e.conv_out.run(a, n, h, w)                                   # [n*h*w, 2*latent] fp32
+        m = self.quant_conv.run(ops.cast_bf16(m), n, h, w)
+        c2 = m.shape[1]
+        moments = ops.tokens_to_ncfhw(m.contiguous(), n, c2, 1, h, w).view(n, c2, h, w)
+        dist = DiagonalGaussianDistribution(moments)
+        return AutoencoderKLOutput(dist) if return_dict else (dist,)
 
     @torch.no_grad()
     def decode(self, z: torch.Tensor, return_dict: bool = True):

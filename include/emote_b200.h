@@ -152,6 +152,11 @@ int emote_latent_im2col(const float* latent, int32_t B, int32_t Cl, int32_t F, i
  * (Downsample3D, resnet.py:99-110; also the fallback for image sizes the TMA conv tile cannot cover). */
 int emote_im2col3x3(const float* x, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t stride, void* out_bf16,
                     void* stream);
+/* stride-2 3x3 gather with the VAE encoder's asymmetric padding: rows/cols padded by (0, 1) instead of (1, 1)
+ * (diffusers Downsample2D(padding=0): F.pad(x, (0,1,0,1)) then conv stride 2 — the `vae.encode` of
+ * EMOAnimationPipeline.py:412); out [n_img*(H/2)*(W/2), 9*C] bf16, H and W even. */
+int emote_im2col3x3_s2_pad01(const float* x, int32_t n_img, int32_t H, int32_t W, int32_t C, void* out_bf16,
+                             void* stream);
 /* same gather from a bf16 NHWC source (fallback path of the fused-norm convs) */
 int emote_im2col3x3_bf16(const void* x, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t stride,
                          void* out_bf16, void* stream);

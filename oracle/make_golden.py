@@ -26,6 +26,8 @@ from util_models import (FULL_CFG, TINY_CFG, make_banks, make_inputs, reader_blo
 GOLD = ROOT / "tests" / "golden"
 # tag -> (block_out_channels, frames, latent size, weight seed); tests/test_oracle.py re-derives weights and inputs
 VAE_CASES = {"tiny": ((32, 32, 64, 64), 2, 8, 1), "mid": ((64, 128, 128, 128), 1, 16, 2)}
+# encoder: tag -> (block_out_channels, images, image size, weight seed)
+VAE_ENC_CASES = {"tiny": ((32, 32, 64, 64), 2, 32, 1), "mid": ((64, 128, 128, 128), 1, 64, 2)}
 
 
 def main():
@@ -107,6 +109,13 @@ def main():
         z = torch.randn(n, 4, hw, hw, generator=torch.Generator().manual_seed(100 + seed))
         vae_out[tag] = dec(z[:, :, None])[:, :, 0].contiguous()
     torch.save(vae_out, GOLD / "vae_decoder_outputs.pt")
+    enc_out = {}
+    for tag, (widths, n, hw, seed) in VAE_ENC_CASES.items():
+        vsd = random_vae_decoder_state_dict(block_out_channels=widths, seed=seed)
+        enc = ref_shim.build_reference_vae_encoder(vsd, block_out_channels=widths)
+        img = torch.rand(n, 3, hw, hw, generator=torch.Generator().manual_seed(200 + seed)) * 2 - 1
+        enc_out[tag] = enc(img[:, :, None])[:, :, 0].contiguous()
+    torch.save(enc_out, GOLD / "vae_encoder_outputs.pt")
     print("golden written:", sorted(p.name for p in GOLD.iterdir()))
 
 

@@ -256,3 +256,55 @@ def build_reference_vae_decoder(state_dict, block_out_channels=(128, 256, 512, 5
         return x
 
     return decode
+
+
+def build_reference_vae_encoder(state_dict, block_out_channels=(128, 256, 512, 512), layers_per_block: int = 2,
+                                groups: int = 32, eps: float = 1e-6):
+    """SD-VAE encoder (+ quant_conv) wired out of the reference's own leaf modules, like build_reference_vae_decoder.
+    The stride-2 downsample uses the reference's InflatedConv3d after a (0, 1) zero pad (diffusers Downsample2D with
+    padding=0; the reference's Downsample3D refuses padding=0, resnet.py:104-105, so only the conv leaf is reference
+    code there).  Input / output: [n, 3, 1, H, W] -> moments [n, 8, 1, H/8, W/8]."""
+    install()
+    from magicanimate.models.orig_attention import AttentionBlock
+    from magicanimate.models.resnet import InflatedConv3d, ResnetBlock3D
+
+    def res(cin, cout):
+        return ResnetBlock3D(in_channels=cin, out_channels=cout, temb_channels=None, groups=groups, eps=eps)
+
+    top = block_out_channels[-1]
+    mods = OrderedDict()
+    mods["encoder.conv_in"] = InflatedConv3d(3, block_out_channels[0], 3, padding=1)
+    cin = block_out_channels[0]
+    for bi, cout in enumerate(block_out_channels):
+        for li in range(layers_per_block):
+            mods[f"encoder.down_blocks.{bi}.resnets.{li}"] = res(cin, cout)
+            cin = cout
+        if bi != len(block_out_channels) - 1:
+            mods[f"encoder.down_blocks.{bi}.downsamplers.0.conv"] = InflatedConv3d(cout, cout, 3, stride=2, padding=0)
+    mods["encoder.mid_block.resnets.0"] = res(top, top)
+    mods["encoder.mid_block.attentions.0"] = AttentionBlock(top, None, groups, 1.0, eps)
+    mods["encoder.mid_block.resnets.1"] = res(top, top)
+    mods["encoder.conv_norm_out"] = nn.GroupNorm(groups, top, eps=eps)
+    mods["encoder.conv_out"] = InflatedConv3d(top, 8, 3, padding=1)
+    mods["quant_conv"] = InflatedConv3d(8, 8, 1)
+    for name, m in mods.items():
+        m.load_state_dict({k: state_dict[f"{name}.{k}"] for k in m.state_dict()}, strict=True)
+        m.eval()
+
+    def encode(x5):
+        x = x5
+        with torch.no_grad():
+            for name, m in mods.items():
+                if isinstance(m, ResnetBlock3D):
+                    x = m(x, None)
+                elif isinstance(m, AttentionBlock):
+                    x = m(x[:, :, 0])[:, :, None]
+                elif name.endswith("downsamplers.0.conv"):
+                    x = m(torch.nn.functional.pad(x, (0, 1, 0, 1)))
+                elif name == "encoder.conv_norm_out":
+                    x = torch.nn.functional.silu(m(x))
+                else:
+                    x = m(x)
+        return x
+
+    return encode

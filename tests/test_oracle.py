@@ -171,6 +171,26 @@ def test_vae_oracle_matches_reference_leaf_golden():
         assert rel_l2(got, gold[tag]) < 1e-5
 
 
+VAE_ENC_CASES = {"tiny": ((32, 32, 64, 64), 2, 32, 1), "mid": ((64, 128, 128, 128), 1, 64, 2)}  # = oracle/make_golden.py
+
+
+def test_vae_encoder_oracle_matches_reference_leaf_golden():
+    """oracle encode() (images2latents, EMOAnimationPipeline.py:402-414) against the encoder wired out of the reference's
+    leaf modules (oracle/ref_shim.build_reference_vae_encoder)."""
+    from oracle.vae_decoder import VAEDecoderOracle, random_vae_decoder_state_dict
+    gold = torch.load(GOLD / "vae_encoder_outputs.pt")
+    for tag, (widths, n, hw, seed) in VAE_ENC_CASES.items():
+        sd = random_vae_decoder_state_dict(block_out_channels=widths, seed=seed)
+        img = torch.rand(n, 3, hw, hw, generator=torch.Generator().manual_seed(200 + seed)) * 2 - 1
+        got = VAEDecoderOracle(sd).encode(img)
+        assert got.shape == gold[tag].shape == (n, 8, hw // 8, hw // 8)
+        assert rel_l2(got, gold[tag]) < 1e-5
+    o = VAEDecoderOracle(random_vae_decoder_state_dict(block_out_channels=(32, 32, 64, 64), seed=1))
+    u8 = torch.randint(0, 256, (2, 16, 16, 3), generator=torch.Generator().manual_seed(3), dtype=torch.uint8)
+    lat = o.images2latents(u8)
+    assert lat.shape == (2, 4, 2, 2) and torch.isfinite(lat).all()
+
+
 def test_vae_oracle_against_live_reference_leaves():
     from oracle import ref_shim
     if not ref_shim.reference_available():

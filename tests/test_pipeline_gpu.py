@@ -78,10 +78,34 @@ def test_vae_decode_video_and_state_dict_aliases(tiny_vae):
     assert rel_l2(vid2, vid) < 1e-5
     sd = {k.replace(".query.", ".to_q.").replace(".key.", ".to_k.").replace(".value.", ".to_v.").replace(".proj_attn.", ".to_out.0."): v
           for k, v in vae.state_dict().items()}
-    sd["encoder.conv_in.weight"] = torch.zeros(1)  # ignored: the encoder is not on the path
     vae2 = AutoencoderKL(block_out_channels=(64, 64, 128, 128)).eval()
     vae2.load_state_dict(sd)
     assert rel_l2(vae2.cuda().decode_video(lat.cuda())[0], vid) < 1e-5
+
+
+def test_vae_encode_and_images2latents(tiny_vae):
+    """`vae.encode(x)['latent_dist'].mean * 0.18215` of images2latents (EMOAnimationPipeline.py:402-414) on CUDA vs the
+    oracle encoder (pinned on the reference's leaf modules, tests/test_oracle.py)."""
+    from emote_hack_b200.pipeline import DDIMScheduler, EMOAnimationPipeline
+    oracle, vae = tiny_vae
+    img = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(6)) * 2 - 1
+    ref = oracle.encode(img)
+    out = vae.encode(img.cuda())
+    dist = out["latent_dist"]
+    assert dist is out.latent_dist and dist.mean.shape == (2, 4, 8, 8)
+    e = rel_l2(torch.cat([dist.mean, dist.logvar], 1), ref.clamp_(min=-1e9))
+    print(f"vae encode moments rel_l2={e:.2e}")
+    assert e < 2e-2
+    assert rel_l2(dist.mode(), ref[:, :4]) < 2e-2 and dist.sample().shape == (2, 4, 8, 8)
+    # decoder-only checkpoints stay loadable (the encoder keeps its weights)
+    missing = vae.load_state_dict({k: v for k, v in vae.state_dict().items() if not k.startswith(("encoder.", "quant_conv."))})
+    assert not missing.missing_keys
+    u8 = torch.randint(0, 256, (3, 32, 32, 3), generator=torch.Generator().manual_seed(7), dtype=torch.uint8)
+    pipe = EMOAnimationPipeline(vae, None, DDIMScheduler())
+    lat = pipe.images2latents(u8.numpy(), torch.float32)
+    assert lat.shape == (3, 4, 4, 4) and rel_l2(lat, oracle.images2latents(u8)) < 2e-2
+    with pytest.raises(ValueError):
+        vae.encode(torch.zeros(1, 3, 20, 20, device="cuda"))
 
 
 def test_scheduler_step_matches_oracle():

@@ -234,6 +234,33 @@ def test_unet_full_width_one_frame_pair():
     assert e < 2e-2
 
 
+def test_unet_full_size_properties():
+    """BASELINE config #2 at FULL size ([2,4,16,64,64], SD-1.5 widths, 77 text tokens) — too large for the fp32 oracle
+    in a test, so checked through size-independent properties of the reference network:
+    (1) samples of a batch do not interact (5-D GroupNorm is per sample, attention is per image): identical halves in,
+        identical halves out, and equal to the single-sample call;
+    (2) determinism: two calls agree to fp32 round-off (GroupNorm statistics are reduced in a fixed order / fp64);
+    (3) the time embedding matters, the context matters (no dead inputs), and the output is finite."""
+    m = _build(FULL_CFG).cuda()
+    g = torch.Generator().manual_seed(99)
+    x1 = torch.randn(1, 4, 16, 64, 64, generator=g).cuda()
+    c1 = torch.randn(1, 77, 768, generator=g).cuda()
+    x2, c2 = x1.repeat(2, 1, 1, 1, 1), c1.repeat(2, 1, 1)
+    out2 = m(x2, 981, c2).sample
+    assert out2.shape == (2, 4, 16, 64, 64) and torch.isfinite(out2).all()
+    assert rel_l2(out2[0], out2[1]) < 1e-5
+    again = m(x2, 981, c2).sample
+    assert rel_l2(again, out2) < 1e-5
+    single = m(x1, 981, c1).sample
+    assert rel_l2(single[0], out2[0]) < 1e-5
+    assert rel_l2(m(x2, 21, c2).sample, out2) > 1e-2
+    other_ctx = torch.cat([c1, torch.randn(1, 77, 768, generator=g).cuda()])
+    out_ctx = m(x2, 981, other_ctx).sample
+    assert rel_l2(out_ctx[0], out2[0]) < 1e-5 and rel_l2(out_ctx[1], out2[1]) > 1e-3
+    del m
+    torch.cuda.empty_cache()
+
+
 def test_unet_non_tileable_latent_size_uses_im2col_path(tiny):
     """BASELINE config #4 geometry class (96x96 latents): image rows that do not pack into 128-pixel TMA boxes take the
     explicit im2col + GEMM path (ops.conv3x3) — still the CUDA kernels, same numerics."""

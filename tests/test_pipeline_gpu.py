@@ -232,6 +232,47 @@ def test_denoise_with_appearance_encoder(tiny_pipe, use_graph):
         pipe.denoise(lat.cuda(), ctx.cuda(), num_inference_steps=1, appearance_encoder=enc)
 
 
+def test_baseline_config0_full_width_plumbing_case():
+    """BASELINE.json configs[0] — 1x64x64 latent, 1 frame, 2 DDIM steps, random-init SD-1.5-width UNet (the reference's
+    own CPU-runnable case) — end to end on CUDA: denoise (CFG pair) + full-width VAE decode, against the oracle pieces
+    evaluated in fp32 (on the GPU with TF32 off, so the check finishes in seconds)."""
+    from emote_hack_b200.pipeline import DDIMScheduler, EMOAnimationPipeline
+    from emote_hack_b200.unet3d import UNet3DConditionModel
+    from emote_hack_b200.vae import AutoencoderKL
+    from oracle.unet3d_port import UNet3DOracle
+    from oracle.vae_decoder import VAEDecoderOracle
+    from oracle.ddim import DDIMOracle, cfg_combine
+    from util_models import FULL_CFG
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        unet = UNet3DConditionModel(**FULL_CFG).eval()
+        vae = AutoencoderKL().eval()
+    rerandomise_zero_inits(unet)
+    o = UNet3DOracle(unet.state_dict(), dict(unet.config), device="cuda")
+    vo = VAEDecoderOracle(vae.state_dict())
+    g = torch.Generator().manual_seed(1234)
+    lat = torch.randn(1, 4, 1, 64, 64, generator=g).cuda()
+    ctx = torch.randn(2, 77, 768, generator=g).cuda()
+    sch = DDIMOracle()
+    ref = lat.clone()
+    for t in sch.set_timesteps(2).tolist():
+        pred = o(ref.repeat(2, 1, 1, 1, 1), torch.tensor(t).cuda(), ctx)
+        ref = sch.step(cfg_combine(pred, torch.ones(1, 1, 1, 1, 1, device="cuda"), 7.5), t, ref)
+    pipe = EMOAnimationPipeline(vae, unet, DDIMScheduler())
+    out = pipe.denoise(lat.clone(), ctx, num_inference_steps=2, guidance_scale=7.5)
+    e = rel_l2(out, ref)
+    want = vo.decode_latents(ref)
+    video = torch.from_numpy(pipe.decode_latents(ref))
+    ev = rel_l2(video, want)
+    print(f"config[0] full width: 2-step denoise rel_l2={e:.2e}; VAE decode 512x512 rel_l2={ev:.2e}")
+    assert video.shape == (1, 3, 1, 512, 512) and float(video.min()) >= 0 and float(video.max()) <= 1
+    assert e < 3e-2 and ev < 2e-2
+    del unet, vae, o, vo
+    torch.cuda.empty_cache()
+
+
 def test_denoise_per_frame_audio_context(tiny_pipe):
     o, pipe = tiny_pipe
     g = torch.Generator().manual_seed(13)

@@ -29,7 +29,7 @@ import torch
 
 from . import ops
 from . import unet3d as _unet3d
-from .unet3d import ReferenceAttentionControl
+from .unet3d import ReferenceAttentionControl, reference_blocks
 
 
 # =============================================================================================== scheduler
@@ -121,6 +121,12 @@ def get_context_scheduler(name: str) -> Callable:
 
 
 # =============================================================================================== CUDA graph
+def _weights_fingerprint(module) -> int:
+    """Changes whenever a parameter is rewritten in place (load_state_dict) or re-allocated (.to / .cuda): a captured
+    graph reads the packed bf16 copies made from the parameters at capture time, so it must be rebuilt then."""
+    return hash(tuple((p.data_ptr(), p._version) for p in module.parameters()))
+
+
 class GraphedUNet:
     """One UNet3D step (all ~650 kernel launches) captured in a CUDA graph and replayed per (timestep, window):
     static input buffers (latents, timestep, context, banks), static output.  Removes the per-launch CPU cost
@@ -132,6 +138,7 @@ class GraphedUNet:
                  alias_banks: bool = False):
         """alias_banks: read the given bank tensors in place (static outputs of a GraphedWriter) instead of private copies."""
         self.unet = unet
+        self.fingerprint = _weights_fingerprint(unet)
         self.lat = torch.zeros(lat_shape, dtype=torch.float32, device=dev)
         self.t = torch.zeros(1, dtype=torch.float32, device=dev)
         self.ctx = torch.empty_like(ctx, dtype=torch.float32).copy_(ctx)
@@ -178,10 +185,8 @@ class GraphedUNet:
 def _writer_reader_pairs(unet, encoder):
     """(reader block name, writer block) pairs in the reference's order: both sides sorted by descending norm1 width
     (mutual_self_attention.py:585-588)."""
-    reader = ReferenceAttentionControl.__new__(ReferenceAttentionControl)
-    reader.fusion_blocks = "midup"
     names = {id(m): n for n, m in unet.named_modules()}
-    return [(names[id(r)], w) for r, w in zip(reader._blocks(unet), reader._blocks(encoder))]
+    return [(names[id(r)], w) for r, w in zip(reference_blocks(unet), reference_blocks(encoder))]
 
 
 class GraphedWriter:
@@ -192,6 +197,7 @@ class GraphedWriter:
 
     def __init__(self, encoder, unet, ref_latents: torch.Tensor, ctx: torch.Tensor, dev):
         self.encoder = encoder
+        self.fingerprint = _weights_fingerprint(encoder)
         self.lat = ref_latents.float().contiguous().clone()
         self.t = torch.zeros(1, dtype=torch.float32, device=dev)
         self.ctx = torch.empty_like(ctx, dtype=torch.float32).copy_(ctx)
@@ -343,6 +349,8 @@ class EMOAnimationPipeline:
             if use_cuda_graph and not per_frame_ctx and len(my_windows) > 0:
                 wkey = ("writer", id(appearance_encoder), tuple(ref_lat2.shape), tuple(writer_ctx.shape))
                 gwriter = self._graphs.get(wkey)
+                if gwriter is not None and gwriter.fingerprint != _weights_fingerprint(appearance_encoder):
+                    gwriter = None                                # weights changed since capture: rebuild
                 if gwriter is None:
                     gwriter = GraphedWriter(appearance_encoder, self.unet, ref_lat2, writer_ctx, dev)
                     self._graphs[wkey] = gwriter
@@ -360,6 +368,8 @@ class EMOAnimationPipeline:
                    None if gwriter is None else id(gwriter))
             if all(len(w) == wlen for w in my_windows):
                 graphed = self._graphs.get(key)
+                if graphed is not None and graphed.fingerprint != _weights_fingerprint(self.unet):
+                    graphed = None                                # weights changed since capture: rebuild
                 if graphed is None:
                     graphed = GraphedUNet(self.unet, (2, latents.shape[1], wlen, latents.shape[3], latents.shape[4]),
                                           text_embeddings, reference_banks, dev, alias_banks=gwriter is not None)

@@ -471,13 +471,12 @@ class BasicTransformerBlock(nn.Module):
         a = ops.layer_norm(x, ln.weight, ln.bias, ln.eps)
         bank_kv, bank_n, bank_first = None, 0, 0
         if self._ref_mode == "write":
-            self.bank.append(a.view(bf, n, c).float())
+            self.bank.append(a.view(bf, n, c).float())          # mutual_self_attention.py:230
         if self.attn1 is None:
-            # writer tail (appearance_encoder.py:613-621): the block was cut down to its norm1, whose output feeds the bank
+            # AppearanceEncoderModel tail (appearance_encoder.py:613-621): the block was cut down to its norm1, whose
+            # output feeds the bank above; the rest of the reference's block is identity stubs
             return hidden_states
-        if self._ref_mode == "write":
-            pass
-        elif self._ref_mode == "read" and len(self.bank) > 0:
+        if self._ref_mode == "read" and len(self.bank) > 0:
             bank = self.bank[0] if len(self.bank) == 1 else torch.cat(list(self.bank), dim=1)
             bank_kv, bank_n = self.attn1.project_kv(bank), bank.shape[1]
             bank_first = bf // 2 if self._ref_cfg else 0
@@ -1219,6 +1218,18 @@ def torch_dfs(model: nn.Module):
     return result
 
 
+def reference_blocks(unet, fusion_blocks: str = "midup"):
+    """The BasicTransformerBlocks a ReferenceAttentionControl hooks, in the reference's pairing order: depth-first over
+    mid + up blocks (or the whole network), sorted by descending norm1 width (mutual_self_attention.py:534-543, 585-588;
+    the sort is stable, so writer and reader lists pair up block by block)."""
+    if fusion_blocks == "midup":
+        mods = torch_dfs(unet.mid_block) + torch_dfs(unet.up_blocks)
+    else:
+        mods = torch_dfs(unet)
+    mods = [m for m in mods if hasattr(m, "norm1") and hasattr(m, "attn1") and hasattr(m, "bank")]
+    return sorted(mods, key=lambda x: -x.norm1.normalized_shape[0])
+
+
 class ReferenceAttentionControl:
     """mutual_self_attention.py:128-641 — reference-attention reader/writer.  Instead of monkey-patching
     `BasicTransformerBlock.forward`, it flips a mode flag the blocks' own forward honours: writer blocks append
@@ -1241,19 +1252,14 @@ class ReferenceAttentionControl:
                 m.attn_weight = float(i) / max(1, len(self._blocks(unet)))
 
     def _blocks(self, unet):
-        if self.fusion_blocks == "midup":
-            mods = torch_dfs(unet.mid_block) + torch_dfs(unet.up_blocks)
-        else:
-            mods = torch_dfs(unet)
-        mods = [m for m in mods if hasattr(m, "norm1") and hasattr(m, "attn1") and hasattr(m, "bank")]
-        return sorted(mods, key=lambda x: -x.norm1.normalized_shape[0])  # stable: same pairing rule as :585-586
+        return reference_blocks(unet, self.fusion_blocks)
 
     def update(self, writer, dtype=torch.float16):
         """:577-617 — copy the writer's banks into the reader blocks (paired by descending width)."""
         if not self.reference_attn:
             return
         src = writer.unet if hasattr(writer, "unet") else writer
-        writer_blocks = ReferenceAttentionControl._blocks(self, src)
+        writer_blocks = reference_blocks(src, self.fusion_blocks)
         for r, w in zip(self._blocks(self.unet), writer_blocks):
             r.bank = [v.clone() for v in w.bank]
 

@@ -162,6 +162,29 @@ def test_denoise_single_window(tiny_pipe):
     assert e < 3e-2
 
 
+def test_cached_graph_is_rebuilt_after_weight_update(tiny_pipe):
+    """The CUDA graph of the UNet step reads packed weight copies made at capture time: a load_state_dict between two
+    denoise() calls must invalidate it (same inputs, new weights -> the eager result of the new weights)."""
+    o, pipe = tiny_pipe
+    g = torch.Generator().manual_seed(13)
+    lat = torch.randn(1, 4, 4, 8, 8, generator=g).cuda()
+    ctx = torch.randn(2, 7, 64, generator=g).cuda()
+    kw = dict(num_inference_steps=2, guidance_scale=7.5, context_frames=16)
+    before = pipe.denoise(lat.clone(), ctx, **kw)
+    sd = {k: v.clone() for k, v in pipe.unet.state_dict().items()}
+    try:
+        with torch.no_grad():
+            pipe.unet.conv_out.weight.mul_(0.5)
+            pipe.unet.conv_out.bias.mul_(0.5)
+        graph_after = pipe.denoise(lat.clone(), ctx, **kw)
+        eager_after = pipe.denoise(lat.clone(), ctx, use_cuda_graph=False, **kw)
+        assert rel_l2(graph_after, eager_after) < 1e-5
+        assert rel_l2(graph_after, before) > 1e-3
+    finally:
+        pipe.unet.load_state_dict(sd)
+    assert rel_l2(pipe.denoise(lat.clone(), ctx, **kw), before) < 1e-5
+
+
 def test_denoise_sliding_windows_with_overlap_and_banks(tiny_pipe):
     """24 frames, windows of 8 with overlap 2 (closed loop): visit-count averaging, per-window reference banks"""
     from emote_hack_b200.pipeline import uniform

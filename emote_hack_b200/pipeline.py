@@ -87,9 +87,9 @@ class DDIMScheduler:
             raise NotImplementedError("DDIMScheduler.step: eta != 0 (stochastic DDIM) is not used by the reference")
         a_t, a_prev = self.alphas_for(int(timestep))
         out = sample.float().contiguous().clone()
-        eps = model_output.float().contiguous()
-        # guidance 1.0 with identical halves == plain epsilon
-        ops.cfg_ddim_step(out, torch.cat([eps, eps]), None, 1.0, a_t, a_prev)
+        eps = model_output.float().contiguous().reshape(1, 1, 1, 1, -1)
+        # guidance 1.0 with identical halves == plain epsilon; the update is elementwise, so any sample rank works
+        ops.cfg_ddim_step(out.view(1, 1, 1, 1, -1), torch.cat([eps, eps]), None, 1.0, a_t, a_prev)
         return DDIMSchedulerOutput(prev_sample=out.to(sample.dtype))
 
 
@@ -273,6 +273,52 @@ class EMOAnimationPipeline:
         x = (images.to(dev).float() / 127.5 - 1).permute(0, 3, 1, 2).contiguous()
         mean = self.vae.encode(x)["latent_dist"].mean
         return (mean * self.vae.config.scaling_factor).to(dtype)
+
+    # -- EMOAnimationPipeline.py:379-400 ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def next_step(self, model_output: torch.Tensor, timestep: int, x: torch.Tensor, eta: float = 0.0, verbose: bool = False):
+        """Inverse DDIM update x_{t - ratio} -> x_t used by `invert`; returns (x_next, pred_x0).  Same algebra as
+        `scheduler.step` with the two alphas swapped, so it runs in the same fused kernel (`emote_cfg_ddim_step`)."""
+        if eta != 0.0:
+            raise NotImplementedError("next_step: eta != 0 is not used by the reference")
+        sch = self.scheduler
+        nxt = int(timestep)
+        cur = min(nxt - sch.config.num_train_timesteps // sch.num_inference_steps, 999)
+        a_cur = float(sch.alphas_cumprod[cur]) if cur >= 0 else float(sch.final_alpha_cumprod)
+        a_next = float(sch.alphas_cumprod[nxt])
+        eps = model_output.float().contiguous().reshape(1, 1, 1, 1, -1)
+        pair = torch.cat([eps, eps])                         # guidance 1.0 on identical halves == plain epsilon
+        x_next = x.float().contiguous().clone()
+        pred_x0 = x_next.clone()
+        ops.cfg_ddim_step(x_next.view(1, 1, 1, 1, -1), pair, None, 1.0, a_cur, a_next)
+        ops.cfg_ddim_step(pred_x0.view(1, 1, 1, 1, -1), pair, None, 1.0, a_cur, 1.0)   # alpha_prev = 1: x0 itself
+        return x_next.to(x.dtype), pred_x0.to(x.dtype)
+
+    # -- EMOAnimationPipeline.py:416-477 ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def invert(self, image, prompt, num_inference_steps: int = 20, num_actual_inference_steps: Optional[int] = 10,
+               eta: float = 0.0, return_intermediates: bool = False, **kwargs):
+        """Deterministic DDIM inversion of real frames into a noise map.  `image`: uint8 frames [f, h, w, 3] (encoded with
+        `images2latents`) or latents [f, 4, h/8, w/8]; `prompt`: the text EMBEDDINGS [1, n, d] (the CLIP text encoder
+        the reference calls here is upstream of the path)."""
+        if isinstance(prompt, (str, list)):
+            raise TypeError("invert: pass the prompt's text embeddings [1, n, d]; the CLIP text encoder is out of scope")
+        image = torch.as_tensor(image)
+        if image.is_floating_point() and image.dim() == 4 and image.shape[1] == self.unet.in_channels:
+            latents = image.to(prompt.device).float()
+        else:
+            latents = self.images2latents(image)
+        self.scheduler.set_timesteps(num_inference_steps)
+        latents_list = [latents]
+        for i, t in enumerate(reversed(self.scheduler.timesteps.tolist())):
+            if num_actual_inference_steps is not None and i >= num_actual_inference_steps:
+                continue
+            model_inputs = latents.permute(1, 0, 2, 3)[None].contiguous()            # f c h w -> 1 c f h w
+            noise_pred = self.unet(model_inputs, t, encoder_hidden_states=prompt).sample
+            noise_pred = noise_pred[0].permute(1, 0, 2, 3).contiguous()                # 1 c f h w -> f c h w
+            latents, _ = self.next_step(noise_pred, t, latents, eta)
+            latents_list.append(latents)
+        return (latents, latents_list) if return_intermediates else latents
 
     # -- EMOAnimationPipeline.py:291-307 ---------------------------------------------------------------------------
     def decode_latents(self, latents, rank=0, decoder_consistency=None):

@@ -162,6 +162,39 @@ def test_denoise_single_window(tiny_pipe):
     assert e < 3e-2
 
 
+def test_ddim_inversion_matches_oracle(tiny_pipe):
+    """`invert` / `next_step` (EMOAnimationPipeline.py:379-477): deterministic DDIM inversion of frame latents, against
+    the same loop on the oracle UNet + the oracle's inversion step (itself a restatement of the reference's next_step)."""
+    from oracle.ddim import DDIMOracle
+    o, pipe = tiny_pipe
+    g = torch.Generator().manual_seed(17)
+    lat = torch.randn(3, 4, 8, 8, generator=g)           # f c h w
+    emb = torch.randn(1, 7, 64, generator=g)
+    sch = DDIMOracle()
+    ts = sch.set_timesteps(5).tolist()
+    ref = lat.clone()
+    for i, t in enumerate(reversed(ts)):
+        if i >= 3:
+            continue
+        eps = o(ref.permute(1, 0, 2, 3)[None], t, emb)[0].permute(1, 0, 2, 3)
+        ref = sch.ddim_inversion_step(eps, t, ref)
+    out, inter = pipe.invert(lat.cuda(), emb.cuda(), num_inference_steps=5, num_actual_inference_steps=3,
+                             return_intermediates=True)
+    assert len(inter) == 4 and out.shape == lat.shape
+    e = rel_l2(out, ref)
+    print(f"DDIM inversion 3 of 5 steps rel_l2={e:.2e}")
+    assert e < 3e-2
+    # next_step followed by scheduler.step with the same epsilon is the identity (round trip of the two updates)
+    eps = torch.randn(3, 4, 8, 8, generator=g).cuda()
+    up, x0 = pipe.next_step(eps, 401, lat.cuda())
+    back = pipe.scheduler.step(eps, 401, up).prev_sample
+    assert rel_l2(back, lat) < 1e-5
+    a_cur = float(pipe.scheduler.alphas_cumprod[201])
+    assert rel_l2(x0, (lat.cuda() - (1 - a_cur) ** 0.5 * eps) / a_cur ** 0.5) < 1e-5
+    with pytest.raises(TypeError):
+        pipe.invert(lat.cuda(), "a prompt")
+
+
 def test_cached_graph_is_rebuilt_after_weight_update(tiny_pipe):
     """The CUDA graph of the UNet step reads packed weight copies made at capture time: a load_state_dict between two
     denoise() calls must invalidate it (same inputs, new weights -> the eager result of the new weights)."""

@@ -20,8 +20,8 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 from oracle import ref_shim  # noqa: E402
-from util_models import (FULL_CFG, TINY_CFG, make_banks, make_inputs, reader_block_names, seeded_unet_state_dict,  # noqa: E402
-                         writer_cfg, writer_inputs)
+from util_models import (FULL_CFG, TINY_CFG, controlnet_residuals, make_banks, make_inputs, reader_block_names,  # noqa: E402
+                         seeded_unet_state_dict, writer_cfg, writer_inputs)
 
 GOLD = ROOT / "tests" / "golden"
 # tag -> (block_out_channels, frames, latent size, weight seed); tests/test_oracle.py re-derives weights and inputs
@@ -66,6 +66,14 @@ def main():
             mods[name].bank = [t.clone() for t in tensors]
         out["with_banks"] = m(x, torch.tensor(301), ctx).sample
         out["without_banks"] = m(x, torch.tensor(301), ctx).sample  # banks were consumed
+        # ControlNet residual inputs (unet_controlnet.py:414-448) and center_input_sample (:373-374)
+        x, ctx = make_inputs(2, 2, 8)
+        down, mid = controlnet_residuals()
+        out["controlnet"] = m(x, torch.tensor(10), ctx, down_block_additional_residuals=tuple(down),
+                              mid_block_additional_residual=mid).sample
+        mc = U(**dict(TINY_CFG, center_input_sample=True)).eval()
+        mc.load_state_dict(sd)
+        out["center_input"] = mc(x, torch.tensor(10), ctx).sample
         # single blocks
         g = torch.Generator().manual_seed(3)
         h = torch.randn(2, 64, 4, 8, 8, generator=g)

@@ -49,6 +49,19 @@ def test_port_reference_attention_golden(port, gold):
     assert rel_l2(gold["with_banks"], gold["without_banks"]) > 1e-2
 
 
+def test_port_controlnet_residuals_and_center_input_golden(port, gold):
+    """cold-but-signature branches of UNet3DConditionModel.forward the GPU tests rely on the oracle for"""
+    from oracle.unet3d_port import UNet3DOracle
+    from util_models import controlnet_residuals
+    x, ctx = make_inputs(2, 2, 8)
+    down, mid = controlnet_residuals()
+    got = port(x, 10, ctx, down_block_additional_residuals=down, mid_block_additional_residual=mid)
+    assert rel_l2(got, gold["controlnet"]) < 1e-5
+    assert rel_l2(port(x, 10, ctx), gold["controlnet"]) > 1e-3   # the residuals matter
+    centred = UNet3DOracle(port.sd, dict(TINY_CFG, center_input_sample=True))(x, 10, ctx)
+    assert rel_l2(centred, gold["center_input"]) < 1e-5
+
+
 def test_port_blocks_golden(port, gold):
     h, emb, ctx = gold["blk_h"], gold["blk_emb"], gold["blk_ctx"]
     assert rel_l2(port._resnet("down_blocks.1.resnets.0", h, emb), gold["blk_resnet"]) < 1e-5

@@ -186,11 +186,9 @@ def test_appearance_encoder_writer_banks_and_reader_update(tiny):
 
 def test_unet_controlnet_residuals(tiny):
     m, o, _ = tiny
+    from util_models import controlnet_residuals
     x, ctx = make_inputs(2, 2, 8)
-    g = torch.Generator().manual_seed(9)
-    shapes = [(64, 8), (64, 8), (64, 8), (64, 4), (128, 4), (128, 4), (128, 2), (128, 2), (128, 2), (128, 1), (128, 1), (128, 1)]
-    down = [torch.randn(2, c, 2, s, s, generator=g) * 0.1 for c, s in shapes]
-    mid = torch.randn(2, 128, 2, 1, 1, generator=g) * 0.1
+    down, mid = controlnet_residuals()
     ref = o(x, torch.tensor(10), ctx, down_block_additional_residuals=down, mid_block_additional_residual=mid)
     out = m(x.cuda(), 10, ctx.cuda(), down_block_additional_residuals=[d.cuda() for d in down],
             mid_block_additional_residual=mid.cuda()).sample

@@ -106,6 +106,15 @@ def seeded_unet_state_dict(shapes, seed=0):
     return seeded_state_dict(shapes, seed, keep)
 
 
+def controlnet_residuals(seed=9, frames=2):
+    """ControlNet residuals for TINY_CFG on an 8x8 latent (unet_controlnet.py:336-337, 414-448): 12 down + 1 mid"""
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(64, 8), (64, 8), (64, 8), (64, 4), (128, 4), (128, 4), (128, 2), (128, 2), (128, 2), (128, 1), (128, 1), (128, 1)]
+    down = [torch.randn(2, c, frames, s, s, generator=g) * 0.1 for c, s in shapes]
+    mid = torch.randn(2, 128, frames, 1, 1, generator=g) * 0.1
+    return down, mid
+
+
 def writer_cfg():
     """tiny ReferenceNet writer = TINY_CFG without motion modules (a 2-D SD UNet run as a one-frame UNet3D)"""
     cfg = dict(TINY_CFG)

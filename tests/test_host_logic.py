@@ -95,3 +95,59 @@ def test_reference_module_paths_resolve_to_b200_classes():
         for k in [k for k in sys.modules if k == "magicanimate" or k.startswith("magicanimate.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_window_scheduler_matches_restatement_and_live_reference_on_random_arguments():
+    """`pipeline.uniform` (product) vs `oracle.ddim.uniform_windows` (restatement) vs the reference's own
+    `magicanimate/pipelines/context.py:uniform` (when /root/reference is present) over a sweep of arguments, including
+    strides > 1, zero overlap and videos shorter than one window."""
+    import itertools
+    from emote_hack_b200.pipeline import uniform
+    from oracle import ref_shim
+    from oracle.ddim import uniform_windows
+    live = ref_shim.load_reference_context_uniform() if ref_shim.reference_available() else None
+    n = 0
+    for nf, cs, stride, ov, step in itertools.product((1, 7, 16, 24, 33, 64, 240), (8, 16, 24), (1, 2, 3), (0, 2, 4), (0, 3, 17)):
+        if ov >= cs:
+            continue
+        ours = [list(map(int, w)) for w in uniform(step, 50, nf, cs, stride, ov)]
+        assert ours == uniform_windows(step, 50, nf, cs, stride, ov), (nf, cs, stride, ov, step)
+        if live is not None:
+            assert ours == [list(map(int, w)) for w in live(step, 50, nf, cs, stride, ov)], (nf, cs, stride, ov, step)
+        assert all(0 <= f < nf for w in ours for f in w)
+        n += 1
+    assert n > 400
+
+
+def test_weights_fingerprint_tracks_in_place_updates_and_reallocation():
+    """graph-cache invalidation key of pipeline.GraphedUNet / GraphedWriter"""
+    from emote_hack_b200.pipeline import _weights_fingerprint
+    m = torch.nn.Linear(4, 4)
+    f0 = _weights_fingerprint(m)
+    assert _weights_fingerprint(m) == f0
+    m.load_state_dict({k: v.clone() for k, v in m.state_dict().items()})     # in-place copy_: versions bump
+    f1 = _weights_fingerprint(m)
+    assert f1 != f0
+    m.double()                                                               # storage re-allocated
+    assert _weights_fingerprint(m) != f1
+
+
+def test_reference_blocks_pairing_order_matches_reference_rule():
+    """writer / reader blocks are paired by descending norm1 width with a stable sort (mutual_self_attention.py:585-588)"""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    from util_models import TINY_CFG, appearance_cfg
+    from emote_hack_b200.appearance_encoder import AppearanceEncoderModel
+    from emote_hack_b200.unet3d import UNet3DConditionModel, reference_blocks
+    with torch.device("meta"):
+        unet, enc = UNet3DConditionModel(**TINY_CFG), AppearanceEncoderModel(**appearance_cfg())
+    r, w = reference_blocks(unet), reference_blocks(enc)
+    assert len(r) == len(w) == 10
+    assert [b.norm1.normalized_shape for b in r] == [b.norm1.normalized_shape for b in w]
+    widths = [b.norm1.normalized_shape[0] for b in r]
+    assert widths == sorted(widths, reverse=True)
+    rn = {id(m): n for n, m in unet.named_modules()}
+    wn = {id(m): n for n, m in enc.named_modules()}
+    assert [rn[id(b)] for b in r] == [wn[id(b)] for b in w]      # same block names on both sides
+    assert len(reference_blocks(unet, "full")) == 16

@@ -57,3 +57,35 @@ def test_sass_uses_blackwell_tensor_and_tma_paths():
     sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, f"{mnemonic} missing from SASS"
+
+
+def test_entry_points_reject_bad_arguments_without_touching_the_gpu():
+    """Argument validation happens before any CUDA call: invalid shapes / null pointers return EMOTE_ERR_INVALID (1)
+    with a message in emote_last_error() — checked here on a box without a GPU."""
+    import ctypes as C
+    from emote_hack_b200 import _lib
+    lib = _lib.load()
+    args = _lib.EmoteGemmArgs()
+    assert lib.emote_gemm_bf16(None, None, None, C.byref(args), None) != 0
+    assert b"null pointer" in lib.emote_last_error()
+    buf = (C.c_char * 4096)()
+    p = C.cast(buf, C.c_void_p)
+    args.M, args.N, args.K, args.conv_taps = 128, 128, 60, 1      # K not a multiple of 8
+    assert lib.emote_gemm_bf16(p, p, p, C.byref(args), None) != 0
+    assert b"multiple of 8" in lib.emote_last_error()
+    args.K, args.conv_taps = 64, 5
+    assert lib.emote_gemm_bf16(p, p, p, C.byref(args), None) != 0
+    assert b"conv_taps" in lib.emote_last_error()
+    args.conv_taps, args.epilogue, args.out_dtype, args.N = 1, 1, 0, 128   # GEGLU needs bf16 output
+    assert lib.emote_gemm_bf16(p, p, p, C.byref(args), None) != 0
+    assert b"GEGLU" in lib.emote_last_error()
+    attn = _lib.EmoteAttnArgs()
+    assert lib.emote_attention_tc_bf16(C.byref(attn), None) != 0
+    assert lib.emote_attention_tc_supported(40) == 1 and lib.emote_attention_tc_supported(64) == 0
+    assert lib.emote_im2col3x3_s2_pad01(p, 1, 7, 8, 8, p, None) != 0      # odd height
+    assert b"even H" in lib.emote_last_error()
+    assert lib.emote_upsample2x(p, 1, 4, 4, 12, p, None) != 0             # C % 8 != 0
+    assert lib.emote_layernorm(p, 4, 100, p, p, 1e-5, None, 0, 0, p, None) != 0
+    assert b"multiple of 64" in lib.emote_last_error()
+    with __import__("pytest").raises(_lib.EmoteKernelError):
+        _lib.check(1, "emote_layernorm")

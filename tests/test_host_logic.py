@@ -151,3 +151,25 @@ def test_reference_blocks_pairing_order_matches_reference_rule():
     wn = {id(m): n for n, m in enc.named_modules()}
     assert [rn[id(b)] for b in r] == [wn[id(b)] for b in w]      # same block names on both sides
     assert len(reference_blocks(unet, "full")) == 16
+
+
+def test_wav2vec_window_features_match_reference_loop():
+    """pipeline.wav2vec_window_features against a literal restatement of the reference loop (Net.py:646-667)"""
+    from emote_hack_b200.pipeline import wav2vec_window_features
+    g = torch.Generator().manual_seed(0)
+    for t, d, m, n in [(9, 6, 2, 2), (3, 4, 2, 2), (1, 4, 2, 2), (7, 5, 0, 3), (6, 8, 1, 0)]:
+        hidden = torch.randn(1, t, d, generator=g)
+        rows = []
+        for f in range(t):                                       # the reference's per-frame cat / pad
+            feat = hidden[0, max(f - m, 0):min(f + n + 1, t), :].flatten()
+            if f - m < 0:
+                feat = torch.cat((torch.zeros((m - f) * d), feat))
+            if f + n + 1 > t:
+                feat = torch.cat((feat, torch.zeros((f + n + 1 - t) * d)))
+            rows.append(feat)
+        want = torch.stack(rows)
+        assert torch.equal(wav2vec_window_features(hidden, m, n, as_tokens=False), want)
+        tok = wav2vec_window_features(hidden[0], m, n)
+        assert tok.shape == (t, m + n + 1, d) and torch.equal(tok.reshape(t, -1), want)
+    with pytest.raises(ValueError):
+        wav2vec_window_features(torch.zeros(2, 3, 4, 5))

@@ -362,9 +362,9 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16" if _lib.OPERAND == "fp16" else "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD,
-                       "precision": "bf16 tensor-core operands, fp32 accumulate / residual stream / statistics",
+                       "precision": f"{_lib.OPERAND} tensor-core operands (EMOTE_OPERAND), fp32 accumulate / residual stream / statistics",
                        "l2": "per-step working set (2.6 GB packed weights + >5 GB activations) >> 126 MB L2; no flush needed",
                        "unet_tflop_per_call": UNET_TFLOP_PER_CALL},
             "clocks": clk,

@@ -11,8 +11,15 @@ import subprocess
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
+# Tensor-core operand type of the process, fixed at import: EMOTE_OPERAND=fp16 (default; libemote_b200.so — the reference
+# pipeline itself runs fp16 and 10 mantissa bits keep the whole network within ~1e-3 of the fp32 reference) or bf16
+# (libemote_b200_bf16.so: same kernels built with -DEMOTE_OPERAND_BF16, ~8x the rounding error, wider exponent range).
+OPERAND = os.environ.get("EMOTE_OPERAND", "fp16").lower()
+if OPERAND not in ("fp16", "bf16"):
+    raise ValueError(f"EMOTE_OPERAND must be 'fp16' or 'bf16', got {OPERAND!r}")
 # EMOTE_B200_LIB: dev override (same-box A/B of two builds of the library); the default is the in-tree build
-LIB_PATH = Path(os.environ.get("EMOTE_B200_LIB") or (_HERE / "lib" / "libemote_b200.so"))
+LIB_PATH = Path(os.environ.get("EMOTE_B200_LIB") or
+                (_HERE / "lib" / ("libemote_b200.so" if OPERAND == "fp16" else "libemote_b200_bf16.so")))
 CSRC = _HERE / "csrc"
 
 
@@ -91,6 +98,7 @@ INTROSPECTION = {
     "emote_last_error": (C.c_char_p, []),
     "emote_launch_count": (C.c_longlong, []),
     "emote_abi_version": (C.c_int, []),
+    "emote_operand_dtype": (C.c_int, []),
     "emote_set_pdl": (None, [C.c_int]),
 }
 
@@ -98,7 +106,8 @@ _lib = None
 
 
 def build(verbose: bool = False) -> Path:
-    """Compile csrc/*.cu for sm_100a into lib/libemote_b200.so (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into lib/libemote_b200.so (fp16 operands) and lib/libemote_b200_bf16.so (nvcc
+    cross-compiles without a GPU)."""
     cmd = ["make", "-C", str(CSRC), "-j8"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -125,8 +134,17 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = restype
+    want = 2 if OPERAND == "fp16" else 1   # EMOTE_OP_F16 / EMOTE_OP_BF16
+    if "EMOTE_B200_LIB" not in os.environ and lib.emote_operand_dtype() != want:
+        raise EmoteKernelError(f"{LIB_PATH} was built for a different operand type than EMOTE_OPERAND={OPERAND}")
     _lib = lib
     return lib
+
+
+def op16_torch_dtype():
+    """torch dtype of the 16-bit tensor-core operand buffers of this process"""
+    import torch
+    return torch.float16 if OPERAND == "fp16" else torch.bfloat16
 
 
 def check(rc: int, what: str) -> None:

@@ -36,14 +36,14 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t&
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32." EMOTE_OP16_PTX "." EMOTE_OP16_PTX ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 struct AttnDev {
-  const __nv_bfloat16 *q, *k0, *v0, *k1, *v1;
-  __nv_bfloat16* out;
+  const op16 *q, *k0, *v0, *k1, *v1;
+  op16* out;
   int heads, d;
   int nq, n0, n1;
   long long q_bs, q_rs, kv0_bs, kv0_rs, kv1_bs, kv1_rs, o_bs, o_rs;
@@ -62,7 +62,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // Load `rows` x d bf16 (row stride rs elements) into smem [rows][DP+8]; rows >= nvalid and cols >= d are zero.
 template <int DP>
-__device__ __forceinline__ void fa_load_tile(__nv_bfloat16* s, const __nv_bfloat16* g, long long rs, int rows,
+__device__ __forceinline__ void fa_load_tile(op16* s, const op16* g, long long rs, int rows,
                                              int nvalid, int d) {
   constexpr int PITCH = DP + 8;
   constexpr int CH = DP / 8;  // 16-byte chunks per padded row
@@ -71,7 +71,7 @@ __device__ __forceinline__ void fa_load_tile(__nv_bfloat16* s, const __nv_bfloat
     const int r = i / CH;
     const int c = i - r * CH;
     const bool ok = (r < nvalid) && (c < dch);
-    const __nv_bfloat16* src = ok ? g + (long long)r * rs + c * 8 : g;
+    const op16* src = ok ? g + (long long)r * rs + c * 8 : g;
     cp_async16(s + r * PITCH + c * 8, src, ok);
   }
 }
@@ -86,21 +86,21 @@ __global__ void __launch_bounds__(FA_THREADS, (DP <= 96) ? 2 : 1) flash_attn_ker
   constexpr int NT = DP / 8;   // output n-tiles
   constexpr int BQ = 64 * MT;
   extern __shared__ __align__(16) uint8_t fa_smem[];
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(fa_smem);
-  __nv_bfloat16* sK = sQ + BQ * PITCH;           // [2][64][PITCH]
-  __nv_bfloat16* sV = sK + 2 * 64 * PITCH;       // [2][64][PITCH]
+  op16* sQ = reinterpret_cast<op16*>(fa_smem);
+  op16* sK = sQ + BQ * PITCH;           // [2][64][PITCH]
+  op16* sV = sK + 2 * 64 * PITCH;       // [2][64][PITCH]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z, h = blockIdx.y;
   const int q0 = blockIdx.x * BQ;
 
-  const __nv_bfloat16* qg = p.q + (long long)b * p.q_bs + (long long)q0 * p.q_rs + h * p.d;
-  const __nv_bfloat16* k0g = p.k0 + (long long)(b / p.kv0_div) * p.kv0_bs + h * p.d;
-  const __nv_bfloat16* v0g = p.v0 + (long long)(b / p.kv0_div) * p.kv0_bs + h * p.d;
+  const op16* qg = p.q + (long long)b * p.q_bs + (long long)q0 * p.q_rs + h * p.d;
+  const op16* k0g = p.k0 + (long long)(b / p.kv0_div) * p.kv0_bs + h * p.d;
+  const op16* v0g = p.v0 + (long long)(b / p.kv0_div) * p.kv0_bs + h * p.d;
   const int n1 = (p.n1 > 0 && b >= p.kv1_first) ? p.n1 : 0;
-  const __nv_bfloat16* k1g = nullptr;
-  const __nv_bfloat16* v1g = nullptr;
+  const op16* k1g = nullptr;
+  const op16* v1g = nullptr;
   if (n1 > 0) {
     k1g = p.k1 + (long long)(b / p.kv1_div) * p.kv1_bs + h * p.d;
     v1g = p.v1 + (long long)(b / p.kv1_div) * p.kv1_bs + h * p.d;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(FA_THREADS, (DP <= 96) ? 2 : 1) flash_attn_ker
   const int ntiles = tiles0 + tiles1;
 
   auto issue_kv = [&](int tile, int buf) {
-    const __nv_bfloat16 *kg, *vg;
+    const op16 *kg, *vg;
     long long rs;
     int nvalid;
     if (tile < tiles0) {
@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(FA_THREADS, (DP <= 96) ? 2 : 1) flash_attn_ker
           ldsm_x4(smem_u32(sQ + row * PITCH + col), qf[mt][ks][0], qf[mt][ks][1], qf[mt][ks][2], qf[mt][ks][3]);
         }
     }
-    const __nv_bfloat16* sKb = sK + buf * 64 * PITCH;
-    const __nv_bfloat16* sVb = sV + buf * 64 * PITCH;
+    const op16* sKb = sK + buf * 64 * PITCH;
+    const op16* sVb = sV + buf * 64 * PITCH;
 
     // ---- S = Q K^T  (MT x 16 x 64 per warp)
     float s_acc[MT][8][4];
@@ -239,11 +239,11 @@ __global__ void __launch_bounds__(FA_THREADS, (DP <= 96) ? 2 : 1) flash_attn_ker
         rs[1] += p2 + p3;
         const int kk = nt >> 1;
         if ((nt & 1) == 0) {
-          pf[mt][kk][0] = pack_bf16x2(p0, p1);
-          pf[mt][kk][1] = pack_bf16x2(p2, p3);
+          pf[mt][kk][0] = pack_op16x2(p0, p1);
+          pf[mt][kk][1] = pack_op16x2(p2, p3);
         } else {
-          pf[mt][kk][2] = pack_bf16x2(p0, p1);
-          pf[mt][kk][3] = pack_bf16x2(p2, p3);
+          pf[mt][kk][2] = pack_op16x2(p0, p1);
+          pf[mt][kk][3] = pack_op16x2(p2, p3);
         }
       }
 #pragma unroll
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(FA_THREADS, (DP <= 96) ? 2 : 1) flash_attn_ker
 
   // ---- finalise: O / l, stage through this warp's Q rows, 16-byte stores
   const int dch = p.d >> 3;
-  __nv_bfloat16* og = p.out + (long long)b * p.o_bs + h * p.d;
+  op16* og = p.out + (long long)b * p.o_bs + h * p.d;
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -285,13 +285,13 @@ __global__ void __launch_bounds__(FA_THREADS, (DP <= 96) ? 2 : 1) flash_attn_ker
     }
     const float inv0 = l_run[mt][0] > 0.f ? 1.f / l_run[mt][0] : 0.f;
     const float inv1 = l_run[mt][1] > 0.f ? 1.f / l_run[mt][1] : 0.f;
-    __nv_bfloat16* sO = sQ + (qrow_w + mt * 16) * PITCH;
+    op16* sO = sQ + (qrow_w + mt * 16) * PITCH;
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
       *reinterpret_cast<uint32_t*>(sO + g * PITCH + i * 8 + 2 * t) =
-          pack_bf16x2(o_acc[mt][i][0] * inv0, o_acc[mt][i][1] * inv0);
+          pack_op16x2(o_acc[mt][i][0] * inv0, o_acc[mt][i][1] * inv0);
       *reinterpret_cast<uint32_t*>(sO + (g + 8) * PITCH + i * 8 + 2 * t) =
-          pack_bf16x2(o_acc[mt][i][2] * inv1, o_acc[mt][i][3] * inv1);
+          pack_op16x2(o_acc[mt][i][2] * inv1, o_acc[mt][i][3] * inv1);
     }
   }
   __syncwarp();
@@ -319,17 +319,17 @@ __global__ void __launch_bounds__(FA_THREADS) short_kv_attn_kernel(const AttnDev
   constexpr int NKEY = NK16 * 16;
   constexpr int SNT = NK16 * 2;  // score n-tiles of 8 keys
   extern __shared__ __align__(16) uint8_t sk_smem[];
-  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(sk_smem);
-  __nv_bfloat16* sV = sK + NKEY * PITCH;
-  __nv_bfloat16* sQ = sV + NKEY * PITCH;  // [2][64][PITCH]
+  op16* sK = reinterpret_cast<op16*>(sk_smem);
+  op16* sV = sK + NKEY * PITCH;
+  op16* sQ = sV + NKEY * PITCH;  // [2][64][PITCH]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z, h = blockIdx.y;
-  const __nv_bfloat16* kg = p.k0 + (long long)(b / p.kv0_div) * p.kv0_bs + h * p.d;
-  const __nv_bfloat16* vg = p.v0 + (long long)(b / p.kv0_div) * p.kv0_bs + h * p.d;
-  const __nv_bfloat16* qb = p.q + (long long)b * p.q_bs + h * p.d;
-  __nv_bfloat16* ob = p.out + (long long)b * p.o_bs + h * p.d;
+  const op16* kg = p.k0 + (long long)(b / p.kv0_div) * p.kv0_bs + h * p.d;
+  const op16* vg = p.v0 + (long long)(b / p.kv0_div) * p.kv0_bs + h * p.d;
+  const op16* qb = p.q + (long long)b * p.q_bs + h * p.d;
+  op16* ob = p.out + (long long)b * p.o_bs + h * p.d;
   const int n_qtiles = (p.nq + 63) / 64;
   const int qt0 = blockIdx.x * q_tiles_per_cta;
   int qt1 = qt0 + q_tiles_per_cta;
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(FA_THREADS) short_kv_attn_kernel(const AttnDev
       cp_async_wait<0>();
     }
     __syncthreads();
-    __nv_bfloat16* sQb = sQ + buf * 64 * PITCH;
+    op16* sQb = sQ + buf * 64 * PITCH;
     float s_acc[SNT][4];
 #pragma unroll
     for (int i = 0; i < SNT; ++i) s_acc[i][0] = s_acc[i][1] = s_acc[i][2] = s_acc[i][3] = 0.f;
@@ -401,11 +401,11 @@ __global__ void __launch_bounds__(FA_THREADS) short_kv_attn_kernel(const AttnDev
       sum[1] += p2 + p3;
       const int kk = nt >> 1;
       if ((nt & 1) == 0) {
-        pf[kk][0] = pack_bf16x2(p0, p1);
-        pf[kk][1] = pack_bf16x2(p2, p3);
+        pf[kk][0] = pack_op16x2(p0, p1);
+        pf[kk][1] = pack_op16x2(p2, p3);
       } else {
-        pf[kk][2] = pack_bf16x2(p0, p1);
-        pf[kk][3] = pack_bf16x2(p2, p3);
+        pf[kk][2] = pack_op16x2(p0, p1);
+        pf[kk][3] = pack_op16x2(p2, p3);
       }
     }
 #pragma unroll
@@ -431,12 +431,12 @@ __global__ void __launch_bounds__(FA_THREADS) short_kv_attn_kernel(const AttnDev
     }
     // stage the warp's 16 output rows through its (consumed) Q rows, then 16-byte stores
     __syncwarp();
-    __nv_bfloat16* sO = sQb + warp * 16 * PITCH;
+    op16* sO = sQb + warp * 16 * PITCH;
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
-      *reinterpret_cast<uint32_t*>(sO + g * PITCH + i * 8 + 2 * t) = pack_bf16x2(o_acc[i][0] * inv0, o_acc[i][1] * inv0);
+      *reinterpret_cast<uint32_t*>(sO + g * PITCH + i * 8 + 2 * t) = pack_op16x2(o_acc[i][0] * inv0, o_acc[i][1] * inv0);
       *reinterpret_cast<uint32_t*>(sO + (g + 8) * PITCH + i * 8 + 2 * t) =
-          pack_bf16x2(o_acc[i][2] * inv1, o_acc[i][3] * inv1);
+          pack_op16x2(o_acc[i][2] * inv1, o_acc[i][3] * inv1);
     }
     __syncwarp();
     for (int i = lane; i < 16 * dch; i += 32) {
@@ -455,8 +455,8 @@ __global__ void __launch_bounds__(FA_THREADS) short_kv_attn_kernel(const AttnDev
 constexpr int TA_WARPS = 4;
 
 template <int DP, int FP>
-__global__ void __launch_bounds__(TA_WARPS * 32) temporal_attn_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                                        __nv_bfloat16* __restrict__ out, int F, int HW,
+__global__ void __launch_bounds__(TA_WARPS * 32) temporal_attn_kernel(const op16* __restrict__ qkv,
+                                                                        op16* __restrict__ out, int F, int HW,
                                                                         int heads, int d, float scale_log2) {
   pdl_prologue();
   constexpr int PITCH = DP + 8;
@@ -473,9 +473,9 @@ __global__ void __launch_bounds__(TA_WARPS * 32) temporal_attn_kernel(const __nv
   if (h >= heads) return;
   const long long b = pix / HW, pidx = pix % HW;
   const int C = heads * d;
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(ta_smem) + warp * 3 * FP * PITCH;
-  __nv_bfloat16* sK = sQ + FP * PITCH;
-  __nv_bfloat16* sV = sK + FP * PITCH;
+  op16* sQ = reinterpret_cast<op16*>(ta_smem) + warp * 3 * FP * PITCH;
+  op16* sK = sQ + FP * PITCH;
+  op16* sV = sK + FP * PITCH;
 
   // rows of this (b, pixel): token (b*F + f)*HW + pidx
   constexpr int CH = DP / 8;
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(TA_WARPS * 32) temporal_attn_kernel(const __nv
     const int rem = i - which * FP * CH;
     const int f = rem / CH, c = rem - f * CH;
     const bool ok = (f < F) && (c < dch);
-    const __nv_bfloat16* src = qkv;
+    const op16* src = qkv;
     if (ok) src = qkv + ((b * F + f) * HW + pidx) * (3LL * C) + (long long)which * C + h * d + c * 8;
     cp_async16(sQ + which * FP * PITCH + f * PITCH + c * 8, src, ok);
   }
@@ -544,11 +544,11 @@ __global__ void __launch_bounds__(TA_WARPS * 32) temporal_attn_kernel(const __nv
       sum[1] += p2 + p3;
       const int kk = nt >> 1;
       if ((nt & 1) == 0) {
-        pf[kk][0] = pack_bf16x2(p0, p1);
-        pf[kk][1] = pack_bf16x2(p2, p3);
+        pf[kk][0] = pack_op16x2(p0, p1);
+        pf[kk][1] = pack_op16x2(p2, p3);
       } else {
-        pf[kk][2] = pack_bf16x2(p0, p1);
-        pf[kk][3] = pack_bf16x2(p2, p3);
+        pf[kk][2] = pack_op16x2(p0, p1);
+        pf[kk][3] = pack_op16x2(p2, p3);
       }
     }
 #pragma unroll
@@ -574,12 +574,12 @@ __global__ void __launch_bounds__(TA_WARPS * 32) temporal_attn_kernel(const __nv
     }
     // all lanes have consumed Q rows of this m-tile -> reuse them as the output staging area
     __syncwarp();
-    __nv_bfloat16* sO = sQ + mt * 16 * PITCH;
+    op16* sO = sQ + mt * 16 * PITCH;
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
-      *reinterpret_cast<uint32_t*>(sO + g * PITCH + i * 8 + 2 * t) = pack_bf16x2(o_acc[i][0] * inv0, o_acc[i][1] * inv0);
+      *reinterpret_cast<uint32_t*>(sO + g * PITCH + i * 8 + 2 * t) = pack_op16x2(o_acc[i][0] * inv0, o_acc[i][1] * inv0);
       *reinterpret_cast<uint32_t*>(sO + (g + 8) * PITCH + i * 8 + 2 * t) =
-          pack_bf16x2(o_acc[i][2] * inv1, o_acc[i][3] * inv1);
+          pack_op16x2(o_acc[i][2] * inv1, o_acc[i][3] * inv1);
     }
   }
   __syncwarp();
@@ -641,7 +641,7 @@ static int dispatch_short_kv(const AttnDev& p, int batch, cudaStream_t stream) {
 }
 
 template <int DP, int FP>
-static int launch_temporal(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int F, int HW, int heads, int d,
+static int launch_temporal(const op16* qkv, op16* out, int B, int F, int HW, int heads, int d,
                            float scale_log2, cudaStream_t stream) {
   constexpr int SMEM = TA_WARPS * 3 * FP * (DP + 8) * 2;
   static bool configured = false;
@@ -695,8 +695,8 @@ extern "C" int emote_attention_bf16(const EmoteAttnArgs* a, void* stream_) {
   for (int64_t s : strides)
     if (s % 8 != 0) return set_error("emote_attention_bf16: strides must keep rows 16-byte aligned");
   AttnDev p{};
-  p.q = (const __nv_bfloat16*)a->q; p.k0 = (const __nv_bfloat16*)a->k0; p.v0 = (const __nv_bfloat16*)a->v0;
-  p.k1 = (const __nv_bfloat16*)a->k1; p.v1 = (const __nv_bfloat16*)a->v1; p.out = (__nv_bfloat16*)a->out;
+  p.q = (const op16*)a->q; p.k0 = (const op16*)a->k0; p.v0 = (const op16*)a->v0;
+  p.k1 = (const op16*)a->k1; p.v1 = (const op16*)a->v1; p.out = (op16*)a->out;
   p.heads = a->heads; p.d = a->head_dim; p.nq = a->nq; p.n0 = a->n0; p.n1 = a->n1;
   p.q_bs = a->q_batch_stride; p.q_rs = a->q_row_stride;
   p.kv0_bs = a->kv0_batch_stride; p.kv0_rs = a->kv0_row_stride;
@@ -722,8 +722,8 @@ extern "C" int emote_temporal_attention_bf16(const void* qkv, void* out, int32_t
   if (head_dim % 8 != 0) return set_error("emote_temporal_attention_bf16: head_dim must be a multiple of 8");
   const int dp = padded_head_dim(head_dim);
   const float sl2 = scale * 1.4426950408889634f;
-  const __nv_bfloat16* qp = (const __nv_bfloat16*)qkv;
-  __nv_bfloat16* op = (__nv_bfloat16*)out;
+  const op16* qp = (const op16*)qkv;
+  op16* op = (op16*)out;
   if (F <= 16) {
     EMOTE_DP_DISPATCH(dp, return (launch_temporal<DPV, 16>(qp, op, B, F, HW, heads, head_dim, sl2, stream)));
   } else {

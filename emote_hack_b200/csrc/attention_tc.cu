@@ -22,8 +22,8 @@
 namespace emote {
 
 struct AttnTcDev {
-  const __nv_bfloat16 *q, *k0, *v0, *k1, *v1;
-  __nv_bfloat16* out;
+  const op16 *q, *k0, *v0, *k1, *v1;
+  op16* out;
   int heads, d;
   int nq, n0, n1;
   long long q_bs, q_rs, kv0_bs, kv0_rs, kv1_bs, kv1_rs, o_bs, o_rs;
@@ -126,8 +126,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint3
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int M, int N) {  // A K-major, B MN-major
-  return umma_idesc_bf16(M, N) | (1u << 16);
+__host__ __device__ constexpr uint32_t umma_idesc_op16_bmn(int M, int N) {  // A K-major, B MN-major
+  return umma_idesc_op16(M, N) | (1u << 16);
 }
 
 // D = head dim (40 or 80).  ATOMS = 64-element swizzle atoms covering D, KSTEPS = 16-wide MMA k-steps over D,
@@ -187,7 +187,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
     for (int i = threadIdx.x; i < n16; i += TC_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
     uint4* o = reinterpret_cast<uint4*>(sOnes);
     for (int i = threadIdx.x; i < C::ONES_BYTES / 16; i += TC_THREADS)
-      o[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0 pairs
+      o[i] = make_uint4(OP16_ONE_PAIR, OP16_ONE_PAIR, OP16_ONE_PAIR, OP16_ONE_PAIR);  // 1.0 pairs
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -209,7 +209,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
   pdl_wait();  // smem / barriers / TMEM are ready; q, k, v of earlier kernels may be read from here on
   {
     // Q tile: rows q0..q0+127, chunks < D/8; atom = chunk/8; physical 16B slot = (chunk%8) ^ (row%8)
-    const __nv_bfloat16* qg = p.q + (long long)b * p.q_bs + (long long)q0 * p.q_rs + h * p.d;
+    const op16* qg = p.q + (long long)b * p.q_bs + (long long)q0 * p.q_rs + h * p.d;
     const int nvq = p.nq - q0;
     for (int i = threadIdx.x; i < TC_BQ * C::CH; i += TC_THREADS) {
       const int r = i / C::CH, c = i - r * C::CH;
@@ -253,9 +253,9 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane)
     {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(TC_BQ, TC_BKV);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16_bmn(TC_BQ, C::NPV);
-      constexpr uint32_t idesc_sum = umma_idesc_bf16(TC_BQ, 16);
+      constexpr uint32_t idesc_s = umma_idesc_op16(TC_BQ, TC_BKV);
+      constexpr uint32_t idesc_pv = umma_idesc_op16_bmn(TC_BQ, C::NPV);
+      constexpr uint32_t idesc_sum = umma_idesc_op16(TC_BQ, 16);
       auto issue_s = [&](int j) {
         const int stage = j % TC_STAGES;
         mbar_wait(&kv_full[stage], (j / TC_STAGES) & 1);
@@ -379,8 +379,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
           }
         }
         uint4 w;
-        w.x = pack_bf16x2(pv[0], pv[1]); w.y = pack_bf16x2(pv[2], pv[3]);
-        w.z = pack_bf16x2(pv[4], pv[5]); w.w = pack_bf16x2(pv[6], pv[7]);
+        w.x = pack_op16x2(pv[0], pv[1]); w.y = pack_op16x2(pv[2], pv[3]);
+        w.z = pack_op16x2(pv[4], pv[5]); w.w = pack_op16x2(pv[6], pv[7]);
         *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = w;
       }
       // publish P (generic-proxy smem writes -> async proxy) and release S[j&1]: one arrival per warp
@@ -397,14 +397,14 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
     const int qrow = q0 + row;
     if (qrow < p.nq) {
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      __nv_bfloat16* og = p.out + (long long)b * p.o_bs + (long long)qrow * p.o_rs + h * p.d;
+      op16* og = p.out + (long long)b * p.o_bs + (long long)qrow * p.o_rs + h * p.d;
 #pragma unroll
       for (int c = 0; c < C::CH; ++c) {
         uint4 w;
-        w.x = pack_bf16x2(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
-        w.y = pack_bf16x2(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
-        w.z = pack_bf16x2(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
-        w.w = pack_bf16x2(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
+        w.x = pack_op16x2(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
+        w.y = pack_op16x2(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
+        w.z = pack_op16x2(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
+        w.w = pack_op16x2(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
         *reinterpret_cast<uint4*>(og + c * 8) = w;
       }
     }
@@ -474,8 +474,8 @@ extern "C" int emote_attention_tc_bf16(const EmoteAttnArgs* a, void* stream_) {
   for (int64_t s : strides)
     if (s % 8 != 0) return set_error("emote_attention_tc_bf16: strides must keep rows 16-byte aligned");
   AttnTcDev p{};
-  p.q = (const __nv_bfloat16*)a->q; p.k0 = (const __nv_bfloat16*)a->k0; p.v0 = (const __nv_bfloat16*)a->v0;
-  p.k1 = (const __nv_bfloat16*)a->k1; p.v1 = (const __nv_bfloat16*)a->v1; p.out = (__nv_bfloat16*)a->out;
+  p.q = (const op16*)a->q; p.k0 = (const op16*)a->k0; p.v0 = (const op16*)a->v0;
+  p.k1 = (const op16*)a->k1; p.v1 = (const op16*)a->v1; p.out = (op16*)a->out;
   p.heads = a->heads; p.d = a->head_dim; p.nq = a->nq; p.n0 = a->n0; p.n1 = a->n1;
   p.q_bs = a->q_batch_stride; p.q_rs = a->q_row_stride;
   p.kv0_bs = a->kv0_batch_stride; p.kv0_rs = a->kv0_row_stride;

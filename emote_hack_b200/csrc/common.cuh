@@ -3,10 +3,53 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// 16-bit tensor-core operand type of the whole library, chosen at build time: fp16 (default build, libemote_b200.so —
+// the reference pipeline itself runs fp16, magicanimate/pipelines/animation.py:96-100; 10 mantissa bits keep the
+// whole-network error vs the fp32 reference near 1e-3) or bf16 (-DEMOTE_OPERAND_BF16, libemote_b200_bf16.so; 7 bits,
+// ~8x the error, wider exponent).  tcgen05.mma.kind::f16 and mma.sync run both at the same rate; everything that is
+// not a tensor-core operand (residual stream, statistics, softmax, accumulators) is fp32 either way.
+#ifdef EMOTE_OPERAND_BF16
+#define EMOTE_OP16_PTX "bf16"
+#define EMOTE_OP16_IS_F16 0
+#else
+#define EMOTE_OP16_PTX "f16"
+#define EMOTE_OP16_IS_F16 1
+#endif
+
 namespace emote {
+
+#if EMOTE_OP16_IS_F16
+typedef __half op16;
+typedef __half2 op16x2;
+constexpr uint32_t OP16_ONE_PAIR = 0x3c003c00u;   // {1.0, 1.0}
+constexpr uint32_t OP16_UMMA_FMT = 0;              // cute::UMMA::F16F32Format::F16
+// round to nearest, saturating at +-65504 instead of overflowing to inf
+__device__ __forceinline__ op16x2 floats2op16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<op16x2*>(&r);
+}
+__device__ __forceinline__ op16 float2op16(float v) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return *reinterpret_cast<op16*>(&r);
+}
+__device__ __forceinline__ float2 op16x2_to_float2(op16x2 v) { return __half22float2(v); }
+__device__ __forceinline__ float op16_to_float(op16 v) { return __half2float(v); }
+#else
+typedef __nv_bfloat16 op16;
+typedef __nv_bfloat162 op16x2;
+constexpr uint32_t OP16_ONE_PAIR = 0x3f803f80u;
+constexpr uint32_t OP16_UMMA_FMT = 1;              // cute::UMMA::F16F32Format::BF16
+__device__ __forceinline__ op16x2 floats2op16x2(float lo, float hi) { return __floats2bfloat162_rn(lo, hi); }
+__device__ __forceinline__ op16 float2op16(float v) { return __float2bfloat16(v); }
+__device__ __forceinline__ float2 op16x2_to_float2(op16x2 v) { return __bfloat1622float2(v); }
+__device__ __forceinline__ float op16_to_float(op16 v) { return __bfloat162float(v); }
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -179,19 +222,27 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, A and B K-major (cute::UMMA::InstrDescriptor).
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) /*c=f32*/ | (1u << 7) /*a=bf16*/ | (1u << 10) /*b=bf16*/ | (static_cast<uint32_t>(N >> 3) << 17) |
+__host__ __device__ constexpr uint32_t umma_idesc_op16(int M, int N) {
+  return (1u << 4) /*c=f32*/ | (OP16_UMMA_FMT << 7) /*a*/ | (OP16_UMMA_FMT << 10) /*b*/ | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- numerics
-// silu(x) = x * sigmoid(x) = 0.5 x (1 + tanh(x / 2)): one MUFU op (tanh.approx, |rel err| < 2^-10.9, below bf16
-// resolution) instead of ex2 + a full-precision divide; the GroupNorm apply kernel was MUFU-limited with the latter.
+// silu(x) = x * sigmoid(x) = x / (1 + 2^(-x log2 e)): MUFU.EX2 + MUFU.RCP (both ~2^-22 relative) + 2 FMA-pipe ops.
+// The one-MUFU tanh.approx form (rel. error 2^-10.9) is good enough for bf16 operands but sits right at the fp16
+// rounding (2^-11), so fp16 builds use the two-MUFU form; the GroupNorm apply kernel stays HBM-bound either way.
 __device__ __forceinline__ float silu_f(float x) {
+#if EMOTE_OP16_IS_F16
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return x * r;
+#else
   float t;
   const float h = 0.5f * x;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
+#endif
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 // exact-GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 output rounding):
@@ -226,8 +277,8 @@ __device__ __forceinline__ float gelu_sig(float x) {
   return x * r;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+__device__ __forceinline__ uint32_t pack_op16x2(float lo, float hi) {
+  op16x2 v = floats2op16x2(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float warp_sum(float v) {

@@ -15,7 +15,7 @@ static inline unsigned grid_for(long long n, int threads, long long cap = 148LL 
 // latents [B, Cl, F, H, W] fp32 -> rows [B*F*H*W, 64] bf16; col (ky*3+kx)*Cl + c
 __global__ void latent_im2col_kernel(const float* __restrict__ lat, int B, int Cl, int F, int H, int W, float pre_scale,
                                      const float* __restrict__ pw_w, const float* __restrict__ pw_b,
-                                     __nv_bfloat16* __restrict__ out) {
+                                     op16* __restrict__ out) {
   pdl_prologue();
   const long long total = (long long)B * F * H * W;
   const long long plane = (long long)H * W;
@@ -26,9 +26,9 @@ __global__ void latent_im2col_kernel(const float* __restrict__ lat, int B, int C
     const long long bf = m / plane;
     const int f = (int)(bf % F);
     const long long b = bf / F;
-    __align__(16) __nv_bfloat16 row[64];
+    __align__(16) op16 row[64];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) row[i] = __float2bfloat16(0.f);
+    for (int i = 0; i < 64; ++i) row[i] = float2op16(0.f);
     for (int ky = 0; ky < 3; ++ky) {
       for (int kx = 0; kx < 3; ++kx) {
         const int yy = y + ky - 1, xx = x + kx - 1;
@@ -45,7 +45,7 @@ __global__ void latent_im2col_kernel(const float* __restrict__ lat, int B, int C
           }
           for (int c = 0; c < Cl; ++c) v[c] = u[c];
         }
-        for (int c = 0; c < Cl; ++c) row[(ky * 3 + kx) * Cl + c] = __float2bfloat16(v[c]);
+        for (int c = 0; c < Cl; ++c) row[(ky * 3 + kx) * Cl + c] = float2op16(v[c]);
       }
     }
     uint4* o = reinterpret_cast<uint4*>(out + m * 64);
@@ -62,19 +62,19 @@ __device__ __forceinline__ uint4 load8_as_bf16<float>(const float* p) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
   const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
   uint4 w;
-  w.x = pack_bf16x2(a.x, a.y); w.y = pack_bf16x2(a.z, a.w);
-  w.z = pack_bf16x2(b.x, b.y); w.w = pack_bf16x2(b.z, b.w);
+  w.x = pack_op16x2(a.x, a.y); w.y = pack_op16x2(a.z, a.w);
+  w.z = pack_op16x2(b.x, b.y); w.w = pack_op16x2(b.z, b.w);
   return w;
 }
 template <>
-__device__ __forceinline__ uint4 load8_as_bf16<__nv_bfloat16>(const __nv_bfloat16* p) {
+__device__ __forceinline__ uint4 load8_as_bf16<op16>(const op16* p) {
   return __ldg(reinterpret_cast<const uint4*>(p));
 }
 
 // x [n,H,W,C] -> out [n*Ho*Wo, 9*C] bf16 (3x3, pad 1, given stride)
 template <typename T>
 __global__ void im2col3x3_kernel(const T* __restrict__ x, int n_img, int H, int W, int C, int stride, int Ho, int Wo,
-                                 __nv_bfloat16* __restrict__ out, int pad_lo) {
+                                 op16* __restrict__ out, int pad_lo) {
   pdl_prologue();
   const int oct = C >> 3;
   const long long total = (long long)n_img * Ho * Wo * 9 * oct;
@@ -96,7 +96,7 @@ __global__ void im2col3x3_kernel(const T* __restrict__ x, int n_img, int H, int 
 }
 
 __global__ void upsample2x_kernel(const float* __restrict__ x, int n_img, int H, int W, int C,
-                                  __nv_bfloat16* __restrict__ out) {
+                                  op16* __restrict__ out) {
   pdl_prologue();
   const int oct = C >> 3;
   const int Ho = 2 * H, Wo = 2 * W;
@@ -114,7 +114,7 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, int n_img, int H,
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ x, long long rows, int C_src, int c_offset, int C_total,
-                                 __nv_bfloat16* __restrict__ out) {
+                                 op16* __restrict__ out) {
   pdl_prologue();
   const int oct = C_src >> 3;
   const long long total = rows * oct;
@@ -126,10 +126,10 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, long long rows, in
   }
 }
 
-__global__ void silu_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ out) {
+__global__ void silu_bf16_kernel(const float* __restrict__ x, long long n, op16* __restrict__ out) {
   pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = __float2bfloat16(silu_f(x[i]));
+    out[i] = float2op16(silu_f(x[i]));
 }
 
 // tok [B,F,HW,C] <-> x [B,C,F,HW]
@@ -169,7 +169,7 @@ __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restr
 
 // embeddings.py:28-68 (scale = 1, max_period = 10000): [sin | cos], optionally flipped to [cos | sin]
 __global__ void timestep_embedding_kernel(const float* __restrict__ ts, int B, int dim, int flip, float freq_shift,
-                                          __nv_bfloat16* __restrict__ out) {
+                                          op16* __restrict__ out) {
   pdl_prologue();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,7 +184,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ ts, int B, i
     const bool is_sin = flip ? second : !second;
     v = is_sin ? sinf(arg) : cosf(arg);
   }
-  out[i] = __float2bfloat16(v);
+  out[i] = float2op16(v);
 }
 
 __global__ void cfg_ddim_kernel(float* __restrict__ lat, const float* __restrict__ np, const float* __restrict__ counter,
@@ -230,7 +230,7 @@ extern "C" int emote_latent_im2col(const float* latent, int32_t B, int32_t Cl, i
   if (!latent || !out_bf16 || B <= 0 || F <= 0 || H <= 0 || W <= 0) return set_error("emote_latent_im2col: bad arguments");
   if (Cl <= 0 || Cl > 7) return set_error("emote_latent_im2col: latent channels must be in [1,7] (9*Cl <= 64)");
   const long long total = (long long)B * F * H * W;
-  launch_kernel(latent_im2col_kernel, dim3(grid_for(total, 128)), dim3(128), 0, STREAM(stream), latent, B, Cl, F, H, W, pre_scale, pw_weight, pw_bias, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  launch_kernel(latent_im2col_kernel, dim3(grid_for(total, 128)), dim3(128), 0, STREAM(stream), latent, B, Cl, F, H, W, pre_scale, pw_weight, pw_bias, reinterpret_cast<op16*>(out_bf16));
   EMOTE_CHECK_LAUNCH("emote_latent_im2col");
   return 0;
 }
@@ -242,7 +242,7 @@ static int im2col_impl(const T* x, int n_img, int H, int W, int C, int stride, v
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const long long total = (long long)n_img * Ho * Wo * 9 * (C / 8);
   launch_kernel(im2col3x3_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, STREAM(stream), x, n_img, H, W, C, stride, Ho, Wo,
-                                                                       reinterpret_cast<__nv_bfloat16*>(out), 1);
+                                                                       reinterpret_cast<op16*>(out), 1);
   EMOTE_CHECK_LAUNCH("emote_im2col3x3");
   return 0;
 }
@@ -257,13 +257,13 @@ extern "C" int emote_im2col3x3_s2_pad01(const float* x, int32_t n_img, int32_t H
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)n_img * Ho * Wo * 9 * (C / 8);
   launch_kernel(im2col3x3_kernel<float>, dim3(grid_for(total, 256)), dim3(256), 0, STREAM(stream), x, n_img, H, W, C, 2, Ho, Wo,
-                reinterpret_cast<__nv_bfloat16*>(out_bf16), 0);
+                reinterpret_cast<op16*>(out_bf16), 0);
   EMOTE_CHECK_LAUNCH("emote_im2col3x3_s2_pad01");
   return 0;
 }
 extern "C" int emote_im2col3x3_bf16(const void* x, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t stride,
                                     void* out_bf16, void* stream) {
-  return im2col_impl<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(x), n_img, H, W, C, stride, out_bf16, stream);
+  return im2col_impl<op16>(reinterpret_cast<const op16*>(x), n_img, H, W, C, stride, out_bf16, stream);
 }
 
 extern "C" int emote_upsample2x(const float* x, int32_t n_img, int32_t H, int32_t W, int32_t C, void* out_bf16,
@@ -271,7 +271,7 @@ extern "C" int emote_upsample2x(const float* x, int32_t n_img, int32_t H, int32_
   if (!x || !out_bf16 || n_img <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0) return set_error("emote_upsample2x: bad arguments");
   const long long total = (long long)n_img * 4 * H * W * (C / 8);
   launch_kernel(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM(stream), x, n_img, H, W, C,
-                                                                     reinterpret_cast<__nv_bfloat16*>(out_bf16));
+                                                                     reinterpret_cast<op16*>(out_bf16));
   EMOTE_CHECK_LAUNCH("emote_upsample2x");
   return 0;
 }
@@ -281,14 +281,14 @@ extern "C" int emote_cast_bf16(const float* x, int64_t rows, int32_t C_src, int3
   if (!x || !out_bf16 || rows <= 0 || C_src <= 0 || C_src % 8 != 0 || c_offset % 8 != 0 || C_total % 8 != 0 ||
       c_offset + C_src > C_total)
     return set_error("emote_cast_bf16: bad arguments");
-  launch_kernel(cast_bf16_kernel, dim3(grid_for(rows * (C_src / 8), 256)), dim3(256), 0, STREAM(stream), x, rows, C_src, c_offset, C_total, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  launch_kernel(cast_bf16_kernel, dim3(grid_for(rows * (C_src / 8), 256)), dim3(256), 0, STREAM(stream), x, rows, C_src, c_offset, C_total, reinterpret_cast<op16*>(out_bf16));
   EMOTE_CHECK_LAUNCH("emote_cast_bf16");
   return 0;
 }
 
 extern "C" int emote_silu_bf16(const float* x, int64_t n, void* out_bf16, void* stream) {
   if (!x || !out_bf16 || n <= 0) return set_error("emote_silu_bf16: bad arguments");
-  launch_kernel(silu_bf16_kernel, dim3(grid_for(n, 256)), dim3(256), 0, STREAM(stream), x, n, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  launch_kernel(silu_bf16_kernel, dim3(grid_for(n, 256)), dim3(256), 0, STREAM(stream), x, n, reinterpret_cast<op16*>(out_bf16));
   EMOTE_CHECK_LAUNCH("emote_silu_bf16");
   return 0;
 }
@@ -320,7 +320,7 @@ extern "C" int emote_timestep_embedding(const float* timesteps, int32_t B, int32
   if (!timesteps || !out_bf16 || B <= 0 || dim <= 1) return set_error("emote_timestep_embedding: bad arguments");
   const int n = B * dim;
   launch_kernel(timestep_embedding_kernel, dim3((n + 127) / 128), dim3(128), 0, STREAM(stream), timesteps, B, dim, flip_sin_to_cos, freq_shift,
-                                                                         reinterpret_cast<__nv_bfloat16*>(out_bf16));
+                                                                         reinterpret_cast<op16*>(out_bf16));
   EMOTE_CHECK_LAUNCH("emote_timestep_embedding");
   return 0;
 }

@@ -193,7 +193,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     // ------------------------------------------------------------------ MMA issuer: one elected lane of the LEADER
     // CTA's warp 1 (warp-uniform loop)
     if (leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      constexpr uint32_t idesc = umma_idesc_op16(2 * BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;

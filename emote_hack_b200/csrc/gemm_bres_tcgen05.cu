@@ -105,7 +105,7 @@ gemm_bres_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    constexpr uint32_t idesc = umma_idesc_op16(BM, BN);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;

@@ -159,12 +159,12 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
           *reinterpret_cast<float2*>(sp) = make_float2(v0, v1);
         } else if constexpr (TMA_OUT) {
           const int lr = quarter * 32 + g + 8 * i, lc = (c_first + ci) * 8 + 2 * t;
-          *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(stage_) + lr * BN + lc) = pack_bf16x2(v0, v1);
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<op16*>(stage_) + lr * BN + lc) = pack_op16x2(v0, v1);
         } else if (rok[i] && c0ok) {
           if (p.out_bf16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[i] + col;
-            if (c1ok) *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(v0, v1);
-            else o[0] = __float2bfloat16(v0);
+            op16* o = reinterpret_cast<op16*>(p.out) + ooff[i] + col;
+            if (c1ok) *reinterpret_cast<uint32_t*>(o) = pack_op16x2(v0, v1);
+            else o[0] = float2op16(v0);
           } else {
             float* o = reinterpret_cast<float*>(p.out) + ooff[i] + col;
             if (c1ok) *reinterpret_cast<float2*>(o) = make_float2(v0, v1);
@@ -243,12 +243,12 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
           const int ri = (i >> 1) * 4 + (i & 1) * 2;
           const float a0 = __uint_as_float(v[ri]) + b[0], a1 = __uint_as_float(v[ri + 1]) + b[1];
           const float q0 = __uint_as_float(gt[ri]) + b[2], q1 = __uint_as_float(gt[ri + 1]) + b[3];
-          const uint32_t packed = pack_bf16x2(a0 * gelu_sig(q0), a1 * gelu_sig(q1));
+          const uint32_t packed = pack_op16x2(a0 * gelu_sig(q0), a1 * gelu_sig(q1));
           if constexpr (TMA_OUT) {
             const int lr = quarter * 32 + g + 8 * i, lc = cc * 8 + 2 * t;
-            *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(stage_) + lr * HALF + lc) = packed;
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<op16*>(stage_) + lr * HALF + lc) = packed;
           } else if (rok[i] && cok)
-            *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[i] + ocol) = packed;
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<op16*>(p.out) + ooff[i] + ocol) = packed;
         }
       }
     };

@@ -15,7 +15,7 @@ constexpr int SK_MAX_M = 8;
 constexpr int SK_WARPS = 8;
 
 __global__ void __launch_bounds__(SK_WARPS * 32)
-gemm_skinny_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ w,
+gemm_skinny_kernel(const op16* __restrict__ a, int lda, const op16* __restrict__ w,
                    const float* __restrict__ bias, int M, int N, int K, float out_scale, void* __restrict__ out, int ldc,
                    int out_bf16) {
   pdl_prologue();
@@ -34,11 +34,11 @@ gemm_skinny_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bflo
     const uint4* wr = reinterpret_cast<const uint4*>(w + (size_t)n * K);
     for (int c = lane; c < kc; c += 32) {
       const uint4 wv = __ldg(wr + c);
-      const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+      const op16x2* w2 = reinterpret_cast<const op16x2*>(&wv);
       float wf[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(w2[j]);
+        const float2 f = op16x2_to_float2(w2[j]);
         wf[2 * j] = f.x;
         wf[2 * j + 1] = f.y;
       }
@@ -46,10 +46,10 @@ gemm_skinny_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bflo
       for (int m = 0; m < SK_MAX_M; ++m) {
         if (m < M) {
           const uint4 av = sk_smem[m * kc + c];
-          const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&av);
+          const op16x2* a2 = reinterpret_cast<const op16x2*>(&av);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 f = __bfloat1622float2(a2[j]);
+            const float2 f = op16x2_to_float2(a2[j]);
             acc[m] = fmaf(f.x, wf[2 * j], acc[m]);
             acc[m] = fmaf(f.y, wf[2 * j + 1], acc[m]);
           }
@@ -62,7 +62,7 @@ gemm_skinny_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bflo
       if (m < M) {
         const float v = (warp_sum(acc[m]) + b) * out_scale;
         if (lane == 0) {
-          if (out_bf16) reinterpret_cast<__nv_bfloat16*>(out)[(size_t)m * ldc + n] = __float2bfloat16(v);
+          if (out_bf16) reinterpret_cast<op16*>(out)[(size_t)m * ldc + n] = float2op16(v);
           else reinterpret_cast<float*>(out)[(size_t)m * ldc + n] = v;
         }
       }
@@ -89,8 +89,8 @@ int launch_gemm_skinny(const void* A, const void* Wt, void* out, const EmoteGemm
   int blocks = (a->N + SK_WARPS - 1) / SK_WARPS;
   if (blocks > 148 * 4) blocks = 148 * 4;
   launch_kernel(gemm_skinny_kernel, dim3(blocks), dim3(SK_WARPS * 32), smem, stream,
-                reinterpret_cast<const __nv_bfloat16*>(A), a->lda, reinterpret_cast<const __nv_bfloat16*>(Wt), a->bias, a->M,
-                a->N, a->K, a->out_scale, out, a->ldc, a->out_dtype == EMOTE_DT_BF16 ? 1 : 0);
+                reinterpret_cast<const op16*>(A), a->lda, reinterpret_cast<const op16*>(Wt), a->bias, a->M,
+                a->N, a->K, a->out_scale, out, a->ldc, a->out_dtype == EMOTE_DT_OP16 ? 1 : 0);
   EMOTE_CHECK_LAUNCH("emote_gemm_bf16(skinny)");
   return 0;
 }

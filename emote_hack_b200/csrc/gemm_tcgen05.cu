@@ -138,7 +138,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one
     // elected lane issues)
     {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = umma_idesc_op16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -345,7 +345,7 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   const bool conv = a->conv_taps == 9;
   if (a->conv_taps != 1 && a->conv_taps != 9) return set_error("emote_gemm_bf16: conv_taps must be 1 or 9");
   const bool geglu = a->epilogue == EMOTE_EPI_GEGLU;
-  if (geglu && (a->N % 2 != 0 || a->out_dtype != EMOTE_DT_BF16 || a->residual || a->row_bias))
+  if (geglu && (a->N % 2 != 0 || a->out_dtype != EMOTE_DT_OP16 || a->residual || a->row_bias))
     return set_error("emote_gemm_bf16: GEGLU epilogue needs even N, bf16 output, no residual/row_bias");
   // Double-buffered residual staging (mode 3, 128-column tiles, single CTA): the HBM-bound 1x1 GEMMs with an fp32
   // residual at the 320-channel level (K <= 320: 97 -> 79 us; slower than mode 2 from K = 640 on; tma_store == 4 forces it).
@@ -357,7 +357,7 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   const int bn = want3 ? 128 : (a->block_n ? a->block_n : ((a->N % 160 == 0) ? 160 : 128));
   if (bn != 128 && bn != 160) return set_error("emote_gemm_bf16: block_n must be 128 or 160");
   if (geglu && a->N % bn != 0) return set_error("emote_gemm_bf16: GEGLU needs N % block_n == 0");
-  if ((a->out_dtype == EMOTE_DT_BF16 && a->ldc % 8 != 0) || (a->out_dtype == EMOTE_DT_F32 && a->ldc % 4 != 0))
+  if ((a->out_dtype == EMOTE_DT_OP16 && a->ldc % 8 != 0) || (a->out_dtype == EMOTE_DT_F32 && a->ldc % 4 != 0))
     return set_error("emote_gemm_bf16: ldc must keep rows 16-byte aligned");
   if (a->residual && a->ldr % 4 != 0) return set_error("emote_gemm_bf16: ldr must be a multiple of 4");
   // M <= 8 (time-embedding products): weight-streaming GEMV instead of a 128-row tensor-core tile
@@ -371,7 +371,7 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   p.residual = a->residual; p.ldr = a->ldr;
   p.out_scale = a->out_scale;
   p.geglu = geglu ? 1 : 0;
-  p.out_bf16 = a->out_dtype == EMOTE_DT_BF16;
+  p.out_bf16 = a->out_dtype == EMOTE_DT_OP16;
   p.ldc = a->ldc;
   p.out = out;
   if (a->colstats) {

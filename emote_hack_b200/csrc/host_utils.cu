@@ -8,6 +8,12 @@
 
 #include "emote_b200.h"
 
+#ifdef EMOTE_OPERAND_BF16
+#define EMOTE_TMAP_OP16 CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#else
+#define EMOTE_TMAP_OP16 CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#endif
+
 namespace emote {
 
 static thread_local char g_err[512] = "";
@@ -68,7 +74,7 @@ int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t
     gstr[i] = strides_bytes[i];
     if (strides_bytes[i] % 16 != 0) return set_error("TMA global strides must be multiples of 16 bytes");
   }
-  CUresult r = g_encode(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr,
+  CUresult r = g_encode(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : EMOTE_TMAP_OP16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr,
                         gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         swizzle == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                         : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -86,4 +92,11 @@ int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t
 extern "C" const char* emote_last_error(void) { return emote::g_err; }
 extern "C" long long emote_launch_count(void) { return emote::g_launches.load(std::memory_order_relaxed); }
 extern "C" int emote_abi_version(void) { return EMOTE_ABI_VERSION; }
+extern "C" int emote_operand_dtype(void) {
+#ifdef EMOTE_OPERAND_BF16
+  return EMOTE_OP_BF16;
+#else
+  return EMOTE_OP_F16;
+#endif
+}
 extern "C" void emote_set_pdl(int enabled) { emote::set_pdl(enabled); }

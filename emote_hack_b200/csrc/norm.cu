@@ -124,8 +124,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
                                                        int cpg, int groups, long long rows_per_batch, int rows_per_block,
                                                        const double* __restrict__ sums, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, float eps, int act_silu,
-                                                       __nv_bfloat16* __restrict__ out,
-                                                       __nv_bfloat16* __restrict__ raw_out) {
+                                                       op16* __restrict__ out,
+                                                       op16* __restrict__ raw_out) {
   pdl_prologue();
   extern __shared__ __align__(16) float gn_smem[];
   float* s_scale = gn_smem;
@@ -187,13 +187,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
             y[j] = act_silu ? silu_f(tt) : tt;
           }
           uint4 w;
-          w.x = pack_bf16x2(y[0], y[1]); w.y = pack_bf16x2(y[2], y[3]);
-          w.z = pack_bf16x2(y[4], y[5]); w.w = pack_bf16x2(y[6], y[7]);
+          w.x = pack_op16x2(y[0], y[1]); w.y = pack_op16x2(y[2], y[3]);
+          w.z = pack_op16x2(y[4], y[5]); w.w = pack_op16x2(y[6], y[7]);
           *reinterpret_cast<uint4*>(out + (row_base + rr) * C_total + c_offset + c0) = w;
           if (raw_out) {
             uint4 q;
-            q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
-            q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+            q.x = pack_op16x2(v[0], v[1]); q.y = pack_op16x2(v[2], v[3]);
+            q.z = pack_op16x2(v[4], v[5]); q.w = pack_op16x2(v[6], v[7]);
             *reinterpret_cast<uint4*>(raw_out + (row_base + rr) * C_total + c_offset + c0) = q;
           }
         }
@@ -210,7 +210,7 @@ template <int NV>
 __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict__ x, long long M, int C_rt,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, const float* __restrict__ pe, int pe_rows_per_frame,
-                                                        int pe_frames, __nv_bfloat16* __restrict__ out) {
+                                                        int pe_frames, op16* __restrict__ out) {
   pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // rows are visited last-to-first: the producing GEMM wrote them in ascending order, so the tail is still in L2, and
@@ -256,12 +256,12 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
         y0 += p2.x;
         y1 += p2.y;
       }
-      o[lane + i * 32] = pack_bf16x2(y0, y1);
+      o[lane + i * 32] = pack_op16x2(y0, y1);
     }
   }
 }
 
-__global__ void softmax_rows_kernel(const float* __restrict__ s, int N, float scale, __nv_bfloat16* __restrict__ out) {
+__global__ void softmax_rows_kernel(const float* __restrict__ s, int N, float scale, op16* __restrict__ out) {
   pdl_prologue();
   // one block per row
   const long long row = blockIdx.x;
@@ -292,8 +292,8 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, int N, float sc
   }
   __syncthreads();
   const float inv = 1.0f / red[0];
-  __nv_bfloat16* o = out + row * N;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) o[i] = __float2bfloat16(__expf(sr[i] * scale - m) * inv);
+  op16* o = out + row * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) o[i] = float2op16(__expf(sr[i] * scale - m) * inv);
 }
 
 }  // namespace emote
@@ -383,8 +383,8 @@ extern "C" int emote_gn_apply(const float* x, int32_t C_src, int32_t c_offset, i
   const size_t smem = 2 * (size_t)C_src * sizeof(float);
   launch_kernel(gn_apply_kernel, dim3(grid), dim3(block), smem, stream, x, C_src, c_offset, C_total, C_total / groups, groups, rows_per_batch,
                                                  rows_per_block, sums, gamma, beta, eps, act_silu,
-                                                 reinterpret_cast<__nv_bfloat16*>(out_bf16),
-                                                 reinterpret_cast<__nv_bfloat16*>(raw_out_bf16));
+                                                 reinterpret_cast<op16*>(out_bf16),
+                                                 reinterpret_cast<op16*>(raw_out_bf16));
   EMOTE_CHECK_LAUNCH("emote_gn_apply");
   return 0;
 }
@@ -398,7 +398,7 @@ extern "C" int emote_layernorm(const float* x, int64_t M, int32_t C, const float
   if (pe && (pe_rows_per_frame <= 0 || pe_frames <= 0)) return set_error("emote_layernorm: bad positional table dims");
   const int warps = 4;
   const long long blocks = (M + warps - 1) / warps;
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  op16* o = reinterpret_cast<op16*>(out_bf16);
 #define EMOTE_LN(NVV) launch_kernel(layernorm_kernel<NVV>, dim3((unsigned)blocks), dim3(warps * 32), 0, stream, \
       x, M, C, gamma, beta, eps, pe, pe_rows_per_frame, pe_frames, o)
   switch (C / 64) {
@@ -420,7 +420,7 @@ extern "C" int emote_softmax_rows_bf16(const float* scores, int64_t R, int32_t N
                                        void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!scores || !out_bf16 || R <= 0 || N <= 0) return set_error("emote_softmax_rows_bf16: bad arguments");
-  launch_kernel(softmax_rows_kernel, dim3((unsigned)R), dim3(256), 0, stream, scores, N, scale, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  launch_kernel(softmax_rows_kernel, dim3((unsigned)R), dim3(256), 0, stream, scores, N, scale, reinterpret_cast<op16*>(out_bf16));
   EMOTE_CHECK_LAUNCH("emote_softmax_rows_bf16");
   return 0;
 }

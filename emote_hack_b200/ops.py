@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from ._lib import EmoteAttnArgs, EmoteGemmArgs, check
 
-F32, BF16 = torch.float32, torch.bfloat16
+F32, OP16 = torch.float32, _lib.op16_torch_dtype()   # OP16: fp16 (default) or bf16, see _lib.OPERAND
 EPI_LINEAR, EPI_GEGLU = 0, 1
 
 
@@ -44,20 +44,20 @@ def auto_block_n(N: int) -> int:
 # ----------------------------------------------------------------------------------------------- weight packing
 def pack_linear(w: torch.Tensor) -> torch.Tensor:
     """nn.Linear / 1x1-conv weight [N, K(,1,1)] -> bf16 [N, K] (K-major B operand)."""
-    return w.detach().reshape(w.shape[0], -1).to(BF16).contiguous()
+    return w.detach().reshape(w.shape[0], -1).to(OP16).contiguous()
 
 
 def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
     """conv weight [N, C, 3, 3] -> bf16 [N, 9*C] with column (ky*3+kx)*C + c (tap-major, matches the TMA tap loop)."""
     n, c = w.shape[0], w.shape[1]
-    return w.detach().permute(0, 2, 3, 1).reshape(n, 9 * c).to(BF16).contiguous()
+    return w.detach().permute(0, 2, 3, 1).reshape(n, 9 * c).to(OP16).contiguous()
 
 
 def pack_conv3x3_small(w: torch.Tensor) -> torch.Tensor:
     """conv weight [N, Cl<=7, 3, 3] -> bf16 [N, 64] matching emote_latent_im2col columns, zero padded."""
     n, c = w.shape[0], w.shape[1]
-    out = torch.zeros(n, 64, dtype=BF16, device=w.device)
-    out[:, : 9 * c] = w.detach().permute(0, 2, 3, 1).reshape(n, 9 * c).to(BF16)
+    out = torch.zeros(n, 64, dtype=OP16, device=w.device)
+    out[:, : 9 * c] = w.detach().permute(0, 2, 3, 1).reshape(n, 9 * c).to(OP16)
     return out
 
 
@@ -74,7 +74,7 @@ def pack_geglu(w: torch.Tensor, b: torch.Tensor):
     wp = torch.stack([wv.reshape(-1, half, k), wg.reshape(-1, half, k)], dim=1).reshape(n2, k)
     bv, bg = b.detach()[:inner], b.detach()[inner:]
     bp = torch.stack([bv.reshape(-1, half), bg.reshape(-1, half)], dim=1).reshape(n2)
-    return wp.to(BF16).contiguous(), bp.to(F32).contiguous()
+    return wp.to(OP16).contiguous(), bp.to(F32).contiguous()
 
 
 # ----------------------------------------------------------------------------------------------- GEMM / conv
@@ -87,7 +87,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, row_bias=None, rows_per
     stats_rows > 0 (fp32 outputs): the epilogue also accumulates per-column (sum, sum of squares) of the output per
     block of `stats_rows` rows; they ride on the returned tensor (`_emote_colstats`) and let group_norm() skip its
     statistics pass over that tensor."""
-    _req(a, BF16, "gemm.a"), _req(w, BF16, "gemm.w")
+    _req(a, OP16, "gemm.a"), _req(w, OP16, "gemm.w")
     N, K = w.shape
     args = EmoteGemmArgs()
     if conv is not None:
@@ -119,7 +119,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, row_bias=None, rows_per
     args.ldr = n_out
     args.out_scale = out_scale
     args.epilogue = EPI_GEGLU if geglu else EPI_LINEAR
-    args.out_dtype = 1 if out_dtype == BF16 else 0
+    if out_dtype not in (F32, OP16):
+        raise _lib.EmoteKernelError(f"gemm: out_dtype must be float32 or the operand type {OP16}, got {out_dtype}")
+    args.out_dtype = 1 if out_dtype == OP16 else 0
     args.ldc = out.shape[-1]
     args.block_n = FORCE_BLOCK_N
     args.pair_mode = pair_mode
@@ -171,7 +173,7 @@ def conv3x3(x_bf16: torch.Tensor, w_packed: torch.Tensor, n_img: int, H: int, W:
     """3x3 / stride 1 / pad 1 conv over NHWC bf16.  Implicit GEMM when the tile geometry allows, else explicit im2col."""
     if conv_tile_ok(H, W) and Cc % 64 == 0:
         return gemm(x_bf16, w_packed, conv=(n_img, H, W, Cc), **epi)
-    cols = torch.empty((n_img * H * W, 9 * Cc), dtype=BF16, device=x_bf16.device)
+    cols = torch.empty((n_img * H * W, 9 * Cc), dtype=OP16, device=x_bf16.device)
     check(_lib.load().emote_im2col3x3_bf16(x_bf16.data_ptr(), n_img, H, W, Cc, 1, cols.data_ptr(), _stream()),
           "emote_im2col3x3_bf16")
     return gemm(cols, w_packed, **epi)
@@ -180,7 +182,7 @@ def conv3x3(x_bf16: torch.Tensor, w_packed: torch.Tensor, n_img: int, H: int, W:
 def im2col_s2(x: torch.Tensor, n_img: int, H: int, W: int, Cc: int) -> torch.Tensor:
     _req(x, F32, "im2col_s2.x")
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-    cols = torch.empty((n_img * Ho * Wo, 9 * Cc), dtype=BF16, device=x.device)
+    cols = torch.empty((n_img * Ho * Wo, 9 * Cc), dtype=OP16, device=x.device)
     check(_lib.load().emote_im2col3x3(x.data_ptr(), n_img, H, W, Cc, 2, cols.data_ptr(), _stream()), "emote_im2col3x3")
     return cols
 
@@ -188,7 +190,7 @@ def im2col_s2(x: torch.Tensor, n_img: int, H: int, W: int, Cc: int) -> torch.Ten
 def im2col_s2_pad01(x: torch.Tensor, n_img: int, H: int, W: int, Cc: int) -> torch.Tensor:
     """stride-2 3x3 operand with (0, 1) padding (VAE encoder downsample) -> bf16 [n_img*(H/2)*(W/2), 9*Cc]"""
     _req(x, F32, "im2col_s2_pad01.x")
-    cols = torch.empty((n_img * (H // 2) * (W // 2), 9 * Cc), dtype=BF16, device=x.device)
+    cols = torch.empty((n_img * (H // 2) * (W // 2), 9 * Cc), dtype=OP16, device=x.device)
     check(_lib.load().emote_im2col3x3_s2_pad01(x.data_ptr(), n_img, H, W, Cc, cols.data_ptr(), _stream()),
           "emote_im2col3x3_s2_pad01")
     return cols
@@ -196,7 +198,7 @@ def im2col_s2_pad01(x: torch.Tensor, n_img: int, H: int, W: int, Cc: int) -> tor
 
 def upsample2x(x: torch.Tensor, n_img: int, H: int, W: int, Cc: int) -> torch.Tensor:
     _req(x, F32, "upsample2x.x")
-    out = torch.empty((n_img * 4 * H * W, Cc), dtype=BF16, device=x.device)
+    out = torch.empty((n_img * 4 * H * W, Cc), dtype=OP16, device=x.device)
     check(_lib.load().emote_upsample2x(x.data_ptr(), n_img, H, W, Cc, out.data_ptr(), _stream()), "emote_upsample2x")
     return out
 
@@ -205,7 +207,7 @@ def latent_im2col(lat: torch.Tensor, pre_scale: float = 1.0, pw_weight=None, pw_
     """lat [B, Cl, F, H, W] fp32 (standard NCFHW contiguous) -> bf16 [B*F*H*W, 64]."""
     _req(lat, F32, "latent_im2col.lat")
     B, Cl, F_, H, W = lat.shape
-    out = torch.empty((B * F_ * H * W, 64), dtype=BF16, device=lat.device)
+    out = torch.empty((B * F_ * H * W, 64), dtype=OP16, device=lat.device)
     check(_lib.load().emote_latent_im2col(lat.data_ptr(), B, Cl, F_, H, W, pre_scale, _ptr(pw_weight), _ptr(pw_bias),
                                           out.data_ptr(), _stream()), "emote_latent_im2col")
     return out
@@ -221,8 +223,8 @@ def group_norm(sources: Sequence[torch.Tensor], groups: int, rows_per_batch: int
     c_total = sum(int(s.shape[-1]) for s in sources)
     dev = sources[0].device
     sums = torch.empty((n_batches, groups, 2), dtype=torch.float64, device=dev)
-    out = torch.empty((rows, c_total), dtype=BF16, device=dev)
-    raw = torch.empty((rows, c_total), dtype=BF16, device=dev) if want_raw else None
+    out = torch.empty((rows, c_total), dtype=OP16, device=dev)
+    raw = torch.empty((rows, c_total), dtype=OP16, device=dev) if want_raw else None
     st = _stream()
     off = 0
     for i, s in enumerate(sources):
@@ -254,7 +256,7 @@ def layer_norm(x: torch.Tensor, gamma, beta, eps: float = 1e-5, pe: Optional[tor
     _req(x, F32, "layer_norm.x")
     Cc = x.shape[-1]
     M = x.numel() // Cc
-    out = torch.empty((M, Cc), dtype=BF16, device=x.device)
+    out = torch.empty((M, Cc), dtype=OP16, device=x.device)
     check(_lib.load().emote_layernorm(x.data_ptr(), M, Cc, gamma.data_ptr(), beta.data_ptr(), eps, _ptr(pe),
                                       rows_per_frame, frames, out.data_ptr(), _stream()), "emote_layernorm")
     return out
@@ -290,8 +292,8 @@ def attention(q: torch.Tensor, k0: torch.Tensor, v0: torch.Tensor, out: torch.Te
 
 
 def temporal_attention(qkv: torch.Tensor, B: int, F_: int, HW: int, heads: int, head_dim: int) -> torch.Tensor:
-    _req(qkv, BF16, "temporal_attention.qkv")
-    out = torch.empty((B * F_ * HW, heads * head_dim), dtype=BF16, device=qkv.device)
+    _req(qkv, OP16, "temporal_attention.qkv")
+    out = torch.empty((B * F_ * HW, heads * head_dim), dtype=OP16, device=qkv.device)
     check(_lib.load().emote_temporal_attention_bf16(qkv.data_ptr(), out.data_ptr(), B, F_, HW, heads, head_dim,
                                                     head_dim ** -0.5, _stream()), "emote_temporal_attention_bf16")
     return out
@@ -301,7 +303,7 @@ def softmax_rows(scores: torch.Tensor, scale: float) -> torch.Tensor:
     _req(scores, F32, "softmax_rows.scores")
     N = scores.shape[-1]
     R = scores.numel() // N
-    out = torch.empty(scores.shape, dtype=BF16, device=scores.device)
+    out = torch.empty(scores.shape, dtype=OP16, device=scores.device)
     check(_lib.load().emote_softmax_rows_bf16(scores.data_ptr(), R, N, scale, out.data_ptr(), _stream()),
           "emote_softmax_rows_bf16")
     return out
@@ -313,7 +315,7 @@ def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None, c_offset: int
     cs = x.shape[-1]
     rows = x.numel() // cs
     if out is None:
-        out = torch.empty((rows, cs), dtype=BF16, device=x.device)
+        out = torch.empty((rows, cs), dtype=OP16, device=x.device)
     check(_lib.load().emote_cast_bf16(x.data_ptr(), rows, cs, c_offset, out.shape[-1], out.data_ptr(), _stream()),
           "emote_cast_bf16")
     return out
@@ -321,7 +323,7 @@ def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None, c_offset: int
 
 def silu_bf16(x: torch.Tensor) -> torch.Tensor:
     _req(x, F32, "silu_bf16.x")
-    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    out = torch.empty(x.shape, dtype=OP16, device=x.device)
     check(_lib.load().emote_silu_bf16(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "emote_silu_bf16")
     return out
 
@@ -352,7 +354,7 @@ def add_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 def timestep_embedding(t: torch.Tensor, dim: int, flip_sin_to_cos: bool, freq_shift: float) -> torch.Tensor:
     _req(t, F32, "timestep_embedding.t")
-    out = torch.empty((t.numel(), dim), dtype=BF16, device=t.device)
+    out = torch.empty((t.numel(), dim), dtype=OP16, device=t.device)
     check(_lib.load().emote_timestep_embedding(t.data_ptr(), t.numel(), dim, 1 if flip_sin_to_cos else 0,
                                                float(freq_shift), out.data_ptr(), _stream()), "emote_timestep_embedding")
     return out

@@ -26,7 +26,7 @@ from torch import nn
 from . import ops
 from ._lib import EmoteKernelError
 
-F32, BF16 = torch.float32, torch.bfloat16
+F32, OP16 = torch.float32, ops.OP16
 
 # The context K/V projections are cached per context tensor (constant over the denoising steps).  CUDA-graph capture
 # switches the cache off so the projections are part of the captured step and replays stay correct when the static
@@ -298,7 +298,7 @@ class FeedForward(_PackedModule):
 
     def run(self, a_bf16: torch.Tensor, residual: Optional[torch.Tensor], out=None, out_dtype=F32) -> torch.Tensor:
         p = self.pk
-        mid = ops.gemm(a_bf16, p["w1"], bias=p["b1"], geglu=True, out_dtype=BF16)
+        mid = ops.gemm(a_bf16, p["w1"], bias=p["b1"], geglu=True, out_dtype=OP16)
         return ops.gemm(mid, p["w2"], bias=p["b2"], residual=residual, out=out, out_dtype=out_dtype)
 
     def forward(self, hidden_states):
@@ -354,8 +354,8 @@ class CrossAttention(_PackedModule):
                        bank_n: int = 0, bank_div: int = 1, bank_first: int = 0) -> torch.Tensor:
         """a: LN output bf16 [batch*n, C] -> attention output bf16 [batch*n, inner] (before to_out)."""
         p, c = self.pk, self.inner_dim
-        qkv = ops.gemm(a_bf16, p["wqkv"], bias=p.get("bqkv"), out_dtype=BF16)
-        out = torch.empty((batch * n, c), dtype=BF16, device=a_bf16.device)
+        qkv = ops.gemm(a_bf16, p["wqkv"], bias=p.get("bqkv"), out_dtype=OP16)
+        out = torch.empty((batch * n, c), dtype=OP16, device=a_bf16.device)
         kw = {}
         if bank_kv is not None:
             kw = dict(k1=bank_kv[:, :c], v1=bank_kv[:, c:], n1=bank_n, kv1_strides=(bank_n * 2 * c, 2 * c),
@@ -375,19 +375,19 @@ class CrossAttention(_PackedModule):
             return cc[2]
         p = self.pk
         flat = ctx.reshape(-1, ctx.shape[-1])
-        a = flat if flat.dtype == BF16 and flat.is_contiguous() else ops.cast_bf16(flat.float().contiguous())
-        kv = ops.gemm(a, p["wkv"], bias=p.get("bkv"), out_dtype=BF16)
+        a = flat if flat.dtype == OP16 and flat.is_contiguous() else ops.cast_bf16(flat.float().contiguous())
+        kv = ops.gemm(a, p["wkv"], bias=p.get("bkv"), out_dtype=OP16)
         self._ctx_cache = (ctx, ctx._version, kv) if CTX_KV_CACHE_ENABLED else None
         return kv
 
     def cross_attention(self, a_bf16: torch.Tensor, batch: int, n: int, ctx: torch.Tensor) -> torch.Tensor:
         p, c = self.pk, self.inner_dim
-        q = ops.gemm(a_bf16, p["wq"], bias=p.get("bq"), out_dtype=BF16)
+        q = ops.gemm(a_bf16, p["wq"], bias=p.get("bq"), out_dtype=OP16)
         kv = self.project_kv(ctx)
         bc, nc = ctx.shape[0], ctx.shape[1]
         if batch % bc != 0:
             raise ValueError(f"context batch {bc} does not divide attention batch {batch}")
-        out = torch.empty((batch * n, c), dtype=BF16, device=a_bf16.device)
+        out = torch.empty((batch * n, c), dtype=OP16, device=a_bf16.device)
         ops.attention(q, kv[:, :c], kv[:, c:], out, batch=batch, heads=self.heads, head_dim=self.dim_head, nq=n, n0=nc,
                       q_strides=(n * c, c), kv0_strides=(nc * 2 * c, 2 * c), o_strides=(n * c, c), scale=self.scale,
                       kv0_batch_div=batch // bc)
@@ -492,7 +492,7 @@ class BasicTransformerBlock(nn.Module):
         ln = self.norm3
         a = ops.layer_norm(x, ln.weight, ln.bias, ln.eps)
         if _emit_bf16:
-            return self.ff.run(a, x, out_dtype=BF16).view(bf, n, c)
+            return self.ff.run(a, x, out_dtype=OP16).view(bf, n, c)
         x = self.ff.run(a, x, out=x)
         return x.view(bf, n, c)
 
@@ -554,7 +554,7 @@ class Transformer3DModel(nn.Module):
                       _emit_bf16=(i == nblk - 1))  # last FF epilogue emits the proj_out operand
         inner = x.shape[-1]
         xa = x.reshape(-1, inner)
-        out = ops.gemm(xa if xa.dtype == BF16 else ops.cast_bf16(xa), p["wo"], bias=p["bo"], residual=tok,
+        out = ops.gemm(xa if xa.dtype == OP16 else ops.cast_bf16(xa), p["wo"], bias=p["bo"], residual=tok,
                        stats_rows=ops.stats_rows_for(h * w, f * h * w))
         out = _untokens(out, b, c, f, h, w)
         return Transformer3DModelOutput(sample=out) if return_dict else (out,)
@@ -609,7 +609,7 @@ class VersatileAttention(CrossAttention):
                 pe = pe.float().contiguous()
         a = ops.layer_norm(x, norm.weight, norm.bias, norm.eps, pe=pe, rows_per_frame=hw, frames=f)
         p = self.pk
-        qkv = ops.gemm(a, p["wqkv"], bias=p.get("bqkv"), out_dtype=BF16)
+        qkv = ops.gemm(a, p["wqkv"], bias=p.get("bqkv"), out_dtype=OP16)
         o = ops.temporal_attention(qkv, b, f, hw, self.heads, self.dim_head)
         return self.out_proj(o, x, out=x)
 
@@ -623,7 +623,7 @@ class VersatileAttention(CrossAttention):
             frame = (torch.arange(bf, device=x.device) % video_length).repeat_interleave(d)
             a = ops.cast_bf16((x + pe[frame]).contiguous())
         p = self.pk
-        qkv = ops.gemm(a, p["wqkv"], bias=p.get("bqkv"), out_dtype=BF16)
+        qkv = ops.gemm(a, p["wqkv"], bias=p.get("bqkv"), out_dtype=OP16)
         o = ops.temporal_attention(qkv, bf // video_length, video_length, d, self.heads, self.dim_head)
         return self.out_proj(o, None).view(bf, d, c)
 
@@ -656,7 +656,7 @@ class TemporalTransformerBlock(nn.Module):
         n = self.ff_norm
         a = ops.layer_norm(x, n.weight, n.bias, n.eps)
         if last_bf16:
-            return self.ff.run(a, x, out_dtype=BF16)
+            return self.ff.run(a, x, out_dtype=OP16)
         return self.ff.run(a, x, out=x)
 
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, video_length=None):
@@ -1002,7 +1002,7 @@ class TimestepEmbedding(nn.Module):
             self._pk = {"w1": ops.pack_linear(self.linear_1.weight), "b1": _f32c(self.linear_1.bias),
                         "w2": ops.pack_linear(self.linear_2.weight), "b2": _f32c(self.linear_2.bias), "ver": ver}
         p = self._pk
-        a = sample if sample.dtype == BF16 else ops.cast_bf16(sample.float().contiguous())
+        a = sample if sample.dtype == OP16 else ops.cast_bf16(sample.float().contiguous())
         h = ops.gemm(a, p["w1"], bias=p["b1"])
         return ops.gemm(ops.silu_bf16(h), p["w2"], bias=p["b2"])
 

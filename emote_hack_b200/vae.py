@@ -23,7 +23,7 @@ from . import ops
 from ._lib import EmoteKernelError
 from .unet3d import AttrDict, _f32c
 
-F32, BF16 = torch.float32, torch.bfloat16
+F32, OP16 = torch.float32, ops.OP16
 
 
 class _Conv(nn.Conv2d):
@@ -123,18 +123,18 @@ class AttentionBlock(nn.Module):
         c, n = self.channels, h * w
         g, p = self.group_norm, self._packed()
         a, _ = ops.group_norm([tok], g.num_groups, n, n_img, g.weight, g.bias, g.eps, False)
-        qk = ops.gemm(a, p["wqk"], bias=p["bqk"], out_dtype=BF16)  # [n_img*n, 2c]
+        qk = ops.gemm(a, p["wqk"], bias=p["bqk"], out_dtype=OP16)  # [n_img*n, 2c]
         q = qk[:, :c].contiguous().view(n_img, n, c)
         k = qk[:, c:].contiguous().view(n_img, n, c)
-        attn = torch.empty((n_img * n, c), dtype=BF16, device=tok.device)
+        attn = torch.empty((n_img * n, c), dtype=OP16, device=tok.device)
         av = a.view(n_img, n, c)
         for i in range(n_img):
             # V^T[c, n] = Wv x_i^T : the operand roles are swapped so the PV GEMM gets a K-major B operand;
             # the value bias is added after PV (softmax rows sum to 1)
-            vt = ops.gemm(p["wv"], av[i], out_dtype=BF16)             # [c, n]
+            vt = ops.gemm(p["wv"], av[i], out_dtype=OP16)             # [c, n]
             s = ops.gemm(q[i], k[i])                                  # [n, n] fp32 scores
             pr = ops.softmax_rows(s, c ** -0.5)                       # bf16 probabilities
-            ops.gemm(pr, vt, bias=p["bv"], out_dtype=BF16, out=attn[i * n:(i + 1) * n])
+            ops.gemm(pr, vt, bias=p["bv"], out_dtype=OP16, out=attn[i * n:(i + 1) * n])
         return ops.gemm(attn, p["wo"], bias=p["bo"], residual=tok)
 
 

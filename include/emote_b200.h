@@ -19,12 +19,22 @@
 extern "C" {
 #endif
 
-#define EMOTE_ABI_VERSION 1
+#define EMOTE_ABI_VERSION 2
 #define EMOTE_ERR_INVALID 1
 #define EMOTE_ERR_CUDA 2
 
+/* The library is built for ONE 16-bit tensor-core operand type ("op16"): fp16 in the default build
+ * (libemote_b200.so; the reference pipeline runs fp16, magicanimate/pipelines/animation.py:96-100) or bf16
+ * (libemote_b200_bf16.so, built with -DEMOTE_OPERAND_BF16).  emote_operand_dtype() tells which.  Wherever this header
+ * says "bf16" / "_bf16" for an operand buffer it means that op16 type (the names predate the fp16 build); statistics,
+ * residual stream, accumulators and softmax are fp32 in both builds. */
+#define EMOTE_OP_BF16 1
+#define EMOTE_OP_F16 2
+int emote_operand_dtype(void); /* EMOTE_OP_BF16 or EMOTE_OP_F16 */
+
+/* EmoteGemmArgs.out_dtype */
 #define EMOTE_DT_F32 0
-#define EMOTE_DT_BF16 1
+#define EMOTE_DT_OP16 1
 
 #define EMOTE_EPI_LINEAR 0
 #define EMOTE_EPI_GEGLU 1
@@ -57,7 +67,7 @@ typedef struct {
   int32_t ldr;
   float out_scale;
   int32_t epilogue;       /* EMOTE_EPI_* */
-  int32_t out_dtype;      /* EMOTE_DT_* */
+  int32_t out_dtype;      /* EMOTE_DT_F32 or EMOTE_DT_OP16 */
   int32_t ldc;            /* out row pitch in elements */
   int32_t block_n;        /* 0 = auto (160 if N % 160 == 0 else 128) */
   int32_t pair_mode;      /* 0 = auto, 1 = force CTA pairs (cta_group::2, 256-row tiles), 2 = force single CTA,

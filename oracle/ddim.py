@@ -11,10 +11,13 @@ timestep_spacing "leading", set_alpha_to_one=True):
     timesteps = (arange(n) * (1000 // n))[::-1] + steps_offset
     x0 = (x_t - sqrt(1 - abar_t) eps) / sqrt(abar_t);   x_prev = sqrt(abar_prev) x0 + sqrt(1 - abar_prev) eps
     with prev = t - 1000 // n and abar_prev = 1 when prev < 0.
-PARITY UNPINNED against diffusers itself (not installed here).  It IS pinned against the reference's own in-repo
-restatement of the same algebra in the inversion direction (`next_step`, EMOAnimationPipeline.py:379-400 and
-magicanimate/utils/util.py:64-74, restated below as `ddim_inversion_step`): tests/test_oracle.py checks that
-step(next_step(x)) round-trips.
+PINNED on executed reference code: the reference carries the same algebra in-repo (`next_step`,
+EMOAnimationPipeline.py:379-400 and magicanimate/utils/util.py:64-74).  oracle/ref_ddim.py cuts those functions out of
+the reference sources with `ast` and runs them unchanged; tests/test_oracle.py holds `ddim_inversion_step` to their
+output and `step` to the output of the SAME reference code run with the two alphas exchanged (golden vectors
+tests/golden/ddim_reference_steps.pt + a live test).  What remains restated from the published diffusers definition
+only: the timestep list ("leading" spacing + steps_offset) — consistent with the reference's own neighbour rule
+`t - num_train_timesteps // num_inference_steps` (:391).
 """
 from __future__ import annotations
 

@@ -30,8 +30,36 @@ VAE_CASES = {"tiny": ((32, 32, 64, 64), 2, 8, 1), "mid": ((64, 128, 128, 128), 1
 VAE_ENC_CASES = {"tiny": ((32, 32, 64, 64), 2, 32, 1), "mid": ((64, 128, 128, 128), 1, 64, 2)}
 
 
+DDIM_CASES = [(50, 981), (50, 481), (50, 21), (50, 1), (20, 951), (20, 1)]   # (num_inference_steps, timestep)
+
+
+def make_ddim_golden():
+    """Known answers of the reference's own DDIM algebra (EMOAnimationPipeline.next_step :379-400 and
+    magicanimate/utils/util.py:64-74), executed from the reference sources (oracle/ref_ddim.py): the inversion step as
+    written, and the same code run with the two alphas exchanged = the forward sampler step of `scheduler.step`."""
+    from oracle import ref_ddim
+    from oracle.ddim import DDIMOracle
+    method, util_fn = ref_ddim.reference_next_step_method(), ref_ddim.reference_next_step_util()
+    abar = DDIMOracle().alphas_cumprod       # betas of configs/inference.yaml:23-26
+    out = {"cases": DDIM_CASES}
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 4, 2, 8, 8, generator=g)
+    eps = torch.randn(1, 4, 2, 8, 8, generator=g)
+    out["x"], out["eps"] = x, eps
+    import types
+    for n, t in DDIM_CASES:
+        stub = ref_ddim.scheduler_stub(abar, n)
+        x_next, pred_x0 = method(types.SimpleNamespace(scheduler=stub), eps, t, x)
+        assert torch.equal(x_next, util_fn(eps, t, x, stub))        # the two reference copies agree bit for bit
+        out[f"invert_{n}_{t}"], out[f"x0_{n}_{t}"] = x_next, pred_x0
+        fwd = ref_ddim.swapped_alpha_stub(abar, t, n)
+        out[f"step_{n}_{t}"] = method(types.SimpleNamespace(scheduler=fwd), eps, t, x)[0]
+    torch.save(out, GOLD / "ddim_reference_steps.pt")
+
+
 def main():
     GOLD.mkdir(parents=True, exist_ok=True)
+    make_ddim_golden()
     U = ref_shim.load_reference_unet_class()
     RC = ref_shim.load_reference_control_class()
     uniform = ref_shim.load_reference_context_uniform()
@@ -128,4 +156,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["ddim"]:
+        make_ddim_golden()
+    else:
+        main()

@@ -41,7 +41,8 @@ def timestep_embedding(t: Tensor, dim: int, flip_sin_to_cos: bool, freq_shift: f
 class UNet3DOracle:
     """Evaluates the reference network from a reference-format state_dict (same key names) and its config."""
 
-    def __init__(self, state_dict: Dict[str, Tensor], config: dict, dtype=torch.float32, device=None):
+    def __init__(self, state_dict: Dict[str, Tensor], config: dict, dtype=torch.float32, device=None,
+                 attention_slice_bytes: Optional[int] = None):
         # dtype=float32 is the oracle; bfloat16 is only used to calibrate "what eager PyTorch bf16 would give"
         self.dtype = dtype
         self.sd = {k: v.detach().to(device=device or v.device, dtype=dtype) for k, v in state_dict.items()}
@@ -59,6 +60,9 @@ class UNet3DOracle:
         self.center = c.get("center_input_sample", False)
         self.n_down = n_blocks
         self._collect = None
+        # like unet.set_attention_slice (unet_controlnet.py:259-322 -> orig_attention.py:686-727): the score matrix is
+        # evaluated in slices over the batch axis when it would exceed this many bytes; same arithmetic per slice
+        self.attention_slice_bytes = attention_slice_bytes
 
     # ------------------------------------------------------------------ primitives
     def _has(self, key: str) -> bool:
@@ -87,8 +91,17 @@ class UNet3DOracle:
         b, n, c = q.shape
         d = c // heads
         sp = lambda t: t.reshape(t.shape[0], t.shape[1], heads, d).transpose(1, 2)
-        s = (sp(q) @ sp(k).transpose(-1, -2)) * d ** -0.5
-        o = (s.softmax(-1) @ sp(v)).transpose(1, 2).reshape(b, n, c)
+        qh, kh, vh = sp(q), sp(k), sp(v)
+        step = b
+        if self.attention_slice_bytes:
+            per_batch = heads * n * k.shape[1] * q.element_size()
+            step = max(1, min(b, self.attention_slice_bytes // max(1, per_batch)))
+        outs = []
+        for i in range(0, b, step):
+            s = (qh[i:i + step] @ kh[i:i + step].transpose(-1, -2)) * d ** -0.5
+            outs.append(s.softmax(-1) @ vh[i:i + step])
+            del s
+        o = (outs[0] if len(outs) == 1 else torch.cat(outs)).transpose(1, 2).reshape(b, n, c)
         return self._lin(p + ".to_out.0", o)
 
     def _ff(self, p: str, x: Tensor) -> Tensor:

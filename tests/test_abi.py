@@ -22,12 +22,27 @@ def test_library_loads_and_exports_every_declared_symbol():
     if not _lib.LIB_PATH.exists():
         _lib.build()
     lib = _lib.load()
-    assert lib.emote_abi_version() == 1
+    assert lib.emote_abi_version() == 2
+    assert lib.emote_operand_dtype() == (2 if _lib.OPERAND == "fp16" else 1)   # EMOTE_OP_F16 / EMOTE_OP_BF16
     assert isinstance(lib.emote_launch_count(), int)
     for name in _declared():
         assert hasattr(lib, name), f"{name} declared in emote_b200.h but not exported"
     bound = set(_lib.SIGNATURES) | set(_lib.INTROSPECTION)
     assert bound == set(_declared()), f"ctypes binding out of sync with the header: {bound ^ set(_declared())}"
+
+
+def test_both_operand_builds_export_the_same_abi():
+    """libemote_b200.so (fp16 operands) and libemote_b200_bf16.so are the same sources built twice"""
+    import ctypes
+    from emote_hack_b200 import _lib
+    libdir = _lib.LIB_PATH.parent
+    for name, want in (("libemote_b200.so", 2), ("libemote_b200_bf16.so", 1)):
+        if not (libdir / name).exists():
+            _lib.build()
+        lib = ctypes.CDLL(str(libdir / name))
+        assert lib.emote_operand_dtype() == want and lib.emote_abi_version() == 2
+        for sym in _declared():
+            assert hasattr(lib, sym), f"{sym} missing from {name}"
 
 
 def test_exported_symbols_are_plain_c():

@@ -133,6 +133,44 @@ def test_ddim_restatement():
         assert rel_l2(back, x) < 1e-5
 
 
+def test_ddim_oracle_pinned_on_executed_reference_code():
+    """oracle/ddim.py against vectors produced by EXECUTING the reference's own DDIM algebra
+    (EMOAnimationPipeline.next_step :379-400 == magicanimate/utils/util.py:64-74, cut out with ast by oracle/ref_ddim.py):
+    the inversion step as written, and the forward `scheduler.step` = the same code with the two alphas exchanged."""
+    from oracle.ddim import DDIMOracle
+    gold = torch.load(GOLD / "ddim_reference_steps.pt")
+    x, eps = gold["x"], gold["eps"]
+    for n, t in gold["cases"]:
+        o = DDIMOracle()
+        o.set_timesteps(n)
+        assert rel_l2(o.ddim_inversion_step(eps, t, x), gold[f"invert_{n}_{t}"]) < 1e-6
+        assert rel_l2(o.step(eps, t, x), gold[f"step_{n}_{t}"]) < 1e-6
+        a_from = o.alphas_cumprod[t - 1000 // n] if t - 1000 // n >= 0 else 1.0
+        x0 = (x - (1 - a_from) ** 0.5 * eps) / a_from ** 0.5
+        assert rel_l2(x0, gold[f"x0_{n}_{t}"]) < 1e-6
+
+
+def test_ddim_oracle_against_live_reference_code():
+    """same check against the reference sources as they lie in /root/reference (no committed vectors involved)"""
+    if not Path("/root/reference/EMOAnimationPipeline.py").exists():
+        pytest.skip("/root/reference only exists in the build container")
+    import types
+    from oracle import ref_ddim
+    from oracle.ddim import DDIMOracle
+    method, util_fn = ref_ddim.reference_next_step_method(), ref_ddim.reference_next_step_util()
+    g = torch.Generator().manual_seed(5)
+    x, eps = torch.randn(2, 4, 3, 8, 8, generator=g), torch.randn(2, 4, 3, 8, 8, generator=g)
+    for n in (50, 25, 20):
+        o = DDIMOracle()
+        for t in o.set_timesteps(n).tolist():
+            stub = ref_ddim.scheduler_stub(o.alphas_cumprod, n)
+            want, _ = method(types.SimpleNamespace(scheduler=stub), eps, t, x)
+            assert torch.equal(want, util_fn(eps, t, x, stub))
+            assert rel_l2(o.ddim_inversion_step(eps, t, x), want) < 1e-6
+            fwd = ref_ddim.swapped_alpha_stub(o.alphas_cumprod, t, n)
+            assert rel_l2(o.step(eps, t, x), method(types.SimpleNamespace(scheduler=fwd), eps, t, x)[0]) < 1e-6
+
+
 def test_oracle_writer_banks_match_reference_golden():
     """ReferenceNet writer: oracle run with collect_banks against banks recorded from the reference's own
     ReferenceAttentionControl(mode="write") on its UNet3D (one frame, no motion modules)."""

@@ -1,5 +1,49 @@
 """Shared test fixtures: seeded configs / weights / inputs for the UNet3D path (no reference needed)."""
+import json
+import os
+from pathlib import Path
+
 import torch
+
+# ------------------------------------------------------------------------------------------------ parity limits
+# Every parity check of the GPU tests goes through check_parity(key, err, default): the limit is 1.5 x the error MEASURED
+# on a B200 for this operand type (tests/parity_limits.json, written by scripts/update_parity_limits.py from the log of a
+# `pytest -m gpu` run with EMOTE_PARITY_LOG set), or `default` for a key that has no measurement yet.
+_LIMITS_FILE = Path(__file__).resolve().parent / "parity_limits.json"
+_LIMITS = json.loads(_LIMITS_FILE.read_text()) if _LIMITS_FILE.exists() else {}
+
+
+def operand() -> str:
+    from emote_hack_b200 import _lib
+    return _lib.OPERAND
+
+
+def parity_limit(key: str, default: float) -> float:
+    return float(_LIMITS.get(operand(), {}).get(key, {}).get("limit", default))
+
+
+_auto_counts = {}
+
+
+def chk(err: float, default: float) -> float:
+    """check_parity keyed by the running test's id (+ a per-test counter): for parametrised kernel tests"""
+    cur = os.environ.get("PYTEST_CURRENT_TEST", "unknown").split(" ")[0].split("::", 1)[-1]
+    n = _auto_counts.get(cur, 0)
+    _auto_counts[cur] = n + 1
+    return check_parity(f"k.{cur}#{n}".replace(" ", ""), err, default)
+
+
+def check_parity(key: str, err: float, default: float) -> float:
+    """assert err < limit(key); logs `operand key err limit` to $EMOTE_PARITY_LOG (one line per check)"""
+    lim = parity_limit(key, default)
+    log = os.environ.get("EMOTE_PARITY_LOG")
+    if log:
+        with open(log, "a") as fh:
+            fh.write(f"{operand()} {key} {err:.6e} {lim:.6e}\n")
+    print(f"parity[{operand()}] {key}: {err:.3e} (limit {lim:.3e})")
+    assert err < lim, f"{key}: rel-L2 {err:.3e} exceeds the limit {lim:.3e} ({operand()} operands)"
+    return err
+
 
 MM_KW = dict(num_attention_heads=4, num_transformer_block=1, attention_block_types=["Temporal_Self", "Temporal_Self"],
              temporal_position_encoding=True, temporal_position_encoding_max_len=24, temporal_attention_dim_div=1)

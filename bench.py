@@ -11,7 +11,11 @@ operands, random-init SD-1.5-width weights with motion modules on, synthetic lat
 
 Under `python -m torch.distributed.run --nproc-per-node N` every rank generates its own clip (weak scaling: the
 noise-sample axis of the per-step latent batch is sharded, no data-path collective) and the decoded uint8 frames are
-all-gathered once per step over NCCL.  One JSON line is printed by rank 0.
+all-gathered once per step over NCCL.  One JSON line is printed by rank 0.  `variants` carries the other BASELINE configs
+measured in the same run: `longform_240f` (config #5: ONE 240-frame clip, its 40 (window x CFG-branch) units dealt to the N
+ranks, one all-reduce per DDIM step — strong scaling, with a sharded-vs-single-GPU equality check) and `cfg4_768`
+(config #4: one 768x768 sample per rank); `parity` carries the rel-L2 of one full-size config #2 UNet call against the
+fp32 oracle evaluated on the same GPU (checker only, outside every timed region).
 """
 from __future__ import annotations
 
@@ -66,12 +70,14 @@ def host_cores() -> int:
 
 def gemm_dram_traffic_per_launch():
     """DRAM bytes per launch of the dominant (GEMM / implicit-GEMM conv) kernels, from the committed ncu capture of one
-    eager UNet call (scripts/one_unet_call.py + scripts/summarize_traffic.py); None when the capture is absent."""
-    try:
-        d = json.loads((ROOT / "profiles" / "r01_unet_call_dram_traffic.json").read_text())
-        return round(float(d["all_gemm_kernels"]["dram_bytes_per_launch"]))
-    except Exception:
-        return None
+    eager UNet call (scripts/one_unet_call.py + scripts/summarize_traffic.py), latest round first; None when absent."""
+    for name in ("r02_unet_call_dram_traffic.json", "r01_unet_call_dram_traffic.json"):
+        try:
+            d = json.loads((ROOT / "profiles" / name).read_text())
+            return round(float(d["all_gemm_kernels"]["dram_bytes_per_launch"]))
+        except Exception:
+            continue
+    return None
 
 
 def measured_peaks():
@@ -133,11 +139,15 @@ class ClockSampler:
 
 
 # =============================================================================================== CPU reference arm
-def cpu_reference_sample(threads: int, unet_sd=None, vae_sd=None, seed: int = 0):
-    """Times the reference's CPU PyTorch path (oracle port of UNet3D + restated VAE decoder) on a bounded sample and
-    extrapolates the clip: t_clip = 50 steps x 32 frame-evaluations x t(frame-eval) + 16 x t(VAE frame).
-    A frame-evaluation = one UNet forward on [1,4,1,64,64] (1.105 TFLOP); 5-D GroupNorm / temporal attention cost
-    scales linearly in frames, so this is the per-frame cost of the [2,4,16,64,64] call up to cache effects."""
+CPU_SAMPLE = ("ONE conditional-branch UNet3D call [1,4,16,64,64] + ctx [1,77,768] (all 16 frames in one call, so the 5-D "
+              "GroupNorm and the temporal attention over 16 frames are in it; attention scores sliced like the reference's "
+              "set_attention_slice) + the 16-frame VAE decode (per-frame loop, EMOAnimationPipeline.py:297-301); "
+              "clip = 50 steps x 2 CFG branches x t(branch call) + t(16-frame decode)")
+
+
+def cpu_reference_sample(threads: int, unet_sd=None, vae_sd=None, seed: int = 0, warm: bool = True):
+    """SURVEY.md §8(d) protocol on the oracle port (the reference itself cannot be imported on the GPU box; the port is
+    timed next to the untouched reference in the build container: profiles/r02_cpu_port_vs_reference.json)."""
     import torch
     from oracle.unet3d_port import UNet3DOracle
     from oracle.vae_decoder import VAEDecoderOracle, random_vae_decoder_state_dict
@@ -149,18 +159,21 @@ def cpu_reference_sample(threads: int, unet_sd=None, vae_sd=None, seed: int = 0)
         unet_sd = UNet3DConditionModel(**cfg).state_dict()
     if vae_sd is None:
         vae_sd = random_vae_decoder_state_dict(seed=seed)
-    unet = UNet3DOracle(unet_sd, cfg)
+    unet = UNet3DOracle(unet_sd, cfg, attention_slice_bytes=1 << 30)
     vae = VAEDecoderOracle(vae_sd)
     g = torch.Generator().manual_seed(1234)
-    x = torch.randn(1, 4, 1, LAT, LAT, generator=g)
+    x = torch.randn(1, 4, FRAMES, LAT, LAT, generator=g)
     ctx = torch.randn(1, 77, 768, generator=g)
-    z = torch.randn(1, 4, LAT, LAT, generator=g)
-    t0 = time.perf_counter(); unet(x, 981, ctx); t_first = time.perf_counter() - t0
-    t0 = time.perf_counter(); unet(x, 961, ctx); t_unet = time.perf_counter() - t0
-    t0 = time.perf_counter(); vae.decode(z); t_vae = time.perf_counter() - t0
-    t_clip = DDIM_STEPS * 2 * FRAMES * t_unet + FRAMES * t_vae
-    return {"fps": FRAMES / t_clip, "t_frame_eval_s": t_unet, "t_frame_eval_first_s": t_first, "t_vae_frame_s": t_vae,
-            "t_clip_extrapolated_s": t_clip}
+    z = torch.randn(FRAMES, 4, LAT, LAT, generator=g)
+    if warm:
+        unet(x[:, :, :1], 981, ctx)                                    # thread pool / allocator warm-up (untimed)
+    t0 = time.perf_counter(); unet(x, 961, ctx); t_branch = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for i in range(FRAMES):
+        vae.decode(z[i:i + 1])
+    t_vae = time.perf_counter() - t0
+    t_clip = DDIM_STEPS * 2 * t_branch + t_vae
+    return {"fps": FRAMES / t_clip, "t_branch_call_s": t_branch, "t_vae_16_frames_s": t_vae, "t_clip_extrapolated_s": t_clip}
 
 
 def run_reference(args):
@@ -168,9 +181,6 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = host_cores()
-    vals = []
-    sample = None
-    # each "step" = one bounded sample (1 UNet frame-evaluation + 1 VAE frame), extrapolated to the clip
     import torch
     torch.set_num_threads(threads)
     from emote_hack_b200.unet3d import UNet3DConditionModel
@@ -178,21 +188,25 @@ def run_reference(args):
     torch.manual_seed(0)
     unet_sd = UNet3DConditionModel(**full_unet_cfg()).state_dict()
     vae_sd = random_vae_decoder_state_dict(seed=0)
-    for i in range(args.warmup + args.steps):
-        s = cpu_reference_sample(threads, unet_sd, vae_sd)
-        if i >= args.warmup:
-            vals.append(s["fps"])
-            sample = s
+    # each "step" = one bounded sample (~40-60 s of CPU work); at most 2 are timed so the run ends within minutes
+    n_samples = max(1, min(args.steps, 2))
+    vals, sample = [], None
+    for i in range(n_samples):
+        sample = cpu_reference_sample(threads, unet_sd, vae_sd, warm=(i == 0))
+        vals.append(sample["fps"])
     v = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * FRAMES / v, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "samples_timed": n_samples,
+        "ms_per_step": 1000.0 * FRAMES / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "oracle port (fp32 restatement of the reference, validated against it): 1 UNet "
-                                   f"frame-evaluation [1,4,1,64,64] ({sample['t_frame_eval_s']:.2f} s) + 1 VAE frame "
-                                   f"({sample['t_vae_frame_s']:.2f} s), extrapolated x(50 steps x 32 frame-evals) + 16 frames"},
+                         "sample": f"oracle port (fp32 restatement of the reference, validated against it): {CPU_SAMPLE}; "
+                                   f"measured t(branch call) = {sample['t_branch_call_s']:.1f} s, t(16-frame decode) = "
+                                   f"{sample['t_vae_16_frames_s']:.1f} s",
+                         "note": "one clip on the host cores of ONE box whatever --gpus is: at N > 1 the driver's ratio "
+                                 "compares N GPUs (N clips) with the same single CPU arm"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -200,6 +214,39 @@ def run_reference(args):
 
 
 # =============================================================================================== CUDA arm
+def _roofline_classes(prof, peaks):
+    """attention and HBM-bound kernel classes of one UNet call next to the GEMM class (`roofline`): algorithmic work from
+    the launch arguments, time from CUDA events on the launching stream (eager pass, one event pair per launch)."""
+    out = []
+    hbm = peaks["hbm_gbs"]
+    tf_peak = peaks["bf16_tflops"]
+    att = [(ms, m) for n, ms, m in prof.times if n == "emote_attention_tc_bf16"]
+    if att:
+        # per (image, head): S = Q K^T and P V, 2 x 2 x nq x (n0 + n1 for the batches that see segment 1) x d
+        fl = sum(4.0 * b * h * nq * d * (n0 + 0.5 * n1) for _, (b, h, d, nq, n0, n1) in att)
+        ms = sum(t for t, _ in att)
+        out.append({"class": "attention (tcgen05 flash kernel, head_dim 40/80)", "bound": "tensor / MUFU.EX2",
+                    "launches": len(att), "ms": round(ms, 3), "achieved": round(fl / 1e12 / (ms / 1e3), 1),
+                    "peak": tf_peak, "unit": "TFLOP/s", "frac": round(fl / 1e12 / (ms / 1e3) / tf_peak, 4)})
+    gna = [(ms, m) for n, ms, m in prof.times if n == "emote_gn_apply"]
+    if gna:
+        # meta = (C_src, c_offset, C_total, groups, rows_per_batch, n_batches): 4 B read + 2 B written per element
+        by = sum(6.0 * m[0] * m[4] * m[5] for _, m in gna)
+        ms = sum(t for t, _ in gna)
+        out.append({"class": "GroupNorm apply (+SiLU) -> 16-bit operand", "bound": "hbm", "launches": len(gna),
+                    "ms": round(ms, 3), "achieved": round(by / 1e9 / (ms / 1e3), 1), "peak": hbm, "unit": "GB/s",
+                    "frac": round(by / 1e9 / (ms / 1e3) / hbm, 4),
+                    "note": "algorithmic bytes exclude the raw-copy output of the shortcut convs"})
+    ln = [(ms, m) for n, ms, m in prof.times if n == "emote_layernorm"]
+    if ln:
+        by = sum(6.0 * m[0] * m[1] for _, m in ln)       # meta = (M, C, ...)
+        ms = sum(t for t, _ in ln)
+        out.append({"class": "LayerNorm (+temporal PE) -> 16-bit operand", "bound": "hbm", "launches": len(ln),
+                    "ms": round(ms, 3), "achieved": round(by / 1e9 / (ms / 1e3), 1), "peak": hbm, "unit": "GB/s",
+                    "frac": round(by / 1e9 / (ms / 1e3) / hbm, 4)})
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -217,7 +264,7 @@ def run_ours(args):
         dist.all_reduce(torch.zeros(1, device=dev))  # communicator warm-up (reference dist_tools.py:55)
 
     from emote_hack_b200 import _lib, ops
-    from emote_hack_b200.pipeline import DDIMScheduler, EMOAnimationPipeline
+    from emote_hack_b200.pipeline import DDIMScheduler, EMOAnimationPipeline, GraphedUNet, plan_units
     from emote_hack_b200.unet3d import UNet3DConditionModel
     from emote_hack_b200.vae import AutoencoderKL
     from util_models import rerandomise_zero_inits
@@ -233,48 +280,54 @@ def run_ours(args):
     g = torch.Generator().manual_seed(1234 + rank)
     host_lat = torch.randn(1, 4, FRAMES, LAT, LAT, generator=g).pin_memory()
     host_ctx = torch.randn(2, 77, 768, generator=g).pin_memory()
-    host_out = torch.empty((1, 3, FRAMES, 8 * LAT, 8 * LAT), dtype=torch.uint8).pin_memory()
+    host_out = torch.empty((world if rank == 0 else 1, 1, 3, FRAMES, 8 * LAT, 8 * LAT), dtype=torch.uint8).pin_memory()
     lat_dev, ctx_dev = host_lat.to(dev), host_ctx.to(dev)
+    gathered = torch.empty((world, 1, 3, FRAMES, 8 * LAT, 8 * LAT), dtype=torch.uint8, device=dev) if world > 1 else None
 
-    def one_clip(lat, ctx, gather: bool):
+    def one_clip(lat, ctx):
+        """denoise + decode of this rank's clip; at N > 1 the decoded frames of all ranks are all-gathered (the single
+        collective of the path) — returns the [world, ...] uint8 videos every rank then holds"""
         lat = pipe.denoise(lat, ctx, num_inference_steps=DDIM_STEPS, guidance_scale=GUIDANCE, context_frames=FRAMES)
         _, u8 = vae.decode_video(lat, want_u8=True)
         u8 = u8.contiguous()
-        if gather and world > 1:
-            outs = [torch.empty_like(u8) for _ in range(world)]
-            dist.all_gather(outs, u8)  # the single collective of the path: decoded frames over NVLink
-        return u8
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, u8)
+            return gathered
+        return u8[None]
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    checksum = torch.zeros((), dtype=torch.float64, device=dev)
     for _ in range(args.warmup):
-        one_clip(lat_dev.clone(), ctx_dev, True)
+        one_clip(lat_dev.clone(), ctx_dev)
     sync_all()
 
     # ---- timed region 1: inputs resident in HBM ("value")
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    from emote_hack_b200.pipeline import GraphedUNet
     launches0 = _lib.launch_count() + GraphedUNet.replayed_kernels
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lats = [lat_dev.clone() for _ in range(args.steps)]
     sync_all()
     e0.record()
     for i in range(args.steps):
-        one_clip(lats[i], ctx_dev, True)
+        vids = one_clip(lats[i], ctx_dev)
+        checksum += vids[:, :, :, ::8, ::64, ::64].sum(dtype=torch.float64)   # the gathered frames are consumed
     e1.record()
     sync_all()
-    ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() + GraphedUNet.replayed_kernels - launches0
     clk = clocks.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = max_over_ranks(e0.elapsed_time(e1))
     value = world * FRAMES * args.steps / (ms_max / 1000.0)
 
     # ---- timed region 2: end to end through the public API with HOST buffers ("e2e")
@@ -283,20 +336,17 @@ def run_ours(args):
     for i in range(args.steps):
         lat = host_lat.to(dev, non_blocking=True)
         ctx = host_ctx.to(dev, non_blocking=True)
-        u8 = one_clip(lat, ctx, True)
-        host_out.copy_(u8, non_blocking=True)
+        vids = one_clip(lat, ctx)
+        host_out.copy_(vids if rank == 0 else vids[rank:rank + 1], non_blocking=True)   # rank 0 takes the whole gather
     e1.record()
     sync_all()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * FRAMES * args.steps / (float(t.item()) / 1000.0)
+    e2e_value = world * FRAMES * args.steps / (max_over_ranks(e0.elapsed_time(e1)) / 1000.0)
     h2d = host_lat.numel() * 4 + host_ctx.numel() * 4
     d2h = host_out.numel()
 
-    # ---- secondary measurement (N=1, rank 0): the same clip with the ReferenceNet on — AppearanceEncoderModel writer once
-    # per timestep + reference attention in the 10 mid/up reader blocks; not part of `value`
-    variants = None
+    variants = {}
+    # ---- variant: the same clip with the ReferenceNet on (N=1) — AppearanceEncoderModel writer once per timestep + reference
+    # attention in the 10 mid/up reader blocks; not part of `value`
     if rank == 0 and world == 1 and not args.no_variants:
         from emote_hack_b200.appearance_encoder import AppearanceEncoderModel
         torch.manual_seed(1)
@@ -317,16 +367,97 @@ def run_ours(args):
             ref_clip(lat_dev.clone())
         e1.record()
         torch.cuda.synchronize()
-        variants = {"reference_net_on": {"value": round(FRAMES * n_var / (e0.elapsed_time(e1) / 1000.0), 4), "unit": UNIT,
-                                         "clips": n_var, "what": "config #2 + AppearanceEncoderModel (2-D SD UNet, 859.5 M "
-                                         "params) run once per DDIM step on the reference-image latents [2,4,64,64]; its 10 "
-                                         "LayerNorm1 banks extend the keys of the mid/up spatial self-attention (cond half)"}}
+        variants["reference_net_on"] = {
+            "value": round(FRAMES * n_var / (e0.elapsed_time(e1) / 1000.0), 4), "unit": UNIT, "clips": n_var,
+            "what": "config #2 + AppearanceEncoderModel (2-D SD UNet, 859.5 M params) run once per DDIM step on the "
+                    "reference-image latents [2,4,64,64]; its 10 LayerNorm1 banks extend the keys of the mid/up spatial "
+                    "self-attention (cond half)"}
+        pipe._graphs.clear()
         del enc
         torch.cuda.empty_cache()
 
+    # ---- variant: BASELINE config #5 — ONE 240-frame clip, 20 sliding windows x 2 CFG branches = 40 units dealt to the N
+    # ranks (strong scaling), one all-reduce of the accumulated prediction per DDIM step, frame-sharded decode + one
+    # uint8 all-gather.  6 DDIM steps are timed (the other 44 are identical work) after a 1-step warm-up.
+    if not args.no_variants:
+        LF, LSTEPS = 240, 6
+        gl = torch.Generator().manual_seed(77)
+        lf_lat = torch.randn(1, 4, LF, LAT, LAT, generator=gl).to(dev)
+        lf_ctx = torch.randn(2, 77, 768, generator=gl).to(dev)
+        shard_pipe = EMOAnimationPipeline(vae, unet, DDIMScheduler(), rank=rank, world_size=world)
+        kw = dict(num_inference_steps=DDIM_STEPS, guidance_scale=GUIDANCE, context_frames=FRAMES, context_overlap=4)
+        shard_pipe.denoise(lf_lat.clone(), lf_ctx, num_actual_inference_steps=1, **kw)      # captures the step graphs
+        sync_all()
+        e0.record()
+        got = shard_pipe.denoise(lf_lat.clone(), lf_ctx, num_actual_inference_steps=LSTEPS, **kw)
+        e1.record()
+        sync_all()
+        step_ms = max_over_ranks(e0.elapsed_time(e1)) / LSTEPS
+        e0.record()
+        shard_pipe.decode_latents_device(got, want_u8=True, shard=True)
+        e1.record()
+        sync_all()
+        dec_ms = max_over_ranks(e0.elapsed_time(e1))
+        lf = {"frames": LF, "windows": 20, "units": 40, "units_per_rank": [sum(2 if m == "pair" else 1 for _, m in
+                                                                               plan_units(20, r, world)) for r in range(world)],
+              "ms_per_ddim_step": round(step_ms, 2), "decode_240_frames_ms": round(dec_ms, 1),
+              "value": round(LF / ((DDIM_STEPS * step_ms + dec_ms) / 1000.0), 4), "unit": UNIT, "scaling": "strong",
+              "timed_ddim_steps": LSTEPS,
+              "what": "BASELINE configs[4]: 512x512, 240 frames, sliding 16-frame windows (overlap 4); value = 240 / (50 x "
+                      "measured step time + measured sharded decode); collectives: one fp32 all-reduce of noise_pred "
+                      "[2,4,240,64,64] (31.5 MB) per step + one uint8 all-gather of the frames"}
+        if world > 1:
+            # sharded == single-GPU: every rank also runs the un-sharded loop (2 steps) and compares its own result
+            one = EMOAnimationPipeline(vae, unet, DDIMScheduler(), rank=0, world_size=1)
+            want = one.denoise(lf_lat.clone(), lf_ctx, num_actual_inference_steps=2, **kw)
+            have = shard_pipe.denoise(lf_lat.clone(), lf_ctx, num_actual_inference_steps=2, **kw)
+            rel = ((have - want).norm() / want.norm()).reshape(1).double()
+            dist.all_reduce(rel, op=dist.ReduceOp.MAX)
+            lf["sharded_vs_single_gpu_rel_l2_max_over_ranks"] = float(rel.item())
+            # the same 6 steps un-sharded on this rank alone -> speed-up measured inside one run
+            torch.cuda.synchronize()
+            e0.record()
+            one.denoise(lf_lat.clone(), lf_ctx, num_actual_inference_steps=LSTEPS, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            single_ms = max_over_ranks(e0.elapsed_time(e1)) / LSTEPS
+            lf["single_gpu_ms_per_ddim_step"] = round(single_ms, 2)
+            lf["step_speedup_vs_single_gpu"] = round(single_ms / step_ms, 3)
+        variants["longform_240f"] = lf
+        pipe._graphs.clear(); shard_pipe._graphs.clear()
+        torch.cuda.empty_cache()
+
+        # ---- variant: BASELINE config #4 — 768x768 (latent 96x96), 16 frames, one sample (CFG pair) per rank, weak scaling
+        L4, S4 = 96, 3
+        g4 = torch.Generator().manual_seed(99 + rank)
+        lat4 = torch.randn(1, 4, FRAMES, L4, L4, generator=g4).to(dev)
+        ctx4 = torch.randn(2, 77, 768, generator=g4).to(dev)
+        kw4 = dict(num_inference_steps=DDIM_STEPS, guidance_scale=GUIDANCE, context_frames=FRAMES)
+        pipe.denoise(lat4.clone(), ctx4, num_actual_inference_steps=1, **kw4)
+        sync_all()
+        e0.record()
+        out4 = pipe.denoise(lat4.clone(), ctx4, num_actual_inference_steps=S4, **kw4)
+        e1.record()
+        sync_all()
+        step4 = max_over_ranks(e0.elapsed_time(e1)) / S4
+        vae.decode_video(out4, want_u8=True, frame_chunk=8)
+        sync_all()
+        e0.record()
+        vae.decode_video(out4, want_u8=True, frame_chunk=8)
+        e1.record()
+        sync_all()
+        dec4 = max_over_ranks(e0.elapsed_time(e1))
+        variants["cfg4_768"] = {
+            "ms_per_ddim_step": round(step4, 2), "decode_16_frames_ms": round(dec4, 1), "timed_ddim_steps": S4,
+            "value": round(world * FRAMES / ((DDIM_STEPS * step4 + dec4) / 1000.0), 4), "unit": UNIT, "scaling": "weak",
+            "what": "BASELINE configs[3]: 768x768, 16 frames, one sample [2,4,16,96,96] per GPU (90.4 TFLOP per UNet call); "
+                    "value = N x 16 / (50 x measured step time + measured decode)"}
+        pipe._graphs.clear()
+        del out4
+        torch.cuda.empty_cache()
+
     # ---- roofline pass (untimed): every launch of one UNet call bracketed by CUDA events on the launching stream
-    roof = None
-    breakdown = None
+    roof, roof_classes, breakdown = None, None, None
     if rank == 0:
         with ops.KernelProfiler() as prof:
             unet(lat_dev.expand(2, -1, -1, -1, -1).contiguous(), 981, ctx_dev)
@@ -337,14 +468,34 @@ def run_ours(args):
         roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": round(achieved, 1),
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": round(achieved / peaks["bf16_tflops"], 4),
                 "traffic": gemm_dram_traffic_per_launch(), "traffic_unit": "bytes/launch (dram__bytes_read.sum + "
-                "dram__bytes_write.sum, mean over the GEMM launches of one UNet call; profiles/r01_unet_call_dram_traffic.json)",
+                "dram__bytes_write.sum, mean over the GEMM launches of one UNet call; profiles/*_unet_call_dram_traffic.json)",
                 "peak_source": peaks["source"],
                 "note": f"{tf:.2f} algorithmic TFLOP (2*M*N*K of the reference's conv/linear ops) in {n_gemm} launches "
-                        f"of one UNet call, {prof.gemm_ms:.2f} ms total"}
+                        f"of one UNet call, {prof.gemm_ms:.2f} ms total; timed per launch with CUDA events in an eager pass "
+                        "(the clip loop replays the same launches from a CUDA graph)"}
+        roof_classes = _roofline_classes(prof, peaks)
         total = sum(ms_ for _, ms_, _ in prof.times)
         breakdown = {k: {"launches": c, "ms": round(v, 3), "share": round(v / total, 4)}
                      for k, (c, v) in sorted(prof.summary().items(), key=lambda kv: -kv[1][1])}
         breakdown["_total_ms_one_unet_call"] = round(total, 3)
+
+    # ---- parity figure (rank 0; checker only, untimed): one full-size config #2 UNet call against the fp32 oracle run on
+    # this GPU with TF32 off, one CFG branch at a time (tests/test_parity_full_gpu.py holds the same check)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle.unet3d_port import UNet3DOracle
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        orc = UNet3DOracle(unet.state_dict(), dict(unet.config), device=dev, attention_slice_bytes=6 << 30)
+        x2 = lat_dev.expand(2, -1, -1, -1, -1).contiguous()
+        tt = torch.tensor(981, device=dev)
+        ref = torch.cat([orc(x2[0:1], tt, ctx_dev[0:1]), orc(x2[1:2], tt, ctx_dev[1:2])])
+        out = unet(x2, 981, ctx_dev).sample
+        parity = {"config2_unet_call_rel_l2_vs_fp32_oracle": float(((out - ref).norm() / ref.norm()).item()),
+                  "operand": _lib.OPERAND, "limit_north_star": 1e-3,
+                  "what": "UNet3DConditionModel.forward on [2,4,16,64,64] + ctx [2,77,768], t = 981, same weights"}
+        del orc, ref, out
+        torch.cuda.empty_cache()
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores
     cpu = None
@@ -354,9 +505,8 @@ def run_ours(args):
         vsd = {k: v.detach().cpu() for k, v in vae.state_dict().items()}
         s = cpu_reference_sample(threads, sd, vsd)
         cpu = {"value": s["fps"], "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"oracle port, same weights: 1 UNet frame-evaluation [1,4,1,64,64] ({s['t_frame_eval_s']:.2f} s) "
-                         f"+ 1 VAE frame 512x512 ({s['t_vae_frame_s']:.2f} s), extrapolated to 50 steps x 32 "
-                         "frame-evaluations + 16 frames"}
+               "sample": f"oracle port, same weights: {CPU_SAMPLE}; measured t(branch call) = {s['t_branch_call_s']:.1f} s, "
+                         f"t(16-frame decode) = {s['t_vae_16_frames_s']:.1f} s"}
 
     if rank == 0:
         line = {
@@ -371,11 +521,14 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": roof,
+            "roofline_classes": roof_classes,
+            "parity": parity,
             "cpu_baseline": cpu,
             "kernel_breakdown_one_unet_call": breakdown,
-            "variants": variants,
-            "model_tflops_per_s": round((DDIM_STEPS * UNET_TFLOP_PER_CALL + FRAMES * VAE_TFLOP_PER_FRAME) * args.steps
+            "variants": variants or None,
+            "model_tflops_per_s": round((DDIM_STEPS * UNET_TFLOP_PER_CALL + FRAMES * VAE_TFLOP_PER_FRAME) * args.steps * world
                                         / (ms_max / 1000.0), 1),
+            "frames_checksum": float(checksum.item()),
         }
         emit(line)
     if world > 1:
@@ -408,7 +561,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-variants", action="store_true", help="skip the secondary ReferenceNet-on measurement")
+    ap.add_argument("--no-variants", action="store_true", help="skip the secondary measurements (ReferenceNet on, 240-frame long form, 768x768)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-size config #2 check against the fp32 oracle")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

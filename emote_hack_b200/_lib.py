@@ -91,7 +91,11 @@ SIGNATURES = {
     "emote_ncfhw_to_tokens": [_vp, _i32, _i32, _i32, _i32, _vp, _vp],
     "emote_add_f32": [_vp, _vp, _vp, _i64, _vp],
     "emote_timestep_embedding": [_vp, _i32, _i32, _i32, _f32, _vp, _vp],
-    "emote_cfg_ddim_step": [_vp, _vp, _vp, _i64, _i32, _i64, _f32, _f32, _f32, _vp],
+    "emote_cfg_ddim_step": [_vp, _vp, _vp, _i64, _i32, _i64, _f32, _f32, _f32, _vp, _f32, _i32, _vp],
+    "emote_ddim_step": [_vp, _vp, _i64, _f32, _f32, _vp, _f32, _vp],
+    "emote_gather_frames": [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, _i32, _vp],
+    "emote_scatter_add_frames": [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, _vp],
+    "emote_fill_f32": [_vp, _f32, _i64, _vp],
     "emote_vae_postprocess": [_vp, _i32, _i32, _i32, _vp, _vp, _vp],
 }
 INTROSPECTION = {

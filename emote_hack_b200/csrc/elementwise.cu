@@ -187,19 +187,68 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ ts, int B, i
   out[i] = float2op16(v);
 }
 
-__global__ void cfg_ddim_kernel(float* __restrict__ lat, const float* __restrict__ np, const float* __restrict__ counter,
-                                long long n, int n_frames, long long inner, float gs, float sa_t, float s1a_t,
-                                float sa_p, float s1a_p) {
+// eps = eps_u/cnt [+ g (eps_c/cnt - eps_u/cnt)];  x0 = (x - sqrt(1-a_t) eps)/sqrt(a_t);
+// x_prev = sqrt(a_prev) x0 + sqrt(1 - a_prev - sigma^2) eps [+ sigma z]      (DDIM, Song et al. 2021 eq. 12 / 16)
+__global__ void cfg_ddim_kernel(float* __restrict__ lat, float* __restrict__ np_u, float* __restrict__ np_c,
+                                const float* __restrict__ counter, const float* __restrict__ noise, long long n,
+                                int n_frames, long long inner, float gs, float sa_t, float s1a_t, float sa_p, float dir_p,
+                                float sigma, int zero_after) {
   pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float cnt = counter ? counter[(i / inner) % n_frames] : 1.f;
-    const float eu = np[i] / cnt;
-    const float ec = np[n + i] / cnt;
-    const float eps = eu + gs * (ec - eu);
+    float eps = np_u[i] / cnt;
+    if (np_c) {
+      const float ec = np_c[i] / cnt;
+      eps = eps + gs * (ec - eps);
+    }
     const float x = lat[i];
     const float x0 = (x - s1a_t * eps) / sa_t;
-    lat[i] = sa_p * x0 + s1a_p * eps;
+    float xp = sa_p * x0 + dir_p * eps;
+    if (noise) xp = fmaf(sigma, noise[i], xp);
+    lat[i] = xp;
+    if (zero_after) {  // the accumulator is ready for the next timestep's windows (EMOAnimationPipeline.py:702-706)
+      np_u[i] = 0.f;
+      if (np_c) np_c[i] = 0.f;
+    }
   }
+}
+
+// Window bookkeeping of the denoise loop (EMOAnimationPipeline.py:759-763, 790-794) as two gather / scatter kernels over
+// tensors viewed as [outer, frames, inner] (inner contiguous, a multiple of 4 floats):
+//   gather:       dst[o, j, :]              = src[(o % src_mod) + src_off, idx[j], :]
+//   scatter-add:  dst[o + dst_off, idx[j], :] += src[o, j, :]          (frames of one window are distinct: no atomics)
+__global__ void gather_frames_kernel(const float4* __restrict__ src, float4* __restrict__ dst, const int* __restrict__ idx,
+                                     int n_outer, int wlen, int F_src, long long inner4, int src_mod, int src_off) {
+  pdl_prologue();
+  const long long total = (long long)n_outer * wlen * inner4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long k = i % inner4;
+    const int j = (int)((i / inner4) % wlen);
+    const int o = (int)(i / (inner4 * wlen));
+    const long long so = (o % src_mod) + src_off;
+    dst[i] = __ldg(src + (so * F_src + idx[j]) * inner4 + k);
+  }
+}
+__global__ void scatter_add_frames_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
+                                          const int* __restrict__ idx, int n_outer, int wlen, int F_dst, long long inner4,
+                                          int dst_off) {
+  pdl_prologue();
+  const long long total = (long long)n_outer * wlen * inner4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long k = i % inner4;
+    const int j = (int)((i / inner4) % wlen);
+    const int o = (int)(i / (inner4 * wlen));
+    float4* d = dst + ((long long)(o + dst_off) * F_dst + idx[j]) * inner4 + k;
+    const float4 a = *d, b = __ldg(src + i);
+    *d = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+__global__ void fill_f32_kernel(float* __restrict__ p, float v, long long n) {
+  pdl_prologue();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = v;
 }
 
 // tok [n, HW, ld>=3] -> [n, 3, HW]
@@ -325,17 +374,71 @@ extern "C" int emote_timestep_embedding(const float* timesteps, int32_t B, int32
   return 0;
 }
 
-extern "C" int emote_cfg_ddim_step(float* latents, const float* noise_pred, const float* counter, int64_t n,
-                                   int32_t n_frames, int64_t inner, float guidance_scale, float alpha_t,
-                                   float alpha_prev, void* stream) {
-  if (!latents || !noise_pred || n <= 0) return set_error("emote_cfg_ddim_step: bad arguments");
-  if (counter && (n_frames <= 0 || inner <= 0)) return set_error("emote_cfg_ddim_step: bad counter geometry");
-  if (!(alpha_t > 0.f && alpha_t <= 1.f && alpha_prev > 0.f && alpha_prev <= 1.f))
-    return set_error("emote_cfg_ddim_step: alphas must lie in (0,1]");
-  launch_kernel(cfg_ddim_kernel, dim3(grid_for(n, 256)), dim3(256), 0, STREAM(stream), latents, noise_pred, counter, n, n_frames > 0 ? n_frames : 1, inner > 0 ? inner : 1, guidance_scale,
-      sqrtf(alpha_t), sqrtf(1.f - alpha_t), sqrtf(alpha_prev), sqrtf(1.f - alpha_prev));
-  EMOTE_CHECK_LAUNCH("emote_cfg_ddim_step");
+extern "C" int emote_gather_frames(const float* src, float* dst, const int32_t* frame_idx, int32_t n_outer, int32_t wlen,
+                                   int32_t F_src, int64_t inner, int32_t src_mod, int32_t src_off, void* stream) {
+  if (!src || !dst || !frame_idx || n_outer <= 0 || wlen <= 0 || F_src <= 0 || inner <= 0 || src_mod <= 0 || src_off < 0)
+    return set_error("emote_gather_frames: bad arguments");
+  if (inner % 4 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
+    return set_error("emote_gather_frames: inner must be a multiple of 4 floats and the buffers 16-byte aligned");
+  const long long total = (long long)n_outer * wlen * (inner / 4);
+  launch_kernel(gather_frames_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM(stream),
+                reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), frame_idx, n_outer, wlen, F_src,
+                (long long)(inner / 4), src_mod, src_off);
+  EMOTE_CHECK_LAUNCH("emote_gather_frames");
   return 0;
+}
+
+extern "C" int emote_scatter_add_frames(const float* src, float* dst, const int32_t* frame_idx, int32_t n_outer,
+                                        int32_t wlen, int32_t F_dst, int64_t inner, int32_t dst_off, void* stream) {
+  if (!src || !dst || !frame_idx || n_outer <= 0 || wlen <= 0 || F_dst <= 0 || inner <= 0 || dst_off < 0)
+    return set_error("emote_scatter_add_frames: bad arguments");
+  if (inner % 4 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
+    return set_error("emote_scatter_add_frames: inner must be a multiple of 4 floats and the buffers 16-byte aligned");
+  const long long total = (long long)n_outer * wlen * (inner / 4);
+  launch_kernel(scatter_add_frames_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM(stream),
+                reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), frame_idx, n_outer, wlen, F_dst,
+                (long long)(inner / 4), dst_off);
+  EMOTE_CHECK_LAUNCH("emote_scatter_add_frames");
+  return 0;
+}
+
+extern "C" int emote_fill_f32(float* p, float value, int64_t n, void* stream) {
+  if (!p || n <= 0) return set_error("emote_fill_f32: bad arguments");
+  launch_kernel(fill_f32_kernel, dim3(grid_for(n, 256)), dim3(256), 0, STREAM(stream), p, value, (long long)n);
+  EMOTE_CHECK_LAUNCH("emote_fill_f32");
+  return 0;
+}
+
+static int ddim_launch(float* latents, float* np_u, float* np_c, const float* counter, const float* noise, int64_t n,
+                       int32_t n_frames, int64_t inner, float gs, float alpha_t, float alpha_prev, float sigma,
+                       int32_t zero_after, void* stream, const char* who) {
+  if (!latents || !np_u || n <= 0) return set_error("emote_(cfg_)ddim_step: bad arguments");
+  if (counter && (n_frames <= 0 || inner <= 0)) return set_error("emote_(cfg_)ddim_step: bad counter geometry");
+  if (!(alpha_t > 0.f && alpha_t <= 1.f && alpha_prev > 0.f && alpha_prev <= 1.f))
+    return set_error("emote_(cfg_)ddim_step: alphas must lie in (0,1]");
+  if (sigma < 0.f || sigma * sigma > 1.f - alpha_prev + 1e-7f || (sigma > 0.f && !noise))
+    return set_error("emote_(cfg_)ddim_step: sigma must satisfy 0 <= sigma^2 <= 1 - alpha_prev and come with a noise tensor");
+  const float dir = sqrtf(fmaxf(1.f - alpha_prev - sigma * sigma, 0.f));
+  launch_kernel(cfg_ddim_kernel, dim3(grid_for(n, 256)), dim3(256), 0, STREAM(stream), latents, np_u, np_c, counter,
+                sigma > 0.f ? noise : (const float*)nullptr, (long long)n, n_frames > 0 ? n_frames : 1,
+                (long long)(inner > 0 ? inner : 1), gs, sqrtf(alpha_t), sqrtf(1.f - alpha_t), sqrtf(alpha_prev), dir, sigma,
+                zero_after);
+  EMOTE_CHECK_LAUNCH(who);
+  return 0;
+}
+
+extern "C" int emote_cfg_ddim_step(float* latents, float* noise_pred, const float* counter, int64_t n,
+                                   int32_t n_frames, int64_t inner, float guidance_scale, float alpha_t,
+                                   float alpha_prev, const float* noise, float sigma, int32_t zero_noise_pred,
+                                   void* stream) {
+  return ddim_launch(latents, noise_pred, noise_pred ? noise_pred + n : nullptr, counter, noise, n, n_frames, inner,
+                     guidance_scale, alpha_t, alpha_prev, sigma, zero_noise_pred, stream, "emote_cfg_ddim_step");
+}
+
+extern "C" int emote_ddim_step(float* latents, const float* eps, int64_t n, float alpha_t, float alpha_prev,
+                               const float* noise, float sigma, void* stream) {
+  return ddim_launch(latents, const_cast<float*>(eps), nullptr, nullptr, noise, n, 1, 1, 1.f, alpha_t, alpha_prev, sigma, 0,
+                     stream, "emote_ddim_step");
 }
 
 extern "C" int emote_vae_postprocess(const float* tok, int32_t n_img, int32_t HW, int32_t ld, float* out_f32,

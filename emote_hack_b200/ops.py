@@ -20,6 +20,8 @@ EPI_LINEAR, EPI_GEGLU = 0, 1
 
 
 def _stream() -> int:
+    # one process drives one GPU (torch.cuda.set_device(local_rank), like the reference's launcher): kernels go to the
+    # current stream of the current device, and _req() rejects tensors that live on another device
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -30,6 +32,9 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     if not t.is_cuda:
         raise _lib.EmoteKernelError(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.device.index != torch.cuda.current_device():
+        raise _lib.EmoteKernelError(f"{name}: tensor on {t.device} but the current device is cuda:{torch.cuda.current_device()} "
+                                    "(one process per GPU: call torch.cuda.set_device first)")
     if t.dtype != dtype:
         raise _lib.EmoteKernelError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -360,15 +365,75 @@ def timestep_embedding(t: torch.Tensor, dim: int, flip_sin_to_cos: bool, freq_sh
     return out
 
 
+def gather_frames(src: torch.Tensor, dst: torch.Tensor, frame_idx: torch.Tensor, n_outer: int, f_src: int, inner: int,
+                  src_mod: int, src_off: int = 0) -> torch.Tensor:
+    """dst[o, j, :] = src[(o % src_mod) + src_off, frame_idx[j], :] over [outer, frames, inner] views (fp32)."""
+    _req(src, F32, "gather_frames.src"), _req(dst, F32, "gather_frames.dst")
+    _req(frame_idx, torch.int32, "gather_frames.frame_idx")
+    wlen = frame_idx.numel()
+    if dst.numel() != n_outer * wlen * inner or (src_mod + src_off) * f_src * inner > src.numel():
+        raise _lib.EmoteKernelError("gather_frames: buffer sizes do not match the [outer, frames, inner] geometry")
+    check(_lib.load().emote_gather_frames(src.data_ptr(), dst.data_ptr(), frame_idx.data_ptr(), n_outer, wlen, f_src,
+                                          inner, src_mod, src_off, _stream()), "emote_gather_frames")
+    return dst
+
+
+def scatter_add_frames(src: torch.Tensor, dst: torch.Tensor, frame_idx: torch.Tensor, n_outer: int, f_dst: int,
+                       inner: int, dst_off: int = 0) -> torch.Tensor:
+    """dst[o + dst_off, frame_idx[j], :] += src[o, j, :] over [outer, frames, inner] views (fp32)."""
+    _req(src, F32, "scatter_add_frames.src"), _req(dst, F32, "scatter_add_frames.dst")
+    _req(frame_idx, torch.int32, "scatter_add_frames.frame_idx")
+    wlen = frame_idx.numel()
+    if src.numel() != n_outer * wlen * inner or (n_outer + dst_off) * f_dst * inner > dst.numel():
+        raise _lib.EmoteKernelError("scatter_add_frames: buffer sizes do not match the [outer, frames, inner] geometry")
+    check(_lib.load().emote_scatter_add_frames(src.data_ptr(), dst.data_ptr(), frame_idx.data_ptr(), n_outer, wlen, f_dst,
+                                               inner, dst_off, _stream()), "emote_scatter_add_frames")
+    return dst
+
+
+def fill_f32(t: torch.Tensor, value: float) -> torch.Tensor:
+    _req(t, F32, "fill_f32.t")
+    check(_lib.load().emote_fill_f32(t.data_ptr(), float(value), t.numel(), _stream()), "emote_fill_f32")
+    return t
+
+
+def ddim_sigma(alpha_t: float, alpha_prev: float, eta: float) -> float:
+    """std of the stochastic DDIM term (Song et al. 2021 eq. 16; diffusers `DDIMScheduler._get_variance`)"""
+    if eta == 0.0:
+        return 0.0
+    var = (1.0 - alpha_prev) / (1.0 - alpha_t) * (1.0 - alpha_t / alpha_prev)
+    return eta * math.sqrt(max(var, 0.0))
+
+
 def cfg_ddim_step(latents: torch.Tensor, noise_pred: torch.Tensor, counter: Optional[torch.Tensor], guidance: float,
-                  alpha_t: float, alpha_prev: float) -> torch.Tensor:
-    """latents [1|B, C, F, H, W] fp32 updated in place; noise_pred [2*B, C, F, H, W] (uncond first)."""
+                  alpha_t: float, alpha_prev: float, zero_noise_pred: bool = False, noise: Optional[torch.Tensor] = None,
+                  sigma: float = 0.0) -> torch.Tensor:
+    """latents [1|B, C, F, H, W] fp32 updated in place; noise_pred [2*B, C, F, H, W] (uncond first), cleared as it is
+    consumed when zero_noise_pred; noise / sigma: the stochastic term of DDIM with eta > 0."""
     _req(latents, F32, "cfg_ddim_step.latents"), _req(noise_pred, F32, "cfg_ddim_step.noise_pred")
     n = latents.numel()
+    if noise_pred.numel() != 2 * n:
+        raise _lib.EmoteKernelError("cfg_ddim_step: noise_pred must hold the (uncond, cond) pair of the latents")
+    if noise is not None:
+        _req(noise, F32, "cfg_ddim_step.noise")
     n_frames = latents.shape[2]
     inner = latents.shape[3] * latents.shape[4]
     check(_lib.load().emote_cfg_ddim_step(latents.data_ptr(), noise_pred.data_ptr(), _ptr(counter), n, n_frames, inner,
-                                          guidance, alpha_t, alpha_prev, _stream()), "emote_cfg_ddim_step")
+                                          guidance, alpha_t, alpha_prev, _ptr(noise), sigma, 1 if zero_noise_pred else 0,
+                                          _stream()), "emote_cfg_ddim_step")
+    return latents
+
+
+def ddim_step(latents: torch.Tensor, eps: torch.Tensor, alpha_t: float, alpha_prev: float,
+              noise: Optional[torch.Tensor] = None, sigma: float = 0.0) -> torch.Tensor:
+    """plain DDIM update of `latents` (in place) with a ready epsilon of the same size"""
+    _req(latents, F32, "ddim_step.latents"), _req(eps, F32, "ddim_step.eps")
+    if eps.numel() != latents.numel():
+        raise _lib.EmoteKernelError("ddim_step: eps and latents differ in size")
+    if noise is not None:
+        _req(noise, F32, "ddim_step.noise")
+    check(_lib.load().emote_ddim_step(latents.data_ptr(), eps.data_ptr(), latents.numel(), alpha_t, alpha_prev, _ptr(noise),
+                                      sigma, _stream()), "emote_ddim_step")
     return latents
 
 

@@ -81,16 +81,25 @@ class DDIMScheduler:
         a_prev = float(self.alphas_cumprod[prev]) if prev >= 0 else float(self.final_alpha_cumprod)
         return a_t, a_prev
 
-    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, eta: float = 0.0, **kwargs):
-        """x_t -> x_{t-1}; the arithmetic runs in emote_cfg_ddim_step (guidance folded out: eps is used as is)."""
-        if eta != 0.0:
-            raise NotImplementedError("DDIMScheduler.step: eta != 0 (stochastic DDIM) is not used by the reference")
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, eta: float = 0.0,
+             use_clipped_model_output: bool = False, generator=None, variance_noise: Optional[torch.Tensor] = None,
+             return_dict: bool = True, **kwargs):
+        """x_t -> x_{t-1} (`emote_ddim_step`).  eta > 0 adds the stochastic DDIM term sigma_t z with
+        sigma_t = eta sqrt((1-a_prev)/(1-a_t) (1 - a_t/a_prev)); z = `variance_noise` or drawn from `generator`."""
+        if use_clipped_model_output:
+            raise NotImplementedError("DDIMScheduler.step: use_clipped_model_output (clip_sample is off in the reference)")
         a_t, a_prev = self.alphas_for(int(timestep))
         out = sample.float().contiguous().clone()
-        eps = model_output.float().contiguous().reshape(1, 1, 1, 1, -1)
-        # guidance 1.0 with identical halves == plain epsilon; the update is elementwise, so any sample rank works
-        ops.cfg_ddim_step(out.view(1, 1, 1, 1, -1), torch.cat([eps, eps]), None, 1.0, a_t, a_prev)
-        return DDIMSchedulerOutput(prev_sample=out.to(sample.dtype))
+        eps = model_output.float().contiguous()
+        sigma = ops.ddim_sigma(a_t, a_prev, float(eta))
+        noise = None
+        if sigma > 0.0:
+            noise = variance_noise if variance_noise is not None else \
+                torch.randn(out.shape, generator=generator, device=out.device, dtype=torch.float32)
+            noise = noise.to(device=out.device, dtype=torch.float32).contiguous()
+        ops.ddim_step(out, eps, a_t, a_prev, noise, sigma)
+        out = out.to(sample.dtype)
+        return DDIMSchedulerOutput(prev_sample=out) if return_dict else (out,)
 
 
 # =============================================================================================== context windows
@@ -144,24 +153,31 @@ def _weights_fingerprint(module) -> int:
 
 
 class GraphedUNet:
-    """One UNet3D step (all ~650 kernel launches) captured in a CUDA graph and replayed per (timestep, window):
-    static input buffers (latents, timestep, context, banks), static output.  Removes the per-launch CPU cost
-    (ctypes + tensor-map encoding + allocator) from the 50-step loop."""
+    """One UNet3D step (all its kernel launches) captured in a CUDA graph and replayed per (timestep, unit): static input
+    buffers (latents, timestep, context, banks), static output.  Removes the per-launch CPU cost (ctypes + tensor-map
+    encoding + allocator) from the 50-step loop.
+
+    mode: "pair" = both CFG branches of a window in one batch-2 call; "uncond" / "cond" = ONE branch (batch 1) — the unit
+    of multi-GPU sharding.  The unconditional branch never sees the reference banks and the conditional
+    branch reads bank row 1 (mutual_self_attention.py:237-255), so a lone branch needs no CFG masking."""
 
     replayed_kernels = 0  # kernels of libemote_b200 launched through graph replays (bench.py "gpu_launches")
 
     def __init__(self, unet, lat_shape, ctx: torch.Tensor, banks: Optional[Dict[str, List[torch.Tensor]]], dev,
-                 alias_banks: bool = False):
+                 alias_banks: bool = False, mode: str = "pair", writer=None):
         """alias_banks: read the given bank tensors in place (static outputs of a GraphedWriter) instead of private copies."""
-        self.unet = unet
+        if mode not in ("pair", "uncond", "cond") or lat_shape[0] != (2 if mode == "pair" else 1):
+            raise ValueError("GraphedUNet: mode must be pair (batch 2) / uncond / cond (batch 1)")
+        self.unet, self.mode, self.writer = unet, mode, writer
         self.fingerprint = _weights_fingerprint(unet)
         self.lat = torch.zeros(lat_shape, dtype=torch.float32, device=dev)
         self.t = torch.zeros(1, dtype=torch.float32, device=dev)
         self.ctx = torch.empty_like(ctx, dtype=torch.float32).copy_(ctx)
-        self.banks = None if banks is None else {k: [t if alias_banks else t.clone() for t in v] for k, v in banks.items()}
-        self.reader = None
-        if self.banks is not None:
-            self.reader = ReferenceAttentionControl(unet, do_classifier_free_guidance=True, mode="read", fusion_blocks="midup")
+        self.bank_src = banks if (banks is not None and mode != "uncond") else None
+        self.banks = None
+        if self.bank_src is not None:
+            sel = (lambda t: t) if mode == "pair" else (lambda t: t[1:2])
+            self.banks = {k: [sel(t) if alias_banks else sel(t).clone() for t in v] for k, v in banks.items()}
         prev = _unet3d.CTX_KV_CACHE_ENABLED
         _unet3d.CTX_KV_CACHE_ENABLED = False
         try:
@@ -178,24 +194,64 @@ class GraphedUNet:
             self.kernels_per_replay = _lib.launch_count() - n0  # kernel nodes of this library inside the graph
         finally:
             _unet3d.CTX_KV_CACHE_ENABLED = prev
-            if self.reader is not None:
-                self.reader.clear()
-                for blk in self.reader._blocks(unet):
-                    blk._ref_mode = None
 
     def _run(self):
-        if self.reader is not None:
-            self.reader.set_banks(self.banks)
-        return self.unet(self.lat, self.t, encoder_hidden_states=self.ctx, return_dict=False)[0]
+        return _run_unet(self.unet, self.mode, self.lat, self.t, self.ctx, self.banks)
 
-    def __call__(self, lat: torch.Tensor, t: int, ctx: Optional[torch.Tensor] = None) -> torch.Tensor:
-        self.lat.copy_(lat)
-        self.t.fill_(float(t))
+    def refresh(self, ctx: Optional[torch.Tensor], banks: Optional[Dict[str, List[torch.Tensor]]]):
+        """new conditioning for a cached graph: contents are copied into the static buffers"""
         if ctx is not None and ctx is not self.ctx:
             self.ctx.copy_(ctx)
+        if banks is not None and self.banks is not None:
+            for k, v in banks.items():
+                for dst, src in zip(self.banks[k], v):
+                    src = src if self.mode == "pair" else src[1:2]
+                    if dst.data_ptr() != src.data_ptr():
+                        dst.copy_(src)
+
+    def replay(self, t) -> torch.Tensor:
+        """inputs were written into .lat / .ctx in place (ops.gather_frames); returns the static output"""
+        ops.fill_f32(self.t, float(t))
         self.graph.replay()
         GraphedUNet.replayed_kernels += self.kernels_per_replay
         return self.out
+
+    def __call__(self, lat: torch.Tensor, t, ctx: Optional[torch.Tensor] = None) -> torch.Tensor:
+        self.lat.copy_(lat)
+        if ctx is not None and ctx is not self.ctx:
+            self.ctx.copy_(ctx)
+        return self.replay(t)
+
+
+def _run_unet(unet, mode: str, lat, t, ctx, banks):
+    """one UNet call of a unit: arms the reference-attention reader for the mode, runs, disarms"""
+    reader = None
+    if banks is not None and mode != "uncond":
+        reader = ReferenceAttentionControl(unet, do_classifier_free_guidance=(mode == "pair"), mode="read",
+                                           fusion_blocks="midup")
+        reader.set_banks(banks)
+    try:
+        return unet(lat, t, encoder_hidden_states=ctx, return_dict=False)[0]
+    finally:
+        if reader is not None:
+            reader.release()
+
+
+class _EagerUNet:
+    """same interface as GraphedUNet without capture (use_cuda_graph=False, debugging)"""
+
+    def __init__(self, unet, lat_shape, ctx, dev, mode):
+        self.unet, self.mode = unet, mode
+        self.lat = torch.zeros(lat_shape, dtype=torch.float32, device=dev)
+        self.ctx = torch.empty_like(ctx, dtype=torch.float32).copy_(ctx)
+        self.banks = None
+
+    def set_banks(self, banks):
+        self.banks = None if (banks is None or self.mode == "uncond") else \
+            {k: [t if self.mode == "pair" else t[1:2] for t in v] for k, v in banks.items()}
+
+    def replay(self, t):
+        return _run_unet(self.unet, self.mode, self.lat, float(t), self.ctx, self.banks)
 
 
 def _writer_reader_pairs(unet, encoder):
@@ -233,19 +289,44 @@ class GraphedWriter:
                 self.reader_banks = {name: [w.bank[0]] for name, w in pairs}
             self.kernels_per_replay = _lib.launch_count() - n0
         finally:
-            self.control.clear()
-            for blk in self.control._blocks(encoder):
-                blk._ref_mode = None
+            self.control.release()
 
     def _run(self):
         self.control.clear()
         self.encoder(self.lat, self.t, encoder_hidden_states=self.ctx, return_dict=False)
 
-    def __call__(self, t: int):
-        self.t.fill_(float(t))
+    def __call__(self, t):
+        ops.fill_f32(self.t, float(t))
         self.graph.replay()
         GraphedUNet.replayed_kernels += self.kernels_per_replay
         return self.reader_banks
+
+
+# =============================================================================================== work partition
+def plan_units(n_windows: int, rank: int, world_size: int, shard: str = "units"):
+    """The UNet calls one rank makes per timestep: [(window index, mode)], mode in {"pair", "uncond", "cond"}.
+
+    shard="units" (default): the (window x CFG-branch) units, window-major with the unconditional branch
+    first, are dealt to the ranks in equal contiguous blocks; two branches of one window that land on the same rank run as
+    one batch-2 call.  240 frames = 20 windows = 40 units -> 5 per rank on 8 GPUs (ideal 8x); one 16-frame clip = 2 units
+    (<= 2x).  shard="windows": the reference's split, whole windows round-robin — `global_context[rank::world_size]`
+    (EMOAnimationPipeline.py:757), 3,3,3,3,2,2,2,2 windows at 240 frames (<= 6.67x)."""
+    if shard == "windows":
+        return [(w, "pair") for w in range(rank, n_windows, world_size)]
+    if shard != "units":
+        raise ValueError(f"unknown shard policy {shard!r}")
+    n = 2 * n_windows
+    lo, hi = rank * n // world_size, (rank + 1) * n // world_size
+    calls, u = [], lo
+    while u < hi:
+        w, branch = divmod(u, 2)
+        if branch == 0 and u + 1 < hi:
+            calls.append((w, "pair"))
+            u += 2
+        else:
+            calls.append((w, "cond" if branch else "uncond"))
+            u += 1
+    return calls
 
 
 # =============================================================================================== pipeline
@@ -254,15 +335,44 @@ class AnimationPipelineOutput:
     videos: object
 
 
-class EMOAnimationPipeline:
-    """Denoise + decode loop of the reference pipeline for pre-computed conditioning."""
+_CALL_KWARGS = {"prompt_embeddings", "reference_banks", "ref_image_latents", "appearance_context", "audio_features",
+                "use_cuda_graph", "shard", "dist", "rank", "world_size"}
 
-    def __init__(self, vae, unet, scheduler: DDIMScheduler, rank: int = 0, world_size: int = 1,
-                 process_group=None):
+
+class EMOAnimationPipeline:
+    """Denoise + decode loop of the reference pipeline (EMOAnimationPipeline.py:543-840) on the sm_100a kernels.
+
+    Optional front-ends (all upstream of the hot path; each may be None): `text_encoder(prompts: List[str]) -> [n, 77, d]`
+    embeddings (the reference's CLIP tokenizer + text encoder, :163-229), `audio_encoder` (`audio.Wav2VecFeatureExtractor`)
+    and `speed_encoder` (`audio.SpeedEncoder`)."""
+
+    MAX_GRAPHS = 12   # cached CUDA graphs (each pins its memory pool): least-recently-used ones are dropped
+
+    def __init__(self, vae, unet, scheduler: DDIMScheduler, rank: int = 0, world_size: int = 1, process_group=None,
+                 text_encoder: Optional[Callable] = None, audio_encoder=None, speed_encoder=None, appearance_encoder=None):
         self.vae, self.unet, self.scheduler = vae, unet, scheduler
+        self.text_encoder, self.audio_encoder, self.speed_encoder = text_encoder, audio_encoder, speed_encoder
+        self.appearance_encoder = appearance_encoder
         self.vae_scale_factor = 8
         self.rank, self.world_size, self.process_group = rank, world_size, process_group
-        self._graphs: Dict[tuple, GraphedUNet] = {}
+        self._graphs: "Dict[tuple, object]" = {}
+        self.last_speed_embeddings = None
+
+    # -- graph cache -------------------------------------------------------------------------------------------------
+    def _cache_get(self, key):
+        g = self._graphs.pop(key, None)
+        if g is not None:
+            self._graphs[key] = g          # most recently used last
+        return g
+
+    def _cache_put(self, key, g):
+        self._graphs[key] = g
+        while len(self._graphs) > self.MAX_GRAPHS:
+            self._graphs.pop(next(iter(self._graphs)))
+
+    def _drop_graphs_of_writer(self, writer):
+        for k in [k for k, g in self._graphs.items() if getattr(g, "writer", None) is writer]:
+            del self._graphs[k]
 
     # -- EMOAnimationPipeline.py:341-368 ---------------------------------------------------------------------------
     def prepare_latents(self, batch_size, num_channels_latents, video_length, height, width, dtype, device, generator,
@@ -294,31 +404,49 @@ class EMOAnimationPipeline:
     @torch.no_grad()
     def next_step(self, model_output: torch.Tensor, timestep: int, x: torch.Tensor, eta: float = 0.0, verbose: bool = False):
         """Inverse DDIM update x_{t - ratio} -> x_t used by `invert`; returns (x_next, pred_x0).  Same algebra as
-        `scheduler.step` with the two alphas swapped, so it runs in the same fused kernel (`emote_cfg_ddim_step`)."""
-        if eta != 0.0:
-            raise NotImplementedError("next_step: eta != 0 is not used by the reference")
+        `scheduler.step` with the two alphas exchanged, so it runs in the same kernel (`emote_ddim_step`).  Like the
+        reference function, `eta` is accepted and unused (the inversion is deterministic)."""
         sch = self.scheduler
         nxt = int(timestep)
         cur = min(nxt - sch.config.num_train_timesteps // sch.num_inference_steps, 999)
         a_cur = float(sch.alphas_cumprod[cur]) if cur >= 0 else float(sch.final_alpha_cumprod)
         a_next = float(sch.alphas_cumprod[nxt])
-        eps = model_output.float().contiguous().reshape(1, 1, 1, 1, -1)
-        pair = torch.cat([eps, eps])                         # guidance 1.0 on identical halves == plain epsilon
+        eps = model_output.float().contiguous()
         x_next = x.float().contiguous().clone()
         pred_x0 = x_next.clone()
-        ops.cfg_ddim_step(x_next.view(1, 1, 1, 1, -1), pair, None, 1.0, a_cur, a_next)
-        ops.cfg_ddim_step(pred_x0.view(1, 1, 1, 1, -1), pair, None, 1.0, a_cur, 1.0)   # alpha_prev = 1: x0 itself
+        ops.ddim_step(x_next, eps, a_cur, a_next)
+        ops.ddim_step(pred_x0, eps, a_cur, 1.0)   # alpha_prev = 1: x0 itself
         return x_next.to(x.dtype), pred_x0.to(x.dtype)
+
+    def _embed_prompt(self, prompt, negative_prompt=None, do_cfg: bool = True, device=None):
+        """EMOAnimationPipeline._encode_prompt (:163-229): [uncond | cond] text embeddings.  A tensor passes through; strings
+        need the optional `text_encoder` front-end (CLIP is upstream of the hot path and not part of this package)."""
+        if torch.is_tensor(prompt):
+            return prompt
+        if self.text_encoder is None:
+            raise NotImplementedError(
+                "string prompts need a text encoder: construct the pipeline with text_encoder=callable(List[str]) -> "
+                "[n, 77, d] embeddings, or pass prompt_embeddings=[uncond | cond] (the CLIP front-end is out of scope)")
+        prompts = [prompt] if isinstance(prompt, str) else list(prompt)
+        cond = self.text_encoder(prompts)
+        if not do_cfg:
+            return cond
+        neg = [""] * len(prompts) if negative_prompt is None else \
+            ([negative_prompt] * len(prompts) if isinstance(negative_prompt, str) else list(negative_prompt))
+        return torch.cat([self.text_encoder(neg), cond])
 
     # -- EMOAnimationPipeline.py:416-477 ---------------------------------------------------------------------------
     @torch.no_grad()
     def invert(self, image, prompt, num_inference_steps: int = 20, num_actual_inference_steps: Optional[int] = 10,
                eta: float = 0.0, return_intermediates: bool = False, **kwargs):
         """Deterministic DDIM inversion of real frames into a noise map.  `image`: uint8 frames [f, h, w, 3] (encoded with
-        `images2latents`) or latents [f, 4, h/8, w/8]; `prompt`: the text EMBEDDINGS [1, n, d] (the CLIP text encoder
-        the reference calls here is upstream of the path)."""
+        `images2latents`) or latents [f, 4, h/8, w/8]; `prompt`: text EMBEDDINGS [1, n, d], or a string when the pipeline
+        has a `text_encoder`."""
         if isinstance(prompt, (str, list)):
-            raise TypeError("invert: pass the prompt's text embeddings [1, n, d]; the CLIP text encoder is out of scope")
+            if self.text_encoder is None:
+                raise TypeError("invert: pass the prompt's text embeddings [1, n, d] (no text_encoder attached; the CLIP "
+                                "text encoder the reference calls here is upstream of the path)")
+            prompt = self._embed_prompt(prompt, do_cfg=False)
         image = torch.as_tensor(image)
         if image.is_floating_point() and image.dim() == 4 and image.shape[1] == self.unet.in_channels:
             latents = image.to(prompt.device).float()
@@ -344,18 +472,19 @@ class EMOAnimationPipeline:
         video, _ = self.decode_latents_device(latents)
         return video.cpu().float().numpy()
 
-    def decode_latents_device(self, latents, want_u8: bool = False, shard: bool = False):
-        """Device-side decode.  With shard=True each rank decodes frames rank::world_size and the uint8 frames are
-        all-gathered once over NCCL (the single collective of the path)."""
+    def decode_latents_device(self, latents, want_u8: bool = False, shard: bool = False, frame_chunk: Optional[int] = None):
+        """Device-side decode (frames decoded `frame_chunk` at a time, default 16: a long-form clip never holds more than
+        one chunk of decoder activations).  With shard=True each rank decodes a contiguous block of frames and the uint8
+        frames are all-gathered once over NCCL (the single collective of the path)."""
         if not shard or self.world_size == 1:
-            return self.vae.decode_video(latents, want_u8=want_u8)
+            return self.vae.decode_video(latents, want_u8=want_u8, frame_chunk=frame_chunk)
         import torch.distributed as dist
         b, c, f, h, w = latents.shape
         per = math.ceil(f / self.world_size)
         lo, hi = min(f, self.rank * per), min(f, (self.rank + 1) * per)
         pad = torch.zeros((b, 3, per, 8 * h, 8 * w), dtype=torch.uint8, device=latents.device)
         if hi > lo:
-            _, u8 = self.vae.decode_video(latents[:, :, lo:hi].contiguous(), want_u8=True)
+            _, u8 = self.vae.decode_video(latents[:, :, lo:hi].contiguous(), want_u8=True, frame_chunk=frame_chunk)
             pad[:, :, : hi - lo] = u8
         gathered = [torch.empty_like(pad) for _ in range(self.world_size)]
         dist.all_gather(gathered, pad, group=self.process_group)
@@ -369,12 +498,17 @@ class EMOAnimationPipeline:
                 context_schedule: str = "uniform", reference_banks: Optional[Dict[str, List[torch.Tensor]]] = None,
                 callback: Optional[Callable] = None, use_cuda_graph: bool = True, appearance_encoder=None,
                 ref_image_latents: Optional[torch.Tensor] = None,
-                appearance_context: Optional[torch.Tensor] = None) -> torch.Tensor:
+                appearance_context: Optional[torch.Tensor] = None, eta: float = 0.0, generator=None,
+                num_actual_inference_steps: Optional[int] = None, callback_steps: int = 1,
+                shard: str = "units") -> torch.Tensor:
         """latents [1, 4, F_total, h, w] fp32 (updated in place and returned); text_embeddings = cat([uncond, cond])
         of shape [2, n, d], or per-frame [2*F_total, n, d] audio tokens (uncond frames first).
         appearance_encoder + ref_image_latents [1, 4, h, w]: run the ReferenceNet writer once per timestep on the
         reference-image latents repeated over the CFG pair (EMOAnimationPipeline.py:711-716) and feed its banks to the
-        reader blocks; its context is `appearance_context` [2, n, d] (default: text_embeddings when that is a CFG pair)."""
+        reader blocks; its context is `appearance_context` [2, n, d] (default: text_embeddings when that is a CFG pair).
+        Multi-GPU (world_size > 1): the (window x CFG-branch) units of a timestep are dealt to the ranks (`plan_units`),
+        every rank accumulates its share into `noise_pred`, ONE all-reduce per step replaces the reference's gather +
+        broadcast + barriers (:796-821) and every rank applies the fused CFG + DDIM update redundantly."""
         writer_ctx = None
         if appearance_encoder is not None:
             if reference_banks is not None:
@@ -384,38 +518,49 @@ class EMOAnimationPipeline:
             writer_ctx = text_embeddings if appearance_context is None else appearance_context
             if writer_ctx.shape[0] != 2:
                 raise ValueError("the ReferenceNet writer needs a [2, n, d] context (pass appearance_context)")
-        do_cfg = guidance_scale > 1.0
-        if not do_cfg:
+        if not guidance_scale > 1.0:
             raise NotImplementedError("the fused sampler implements the classifier-free-guidance path the reference runs")
-        if latents.shape[0] != 1:
-            raise ValueError("denoise() handles one sample per call (run samples on different ranks / sequentially)")
+        if latents.dim() != 5 or latents.shape[0] != 1:
+            raise ValueError("denoise() handles one sample [1, c, f, h, w] per call (run samples on different ranks / sequentially)")
         dev = latents.device
         latents = latents.float().contiguous()
-        f_total = latents.shape[2]
-        self.scheduler.set_timesteps(num_inference_steps, device=dev)
-        windows = list(get_context_scheduler(context_schedule)(0, num_inference_steps, f_total, context_frames,
-                                                               context_stride, context_overlap))
+        _, cl, f_total, h, w = latents.shape
+        inner = h * w
+        sch = self.scheduler
+        sch.set_timesteps(num_inference_steps, device=dev)
+        windows = [list(map(int, c)) for c in get_context_scheduler(context_schedule)(
+            0, num_inference_steps, f_total, context_frames, context_stride, context_overlap)]
         counter = torch.zeros(f_total, dtype=torch.float32)
         for c in windows:
             counter[c] += 1
         counter = counter.to(dev)
-        my_windows = windows[self.rank::self.world_size]
-        need_reduce = self.world_size > 1 and len(windows) > 1
-        per_frame_ctx = text_embeddings.shape[0] == 2 * f_total and f_total > 1
-        reader = None
-        single_window = len(windows) == 1 and windows[0] == list(range(f_total))
-        noise_pred = torch.zeros((2,) + tuple(latents.shape[1:]), dtype=torch.float32, device=dev)
-        graphed, gwriter, writer, ref_lat2 = None, None, None, None
-        if appearance_encoder is not None:
+        calls = plan_units(len(windows), self.rank, self.world_size, shard)
+        need_reduce = self.world_size > 1      # ranks without a unit still contribute zeros and receive the sum
+        ctx_all = text_embeddings.to(device=dev, dtype=torch.float32).contiguous()
+        per_frame_ctx = ctx_all.shape[0] == 2 * f_total and f_total > 1
+        if not per_frame_ctx and ctx_all.shape[0] != 2:
+            raise ValueError("text_embeddings must be [2, n, d] (uncond | cond) or per-frame [2*F, n, d]")
+        ctx_inner = ctx_all.shape[1] * ctx_all.shape[2]
+        idx_dev = {wi: torch.tensor(windows[wi], dtype=torch.int32, device=dev) for wi in {wi for wi, _ in calls}}
+        # direct: the one window is the whole clip in order and both branches are here — the UNet output IS the accumulator
+        direct = (not need_reduce and calls == [(0, "pair")] and len(windows) == 1 and windows[0] == list(range(f_total)))
+        noise_pred = None if direct else torch.zeros((2, cl, f_total, h, w), dtype=torch.float32, device=dev)
+
+        # ---- ReferenceNet writer (once per timestep)
+        gwriter, writer, ref_lat2 = None, None, None
+        if appearance_encoder is not None and calls:
             ref_lat2 = ref_image_latents.to(dev).float().repeat(2, 1, 1, 1).contiguous()
-            if use_cuda_graph and not per_frame_ctx and len(my_windows) > 0:
+            if use_cuda_graph:
                 wkey = ("writer", id(appearance_encoder), tuple(ref_lat2.shape), tuple(writer_ctx.shape))
-                gwriter = self._graphs.get(wkey)
-                if gwriter is not None and gwriter.fingerprint != _weights_fingerprint(appearance_encoder):
-                    gwriter = None                                # weights changed since capture: rebuild
+                gwriter = self._cache_get(wkey)
+                if gwriter is not None and (gwriter.encoder is not appearance_encoder or
+                                            gwriter.fingerprint != _weights_fingerprint(appearance_encoder)):
+                    self._drop_graphs_of_writer(gwriter)          # UNet graphs alias the old writer's bank buffers
+                    self._graphs.pop(wkey, None)
+                    gwriter = None
                 if gwriter is None:
                     gwriter = GraphedWriter(appearance_encoder, self.unet, ref_lat2, writer_ctx, dev)
-                    self._graphs[wkey] = gwriter
+                    self._cache_put(wkey, gwriter)
                 else:
                     gwriter.lat.copy_(ref_lat2)
                     gwriter.ctx.copy_(writer_ctx)
@@ -423,92 +568,173 @@ class EMOAnimationPipeline:
             else:
                 writer = ReferenceAttentionControl(appearance_encoder, do_classifier_free_guidance=True, mode="write",
                                                    fusion_blocks="midup")
-        if use_cuda_graph and not per_frame_ctx and len(my_windows) > 0:
-            wlen = len(my_windows[0])
-            key = (2, latents.shape[1], wlen, latents.shape[3], latents.shape[4], tuple(text_embeddings.shape),
-                   None if reference_banks is None else tuple(sorted((k, tuple(v[0].shape)) for k, v in reference_banks.items())),
-                   None if gwriter is None else id(gwriter))
-            if all(len(w) == wlen for w in my_windows):
-                graphed = self._graphs.get(key)
-                if graphed is not None and graphed.fingerprint != _weights_fingerprint(self.unet):
-                    graphed = None                                # weights changed since capture: rebuild
-                if graphed is None:
-                    graphed = GraphedUNet(self.unet, (2, latents.shape[1], wlen, latents.shape[3], latents.shape[4]),
-                                          text_embeddings, reference_banks, dev, alias_banks=gwriter is not None)
-                    self._graphs[key] = graphed
+                pairs = _writer_reader_pairs(self.unet, appearance_encoder)
+
+        # ---- one runner per (mode, window length) this rank needs: static input buffers + captured step
+        def mode_ctx(mode, wlen):
+            if per_frame_ctx:
+                return ctx_all.new_zeros(((2 if mode == "pair" else 1) * wlen, ctx_all.shape[1], ctx_all.shape[2]))
+            return ctx_all if mode == "pair" else (ctx_all[0:1] if mode == "uncond" else ctx_all[1:2])
+
+        runners = {}
+        for wi, mode in calls:
+            wlen = len(windows[wi])
+            if (mode, wlen) in runners:
+                continue
+            nb = 2 if mode == "pair" else 1
+            shape = (nb, cl, wlen, h, w)
+            mctx = mode_ctx(mode, wlen)
+            if use_cuda_graph:
+                bsig = None if reference_banks is None else tuple(sorted((k, tuple(v[0].shape)) for k, v in reference_banks.items()))
+                key = ("unet", mode, shape, tuple(mctx.shape), bsig)
+                g = self._cache_get(key)
+                if g is not None and (g.fingerprint != _weights_fingerprint(self.unet) or g.unet is not self.unet or
+                                      g.writer is not gwriter):
+                    self._graphs.pop(key, None)
+                    g = None                                      # weights / writer changed since capture: rebuild
+                if g is None:
+                    g = GraphedUNet(self.unet, shape, mctx, reference_banks, dev, alias_banks=gwriter is not None, mode=mode,
+                                    writer=gwriter)
+                    self._cache_put(key, g)
                 else:
-                    graphed.ctx.copy_(text_embeddings)
-                    if reference_banks is not None:
-                        for k, v in reference_banks.items():
-                            for dst, src in zip(graphed.banks[k], v):
-                                if dst is not src:
-                                    dst.copy_(src)
-        if graphed is None and (reference_banks is not None or writer is not None):  # eager path: banks are re-armed before every UNet call
-            reader = ReferenceAttentionControl(self.unet, do_classifier_free_guidance=True, mode="read",
-                                               fusion_blocks="midup")
+                    g.refresh(None if per_frame_ctx else mctx, None if gwriter is not None else reference_banks)
+                runners[(mode, wlen)] = g
+            else:
+                e = _EagerUNet(self.unet, shape, mctx, dev, mode)
+                e.set_banks(reference_banks)
+                runners[(mode, wlen)] = e
+
+        timesteps = sch.timesteps.tolist()
+        skip = 0 if num_actual_inference_steps is None else max(0, num_inference_steps - int(num_actual_inference_steps))
         try:
-            for i, t in enumerate(self.scheduler.timesteps.tolist()):
-                if not single_window:
-                    noise_pred.zero_()
+            for i, t in enumerate(timesteps):
+                if i < skip:                                      # img2img setting (EMOAnimationPipeline.py:699-700)
+                    continue
                 if gwriter is not None:
-                    gwriter(t)                                   # banks of this timestep land in the UNet graph's inputs
+                    gwriter(t)                                    # banks of this timestep land in the UNet graphs' inputs
                 elif writer is not None:
                     writer.clear()
                     appearance_encoder(ref_lat2, t, encoder_hidden_states=writer_ctx, return_dict=False)
-                for c in my_windows:
-                    lat_in = latents if single_window else latents[:, :, c]
-                    lat_in = lat_in.expand(2, -1, -1, -1, -1) if single_window else lat_in.repeat(2, 1, 1, 1, 1)
+                    step_banks = {name: [wblk.bank[0]] for name, wblk in pairs}   # EMOAnimationPipeline.py:774
+                    for r in runners.values():
+                        r.set_banks(step_banks)
+                for wi, mode in calls:
+                    r = runners[(mode, len(windows[wi]))]
+                    nb = 2 if mode == "pair" else 1
+                    b0 = 1 if mode == "cond" else 0
+                    # latents[:, :, c].repeat(nb) (:759-763) and the per-frame audio tokens of the window, written
+                    # straight into the step's static inputs
+                    ops.gather_frames(latents, r.lat, idx_dev[wi], nb * cl, f_total, inner, src_mod=cl)
                     if per_frame_ctx:
-                        idx = torch.as_tensor(c, device=dev)
-                        ctx = torch.cat([text_embeddings[:f_total][idx], text_embeddings[f_total:][idx]])
-                    else:
-                        ctx = text_embeddings
-                    if graphed is not None:
-                        pred = graphed(lat_in, t)
-                    else:
-                        if reader is not None and writer is not None:
-                            reader.update(writer)            # EMOAnimationPipeline.py:774
-                        elif reader is not None:
-                            reader.set_banks(reference_banks)
-                        pred = self.unet(lat_in.contiguous(), t, encoder_hidden_states=ctx, return_dict=False)[0]
-                    if single_window:
-                        noise_pred = pred  # (a static graph output: consumed by the fused update below before the next replay)
-                    else:
-                        noise_pred[:, :, c] += pred
+                        ops.gather_frames(ctx_all, r.ctx, idx_dev[wi], nb, f_total, ctx_inner, src_mod=2, src_off=b0)
+                    pred = r.replay(t)
+                    if direct:
+                        noise_pred = pred   # static graph output: consumed by the fused update below before the next replay
+                    else:                   # noise_pred[b0:b0+nb, :, c] += pred (:790-794)
+                        ops.scatter_add_frames(pred, noise_pred, idx_dev[wi], nb * cl, f_total, inner, dst_off=b0 * cl)
                 if need_reduce:
                     import torch.distributed as dist
                     dist.all_reduce(noise_pred, group=self.process_group)
-                a_t, a_prev = self.scheduler.alphas_for(int(t))
-                ops.cfg_ddim_step(latents, noise_pred.contiguous(), counter, guidance_scale, a_t, a_prev)
-                if callback is not None:
+                a_t, a_prev = sch.alphas_for(int(t))
+                sigma = ops.ddim_sigma(a_t, a_prev, float(eta))
+                z = None
+                if sigma > 0.0:
+                    z = torch.randn(latents.shape, generator=generator, device=dev, dtype=torch.float32)
+                ops.cfg_ddim_step(latents, noise_pred, counter, guidance_scale, a_t, a_prev, zero_noise_pred=not direct,
+                                  noise=z, sigma=sigma)
+                if callback is not None and i % max(1, callback_steps) == 0:
                     callback(i, t, latents)
         finally:
-            if reader is not None:
-                reader.clear()
-                for blk in reader._blocks(self.unet):
-                    blk._ref_mode = None
             if writer is not None:
-                writer.clear()                                   # EMOAnimationPipeline.py:823
-                for blk in writer._blocks(appearance_encoder):
-                    blk._ref_mode = None
+                writer.release()                                  # EMOAnimationPipeline.py:823
         return latents
 
     @torch.no_grad()
-    def __call__(self, text_embeddings: torch.Tensor, video_length: int, height: int = 512, width: int = 512,
-                 num_inference_steps: int = 50, guidance_scale: float = 7.5, generator=None, latents=None,
-                 output_type: str = "tensor", return_dict: bool = True, context_frames: int = 16,
-                 context_stride: int = 1, context_overlap: int = 4, context_schedule: str = "uniform",
-                 reference_banks=None, callback=None, appearance_encoder=None, ref_image_latents=None,
-                 appearance_context=None, **unused):
-        dev = text_embeddings.device
-        lat = self.prepare_latents(1, self.unet.in_channels, video_length, height, width, torch.float32, dev, generator,
-                                   latents, clip_length=min(context_frames, video_length))
+    def __call__(self, prompt, video_length: Optional[int], height: Optional[int] = None, width: Optional[int] = None,
+                 num_inference_steps: int = 50, guidance_scale: float = 7.5, negative_prompt=None,
+                 num_videos_per_prompt: Optional[int] = 1, eta: float = 0.0, generator=None,
+                 latents: Optional[torch.Tensor] = None, output_type: Optional[str] = "tensor", return_dict: bool = True,
+                 callback: Optional[Callable] = None, callback_steps: Optional[int] = 1, controlnet_condition=None,
+                 controlnet_conditioning_scale: float = 1.0, context_frames: int = 16, context_stride: int = 1,
+                 context_overlap: int = 4, context_batch_size: int = 1, context_schedule: str = "uniform",
+                 init_latents: Optional[torch.Tensor] = None, num_actual_inference_steps: Optional[int] = None,
+                 appearance_encoder=None, reference_control_writer=None, reference_control_reader=None,
+                 source_image=None, decoder_consistency=None, audio=None, head_rotation_speeds=None, **kwargs):
+        """The reference's call surface (EMOAnimationPipeline.py:543-578), same argument names and meaning.
+
+        `prompt`: a string / list (needs the pipeline's `text_encoder`) or the [uncond | cond] embeddings tensor; the keyword
+        `prompt_embeddings=` does the same.  `audio`: a waveform tensor / wav path for the pipeline's `audio_encoder`
+        (wav2vec2 -> per-frame [T, 5, 768] tokens used as `encoder_hidden_states`, Net.py:614-667), or pass ready tokens as
+        `audio_features=` [T, n, d].  `source_image`: uint8 RGB array [H, W, 3] (or an image path) -> ReferenceNet latents
+        through `images2latents`; `ref_image_latents=` passes them directly.  `reference_control_writer` / `_reader` are
+        accepted and ignored exactly like the reference, which overwrites both (:633-634).
+        Not on this path (raise): `controlnet_condition` (pose ControlNet, out of scope), `decoder_consistency`,
+        context_batch_size != 1 and num_videos_per_prompt != 1 (the reference asserts both, :641-642).
+        Extra keywords: reference_banks, appearance_context, use_cuda_graph, shard, and the reference's dist / rank /
+        world_size (:636-638; the pipeline's own rank / world_size are used)."""
+        unknown = set(kwargs) - _CALL_KWARGS
+        if unknown:
+            raise TypeError(f"EMOAnimationPipeline.__call__: unexpected keyword arguments {sorted(unknown)}")
+        if controlnet_condition is not None:
+            raise NotImplementedError("controlnet_condition: the pose ControlNet is not part of this path (EMO has none)")
+        if context_batch_size != 1 or num_videos_per_prompt != 1:
+            raise NotImplementedError("context_batch_size and num_videos_per_prompt must be 1 (as the reference asserts)")
+        if video_length is None:
+            raise ValueError("video_length is required")
+        emb = kwargs.get("prompt_embeddings")
+        if emb is None:
+            emb = self._embed_prompt(prompt, negative_prompt, do_cfg=True)
+        dev = emb.device
+        height = height or self.unet.config.sample_size * self.vae_scale_factor
+        width = width or self.unet.config.sample_size * self.vae_scale_factor
+        # audio cross-attention context: per-frame wav2vec tokens replace the text embeddings as encoder_hidden_states
+        tokens = kwargs.get("audio_features")
+        if tokens is None and audio is not None:
+            if self.audio_encoder is None:
+                raise NotImplementedError("audio= needs the pipeline's audio_encoder (audio.Wav2VecFeatureExtractor), or pass "
+                                          "ready per-frame tokens as audio_features=[T, n, d]")
+            tokens = self.audio_encoder.extract_tokens(audio, m=2, n=2)
+        appearance_context = kwargs.get("appearance_context")
+        ctx = emb
+        if tokens is not None:
+            tokens = tokens.to(dev).float()
+            if tokens.shape[0] < video_length:
+                raise ValueError(f"audio features cover {tokens.shape[0]} frames, video_length is {video_length}")
+            tokens = tokens[:video_length]
+            ctx = torch.cat([torch.zeros_like(tokens), tokens])   # unconditional branch: silence (zero tokens)
+            if appearance_context is None:
+                appearance_context = emb
+        if head_rotation_speeds is not None:
+            # the reference computes these and hands them to a UNet signature that has no such argument
+            # (EMOAnimationPipeline.py:597-601,784 vs unet_controlnet.py:328-339): computed and exposed, not consumed
+            if self.speed_encoder is None:
+                raise NotImplementedError("head_rotation_speeds needs the pipeline's speed_encoder (audio.SpeedEncoder)")
+            self.last_speed_embeddings = self.speed_encoder(head_rotation_speeds)
+        # latents
+        if init_latents is not None:                              # "(b f) c h w -> b c f h w" (:656-657)
+            lat = init_latents.to(dev).float().reshape(-1, video_length, *init_latents.shape[1:]).permute(0, 2, 1, 3, 4)
+        else:
+            lat = self.prepare_latents(1, self.unet.in_channels, video_length, height, width, torch.float32, dev, generator,
+                                       latents, clip_length=video_length if latents is not None else min(context_frames, video_length))
         lat = lat[:, :, :video_length].contiguous()
-        lat = self.denoise(lat, text_embeddings, num_inference_steps, guidance_scale, context_frames, context_stride,
-                           context_overlap, context_schedule, reference_banks, callback,
-                           appearance_encoder=appearance_encoder, ref_image_latents=ref_image_latents,
-                           appearance_context=appearance_context)
-        video = self.decode_latents(lat, self.rank)
+        # ReferenceNet
+        appearance_encoder = appearance_encoder if appearance_encoder is not None else self.appearance_encoder
+        ref_lat = kwargs.get("ref_image_latents")
+        if ref_lat is None and source_image is not None and appearance_encoder is not None:
+            if isinstance(source_image, str):
+                from PIL import Image   # optional dependency, only for the path form of the argument
+                source_image = np.array(Image.open(source_image).convert("RGB").resize((width, height)))
+            ref_lat = self.images2latents(np.asarray(source_image)[None], torch.float32)
+        banks = kwargs.get("reference_banks")
+        if appearance_encoder is not None and ref_lat is None and banks is None:
+            raise ValueError("appearance_encoder needs source_image= (or ref_image_latents=)")
+        lat = self.denoise(lat, ctx, num_inference_steps, guidance_scale, context_frames, context_stride, context_overlap,
+                           context_schedule, banks, callback, use_cuda_graph=kwargs.get("use_cuda_graph", True),
+                           appearance_encoder=appearance_encoder if banks is None else None, ref_image_latents=ref_lat,
+                           appearance_context=appearance_context, eta=eta, generator=generator,
+                           num_actual_inference_steps=num_actual_inference_steps, callback_steps=callback_steps or 1,
+                           shard=kwargs.get("shard", "units"))
+        video = self.decode_latents(lat, self.rank, decoder_consistency=decoder_consistency)
         if output_type == "tensor":
             video = torch.from_numpy(video)
         return AnimationPipelineOutput(videos=video) if return_dict else video

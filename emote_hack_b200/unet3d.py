@@ -70,31 +70,32 @@ def _untokens(tok: torch.Tensor, b: int, c: int, f: int, h: int, w: int) -> torc
     return v
 
 
+def _sig(*tensors) -> tuple:
+    """identity + in-place version of the source parameters of a packed copy: changes on load_state_dict / copy_ / mul_
+    (version bump) and on .to() / .cuda() (new storage)"""
+    return tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+
+
 class _PackedModule(nn.Module):
-    """Caches kernel-layout (bf16, packed) copies of the fp32 parameters; rebuilt after load_state_dict / .to()."""
+    """Caches kernel-layout (16-bit, packed) copies of the fp32 parameters; rebuilt whenever a source parameter (weight or
+    bias) was rewritten in place or re-allocated since the copy was made (load_state_dict, .to(), param.copy_(), a LoRA
+    merge ...)."""
 
     def __init__(self):
         super().__init__()
         self._pk: Optional[dict] = None
-        self._register_load_state_dict_pre_hook(lambda *a, **k: self._invalidate())
-
-    def _invalidate(self):
-        for m in self.modules():
-            if isinstance(m, _PackedModule):
-                m._pk = None
-
-    def _apply(self, fn, *a, **k):
-        self._pk = None
-        return super()._apply(fn, *a, **k)
+        self._pk_sig: Optional[tuple] = None
 
     def _pack(self) -> dict:
         raise NotImplementedError
 
     @property
     def pk(self) -> dict:
-        if self._pk is None:
+        sig = _sig(*self.parameters())
+        if self._pk is None or self._pk_sig != sig:
             with torch.no_grad():
                 self._pk = self._pack()
+            self._pk_sig = sig
         return self._pk
 
 
@@ -110,12 +111,9 @@ class InflatedConv3d(nn.Conv2d):
         super().__init__(*a, **k)
         self._pk = None
 
-    def _apply(self, fn, *a, **k):
-        self._pk = None
-        return super()._apply(fn, *a, **k)
-
     def packed(self):
-        if self._pk is None or self._pk[2] != self.weight._version:
+        sig = _sig(self.weight, self.bias)
+        if self._pk is None or self._pk[2] != sig:
             ks = self.kernel_size[0]
             with torch.no_grad():
                 if ks == 1:
@@ -125,7 +123,7 @@ class InflatedConv3d(nn.Conv2d):
                 else:
                     w = ops.pack_conv3x3(self.weight)
                 b = _f32c(self.bias) if self.bias is not None else None
-            self._pk = (w, b, self.weight._version)
+            self._pk = (w, b, sig)
         return self._pk[0], self._pk[1]
 
     def forward_tokens(self, a_bf16: torch.Tensor, n_img: int, h: int, w: int, **epi) -> torch.Tensor:
@@ -235,8 +233,9 @@ class ResnetBlock3D(nn.Module):
 
     def _temb_packed(self):
         p = self.time_emb_proj
-        if self._temb_pk is None or self._temb_pk[2] != p.weight._version or self._temb_pk[0].device != p.weight.device:
-            self._temb_pk = (ops.pack_linear(p.weight), _f32c(p.bias), p.weight._version)
+        sig = _sig(p.weight, p.bias)
+        if self._temb_pk is None or self._temb_pk[2] != sig:
+            self._temb_pk = (ops.pack_linear(p.weight), _f32c(p.bias), sig)
         return self._temb_pk[0], self._temb_pk[1]
 
     def forward(self, input_tensor, temb):
@@ -525,13 +524,9 @@ class Transformer3DModel(nn.Module):
         self.proj_out = nn.Linear(in_channels, inner) if use_linear_projection else nn.Conv2d(inner, in_channels, 1)
         self._pk = None
 
-    def _apply(self, fn, *a, **k):
-        self._pk = None
-        return super()._apply(fn, *a, **k)
-
     def _packed(self):
         tail = self.proj_out is None   # AppearanceEncoderModel's last transformer: GroupNorm -> proj_in -> norm1 only
-        ver = (self.proj_in.weight._version, None if tail else self.proj_out.weight._version)
+        ver = _sig(self.proj_in.weight, self.proj_in.bias) + (() if tail else _sig(self.proj_out.weight, self.proj_out.bias))
         if self._pk is None or self._pk["ver"] != ver:
             self._pk = {"wi": ops.pack_linear(self.proj_in.weight), "bi": _f32c(self.proj_in.bias),
                         "wo": None if tail else ops.pack_linear(self.proj_out.weight),
@@ -688,12 +683,8 @@ class TemporalTransformer3DModel(nn.Module):
         self.proj_out = nn.Linear(inner, in_channels)
         self._pk = None
 
-    def _apply(self, fn, *a, **k):
-        self._pk = None
-        return super()._apply(fn, *a, **k)
-
     def _packed(self):
-        ver = (self.proj_in.weight._version, self.proj_out.weight._version)
+        ver = _sig(self.proj_in.weight, self.proj_in.bias, self.proj_out.weight, self.proj_out.bias)
         if self._pk is None or self._pk["ver"] != ver:
             self._pk = {"wi": ops.pack_linear(self.proj_in.weight), "bi": _f32c(self.proj_in.bias),
                         "wo": ops.pack_linear(self.proj_out.weight), "bo": _f32c(self.proj_out.bias), "ver": ver}
@@ -990,14 +981,10 @@ class TimestepEmbedding(nn.Module):
         self.linear_2 = nn.Linear(time_embed_dim, out_dim if out_dim is not None else time_embed_dim)
         self._pk = None
 
-    def _apply(self, fn, *a, **k):
-        self._pk = None
-        return super()._apply(fn, *a, **k)
-
     def forward(self, sample, condition=None):
         if condition is not None:
             raise NotImplementedError
-        ver = (self.linear_1.weight._version, self.linear_2.weight._version)
+        ver = _sig(self.linear_1.weight, self.linear_1.bias, self.linear_2.weight, self.linear_2.bias)
         if self._pk is None or self._pk["ver"] != ver:
             self._pk = {"w1": ops.pack_linear(self.linear_1.weight), "b1": _f32c(self.linear_1.bias),
                         "w2": ops.pack_linear(self.linear_2.weight), "b2": _f32c(self.linear_2.bias), "ver": ver}
@@ -1261,6 +1248,10 @@ class ReferenceAttentionControl:
         src = writer.unet if hasattr(writer, "unet") else writer
         writer_blocks = reference_blocks(src, self.fusion_blocks)
         for r, w in zip(self._blocks(self.unet), writer_blocks):
+            # the reference clones and casts to `dtype` (fp16, :587-588); the banks here stay fp32 until the attention
+            # kernel's K/V projection rounds them to the operand type, so `dtype` only has to be a float type
+            if dtype is not None and not torch.empty(0, dtype=dtype).is_floating_point():
+                raise TypeError(f"ReferenceAttentionControl.update: dtype must be a floating type, got {dtype}")
             r.bank = [v.clone() for v in w.bank]
 
     def set_banks(self, banks: Dict[str, List[torch.Tensor]]):
@@ -1274,3 +1265,11 @@ class ReferenceAttentionControl:
         if self.reference_attn:
             for m in self._blocks(self.unet):
                 m.bank = []
+
+    def release(self):
+        """clear() + switch the blocks back to plain self-attention (the reference's monkey patch stays installed for the
+        life of the module; here the mode is a flag, so a control object can hand the network back)"""
+        if self.reference_attn:
+            for m in self._blocks(self.unet):
+                m.bank = []
+                m._ref_mode = None

@@ -21,7 +21,7 @@ from torch import nn
 
 from . import ops
 from ._lib import EmoteKernelError
-from .unet3d import AttrDict, _f32c
+from .unet3d import AttrDict, _f32c, _sig
 
 F32, OP16 = torch.float32, ops.OP16
 
@@ -33,12 +33,9 @@ class _Conv(nn.Conv2d):
         super().__init__(cin, cout, k, padding=k // 2)
         self._pk = None
 
-    def _apply(self, fn, *a, **kw):
-        self._pk = None
-        return super()._apply(fn, *a, **kw)
-
     def packed(self):
-        if self._pk is None or self._pk[2] != self.weight._version:
+        sig = _sig(self.weight, self.bias)
+        if self._pk is None or self._pk[2] != sig:
             with torch.no_grad():
                 k = self.kernel_size[0]
                 if k == 1:
@@ -47,7 +44,7 @@ class _Conv(nn.Conv2d):
                     w = ops.pack_conv3x3_small(self.weight)
                 else:
                     w = ops.pack_conv3x3(self.weight)
-            self._pk = (w, _f32c(self.bias), self.weight._version)
+            self._pk = (w, _f32c(self.bias), sig)
         return self._pk[0], self._pk[1]
 
     def run(self, a_bf16, n_img, h, w, **epi):
@@ -104,12 +101,8 @@ class AttentionBlock(nn.Module):
                 if k in state_dict:
                     state_dict[f"{prefix}{old}.{suffix}"] = state_dict.pop(k)
 
-    def _apply(self, fn, *a, **kw):
-        self._pk = None
-        return super()._apply(fn, *a, **kw)
-
     def _packed(self):
-        ver = tuple(m.weight._version for m in (self.query, self.key, self.value, self.proj_attn))
+        ver = _sig(*[t for m in (self.query, self.key, self.value, self.proj_attn) for t in (m.weight, m.bias)])
         if self._pk is None or self._pk["ver"] != ver:
             with torch.no_grad():
                 self._pk = {
@@ -341,7 +334,9 @@ class AutoencoderKL(nn.Module):
         Fuses `1/0.18215 *`, the frame batching and `(x/2+0.5).clamp(0,1)` (EMOAnimationPipeline.py:293-304)."""
         b, c, f, h, w = latents.shape
         z = latents.float().permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
-        chunk = frame_chunk or b * f
+        # frames per decoder pass: bounded so a long-form clip (240 frames) never holds more than one chunk of 512x512
+        # decoder activations (~0.6 GB per frame); the reference decodes frame by frame (EMOAnimationPipeline.py:297-301)
+        chunk = frame_chunk or min(b * f, 16)
         outs_f, outs_u = [], []
         for s in range(0, b * f, chunk):
             zc = z[s:s + chunk].contiguous()

@@ -187,13 +187,32 @@ int emote_timestep_embedding(const float* timesteps, int32_t B, int32_t dim, int
                              float freq_shift, void* out_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ sampler
- * Fused window-average + classifier-free guidance + DDIM update (EMOAnimationPipeline.py:790-817, eta = 0):
+ * Fused window-average + classifier-free guidance + DDIM update (EMOAnimationPipeline.py:790-817):
  *   eps = eps_u/cnt + g * (eps_c/cnt - eps_u/cnt);  x0 = (x - sqrt(1-a_t) eps)/sqrt(a_t);
- *   x_prev = sqrt(a_prev) x0 + sqrt(1-a_prev) eps.
+ *   x_prev = sqrt(a_prev) x0 + sqrt(1 - a_prev - sigma^2) eps + sigma z.
+ * sigma = eta * sqrt((1-a_prev)/(1-a_t) (1 - a_t/a_prev)) is computed by the caller (0 for the reference's eta = 0, then
+ * `noise` may be NULL); noise: [n] standard-normal z.
  * noise_pred: [2, n] (uncond, cond) accumulated predictions; counter: [n_frames] visit counts, frame index of
- * element i = (i / inner) % n_frames; latents updated in place. */
-int emote_cfg_ddim_step(float* latents, const float* noise_pred, const float* counter, int64_t n, int32_t n_frames,
-                        int64_t inner, float guidance_scale, float alpha_t, float alpha_prev, void* stream);
+ * element i = (i / inner) % n_frames; latents updated in place.  zero_noise_pred != 0: the accumulator is cleared as it
+ * is consumed (the per-timestep torch.zeros of EMOAnimationPipeline.py:702-706). */
+int emote_cfg_ddim_step(float* latents, float* noise_pred, const float* counter, int64_t n, int32_t n_frames,
+                        int64_t inner, float guidance_scale, float alpha_t, float alpha_prev, const float* noise,
+                        float sigma, int32_t zero_noise_pred, void* stream);
+/* The same update for a ready epsilon [n] (no guidance, no window average): `scheduler.step(noise_pred, t, latents)` as a
+ * stand-alone call (EMOAnimationPipeline.py:817) and, with the two alphas exchanged, the inversion `next_step` (:379-400). */
+int emote_ddim_step(float* latents, const float* eps, int64_t n, float alpha_t, float alpha_prev, const float* noise,
+                    float sigma, void* stream);
+/* Context-window bookkeeping of the denoise loop (EMOAnimationPipeline.py:759-763 `latents[:, :, c]` + repeat, :790-794
+ * `noise_pred[:, :, c] += pred`) over fp32 tensors viewed as [outer, frames, inner] (inner contiguous, multiple of 4):
+ *   gather:       dst[o, j, :] = src[(o % src_mod) + src_off, frame_idx[j], :]         o < n_outer, j < wlen
+ *   scatter-add:  dst[o + dst_off, frame_idx[j], :] += src[o, j, :]                   (frames of a window are distinct)
+ * frame_idx: device int32 [wlen].  Also serves the per-frame audio-token context gather (Net.py:646-667 tokens). */
+int emote_gather_frames(const float* src, float* dst, const int32_t* frame_idx, int32_t n_outer, int32_t wlen,
+                        int32_t F_src, int64_t inner, int32_t src_mod, int32_t src_off, void* stream);
+int emote_scatter_add_frames(const float* src, float* dst, const int32_t* frame_idx, int32_t n_outer, int32_t wlen,
+                             int32_t F_dst, int64_t inner, int32_t dst_off, void* stream);
+/* p[0..n) = value (timestep scalar of a captured UNet step, accumulator clears) */
+int emote_fill_f32(float* p, float value, int64_t n, void* stream);
 /* decoded frames: tokens-major [n,H*W,ld>=3] fp32 -> clamp(x/2+0.5,0,1) as fp32 [n,3,H,W] and/or uint8 [n,3,H,W]
  * (EMOAnimationPipeline.py:304) */
 int emote_vae_postprocess(const float* tok, int32_t n_img, int32_t HW, int32_t ld, float* out_f32, uint8_t* out_u8,

@@ -25,6 +25,8 @@ def main(paths):
             if len(f) != 4:
                 continue
             op, key, err = f[0], f[1], float(f[2])
+            if key.startswith("info."):
+                continue
             seen.setdefault(op, {})
             seen[op][key] = max(seen[op].get(key, 0.0), err)
     for op, keys in seen.items():

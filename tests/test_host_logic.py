@@ -24,6 +24,29 @@ def test_counter_and_partition_cover_all_frames():
     assert len(list(uniform(0, 50, 32, 16, 1, 4))) == 3
 
 
+def test_unit_partition_is_exact_balanced_and_pairs_branches():
+    """plan_units: the (window x CFG-branch) units are dealt to the ranks in equal contiguous blocks — every
+    unit exactly once, per-rank loads differ by at most one unit, both branches of a window on one rank fuse into a pair"""
+    from emote_hack_b200.pipeline import plan_units
+    for n_win in (1, 3, 4, 15, 20):
+        for world in (1, 2, 3, 4, 8):
+            seen, loads = [], []
+            for r in range(world):
+                calls = plan_units(n_win, r, world)
+                units = [(w, b) for w, mode in calls for b in ((0, 1) if mode == "pair" else ((0,) if mode == "uncond" else (1,)))]
+                loads.append(len(units))
+                seen += units
+                assert all(mode == "pair" or (w, mode) not in [(ww, "pair") for ww, _ in calls] for w, mode in calls)
+            assert sorted(seen) == [(w, b) for w in range(n_win) for b in (0, 1)]
+            assert max(loads) - min(loads) <= 1
+    assert [len(plan_units(20, r, 8)) for r in range(8)] == [3] * 8            # 40 units -> 5 per rank = 2 pairs + 1 branch
+    assert plan_units(1, 0, 2) == [(0, "uncond")] and plan_units(1, 1, 2) == [(0, "cond")]   # one clip: <= 2x
+    assert plan_units(1, 2, 4) == []                                          # idle ranks still join the all-reduce
+    # the reference's own split (EMOAnimationPipeline.py:757): whole windows round-robin
+    assert plan_units(20, 3, 8, shard="windows") == [(3, "pair"), (11, "pair"), (19, "pair")]
+    assert max(len(plan_units(20, r, 8, shard="windows")) for r in range(8)) == 3   # 3,3,3,3,2,2,2,2 -> <= 6.67x
+
+
 def test_ops_refuse_cpu_tensors():
     from emote_hack_b200 import ops
     from emote_hack_b200._lib import EmoteKernelError
@@ -46,9 +69,11 @@ def _worker(rank, world, port, nf, cs, ov, ret):
     wins = list(uniform(0, 50, nf, cs, 1, ov))
     g = torch.Generator().manual_seed(0)
     table = torch.randn(len(wins), 2, 4, cs, 2, 2, generator=g)  # stand-in per-window predictions
+    from emote_hack_b200.pipeline import plan_units
     acc = torch.zeros(2, 4, nf, 2, 2)
-    for wi in range(rank, len(wins), world):  # == windows[rank::world], EMOAnimationPipeline.py:757
-        acc[:, :, wins[wi]] += table[wi]
+    for wi, mode in plan_units(len(wins), rank, world):   # (window x CFG-branch) units of this rank
+        b0, nb = (0, 2) if mode == "pair" else ((0, 1) if mode == "uncond" else (1, 1))
+        acc[b0:b0 + nb, :, wins[wi]] += table[wi][b0:b0 + nb]
     dist.all_reduce(acc)  # the single per-step collective (replaces gather->rank0 sum->broadcast, :796-821)
     if rank == 0:
         full = torch.zeros(2, 4, nf, 2, 2)
@@ -62,13 +87,15 @@ def test_world_size_2_window_sharding_all_reduce_equals_single_process():
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 40, 16, 4, ret)) for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(120)
-        assert p.exitcode == 0
-    assert ret.get(timeout=10) is True
+    for nf in (40, 28, 16):   # 4 windows (whole pairs per rank), 3 windows (one window split by branch), 1 window
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, nf, 16, 4, ret)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+        assert ret.get(timeout=10) is True
 
 
 def test_reference_module_paths_resolve_to_b200_classes():

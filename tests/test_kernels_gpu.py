@@ -366,6 +366,56 @@ def test_timestep_embedding(ops):
     assert (out.float() - ref).abs().max() < 1.5e-2  # bf16 output + large-argument sin/cos
 
 
+def test_window_gather_scatter_and_fill(ops):
+    """emote_gather_frames / emote_scatter_add_frames / emote_fill_f32 against torch indexing: the `latents[:, :, c]`
+    gather + CFG repeat, the per-frame audio-token gather and `noise_pred[:, :, c] += pred` of the denoise loop, bit-exact
+    (wrapping windows, strided windows, single-branch offsets)."""
+    g = _gen(31)
+    C, F_, H, W = 4, 24, 8, 8
+    lat = torch.randn(1, C, F_, H, W, device="cuda", generator=g)
+    for win in ([0, 1, 2, 3, 4, 5, 6, 7], [20, 21, 22, 23, 0, 1, 2, 3], [1, 5, 9, 13, 17, 21]):
+        idx = torch.tensor(win, dtype=torch.int32, device="cuda")
+        for nb in (1, 2):
+            dst = torch.empty(nb, C, len(win), H, W, device="cuda")
+            ops.gather_frames(lat, dst, idx, nb * C, F_, H * W, src_mod=C)
+            assert torch.equal(dst, lat[:, :, win].repeat(nb, 1, 1, 1, 1))
+        ctx = torch.randn(2 * F_, 5, 64, device="cuda", generator=g)          # [uncond frames | cond frames]
+        for nb, b0 in ((2, 0), (1, 0), (1, 1)):
+            cdst = torch.empty(nb * len(win), 5, 64, device="cuda")
+            ops.gather_frames(ctx, cdst, idx, nb, F_, 5 * 64, src_mod=2, src_off=b0)
+            want = torch.cat([ctx[(b0 + b) * F_:(b0 + b + 1) * F_][win] for b in range(nb)])
+            assert torch.equal(cdst, want)
+        acc = torch.randn(2, C, F_, H, W, device="cuda", generator=g)
+        for nb, b0 in ((2, 0), (1, 0), (1, 1)):
+            pred = torch.randn(nb, C, len(win), H, W, device="cuda", generator=g)
+            want = acc.clone()
+            want[b0:b0 + nb, :, win] += pred
+            ops.scatter_add_frames(pred, acc, idx, nb * C, F_, H * W, dst_off=b0 * C)
+            assert torch.equal(acc, want)
+    t = torch.empty(5, device="cuda")
+    assert torch.equal(ops.fill_f32(t, 481.0), torch.full((5,), 481.0, device="cuda"))
+    with pytest.raises(Exception):
+        ops.gather_frames(lat, torch.empty(1, C, 2, H, W, device="cuda"), torch.zeros(3, dtype=torch.int32, device="cuda"),
+                          C, F_, H * W, src_mod=C)
+
+
+def test_ddim_step_plain_and_accumulator_clear(ops):
+    g = _gen(17)
+    x = torch.randn(3, 4, 8, 8, device="cuda", generator=g)                 # any rank: the plain step is elementwise
+    eps = torch.randn(3, 4, 8, 8, device="cuda", generator=g)
+    a_t, a_p = 0.41, 0.63
+    want = a_p ** 0.5 * (x - (1 - a_t) ** 0.5 * eps) / a_t ** 0.5 + (1 - a_p) ** 0.5 * eps
+    assert rel_l2(ops.ddim_step(x.clone(), eps, a_t, a_p), want) < 1e-6
+    lat = torch.randn(1, 4, 6, 8, 8, device="cuda", generator=g)
+    npred = torch.randn(2, 4, 6, 8, 8, device="cuda", generator=g)
+    keep = ops.cfg_ddim_step(lat.clone(), npred.clone(), None, 7.5, a_t, a_p)
+    acc = npred.clone()
+    out = ops.cfg_ddim_step(lat.clone(), acc, None, 7.5, a_t, a_p, zero_noise_pred=True)
+    assert torch.equal(out, keep) and acc.abs().sum() == 0            # consumed and cleared for the next timestep
+    with pytest.raises(Exception):
+        ops.cfg_ddim_step(lat.clone(), npred, None, 7.5, a_t, a_p, sigma=0.9)    # sigma^2 > 1 - a_prev / no noise tensor
+
+
 def test_cfg_ddim_step(ops):
     g = _gen(16)
     lat = torch.randn(1, 4, 6, 8, 8, device="cuda", generator=g)

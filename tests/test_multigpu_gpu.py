@@ -1,7 +1,10 @@
-"""Multi-GPU path on real NCCL (skipped with fewer than 2 GPUs): context windows of one timestep sharded over ranks
-(`windows[rank::world]`, EMOAnimationPipeline.py:757) with ONE all-reduce of the accumulated prediction per step instead of
-the reference's gather + broadcast + barriers (:796-821), and the frame-sharded VAE decode with its single uint8
-all-gather.  Both must reproduce the single-GPU result.  The CPU/gloo twin of the reduction lives in test_host_logic.py."""
+"""Multi-GPU path on real NCCL (skipped with fewer than 2 GPUs): the (window x CFG-branch) units of one timestep dealt to
+the ranks (`pipeline.plan_units`; the reference splits whole windows, EMOAnimationPipeline.py:757) with ONE
+all-reduce of the accumulated prediction per step instead of the reference's gather + broadcast + barriers (:796-821), and
+the frame-sharded VAE decode with its single uint8 all-gather.  Every scenario must reproduce the single-GPU result:
+4 windows (whole pairs per rank), 3 windows (one window's two branches on different ranks), 1 window (one branch per rank —
+the case where ranks > 0 used to diverge), and the reference's own window split.  The CPU/gloo twin of the reduction lives
+in test_host_logic.py."""
 import os
 import socket
 
@@ -36,23 +39,27 @@ def _worker(rank, world, port, ret):
     unet = rerandomise_zero_inits(UNet3DConditionModel(**TINY_CFG).eval()).to(dev)
     torch.manual_seed(1)
     vae = AutoencoderKL(block_out_channels=(64, 64, 128, 128)).eval().to(dev)
-    g = torch.Generator().manual_seed(31)
-    lat = torch.randn(1, 4, 24, 8, 8, generator=g).to(dev)
-    ctx = torch.randn(2, 7, 64, generator=g).to(dev)
     banks = {k: [t.to(dev) for t in v] for k, v in make_banks(unet, 8).items()}
-    kw = dict(num_inference_steps=2, guidance_scale=7.5, context_frames=8, context_overlap=2, reference_banks=banks)
     single = EMOAnimationPipeline(vae, unet, DDIMScheduler(), rank=0, world_size=1)
-    want = single.denoise(lat.clone(), ctx, **kw)
-    _, want_u8 = single.decode_latents_device(want, want_u8=True)
     sharded = EMOAnimationPipeline(vae, unet, DDIMScheduler(), rank=rank, world_size=world)
-    got = sharded.denoise(lat.clone(), ctx, **kw)
-    _, got_u8 = sharded.decode_latents_device(got, want_u8=True, shard=True)
-    err = ((got - want).norm() / want.norm()).item()
-    px = (got_u8.int() - want_u8.int()).abs().max().item()
-    ok = torch.tensor([1.0 if (err < 1e-5 and px <= 1) else 0.0], device=dev)
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    results = []
+    for frames, shard, use_banks in ((24, "units", True), (18, "units", True), (8, "units", False), (24, "windows", True)):
+        g = torch.Generator().manual_seed(31 + frames)
+        lat = torch.randn(1, 4, frames, 8, 8, generator=g).to(dev)
+        ctx = torch.randn(2, 7, 64, generator=g).to(dev)
+        kw = dict(num_inference_steps=2, guidance_scale=7.5, context_frames=8, context_overlap=2,
+                  reference_banks=banks if use_banks else None)
+        want = single.denoise(lat.clone(), ctx, **kw)
+        _, want_u8 = single.decode_latents_device(want, want_u8=True)
+        got = sharded.denoise(lat.clone(), ctx, shard=shard, **kw)
+        _, got_u8 = sharded.decode_latents_device(got, want_u8=True, shard=True)
+        err = ((got - want).norm() / want.norm()).item()
+        px = (got_u8.int() - want_u8.int()).abs().max().item()
+        ok = torch.tensor([1.0 if (err < 1e-5 and px <= 1) else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # every rank must hold the right latents, not only rank 0
+        results.append((frames, shard, bool(ok.item() == 1.0), err, px))
     if rank == 0:
-        ret.put((bool(ok.item() == 1.0), err, px))
+        ret.put(results)
     dist.destroy_process_group()
 
 
@@ -68,6 +75,6 @@ def test_two_gpu_window_sharding_and_frame_sharded_decode():
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
-    ok, err, px = ret.get(timeout=10)
-    print(f"2-GPU window sharding: rel diff vs single GPU {err:.2e}, max pixel diff {px}")
-    assert ok
+    for frames, shard, ok, err, px in ret.get(timeout=10):
+        print(f"2-GPU {shard} sharding, {frames} frames: rel diff vs single GPU {err:.2e}, max pixel diff {px}")
+        assert ok, (frames, shard, err, px)

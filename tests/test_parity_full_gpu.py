@@ -12,7 +12,7 @@ import copy
 import pytest
 import torch
 
-from util_models import FULL_CFG, check_parity, make_banks, rel_l2, rerandomise_zero_inits
+from util_models import FULL_CFG, check_parity, make_banks, record_only, rel_l2, rerandomise_zero_inits
 
 pytestmark = [pytest.mark.gpu, pytest.mark.slow]
 
@@ -67,7 +67,7 @@ def test_config2_full_size_call(full):
         lo = UNet3DOracle(m.state_dict(), dict(m.config), dtype=dt, device="cuda", attention_slice_bytes=6 << 30)
         eager = _oracle_cfg_pair(lo, x, 981, ctx).float()
         e = rel_l2(eager, ref) if torch.isfinite(eager).all() else float("inf")
-        print(f"eager PyTorch {dt} on the same network vs fp32: rel_l2={e:.3e}")
+        record_only(f"config2_eager_pytorch_{str(dt).split('.')[-1]}_vs_fp32", e)
         del lo
         torch.cuda.empty_cache()
 

@@ -352,6 +352,90 @@ def test_pipeline_call_returns_video(tiny_pipe, tiny_vae):
     assert (v - voracle.decode_latents(ref_lat)).abs().max() < 5e-2
 
 
+def test_pipeline_call_reference_keyword_surface(tiny_pipe, tiny_vae):
+    """the reference's `__call__` keywords (EMOAnimationPipeline.py:543-578) are accepted with their meaning; unknown ones
+    and the out-of-scope ones fail loudly instead of being swallowed"""
+    from emote_hack_b200.pipeline import DDIMScheduler, EMOAnimationPipeline
+    o, pipe = tiny_pipe
+    voracle, vae = tiny_vae
+    p = EMOAnimationPipeline(vae, pipe.unet, DDIMScheduler())
+    g = torch.Generator(device="cuda").manual_seed(5)
+    emb = torch.randn(2, 7, 64, device="cuda", generator=g)
+    init = torch.randn(4, 4, 8, 8, device="cuda", generator=g)          # (b f) c h w, the `invert` output layout
+    seen = []
+    out = p(prompt=None, video_length=4, height=64, width=64, num_inference_steps=4, guidance_scale=7.5,
+            negative_prompt=None, num_videos_per_prompt=1, eta=0.0, generator=None, latents=None, output_type="tensor",
+            return_dict=False, callback=lambda i, t, lat: seen.append((i, t)), callback_steps=1, controlnet_condition=None,
+            controlnet_conditioning_scale=1.0, context_frames=16, context_stride=1, context_overlap=4, context_batch_size=1,
+            context_schedule="uniform", init_latents=init, num_actual_inference_steps=2, appearance_encoder=None,
+            reference_control_writer=None, reference_control_reader=None, source_image=None, decoder_consistency=None,
+            audio=None, head_rotation_speeds=None, prompt_embeddings=emb)
+    assert out.shape == (1, 3, 4, 64, 64)
+    assert [i for i, _ in seen] == [2, 3]                                 # num_actual_inference_steps skips the first two
+    # the same two steps on the oracle
+    from oracle.ddim import DDIMOracle, cfg_combine
+    sch = DDIMOracle()
+    lat = init.cpu().reshape(1, 4, 4, 8, 8).permute(0, 2, 1, 3, 4).contiguous()
+    for t in sch.set_timesteps(4).tolist()[2:]:
+        pred = o(lat.repeat(2, 1, 1, 1, 1), t, emb.cpu())
+        lat = sch.step(cfg_combine(pred, torch.ones(1, 1, 4, 1, 1), 7.5), t, lat)
+    assert (out - voracle.decode_latents(lat)).abs().max() < 5e-2
+    with pytest.raises(TypeError):
+        p(emb, video_length=4, height=64, width=64, num_inference_steps=1, not_a_reference_kwarg=1)
+    with pytest.raises(NotImplementedError):
+        p("a portrait", video_length=4, height=64, width=64, num_inference_steps=1)      # no text_encoder attached
+    with pytest.raises(NotImplementedError):
+        p(emb, video_length=4, height=64, width=64, num_inference_steps=1, controlnet_condition=[0])
+    # a text_encoder front-end makes string prompts work (stand-in encoder: the CLIP model itself is out of scope)
+    p2 = EMOAnimationPipeline(vae, pipe.unet, DDIMScheduler(),
+                              text_encoder=lambda prompts: torch.full((len(prompts), 7, 64), 0.1 * len(prompts[0]), device="cuda"))
+    v = p2("hello", video_length=4, height=64, width=64, num_inference_steps=1, negative_prompt="no").videos
+    assert v.shape == (1, 3, 4, 64, 64)
+
+
+def test_stochastic_ddim_eta_matches_the_published_update(tiny_pipe):
+    """eta > 0 (EMOAnimationPipeline.py:553,817 `extra_step_kwargs`): x_prev = sqrt(a_prev) x0 + sqrt(1-a_prev-s^2) eps + s z
+    with s = eta sqrt((1-a_prev)/(1-a_t) (1-a_t/a_prev)) (Song et al. 2021 eq. 12/16) — scheduler.step and the fused
+    CFG kernel against a direct fp64 evaluation; eta = 0 reproduces the deterministic step."""
+    from emote_hack_b200 import ops
+    o, pipe = tiny_pipe
+    s = pipe.scheduler
+    s.set_timesteps(50)
+    g = torch.Generator().manual_seed(3)
+    x, eps, z = (torch.randn(1, 4, 3, 8, 8, generator=g) for _ in range(3))
+    for t, eta in ((981, 1.0), (481, 0.3), (21, 0.7)):
+        a_t, a_p = s.alphas_for(t)
+        sig = eta * ((1 - a_p) / (1 - a_t) * (1 - a_t / a_p)) ** 0.5
+        xd, ed, zd = x.double(), eps.double(), z.double()
+        x0 = (xd - (1 - a_t) ** 0.5 * ed) / a_t ** 0.5
+        want = a_p ** 0.5 * x0 + (1 - a_p - sig ** 2) ** 0.5 * ed + sig * zd
+        got = s.step(eps.cuda(), t, x.cuda(), eta=eta, variance_noise=z.cuda()).prev_sample
+        assert rel_l2(got, want.float()) < 1e-5
+        pair = torch.cat([eps, eps + 0.0]).cuda().contiguous()
+        fused = ops.cfg_ddim_step(x.cuda().clone(), pair, None, 7.5, a_t, a_p, noise=z.cuda().contiguous(),
+                                  sigma=ops.ddim_sigma(a_t, a_p, eta))
+        assert rel_l2(fused, want.float()) < 1e-5
+    det = s.step(eps.cuda(), 481, x.cuda()).prev_sample
+    assert rel_l2(s.step(eps.cuda(), 481, x.cuda(), eta=0.0, variance_noise=z.cuda()).prev_sample, det) == 0.0
+    # inside the loop: a generator makes the stochastic sampler reproducible, and it differs from eta = 0
+    lat = torch.randn(1, 4, 4, 8, 8, generator=g).cuda()
+    ctx = torch.randn(2, 7, 64, generator=g).cuda()
+    kw = dict(num_inference_steps=3, guidance_scale=7.5, context_frames=16)
+    a = pipe.denoise(lat.clone(), ctx, eta=0.5, generator=torch.Generator(device="cuda").manual_seed(1), **kw)
+    b = pipe.denoise(lat.clone(), ctx, eta=0.5, generator=torch.Generator(device="cuda").manual_seed(1), **kw)
+    assert rel_l2(a, b) < 1e-6 and rel_l2(a, pipe.denoise(lat.clone(), ctx, **kw)) > 1e-2
+
+
+def test_long_clip_decode_is_chunked(tiny_vae):
+    """decode of a long clip walks the frames in bounded chunks (default 16): same frames as one big batch"""
+    oracle, vae = tiny_vae
+    lat = torch.randn(1, 4, 37, 8, 8, generator=torch.Generator().manual_seed(9)).cuda() * 0.3
+    whole, _ = vae.decode_video(lat, frame_chunk=37)
+    chunked, u8 = vae.decode_video(lat, want_u8=True)          # default chunking: 16 + 16 + 5
+    assert chunked.shape == (1, 3, 37, 64, 64) and u8.shape == chunked.shape
+    assert rel_l2(chunked, whole) < 1e-5
+
+
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()

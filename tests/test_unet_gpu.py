@@ -134,6 +134,51 @@ def test_unet_tiny_reference_attention(tiny):
             blk._ref_mode = None
 
 
+def test_single_branch_calls_equal_the_cfg_pair(tiny):
+    """the unit of multi-GPU work is (window x CFG branch).  A batch-1 call of one branch — the
+    unconditional one without banks, the conditional one with bank row 1 and no CFG masking — reproduces its half of the
+    batch-2 call (pipeline._run_unet modes "uncond" / "cond" vs "pair")."""
+    from emote_hack_b200.pipeline import _run_unet
+    m = tiny[2]
+    x, ctx = make_inputs(2, 4, 16)
+    x, ctx = x.cuda(), ctx.cuda()
+    banks = {k: [v.cuda() for v in vs] for k, vs in make_banks(m, 16).items()}
+    t = torch.tensor([301.0], device="cuda")
+    pair = _run_unet(m, "pair", x, t, ctx, banks)
+    un = _run_unet(m, "uncond", x[0:1].contiguous(), t, ctx[0:1], None)
+    co = _run_unet(m, "cond", x[1:2].contiguous(), t, ctx[1:2], {k: [v[0][1:2]] for k, v in banks.items()})
+    assert rel_l2(un, pair[0:1]) < 1e-5 and rel_l2(co, pair[1:2]) < 1e-5
+    plain = _run_unet(m, "pair", x, t, ctx, None)
+    assert rel_l2(plain[1:2], pair[1:2]) > 1e-2          # the bank mattered for the conditional half
+    assert all(blk._ref_mode is None and not blk.bank for blk in m.modules() if hasattr(blk, "_ref_mode"))  # disarmed
+
+
+def test_in_place_weight_updates_refresh_every_packed_copy(tiny):
+    """param.mul_() / copy_() (a LoRA merge, an optimiser step) must refresh the packed 16-bit copies of EVERY module kind —
+    attention projections, feed-forward, convolutions, biases — not only after load_state_dict."""
+    m, o, _ = tiny
+    x, ctx = make_inputs(2, 2, 8)
+    base = m(x.cuda(), 5, ctx.cuda()).sample
+    names = ["down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q.weight",
+             "down_blocks.0.attentions.0.transformer_blocks.0.ff.net.2.weight",
+             "down_blocks.0.attentions.0.transformer_blocks.0.ff.net.0.proj.bias",
+             "down_blocks.0.motion_modules.0.temporal_transformer.transformer_blocks.0.attention_blocks.0.to_out.0.bias",
+             "down_blocks.0.resnets.0.conv1.bias", "down_blocks.0.resnets.0.time_emb_proj.weight",
+             "down_blocks.0.attentions.0.proj_in.bias", "time_embedding.linear_2.bias"]
+    params = dict(m.named_parameters())
+    for n in names:
+        saved = params[n].detach().clone()
+        try:
+            with torch.no_grad():
+                params[n].mul_(1.5).add_(0.05)
+            changed = m(x.cuda(), 5, ctx.cuda()).sample
+            assert rel_l2(changed, base) > 1e-5, f"in-place update of {n} was not picked up"
+        finally:
+            with torch.no_grad():
+                params[n].copy_(saved)
+    assert rel_l2(m(x.cuda(), 5, ctx.cuda()).sample, base) < 1e-5
+
+
 def test_appearance_encoder_writer_banks_and_reader_update(tiny):
     """ReferenceNet writer (AppearanceEncoderModel, appearance_encoder.py) on CUDA: banks against the oracle run as a
     writer, then ReferenceAttentionControl.update() hands them to the UNet3D reader (EMOAnimationPipeline.py:711-788)."""

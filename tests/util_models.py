@@ -33,6 +33,16 @@ def chk(err: float, default: float) -> float:
     return check_parity(f"k.{cur}#{n}".replace(" ", ""), err, default)
 
 
+def record_only(key: str, value: float) -> float:
+    """log a context figure (e.g. what eager PyTorch fp16 gives on the same network) without gating on it"""
+    log = os.environ.get("EMOTE_PARITY_LOG")
+    if log:
+        with open(log, "a") as fh:
+            fh.write(f"{operand()} info.{key} {value:.6e} nan\n")
+    print(f"info[{operand()}] {key}: {value:.3e}")
+    return value
+
+
 def check_parity(key: str, err: float, default: float) -> float:
     """assert err < limit(key); logs `operand key err limit` to $EMOTE_PARITY_LOG (one line per check)"""
     lim = parity_limit(key, default)

@@ -75,6 +75,12 @@ SIGNATURES = {
     "emote_gn_colstats_reduce": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "emote_gn_apply": [_vp, _i32, _i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _f32, _i32, _vp, _vp, _vp],
     "emote_layernorm": [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _i32, _i32, _vp, _vp],
+    "emote_layernorm_dual": [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp],
+    "emote_wave_stats": [_vp, _i64, _f32, _vp, _vp],
+    "emote_wave_im2col": [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp],
+    "emote_channel_norm_gelu": [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp],
+    "emote_tokens_to_groups": [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
+    "emote_speed_encoder": [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
     "emote_attention_bf16": [C.POINTER(EmoteAttnArgs), _vp],
     "emote_attention_tc_bf16": [C.POINTER(EmoteAttnArgs), _vp],
     "emote_attention_tc_supported": [_i32],

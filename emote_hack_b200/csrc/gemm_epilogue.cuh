@@ -23,6 +23,7 @@ struct GemmDev {
   int ldr;
   float out_scale;
   int geglu;
+  int act_gelu;      // EMOTE_EPI_GELU: exact (erf) GELU of acc + bias, applied before the residual add
   int out_bf16;
   int ldc;
   void* out;
@@ -139,6 +140,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
         // rows g, g+8 come from the low 16-lane load, rows g+16, g+24 from the high one
         const int ri = (i >> 1) * 4 + (i & 1) * 2;
         float v0 = __uint_as_float(a[ri]) + b0, v1 = __uint_as_float(a[ri + 1]) + b1;
+        if (p.act_gelu) { v0 = gelu_erf_fast(v0); v1 = gelu_erf_fast(v1); }
         if constexpr (HAS_ADD) { v0 += add[ci][2 * i]; v1 += add[ci][2 * i + 1]; }
         float* sp = nullptr;
         if constexpr (OUT_MODE == 2) {

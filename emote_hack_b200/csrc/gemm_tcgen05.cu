@@ -345,6 +345,9 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   const bool conv = a->conv_taps == 9;
   if (a->conv_taps != 1 && a->conv_taps != 9) return set_error("emote_gemm_bf16: conv_taps must be 1 or 9");
   const bool geglu = a->epilogue == EMOTE_EPI_GEGLU;
+  const bool act_gelu = a->epilogue == EMOTE_EPI_GELU;
+  if (a->epilogue != EMOTE_EPI_LINEAR && !geglu && !act_gelu) return set_error("emote_gemm_bf16: unknown epilogue");
+  if (act_gelu && (a->row_bias || a->colstats)) return set_error("emote_gemm_bf16: the GELU epilogue takes no row_bias / colstats");
   if (geglu && (a->N % 2 != 0 || a->out_dtype != EMOTE_DT_OP16 || a->residual || a->row_bias))
     return set_error("emote_gemm_bf16: GEGLU epilogue needs even N, bf16 output, no residual/row_bias");
   // Double-buffered residual staging (mode 3, 128-column tiles, single CTA): the HBM-bound 1x1 GEMMs with an fp32
@@ -371,6 +374,7 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   p.residual = a->residual; p.ldr = a->ldr;
   p.out_scale = a->out_scale;
   p.geglu = geglu ? 1 : 0;
+  p.act_gelu = act_gelu ? 1 : 0;
   p.out_bf16 = a->out_dtype == EMOTE_DT_OP16;
   p.ldc = a->ldc;
   p.out = out;
@@ -403,7 +407,9 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
     uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnimg};
     if (int rc = make_tensor_map(&tmA, A, 4, dims, strides, box)) return rc;
   } else {
-    if (a->lda % 8 != 0 || a->lda < a->K) return set_error("emote_gemm_bf16: lda must be >= K and a multiple of 8");
+    // lda < K is allowed: rows then overlap in memory — the zero-copy operand of a strided 1-D convolution over a
+    // [T, C] token matrix (row t = tokens stride*t .. stride*t + k - 1; lda = stride*C, K = k*C)
+    if (a->lda % 8 != 0 || a->lda <= 0) return set_error("emote_gemm_bf16: lda must be a positive multiple of 8");
     p.kb_per_tap = (a->K + BK - 1) / BK;
     p.num_kb = p.kb_per_tap;
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};

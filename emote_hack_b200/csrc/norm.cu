@@ -210,7 +210,8 @@ template <int NV>
 __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict__ x, long long M, int C_rt,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, const float* __restrict__ pe, int pe_rows_per_frame,
-                                                        int pe_frames, op16* __restrict__ out) {
+                                                        int pe_frames, op16* __restrict__ out,
+                                                        float* __restrict__ out_f32) {
   pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // rows are visited last-to-first: the producing GEMM wrote them in ascending order, so the tail is still in L2, and
@@ -256,7 +257,8 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
         y0 += p2.x;
         y1 += p2.y;
       }
-      o[lane + i * 32] = pack_op16x2(y0, y1);
+      if (out) o[lane + i * 32] = pack_op16x2(y0, y1);
+      if (out_f32) *reinterpret_cast<float2*>(out_f32 + row * C + c) = make_float2(y0, y1);
     }
   }
 }
@@ -389,18 +391,18 @@ extern "C" int emote_gn_apply(const float* x, int32_t C_src, int32_t c_offset, i
   return 0;
 }
 
-extern "C" int emote_layernorm(const float* x, int64_t M, int32_t C, const float* gamma, const float* beta, float eps,
-                               const float* pe, int32_t pe_rows_per_frame, int32_t pe_frames, void* out_bf16,
-                               void* stream_) {
+static int layernorm_impl(const float* x, int64_t M, int32_t C, const float* gamma, const float* beta, float eps,
+                          const float* pe, int32_t pe_rows_per_frame, int32_t pe_frames, void* out_bf16, float* out_f32,
+                          void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (!x || !gamma || !beta || !out_bf16 || M <= 0) return set_error("emote_layernorm: bad arguments");
+  if (!x || !gamma || !beta || (!out_bf16 && !out_f32) || M <= 0) return set_error("emote_layernorm: bad arguments");
   if (C % 64 != 0 || C > 64 * LN_MAX_V) return set_error("emote_layernorm: C must be a multiple of 64 and <= 2048");
   if (pe && (pe_rows_per_frame <= 0 || pe_frames <= 0)) return set_error("emote_layernorm: bad positional table dims");
   const int warps = 4;
   const long long blocks = (M + warps - 1) / warps;
   op16* o = reinterpret_cast<op16*>(out_bf16);
 #define EMOTE_LN(NVV) launch_kernel(layernorm_kernel<NVV>, dim3((unsigned)blocks), dim3(warps * 32), 0, stream, \
-      x, M, C, gamma, beta, eps, pe, pe_rows_per_frame, pe_frames, o)
+      x, M, C, gamma, beta, eps, pe, pe_rows_per_frame, pe_frames, o, out_f32)
   switch (C / 64) {
     case 1: EMOTE_LN(1); break;
     case 2: EMOTE_LN(2); break;
@@ -414,6 +416,18 @@ extern "C" int emote_layernorm(const float* x, int64_t M, int32_t C, const float
 #undef EMOTE_LN
   EMOTE_CHECK_LAUNCH("emote_layernorm");
   return 0;
+}
+
+extern "C" int emote_layernorm(const float* x, int64_t M, int32_t C, const float* gamma, const float* beta, float eps,
+                               const float* pe, int32_t pe_rows_per_frame, int32_t pe_frames, void* out_bf16,
+                               void* stream_) {
+  if (!out_bf16) return set_error("emote_layernorm: bad arguments");
+  return layernorm_impl(x, M, C, gamma, beta, eps, pe, pe_rows_per_frame, pe_frames, out_bf16, nullptr, stream_);
+}
+
+extern "C" int emote_layernorm_dual(const float* x, int64_t M, int32_t C, const float* gamma, const float* beta, float eps,
+                                    void* out_bf16, float* out_f32, void* stream_) {
+  return layernorm_impl(x, M, C, gamma, beta, eps, nullptr, 0, 0, out_bf16, out_f32, stream_);
 }
 
 extern "C" int emote_softmax_rows_bf16(const float* scores, int64_t R, int32_t N, float scale, void* out_bf16,

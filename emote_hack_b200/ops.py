@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import EmoteAttnArgs, EmoteGemmArgs, check
 
 F32, OP16 = torch.float32, _lib.op16_torch_dtype()   # OP16: fp16 (default) or bf16, see _lib.OPERAND
-EPI_LINEAR, EPI_GEGLU = 0, 1
+EPI_LINEAR, EPI_GEGLU, EPI_GELU = 0, 1, 2
 
 
 def _stream() -> int:
@@ -86,12 +86,15 @@ def pack_geglu(w: torch.Tensor, b: torch.Tensor):
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, row_bias=None, rows_per_group: int = 0, residual=None,
          out_scale: float = 1.0, geglu: bool = False, out_dtype=F32, out: Optional[torch.Tensor] = None,
          conv: Optional[tuple] = None, M: Optional[int] = None, pair_mode: int = 0, tma_store: int = 0,
-         stats_rows: int = 0) -> torch.Tensor:
+         stats_rows: int = 0, gelu: bool = False, lda: Optional[int] = None, out_col: int = 0) -> torch.Tensor:
     """out = epilogue(a @ w.T).  a: bf16 [M, K] (or NHWC [n_img, H, W, C] when conv=(n_img, H, W, C)); w: bf16 [N, K].
 
     stats_rows > 0 (fp32 outputs): the epilogue also accumulates per-column (sum, sum of squares) of the output per
     block of `stats_rows` rows; they ride on the returned tensor (`_emote_colstats`) and let group_norm() skip its
-    statistics pass over that tensor."""
+    statistics pass over that tensor.
+    gelu: out = gelu_erf(a @ w.T + bias) (+ residual).  lda: row pitch of `a` in elements when it differs from K — may be
+    smaller than K (overlapping rows: the zero-copy operand of a strided 1-D convolution; pass M).  out_col: first column
+    of `out` (a wider [M, ld] tensor) the N outputs are written to."""
     _req(a, OP16, "gemm.a"), _req(w, OP16, "gemm.w")
     N, K = w.shape
     args = EmoteGemmArgs()
@@ -104,7 +107,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, row_bias=None, rows_per
         if M is None:
             M = a.numel() // K
         args.conv_taps = 1
-        args.lda = K
+        args.lda = K if lda is None else lda
+        if (M - 1) * args.lda + K > a.numel():
+            raise _lib.EmoteKernelError("gemm: the A operand (M, lda, K) reaches past the end of its buffer")
     args.M, args.N, args.K = M, N, K
     n_out = N // 2 if geglu else N
     if out is None:
@@ -123,7 +128,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, row_bias=None, rows_per
     args.residual = _ptr(residual)
     args.ldr = n_out
     args.out_scale = out_scale
-    args.epilogue = EPI_GEGLU if geglu else EPI_LINEAR
+    args.epilogue = EPI_GEGLU if geglu else (EPI_GELU if gelu else EPI_LINEAR)
     if out_dtype not in (F32, OP16):
         raise _lib.EmoteKernelError(f"gemm: out_dtype must be float32 or the operand type {OP16}, got {out_dtype}")
     args.out_dtype = 1 if out_dtype == OP16 else 0
@@ -136,8 +141,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, row_bias=None, rows_per
             and M % stats_rows == 0):
         colstats = torch.zeros((M // stats_rows, n_out, 2), dtype=torch.float64, device=a.device)
         args.colstats, args.stats_rows = colstats.data_ptr(), stats_rows
-    check(_lib.load().emote_gemm_bf16(a.data_ptr(), w.data_ptr(), out.data_ptr(), C.byref(args), _stream()),
-          "emote_gemm_bf16")
+    if out_col:
+        if out_col + n_out > out.shape[-1] or (out_col * out.element_size()) % 16 != 0:
+            raise _lib.EmoteKernelError("gemm: out_col must keep the output window inside `out` and 16-byte aligned")
+    check(_lib.load().emote_gemm_bf16(a.data_ptr(), w.data_ptr(), out.data_ptr() + out_col * out.element_size(),
+                                      C.byref(args), _stream()), "emote_gemm_bf16")
     if colstats is not None:
         out._emote_colstats = (colstats, stats_rows, out._version)
     elif getattr(out, "_emote_colstats", None) is not None:
@@ -256,6 +264,19 @@ def group_norm(sources: Sequence[torch.Tensor], groups: int, rows_per_batch: int
     return out, raw
 
 
+def layer_norm_dual(x: torch.Tensor, gamma, beta, eps: float = 1e-5, want_op16: bool = True):
+    """LayerNorm of fp32 rows -> (op16 copy or None, fp32 copy): post-LN transformers continue their fp32 residual stream
+    from the normalised value (wav2vec2 encoder layers)."""
+    _req(x, F32, "layer_norm_dual.x")
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    o16 = torch.empty((M, Cc), dtype=OP16, device=x.device) if want_op16 else None
+    o32 = torch.empty((M, Cc), dtype=F32, device=x.device)
+    check(_lib.load().emote_layernorm_dual(x.data_ptr(), M, Cc, gamma.data_ptr(), beta.data_ptr(), eps, _ptr(o16),
+                                           o32.data_ptr(), _stream()), "emote_layernorm_dual")
+    return o16, o32
+
+
 def layer_norm(x: torch.Tensor, gamma, beta, eps: float = 1e-5, pe: Optional[torch.Tensor] = None,
                rows_per_frame: int = 0, frames: int = 0) -> torch.Tensor:
     _req(x, F32, "layer_norm.x")
@@ -371,7 +392,7 @@ def gather_frames(src: torch.Tensor, dst: torch.Tensor, frame_idx: torch.Tensor,
     _req(src, F32, "gather_frames.src"), _req(dst, F32, "gather_frames.dst")
     _req(frame_idx, torch.int32, "gather_frames.frame_idx")
     wlen = frame_idx.numel()
-    if dst.numel() != n_outer * wlen * inner or (src_mod + src_off) * f_src * inner > src.numel():
+    if dst.numel() != n_outer * wlen * inner or (min(n_outer, src_mod) + src_off) * f_src * inner > src.numel():
         raise _lib.EmoteKernelError("gather_frames: buffer sizes do not match the [outer, frames, inner] geometry")
     check(_lib.load().emote_gather_frames(src.data_ptr(), dst.data_ptr(), frame_idx.data_ptr(), n_outer, wlen, f_src,
                                           inner, src_mod, src_off, _stream()), "emote_gather_frames")
@@ -445,6 +466,53 @@ def vae_postprocess(tok: torch.Tensor, n_img: int, H: int, W: int, want_f32: boo
     check(_lib.load().emote_vae_postprocess(tok.data_ptr(), n_img, H * W, ld, _ptr(of), _ptr(ou), _stream()),
           "emote_vae_postprocess")
     return of, ou
+
+
+# ----------------------------------------------------------------------------------------------- audio front-end
+def wave_stats(wave: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
+    _req(wave, F32, "wave_stats.wave")
+    stats = torch.empty(2, dtype=F32, device=wave.device)
+    check(_lib.load().emote_wave_stats(wave.data_ptr(), wave.numel(), eps, stats.data_ptr(), _stream()), "emote_wave_stats")
+    return stats
+
+
+def wave_im2col(wave: torch.Tensor, stats: Optional[torch.Tensor], kernel: int, stride: int, kpad: int) -> torch.Tensor:
+    _req(wave, F32, "wave_im2col.wave")
+    t_out = (wave.numel() - kernel) // stride + 1
+    out = torch.empty((t_out, kpad), dtype=OP16, device=wave.device)
+    check(_lib.load().emote_wave_im2col(wave.data_ptr(), wave.numel(), _ptr(stats), kernel, stride, kpad, out.data_ptr(),
+                                        _stream()), "emote_wave_im2col")
+    return out
+
+
+def channel_norm_gelu(x: torch.Tensor, gamma, beta, eps: float = 1e-5) -> torch.Tensor:
+    """GroupNorm(num_groups == channels) over the rows of x [T, C] + GELU -> op16"""
+    _req(x, F32, "channel_norm_gelu.x")
+    T, Cc = x.shape
+    scratch = torch.empty(2 * Cc, dtype=torch.float64, device=x.device)
+    out = torch.empty((T, Cc), dtype=OP16, device=x.device)
+    check(_lib.load().emote_channel_norm_gelu(x.data_ptr(), T, Cc, gamma.data_ptr(), beta.data_ptr(), eps,
+                                              scratch.data_ptr(), out.data_ptr(), _stream()), "emote_channel_norm_gelu")
+    return out
+
+
+def tokens_to_groups(x: torch.Tensor, groups: int, pad_front: int, pad_back: int) -> torch.Tensor:
+    _req(x, F32, "tokens_to_groups.x")
+    T, Cc = x.shape
+    out = torch.empty((groups, T + pad_front + pad_back, Cc // groups), dtype=OP16, device=x.device)
+    check(_lib.load().emote_tokens_to_groups(x.data_ptr(), T, Cc, groups, pad_front, pad_back, out.data_ptr(), _stream()),
+          "emote_tokens_to_groups")
+    return out
+
+
+def speed_encoder(speeds, centers, radii, w1, b1, w2, b2) -> torch.Tensor:
+    for t, n in ((speeds, "speeds"), (centers, "centers"), (radii, "radii"), (w1, "w1"), (b1, "b1"), (w2, "w2"), (b2, "b2")):
+        _req(t, F32, f"speed_encoder.{n}")
+    out = torch.empty((speeds.numel(), w2.shape[0]), dtype=F32, device=speeds.device)
+    check(_lib.load().emote_speed_encoder(speeds.data_ptr(), speeds.numel(), centers.data_ptr(), radii.data_ptr(),
+                                          centers.numel(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                          w2.shape[0], out.data_ptr(), _stream()), "emote_speed_encoder")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- profiling

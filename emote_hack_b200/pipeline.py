@@ -131,18 +131,12 @@ def get_context_scheduler(name: str) -> Callable:
 
 # =============================================================================================== audio tokens
 def wav2vec_window_features(hidden_states: torch.Tensor, m: int = 2, n: int = 2, as_tokens: bool = True) -> torch.Tensor:
-    """Neighbour-frame windows of wav2vec2 hidden states (Net.py:646-667, `extract_features_from_wav`): frame f gets the
-    features of frames f-m .. f+n, zero-padded past either end.  hidden_states [T, d] (or [1, T, d]) ->
-    [T, m+n+1, d] tokens (as_tokens, the per-frame `encoder_hidden_states` of the audio cross-attention) or the
-    reference's flattened [T, (m+n+1)*d].  A gather only — the wav2vec2 forward itself is upstream of the path."""
-    h = hidden_states[0] if hidden_states.dim() == 3 else hidden_states
-    if h.dim() != 2 or m < 0 or n < 0:
+    """Neighbour-frame windows of wav2vec2 hidden states (Net.py:646-667) — see `audio.window_features`; the wav2vec2 forward
+    that produces the hidden states is `audio.Wav2Vec2Model`."""
+    from .audio import window_features
+    if hidden_states.dim() not in (2, 3):
         raise ValueError("wav2vec_window_features: expected hidden states [T, d] and m, n >= 0")
-    t, d = h.shape
-    padded = torch.cat([h.new_zeros(m, d), h, h.new_zeros(n, d)])
-    idx = torch.arange(t, device=h.device)[:, None] + torch.arange(m + n + 1, device=h.device)[None]
-    win = padded[idx]                                            # [T, m+n+1, d]
-    return win if as_tokens else win.reshape(t, (m + n + 1) * d)
+    return window_features(hidden_states, m, n, as_tokens)
 
 
 # =============================================================================================== CUDA graph

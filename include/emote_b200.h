@@ -38,6 +38,7 @@ int emote_operand_dtype(void); /* EMOTE_OP_BF16 or EMOTE_OP_F16 */
 
 #define EMOTE_EPI_LINEAR 0
 #define EMOTE_EPI_GEGLU 1
+#define EMOTE_EPI_GELU 2   /* out = out_scale * (gelu_erf(acc + bias) + residual): wav2vec2 conv / feed-forward layers */
 
 const char* emote_last_error(void);
 long long emote_launch_count(void); /* kernels launched by this library so far (bench.py "gpu_launches") */
@@ -57,7 +58,8 @@ void emote_set_pdl(int enabled);
  * (acc_v + b_v) * gelu_erf(acc_g + b_g)   (orig_attention.py:817-827). */
 typedef struct {
   int32_t M, N, K;
-  int32_t lda;            /* A row pitch in elements (plain GEMM) */
+  int32_t lda;            /* A row pitch in elements (plain GEMM); may be < K: overlapping rows = the zero-copy operand of a
+                             strided 1-D convolution over a [T, C] token matrix (lda = stride*C, K = kernel*C) */
   int32_t conv_taps;      /* 1 or 9 */
   int32_t n_img, H, W, C; /* conv mode */
   const float* bias;      /* [N] or NULL */
@@ -110,6 +112,11 @@ int emote_gn_apply(const float* x, int32_t C_src, int32_t c_offset, int32_t C_to
  * sinusoidal PositionalEncoding applied after the norm (motion_module.py:246-248,283). */
 int emote_layernorm(const float* x, int64_t M, int32_t C, const float* gamma, const float* beta, float eps,
                     const float* pe, int32_t pe_rows_per_frame, int32_t pe_frames, void* out_bf16, void* stream);
+/* same, additionally writing the normalised rows in fp32 (post-LN transformers — wav2vec2's encoder layers,
+ * transformers Wav2Vec2EncoderLayer — continue their fp32 residual stream from the LayerNorm output); out_bf16 may be
+ * NULL when only the fp32 copy is wanted */
+int emote_layernorm_dual(const float* x, int64_t M, int32_t C, const float* gamma, const float* beta, float eps,
+                         void* out_bf16, float* out_f32, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ attention
  * Flash-style softmax(Q K^T * scale) V on bf16 with fp32 softmax/accumulation (orig_attention.py:655-684).
@@ -217,6 +224,30 @@ int emote_fill_f32(float* p, float value, int64_t n, void* stream);
  * (EMOAnimationPipeline.py:304) */
 int emote_vae_postprocess(const float* tok, int32_t n_img, int32_t HW, int32_t ld, float* out_f32, uint8_t* out_u8,
                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------ audio front-end
+ * wav2vec2-base forward behind `Wav2VecFeatureExtractor` (Net.py:607-667 -> transformers Wav2Vec2Model).
+ * The convolutions, linears, LayerNorms and the 12-head attention run on emote_gemm_bf16 (EMOTE_EPI_GELU, overlapping-row
+ * operands for the strided 1-D convs), emote_layernorm(_dual) and emote_attention_bf16; these entries cover the rest. */
+/* stats[0] = mean, stats[1] = 1/sqrt(var + eps) of the waveform (Wav2Vec2FeatureExtractor.zero_mean_unit_var_norm) */
+int emote_wave_stats(const float* wave, int64_t n, float eps, float* stats, void* stream);
+/* layer-0 operand: out[t, j] = op16((wave[stride*t + j] - mean) * rstd), j < kernel, zero up to kpad (multiple of 8);
+ * t < (n - kernel)/stride + 1; stats may be NULL (no normalisation) */
+int emote_wave_im2col(const float* wave, int64_t n, const float* stats, int32_t kernel, int32_t stride, int32_t kpad,
+                      void* out_op16, void* stream);
+/* GroupNorm with one channel per group over the time axis + exact GELU (Wav2Vec2GroupNormConvLayer): x fp32 [T, C] ->
+ * op16 [T, C]; sums_scratch: 2*C doubles (cleared by the call) */
+int emote_channel_norm_gelu(const float* x, int64_t T, int32_t C, const float* gamma, const float* beta, float eps,
+                            double* sums_scratch, void* out_op16, void* stream);
+/* x fp32 [T, C] -> op16 [groups, pad_front + T + pad_back, C/groups] zero padded in time: row t of group g then holds the
+ * `kernel` consecutive frames of the grouped positional convolution contiguously (Wav2Vec2PositionalConvEmbedding) */
+int emote_tokens_to_groups(const float* x, int64_t T, int32_t C, int32_t groups, int32_t pad_front, int32_t pad_back,
+                           void* out_op16, void* stream);
+/* SpeedEncoder (Net.py:198-258): v_i = tanh((s - center_i)/radius_i * 3); out = W2 relu(W1 v + b1) + b2, fp32.
+ * speeds [batch]; w1 [embed_dim, n_buckets]; w2 [embed_dim, embed_dim]; out [batch, embed_dim] */
+int emote_speed_encoder(const float* speeds, int32_t batch, const float* centers, const float* radii, int32_t n_buckets,
+                        const float* w1, const float* b1, const float* w2, const float* b2, int32_t embed_dim, float* out,
+                        void* stream);
 
 #ifdef __cplusplus
 }

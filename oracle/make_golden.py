@@ -57,9 +57,24 @@ def make_ddim_golden():
     torch.save(out, GOLD / "ddim_reference_steps.pt")
 
 
+def make_speed_encoder_golden():
+    """SpeedEncoder (Net.py:198-258) executed from the reference source: inputs, its own randomly initialised MLP weights
+    and outputs."""
+    from oracle import ref_audio
+    SE = ref_audio.reference_speed_encoder_class()
+    torch.manual_seed(5)
+    enc = SE(9, 64)
+    speeds = torch.tensor([-1.3, -0.55, -0.12, 0.0, 0.07, 0.21, 0.5, 0.93, 2.0], dtype=torch.float32)
+    with torch.no_grad():
+        out = enc(speeds)
+    torch.save({"speeds": speeds, "out": out, "state_dict": {k: v.clone() for k, v in enc.state_dict().items()},
+                "centers": list(enc.bucket_centers), "radii": list(enc.bucket_radii)}, GOLD / "speed_encoder.pt")
+
+
 def main():
     GOLD.mkdir(parents=True, exist_ok=True)
     make_ddim_golden()
+    make_speed_encoder_golden()
     U = ref_shim.load_reference_unet_class()
     RC = ref_shim.load_reference_control_class()
     uniform = ref_shim.load_reference_context_uniform()
@@ -158,5 +173,7 @@ def main():
 if __name__ == "__main__":
     if sys.argv[1:] == ["ddim"]:
         make_ddim_golden()
+    elif sys.argv[1:] == ["speed"]:
+        make_speed_encoder_golden()
     else:
         main()

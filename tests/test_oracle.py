@@ -171,6 +171,38 @@ def test_ddim_oracle_against_live_reference_code():
             assert rel_l2(o.step(eps, t, x), method(types.SimpleNamespace(scheduler=fwd), eps, t, x)[0]) < 1e-6
 
 
+def test_speed_encoder_restatement_pinned_on_reference_class():
+    """oracle/ref_audio.speed_encoder_restated against vectors recorded by executing the reference's SpeedEncoder
+    (Net.py:198-258, cut out with ast) — and against the live class when /root/reference is present"""
+    from oracle import ref_audio
+    gold = torch.load(GOLD / "speed_encoder.pt")
+    sd = gold["state_dict"]
+    got = ref_audio.speed_encoder_restated(gold["speeds"], gold["centers"], gold["radii"], sd["mlp.0.weight"], sd["mlp.0.bias"],
+                                           sd["mlp.2.weight"], sd["mlp.2.bias"])
+    assert rel_l2(got, gold["out"]) < 1e-6
+    if ref_audio.REFERENCE_NET.exists():
+        SE = ref_audio.reference_speed_encoder_class()
+        enc = SE(9, 64)
+        enc.load_state_dict(sd)
+        with torch.no_grad():
+            assert torch.equal(enc(gold["speeds"]), gold["out"])
+        with pytest.raises(AssertionError):
+            SE(10, 64)          # 9 hard-coded bucket centres (Net.py:225-229): what the pipeline's SpeedEncoder(10, 64) hits
+
+
+def test_wav2vec2_module_tree_matches_transformers_state_dict():
+    """boundary of the audio front-end: same parameter names / shapes as transformers.Wav2Vec2Model (wav2vec2-base)"""
+    from emote_hack_b200.audio import Wav2Vec2Model
+    from oracle import ref_audio
+    hf = ref_audio.hf_wav2vec2()
+    with torch.device("meta"):
+        ours = Wav2Vec2Model()
+    a = {k: tuple(v.shape) for k, v in hf.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    assert a == b and len(a) == 211
+    assert ours.frames_for(16000) == 49 and ours.frames_for(160000) == 499
+
+
 def test_oracle_writer_banks_match_reference_golden():
     """ReferenceNet writer: oracle run with collect_banks against banks recorded from the reference's own
     ReferenceAttentionControl(mode="write") on its UNet3D (one frame, no motion modules)."""

@@ -309,7 +309,7 @@ def attention(q: torch.Tensor, k0: torch.Tensor, v0: torch.Tensor, out: torch.Te
     lib = _lib.load()
     # tcgen05 kernel for the long-sequence self-attention shapes; warp-level mma kernel for short key sets (text /
     # audio context) and the other head dims
-    use_tc = impl == "tc" or (impl == "auto" and head_dim in (40, 80) and n0 >= 256)
+    use_tc = impl == "tc" or (impl == "auto" and n0 >= 256 and lib.emote_attention_tc_supported(head_dim) == 1)
     if use_tc:
         check(lib.emote_attention_tc_bf16(C.byref(a), _stream()), "emote_attention_tc_bf16")
     else:

@@ -449,8 +449,34 @@ def test_errors_are_loud(ops):
         ops.gemm(a.cpu(), w)
 
 
+def test_flash_attention_tcgen05_lazy_rescale_with_growing_scores(ops):
+    """The tcgen05 kernel keeps O in TMEM and rescales it only when a row's running maximum has grown by more than 2^8:
+    keys whose scores rise steadily along the key axis (every tile beats the previous maximum by far more than that) force
+    the rescale path on every tile, a row-dependent ramp makes the warp-uniform decision fire for rows that do not need
+    it, and a flat tail exercises the no-rescale path after many rescales."""
+    g = _gen(23)
+    batch, heads, d, n = 2, 2, 40, 1024
+    C = heads * d
+    u = torch.nn.functional.normalize(torch.randn(d, device="cuda", generator=g), dim=0)
+    ramp = torch.cat([torch.linspace(0, 60, n - 256, device="cuda"), torch.full((256,), 60.0, device="cuda")])
+    k = ramp[:, None] * u[None] + 0.3 * torch.randn(n, d, device="cuda", generator=g)
+    qscale = torch.linspace(0.5, 4.0, n, device="cuda")                       # rows see ramps of different steepness
+    q = qscale[:, None] * u[None] * d ** 0.5 + 0.3 * torch.randn(n, d, device="cuda", generator=g)
+    v = torch.randn(n, d, device="cuda", generator=g)
+    rep = lambda t: t[None, :, None, :].expand(batch, n, heads, d).reshape(batch, n, C).to(OP16).contiguous()
+    qq, kk, vv = rep(q), rep(k), rep(v)
+    out = torch.zeros(batch, n, C, device="cuda", dtype=OP16)
+    ops.attention(qq, kk, vv, out, batch=batch, heads=heads, head_dim=d, nq=n, n0=n, q_strides=(n * C, C),
+                  kv0_strides=(n * C, C), o_strides=(n * C, C), scale=d ** -0.5, impl="tc")
+    sp = lambda t: t.reshape(batch, n, heads, d).permute(0, 2, 1, 3)
+    ref = _sdpa_ref(sp(qq), sp(kk), sp(vv), d ** -0.5).permute(0, 2, 1, 3).reshape(batch, n, C)
+    assert torch.isfinite(out.float()).all()
+    chk(rel_l2(out, ref), 6e-3)
+
+
 @pytest.mark.parametrize("heads,d,nq,nk", [(8, 40, 256, 256), (8, 40, 1024, 1024), (8, 80, 256, 256), (2, 40, 200, 300),
-                                           (8, 40, 4096, 4096), (4, 80, 1024, 1024), (1, 40, 64, 64)])
+                                           (8, 40, 4096, 4096), (4, 80, 1024, 1024), (1, 40, 64, 64),
+                                           (8, 160, 256, 256), (12, 64, 499, 499), (2, 160, 100, 333), (3, 64, 1024, 77)])
 def test_flash_attention_tcgen05(ops, heads, d, nq, nk):
     g = _gen(20)
     batch = 3

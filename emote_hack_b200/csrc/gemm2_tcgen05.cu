@@ -157,11 +157,8 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         const int nb0 = tn * BN + static_cast<int>(rank) * (BN / 2);
         int img0 = 0, y0 = 0, x0 = 0;
         if (p.taps > 1) {
-          const int hw = p.H * p.W;
-          img0 = m0 / hw;
-          const int rem = m0 - img0 * hw;
-          y0 = rem / p.W;
-          x0 = rem - y0 * p.W;
+          const TileOrigin o = tile_origin(p, m0);   // a sub-tile past the last one maps beyond n_img: zero-filled loads
+          img0 = o.img0; y0 = o.y0; x0 = o.x0;
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -249,7 +246,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       int nb = 0;
       for (int b = 0; b < NBOX; ++b) nb += (tn * BN + b * 32 < p.N) ? 1 : 0;
       mbar_expect_tx(res_full, static_cast<uint32_t>(nb) * (BM * 128));
-      for (int b = 0; b < nb; ++b) tma_load_2d(stage_out + b * (BM * 128), &tmR, res_full, tn * BN + b * 32, rb);
+      for (int b = 0; b < nb; ++b) tile_box_load(p, stage_out + b * (BM * 128), &tmR, res_full, tn * BN + b * 32, rb);
     };
     if (res_tma && threadIdx.x == 64 && pair < num_tiles) load_residual(pair);
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -263,7 +260,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             const int nt = tile + num_pairs, ntm = nt / p.tiles_n, ntn = nt - ntm * p.tiles_n;
             const int nrb = ntm * (2 * BM) + static_cast<int>(rank) * BM;
             for (int b = 0; b < NBOX; ++b)
-              if (ntn * BN + b * 32 < p.N) tma_prefetch_2d(&tmR, ntn * BN + b * 32, nrb);
+              if (ntn * BN + b * 32 < p.N) tile_box_prefetch(p, &tmR, ntn * BN + b * 32, nrb);
           }
           mbar_wait(res_full, rphase);
           rphase ^= 1;
@@ -285,12 +282,12 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         fence_proxy_async_smem();
         named_bar_sync(1, EPI_WARPS * 32);
         if (threadIdx.x == 64) {
-          if (row_base < p.M) {   // the second CTA of the last pair may own no valid rows
+          if (p.patch ? (row_base / BM < p.subtiles) : (row_base < p.M)) {   // the second CTA of the last pair may own no valid rows
             if constexpr (OUT_MODE == 1) {
               store_bf16_boxes<BN>(&tmC, stage_out, p, tn, row_base);
             } else {
               for (int b = 0; b < NBOX; ++b)
-                if (tn * BN + b * 32 < p.N) tma_store_2d(&tmC, stage_out + b * (BM * 128), tn * BN + b * 32, row_base);
+                if (tn * BN + b * 32 < p.N) tile_box_store(p, &tmC, stage_out + b * (BM * 128), tn * BN + b * 32, row_base);
             }
           }
           bulk_commit();
@@ -331,7 +328,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(gemm2)", e);
     configured = true;
   }
-  p.tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
+  p.tiles_m = p.patch ? (p.subtiles + 1) / 2 : (p.M + 2 * BM - 1) / (2 * BM);
   p.tiles_n = (p.N + BN - 1) / BN;
   const int tiles = p.tiles_m * p.tiles_n;
   if (g2_num_sms == 0) {

@@ -14,7 +14,12 @@ struct GemmDev {
   int kb_per_tap;    // C/64 in conv mode
   int taps;          // 1 or 9
   int H, W;          // conv image dims
-  int bw, bh;        // TMA box extents in W and H (bw*bh*bn = 128)
+  int bw, bh;        // TMA box extents in W and H (bw*bh*bnimg = 128)
+  int bnimg, n_img;  // images per box / images in the tensor
+  int patch;         // conv only: the 128 rows of a sub-tile are a 2-D patch bw x bh (x bnimg images) of the image instead
+                     // of 128 consecutive pixels (W neither divides nor is a multiple of 128: 96x96, 48x48, 24x24 ... maps)
+  int tiles_x, tiles_y;  // patch mode: patches per image row / column
+  int subtiles;          // patch mode: number of 128-row sub-tiles (image groups x tiles_x x tiles_y)
   int tiles_m, tiles_n;
   const float* bias;
   const float* row_bias;
@@ -31,6 +36,85 @@ struct GemmDev {
   int stats_rows;    // rows per statistics batch (multiple of 128: a tile never straddles two batches)
 };
 
+
+// ---- where the 128 rows of a sub-tile live.  `row_base` is the sub-tile index x 128: in the ordinary layout that IS the first
+// global row; in patch mode (implicit-GEMM conv over maps whose rows do not pack into 128-pixel runs) sub-tile
+// st = row_base / 128 is patch (tx, ty) of image group st / (tiles_x * tiles_y), and local row lr is pixel
+// (x0 + lr % bw, y0 + (lr / bw) % bh) of image img0 + lr / (bw * bh).
+struct TileOrigin { int img0, y0, x0; };
+__device__ __forceinline__ TileOrigin tile_origin(const GemmDev& p, int row_base) {
+  TileOrigin o;
+  if (p.patch) {
+    const int st = row_base / BM;
+    const int tpg = p.tiles_x * p.tiles_y;
+    const int grp = st / tpg, rem = st - grp * tpg;
+    const int ty = rem / p.tiles_x;
+    o.img0 = grp * p.bnimg;
+    o.y0 = ty * p.bh;
+    o.x0 = (rem - ty * p.tiles_x) * p.bw;
+  } else {
+    const int hw = p.H * p.W;
+    o.img0 = row_base / hw;
+    const int rem = row_base - o.img0 * hw;
+    o.y0 = rem / p.W;
+    o.x0 = rem - o.y0 * p.W;
+  }
+  return o;
+}
+// global output row of local row lr of the sub-tile, or -1 when that row does not exist
+__device__ __forceinline__ int tile_global_row(const GemmDev& p, int row_base, int lr) {
+  if (!p.patch) {
+    const int r = row_base + lr;
+    return r < p.M ? r : -1;
+  }
+  const TileOrigin o = tile_origin(p, row_base);
+  const int pix = p.bw * p.bh;
+  const int li = lr / pix, q = lr - li * pix;
+  const int img = o.img0 + li;
+  const int yy = q / p.bw;
+  return img < p.n_img ? (img * p.H + o.y0 + yy) * p.W + o.x0 + (q - yy * p.bw) : -1;
+}
+// fp32 staging boxes [128 rows][32 floats] <-> global memory: 2-D tensor maps over [M, N] in the ordinary layout, 4-D maps
+// over [n_img, H, W, N] with a {32, bw, bh, bnimg} box in patch mode (same order of the 128 rows in shared memory)
+__device__ __forceinline__ void tma_store_4d(const void* desc, const void* smem_src, int32_t c0, int32_t c1, int32_t c2,
+                                             int32_t c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const void* desc, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tile_box_store(const GemmDev& p, const void* desc, const void* smem_src, int col,
+                                               int row_base) {
+  if (p.patch) {
+    const TileOrigin o = tile_origin(p, row_base);
+    tma_store_4d(desc, smem_src, col, o.x0, o.y0, o.img0);
+  } else {
+    tma_store_2d(desc, smem_src, col, row_base);
+  }
+}
+__device__ __forceinline__ void tile_box_load(const GemmDev& p, void* smem_dst, const void* desc, uint64_t* bar, int col,
+                                              int row_base) {
+  if (p.patch) {
+    const TileOrigin o = tile_origin(p, row_base);
+    tma_load_4d(smem_dst, desc, bar, col, o.x0, o.y0, o.img0);
+  } else {
+    tma_load_2d(smem_dst, desc, bar, col, row_base);
+  }
+}
+__device__ __forceinline__ void tile_box_prefetch(const GemmDev& p, const void* desc, int col, int row_base) {
+  if (p.patch) {
+    const TileOrigin o = tile_origin(p, row_base);
+    tma_prefetch_4d(desc, col, o.x0, o.y0, o.img0);
+  } else {
+    tma_prefetch_2d(desc, col, row_base);
+  }
+}
 
 // OUT_MODE 1: bulk-store the staged bf16 tile (issued by one thread; TMA clips rows >= M and columns >= N).
 template <int BN>
@@ -56,10 +140,15 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
   constexpr bool TMA_OUT = OUT_MODE == 1;
   constexpr int NP = EPI_WARPS / 4;   // warps per lane quarter
   const int g = lane >> 2, t = lane & 3;
-  const int row0 = row_base + quarter * 32 + g;  // this thread's rows: row0 + 8*i, i = 0..3
+  // this thread's rows: local rows quarter*32 + g + 8*i, i = 0..3 (global row -1 = not there)
+  int rows[4];
   bool rok[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) rok[i] = (row0 + 8 * i) < p.M;
+  for (int i = 0; i < 4; ++i) {
+    rows[i] = tile_global_row(p, row_base, quarter * 32 + g + 8 * i);
+    rok[i] = rows[i] >= 0;
+  }
+  const int first_row = tile_global_row(p, row_base, 0);   // selects the tile's bias group / statistics batch
 
   if (!p.geglu) {
     constexpr int NCT = BN / 8;                     // 8-column chunks in the tile
@@ -68,7 +157,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
     const int c_first = part * NCH;
     size_t ooff[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ooff[i] = (size_t)(row0 + 8 * i) * p.ldc;
+    for (int i = 0; i < 4; ++i) ooff[i] = (size_t)(rok[i] ? rows[i] : 0) * p.ldc;
     // ---- residual / per-sample bias of this warp's whole column span, issued before the accumulator wait
     float add[HAS_ADD ? NCH : 1][8];
     if constexpr (HAS_ADD) {
@@ -79,7 +168,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
         const bool c0ok = col < p.N, c1ok = col + 1 < p.N;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int row = row0 + 8 * i;
+          const int row = rows[i];
           float v0 = 0.f, v1 = 0.f;
           if (rok[i]) {
             if (has_res) {
@@ -111,8 +200,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
         if (c1ok) b1 = __ldg(p.bias + col + 1);
       }
       if constexpr (OUT_MODE == 2) {
-        if (p.row_bias) {  // host guarantees the 128 rows of a tile share one group (rows_per_group % 128 == 0)
-          const float* rb = p.row_bias + (size_t)(row_base / p.rows_per_group) * p.N + col;
+        if (p.row_bias && first_row >= 0) {  // host guarantees the 128 rows of a tile share one group
+          const float* rb = p.row_bias + (size_t)(first_row / p.rows_per_group) * p.N + col;
           if (c0ok) b0 += __ldg(rb);
           if (c1ok) b1 += __ldg(rb + 1);
         }
@@ -185,8 +274,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
           cs1 += __shfl_xor_sync(0xffffffffu, cs1, off);
           cq1 += __shfl_xor_sync(0xffffffffu, cq1, off);
         }
-        if (g == 0 && row_base < p.M) {
-          double* cs = p.colstats + ((size_t)(row_base / p.stats_rows) * p.N + col) * 2;
+        if (g == 0 && first_row >= 0) {
+          double* cs = p.colstats + ((size_t)(first_row / p.stats_rows) * p.N + col) * 2;
           if (c0ok) { atomicAdd(cs, (double)cs0); atomicAdd(cs + 1, (double)cq0); }
           if (c1ok) { atomicAdd(cs + 2, (double)cs1); atomicAdd(cs + 3, (double)cq1); }
         }
@@ -209,7 +298,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
     const int n_out = p.N / 2;
     size_t ooff[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ooff[i] = (size_t)(row0 + 8 * i) * p.ldc;
+    for (int i = 0; i < 4; ++i) ooff[i] = (size_t)(rok[i] ? rows[i] : 0) * p.ldc;
     uint32_t av[2][8], ag[2][8];
     float bb[NCH][4];   // value / gate biases of this warp's chunks, loaded before the accumulator wait
 #pragma unroll

@@ -103,11 +103,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int n0 = tn * BN;
         int img0 = 0, y0 = 0, x0 = 0;
         if (p.taps > 1) {
-          const int hw = p.H * p.W;
-          img0 = m0 / hw;
-          const int rem = m0 - img0 * hw;
-          y0 = rem / p.W;
-          x0 = rem - y0 * p.W;
+          const TileOrigin o = tile_origin(p, m0);
+          img0 = o.img0; y0 = o.y0; x0 = o.x0;
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -204,7 +201,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int b = 0; b < NBOX; ++b) nb += (tn * BN + b * 32 < p.N) ? 1 : 0;
       mbar_expect_tx(&res_full[buf], static_cast<uint32_t>(nb) * (BM * 128));
       for (int b = 0; b < nb; ++b)
-        tma_load_2d(stage_out + buf * S::OUT_BUF + b * (BM * 128), &tmR, &res_full[buf], tn * BN + b * 32, tm * BM);
+        tile_box_load(p, stage_out + buf * S::OUT_BUF + b * (BM * 128), &tmR, &res_full[buf], tn * BN + b * 32, tm * BM);
     };
     if (res_tma && threadIdx.x == 64) {
       for (int k = 0; k < NBUF; ++k)
@@ -224,7 +221,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             // waiting in L2 by then
             const int nt = tile + gridDim.x, ntm = nt / p.tiles_n, ntn = nt - ntm * p.tiles_n;
             for (int b = 0; b < NBOX; ++b)
-              if (ntn * BN + b * 32 < p.N) tma_prefetch_2d(&tmR, ntn * BN + b * 32, ntm * BM);
+              if (ntn * BN + b * 32 < p.N) tile_box_prefetch(p, &tmR, ntn * BN + b * 32, ntm * BM);
           }
           mbar_wait(&res_full[buf], rphase[buf]);
           rphase[buf] ^= 1;
@@ -251,7 +248,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             store_bf16_boxes<BN>(&tmC, stage_buf, p, tn, tm * BM);
           } else {
             for (int b = 0; b < NBOX; ++b)
-              if (tn * BN + b * 32 < p.N) tma_store_2d(&tmC, stage_buf + b * (BM * 128), tn * BN + b * 32, tm * BM);
+              if (tn * BN + b * 32 < p.N) tile_box_store(p, &tmC, stage_buf + b * (BM * 128), tn * BN + b * 32, tm * BM);
           }
           bulk_commit();
           const int nxt = tile + NBUF * static_cast<int>(gridDim.x);
@@ -309,7 +306,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(gemm)", e);
     configured = true;
   }
-  p.tiles_m = (p.M + BM - 1) / BM;
+  p.tiles_m = p.patch ? p.subtiles : (p.M + BM - 1) / BM;
   p.tiles_n = (p.N + BN - 1) / BN;
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -387,19 +384,31 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   }
 
   CUtensorMap tmA, tmB;
+  bool patch_rowbias_per_row = false;   // patch mode with bias groups smaller than an image group: per-row bias (mode 0)
   if (conv) {
     const int C = a->C, H = a->H, W = a->W, NI = a->n_img;
     if (C <= 0 || C % 64 != 0) return set_error("emote_gemm_bf16(conv): C must be a multiple of 64");
     if (a->K != 9 * C) return set_error("emote_gemm_bf16(conv): K must equal 9*C");
     if ((long long)NI * H * W != a->M) return set_error("emote_gemm_bf16(conv): M must equal n_img*H*W");
-    int bw = W < 128 ? W : 128;
-    if (128 % bw != 0 || W % bw != 0) return set_error("emote_gemm_bf16(conv): W must divide or be a multiple of 128");
-    int bh = 128 / bw;
-    if (bh > H) bh = H;
-    if (H % bh != 0) return set_error("emote_gemm_bf16(conv): H incompatible with the 128-row tile");
-    int bnimg = 128 / (bw * bh);
-    if (bnimg * bw * bh != 128) return set_error("emote_gemm_bf16(conv): H*W must divide or be a multiple of 128");
-    p.H = H; p.W = W; p.bw = bw; p.bh = bh;
+    // 128 output pixels per sub-tile = one TMA box {64 channels, bw, bh, bnimg}: the widest power-of-two run of a row,
+    // then rows, then images.  When the runs are whole rows (bw == W) or single-row (bh == 1) the 128 pixels are
+    // consecutive output rows; otherwise (96x96, 48x48, 24x24, 12x12 ... maps) the sub-tile is a 2-D patch ("patch mode").
+    auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+    const int bw = gcd(W, 128);
+    const int bh = gcd(H, 128 / bw);
+    const int bnimg = 128 / (bw * bh);
+    p.H = H; p.W = W; p.bw = bw; p.bh = bh; p.bnimg = bnimg; p.n_img = NI;
+    const bool contiguous = bw == 128 || (bw == W && (bnimg == 1 || bh == H));
+    p.patch = contiguous ? 0 : 1;
+    if (p.patch) {
+      p.tiles_x = W / bw;
+      p.tiles_y = H / bh;
+      p.subtiles = ((NI + bnimg - 1) / bnimg) * p.tiles_x * p.tiles_y;
+      const long long group_rows = (long long)H * W * bnimg;   // a sub-tile never leaves its group of bnimg images
+      if (p.colstats && p.stats_rows % group_rows != 0)
+        return set_error("emote_gemm_bf16(conv): stats_rows must be a multiple of H*W*images-per-tile for this map size");
+      if (a->row_bias && p.rows_per_group % group_rows != 0) patch_rowbias_per_row = true;
+    }
     p.kb_per_tap = C / 64;
     p.num_kb = 9 * p.kb_per_tap;
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
@@ -421,6 +430,7 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   // convolutions and the large-K GEMMs, when there are enough 256-row tiles to occupy the 74 pairs.
   const long long pair_tiles = ((long long)(a->M + 255) / 256) * ((a->N + bn - 1) / bn);
   bool use_pair = (conv || a->K >= 1024) && a->M >= 256 && pair_tiles >= 64;
+  if (p.patch && p.subtiles < 2) use_pair = false;
   if (a->pair_mode == 1) use_pair = true;
   if (a->pair_mode == 2 || want3) use_pair = false;
   {
@@ -438,8 +448,8 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   int out_mode = 0;
   if (a->tma_store != 2) {
     if (p.out_bf16 && !(p.residual || p.row_bias)) {
-      out_mode = 1;
-    } else if (mode2_ok && (a->K <= 4096 || want3)) {
+      out_mode = p.patch ? 0 : 1;   // patch mode: 16-bit outputs leave through the register path
+    } else if (mode2_ok && !patch_rowbias_per_row && (a->K <= 4096 || want3)) {
       out_mode = want3 ? 3 : 2;
     }
   }
@@ -449,6 +459,17 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
     uint64_t strides[1] = {(uint64_t)a->ldc * 2};
     uint32_t box[2] = {(uint32_t)(geglu ? bn / 2 : bn), 128};
     if (int rc = make_tensor_map(&tmC, out, 2, dims, strides, box, /*swizzle=*/0)) return rc;
+  } else if (out_mode >= 2 && p.patch) {
+    // the fp32 output / residual as [n_img, H, W, N] tensors: the staging boxes of a sub-tile are {32, bw, bh, bnimg}
+    uint64_t dims[4] = {(uint64_t)a->N, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.n_img};
+    uint64_t strides[3] = {(uint64_t)a->ldc * 4, (uint64_t)p.W * a->ldc * 4, (uint64_t)p.H * p.W * a->ldc * 4};
+    uint32_t box[4] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bnimg};
+    if (int rc = make_tensor_map(&tmC, out, 4, dims, strides, box, true, 4)) return rc;
+    tmR = tmC;
+    if (p.residual) {
+      uint64_t rs[3] = {(uint64_t)a->ldr * 4, (uint64_t)p.W * a->ldr * 4, (uint64_t)p.H * p.W * a->ldr * 4};
+      if (int rc = make_tensor_map(&tmR, p.residual, 4, dims, rs, box, true, 4)) return rc;
+    }
   } else if (out_mode >= 2) {
     uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M};
     uint64_t strides[1] = {(uint64_t)a->ldc * 4};

@@ -172,14 +172,9 @@ def stats_rows_for(rows_per_frame: int, rows_per_sample: int) -> int:
 
 
 def conv_tile_ok(H: int, W: int) -> bool:
-    """Whether the TMA implicit-GEMM tile (128 consecutive pixels as whole rows / whole images) covers H x W."""
-    bw = min(W, 128)
-    if 128 % bw or W % bw:
-        return False
-    bh = min(128 // bw, H)
-    if H % bh:
-        return False
-    return (128 // (bw * bh)) * bw * bh == 128
+    """Whether the TMA implicit-GEMM conv covers an H x W map: always — a 128-pixel sub-tile is the box {gcd(W, 128) pixels
+    of a row, rows, images}, a 2-D patch when rows do not pack into 128-pixel runs (96 / 48 / 24 / 12 latents)."""
+    return H >= 1 and W >= 1
 
 
 def conv3x3(x_bf16: torch.Tensor, w_packed: torch.Tensor, n_img: int, H: int, W: int, Cc: int, **epi) -> torch.Tensor:

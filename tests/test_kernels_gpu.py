@@ -129,13 +129,52 @@ def test_conv3x3_implicit(ops, n_img, H, W, C, N):
     assert rel_l2(out[:, :N], ref) < 2e-5
 
 
-def test_conv3x3_fallback_im2col(ops):
+@pytest.mark.parametrize("n_img,H,W,C,N,mode", [
+    (2, 96, 96, 64, 320, "plain"), (4, 48, 48, 128, 160, "res"), (6, 24, 24, 64, 128, "rowbias"), (16, 12, 12, 64, 128, "res"),
+    (3, 24, 24, 64, 136, "plain"),       # images not a multiple of the 2 per sub-tile, ragged N
+    (5, 12, 12, 128, 64, "res"),         # 8 images per sub-tile, 5 present
+    (2, 48, 96, 64, 128, "stats"), (32, 6, 6, 64, 128, "plain"), (2, 96, 96, 512, 160, "res"),   # K = 4608: register epilogue
+    (2, 40, 24, 64, 128, "rowbias_small"), (4, 24, 24, 640, 320, "stats")])
+def test_conv3x3_implicit_2d_patch_tiles(ops, n_img, H, W, C, N, mode):
+    """Implicit-GEMM 3x3 conv over maps whose rows do not pack into 128-pixel runs (BASELINE config #4: 96 / 48 / 24 / 12
+    latents): the 128 rows of a sub-tile are a {bw, bh, images} patch, loaded, staged and stored through 4-D TMA boxes —
+    no im2col copy.  Single-CTA and CTA-pair kernels, staged (K <= 4096) and register epilogues, fused residual /
+    per-sample bias / GroupNorm statistics."""
+    g = _gen(40)
+    x = torch.randn(n_img, H, W, C, device="cuda", generator=g).to(OP16)
+    w = (torch.randn(N, C, 3, 3, device="cuda", generator=g) / math.sqrt(9 * C)).to(OP16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    wp = ops.pack_conv3x3(w.float())
+    M = n_img * H * W
+    kw = {}
+    if mode == "res":
+        res = torch.randn(M, N, device="cuda", generator=g)
+        kw = dict(residual=res, out_scale=0.5)
+        ref = (ref + res) * 0.5
+    elif mode in ("rowbias", "rowbias_small"):
+        # per-sample bias: groups of whole images (the time-embedding bias of resnet.py:186-189) / of single images
+        per = 2 * H * W if mode == "rowbias" else H * W
+        rb = torch.randn(M // per, N, device="cuda", generator=g)
+        kw = dict(row_bias=rb, rows_per_group=per)
+        ref = ref + rb.repeat_interleave(per, 0)
+    elif mode == "stats":
+        kw = dict(stats_rows=2 * H * W)
+    for pair_mode in (1, 2):
+        out = ops.conv3x3(x, wp, n_img, H, W, C, bias=bias, pair_mode=pair_mode, **kw)
+        assert rel_l2(out, ref) < 2e-5, pair_mode
+        if mode == "stats":
+            _check_colstats(out, 2 * H * W)
+
+
+def test_conv3x3_narrow_channels_take_the_im2col_path(ops):
+    """channel counts that are not a multiple of the 64-wide TMA box still go through the explicit im2col gather"""
     g = _gen(5)
-    n_img, H, W, C, N = 2, 12, 12, 64, 128
+    n_img, H, W, C, N = 2, 12, 12, 32, 128
     x = torch.randn(n_img, H, W, C, device="cuda", generator=g).to(OP16)
     w = (torch.randn(N, C, 3, 3, device="cuda", generator=g) / math.sqrt(9 * C)).to(OP16)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
-    assert not ops.conv_tile_ok(H, W)
     out = ops.conv3x3(x, ops.pack_conv3x3(w.float()), n_img, H, W, C)
     assert rel_l2(out, ref) < 2e-5
 

@@ -311,17 +311,17 @@ def test_unet_full_size_properties():
     torch.cuda.empty_cache()
 
 
-def test_unet_non_tileable_latent_size_uses_im2col_path(tiny):
-    """BASELINE config #4 geometry class (96x96 latents): image rows that do not pack into 128-pixel TMA boxes take the
-    explicit im2col + GEMM path (ops.conv3x3) — still the CUDA kernels, same numerics."""
-    from emote_hack_b200 import ops
+def test_unet_latent_sizes_that_need_2d_conv_tiles(tiny):
+    """BASELINE config #4 geometry class (96x96 latents and their 48 / 24 / 12 levels): image rows that do not pack into
+    128-pixel runs are convolved through 2-D patch tiles (4-D TMA boxes) — no im2col copy is launched."""
+    from emote_hack_b200 import _lib, ops
     m, o, _ = tiny
-    assert not ops.conv_tile_ok(24, 24) and not ops.conv_tile_ok(12, 12)
     x, ctx = make_inputs(2, 2, 24)
     ref = o(x, 201, ctx)
-    out = m(x.cuda(), 201, ctx.cuda()).sample
-    e = rel_l2(out, ref)
-    check_parity("unet.tiny_24x24_latent", e, 2e-2)
+    with ops.KernelProfiler() as prof:
+        out = m(x.cuda(), 201, ctx.cuda()).sample
+    assert "emote_im2col3x3_bf16" not in prof.summary()
+    check_parity("unet.tiny_24x24_latent", rel_l2(out, ref), 2e-2)
 
 
 def test_unet_32_frame_window_audio_tokens_and_banks():

@@ -91,6 +91,7 @@ SIGNATURES = {
     "emote_im2col3x3_bf16": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
     "emote_im2col3x3_s2_pad01": [_vp, _i32, _i32, _i32, _i32, _vp, _vp],
     "emote_upsample2x": [_vp, _i32, _i32, _i32, _i32, _vp, _vp],
+    "emote_upsample_nearest": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
     "emote_cast_bf16": [_vp, _i64, _i32, _i32, _i32, _vp, _vp],
     "emote_silu_bf16": [_vp, _i64, _vp, _vp],
     "emote_tokens_to_ncfhw": [_vp, _i32, _i32, _i32, _i32, _vp, _vp],

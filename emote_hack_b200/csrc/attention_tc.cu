@@ -422,17 +422,13 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
 // v2: O and the row sums accumulate in TMEM (PV / P x ones MMAs with the accumulate flag) and are rescaled LAZILY.
 //
 // The v1 kernel above folds every tile's P V into per-thread registers (O = O*corr + PV: a TMEM read of the whole PV tile
-// plus D FMAs per row and tile, 48-80 live registers).  ncu showed its softmax warps neither MUFU- nor tensor-bound but
-// latency-bound: 2 softmax warps per scheduler, ~410 issued instructions per warp and tile, issue slots 53 % busy, XU 48 %.
-// Here the softmax thread only produces P.  It keeps the exponent reference m_used of its row and moves it only when the
-// running maximum has grown by more than 2^8 (log2 units): then — rarely after the first tiles — the thread rescales its
-// own O row and row sum in TMEM (tcgen05.ld -> multiply -> tcgen05.st) before publishing P.  P values are therefore bounded
-// by 2^8 instead of 1 (fp32 accumulation; exact after the final division by the equally scaled row sum).
-// Without the O registers a thread needs ~100 registers, S / P are single-buffered (the next S is issued as soon as P is
-// published) and K/V use a 2-stage ring: 128 TMEM columns and 69 KB of shared memory per CTA at head_dim 40 -> THREE CTAs
-// per SM (12 softmax warps, 3 per scheduler) overlap each other's MMA / barrier latencies.  head_dim 64 / 80 run two CTAs
-// per SM, head_dim 160 one.
-constexpr int TC2_STAGES = 2;
+// plus D FMAs per row and tile, 48-80 live registers).  Timing shows one CTA needs ~1600 cycles per 64-key tile whatever
+// else runs on the SM: the softmax warp's dependent chain (S load -> max -> 64 exponentials -> P store -> P V fold) is
+// what bounds it, not MUFU (48 % busy) or the tensor pipe (27 %).  Here the softmax thread only produces P: it keeps the
+// exponent reference m_used of its row and moves it only when the running maximum has grown by more than 2^8 (log2 units);
+// then — rarely after the first tiles — the thread rescales its own O row and row sum in TMEM (tcgen05.ld -> multiply ->
+// tcgen05.st) before publishing P.  P is therefore bounded by 2^8 instead of 1 (fp32 accumulation; exact after the final
+// division by the equally scaled row sum).  S and P stay double-buffered so S(j+1) is computed while softmax(j) runs.
 constexpr float TC2_TAU = 8.0f;   // lazy-rescale threshold in log2 units: P <= 2^8
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -454,17 +450,18 @@ struct Tc2Cfg {
   static constexpr int KSTEPS = (D + 15) / 16;
   static constexpr int NPV = KSTEPS * 16;
   static constexpr int CH = D / 8;
+  static constexpr int STAGES = (D <= 64) ? 3 : 2;       // K/V ring
   static constexpr int Q_BYTES = ATOMS * TC_BQ * 128;
   static constexpr int KV_TILE = ATOMS * TC_BKV * 128;
   static constexpr int STAGE = 2 * KV_TILE;
   static constexpr int P_BYTES = TC_BQ * 128;
   static constexpr int ONES_BYTES = 16 * 128;
-  static constexpr int SMEM = Q_BYTES + TC2_STAGES * STAGE + P_BYTES + ONES_BYTES + 256 + 1024;
-  static constexpr int O_COL0 = TC_BKV;                 // S occupies columns [0, 64)
+  static constexpr int SMEM = Q_BYTES + STAGES * STAGE + 2 * P_BYTES + ONES_BYTES + 256 + 1024;
+  static constexpr int O_COL0 = 2 * TC_BKV;             // S double buffer occupies columns [0, 128)
   static constexpr int SUM_COL0 = O_COL0 + NPV;         // 16 columns: every one holds the row sum (column 0 is used)
   static constexpr int USED_COLS = SUM_COL0 + 16;
-  static constexpr int TMEM_COLS = USED_COLS <= 128 ? 128 : (USED_COLS <= 256 ? 256 : 512);
-  static constexpr int CTAS = (D <= 48) ? 3 : (D <= 96 ? 2 : 1);
+  static constexpr int TMEM_COLS = USED_COLS <= 256 ? 256 : 512;
+  static constexpr int CTAS = (2 * SMEM <= 226 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
 };
 
 template <int D, int EMU>
@@ -478,15 +475,15 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + C::Q_BYTES;
-  uint8_t* sP = sKV + TC2_STAGES * C::STAGE;
-  uint8_t* sOnes = sP + C::P_BYTES;
+  uint8_t* sP = sKV + C::STAGES * C::STAGE;
+  uint8_t* sOnes = sP + 2 * C::P_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + C::ONES_BYTES);
   uint64_t* kv_full = bars;                   // [STAGES] TMA (expect_tx) -> MMA
-  uint64_t* kv_empty = kv_full + TC2_STAGES;  // [STAGES] MMA commit -> loader
-  uint64_t* s_full = kv_empty + TC2_STAGES;   // MMA commit -> softmax: S of tile j ready (phase j)
-  uint64_t* p_full = s_full + 1;              // softmax (4 warp arrivals) -> MMA: P of tile j stored, S free (phase j)
-  uint64_t* o_done = p_full + 1;              // MMA commit -> softmax: P V of tile j accumulated, P buffer free (phase j)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+  uint64_t* kv_empty = kv_full + C::STAGES;   // [STAGES] MMA commit -> loader
+  uint64_t* s_full = kv_empty + C::STAGES;    // [2] MMA commit -> softmax: S of tile j in buffer j&1
+  uint64_t* p_full = s_full + 2;              // [2] softmax (4 warp arrivals) -> MMA: P of tile j stored, S buffer j&1 free
+  uint64_t* o_done = p_full + 2;              // [2] MMA commit -> softmax: P V of tile j accumulated, P buffer j&1 free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y;
@@ -499,20 +496,22 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
 
   {
     uint4* z = reinterpret_cast<uint4*>(smem);
-    const int n16 = (C::Q_BYTES + TC2_STAGES * C::STAGE + C::P_BYTES) / 16;
+    const int n16 = (C::Q_BYTES + C::STAGES * C::STAGE + 2 * C::P_BYTES) / 16;
     for (int i = threadIdx.x; i < n16; i += TC_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
     uint4* o = reinterpret_cast<uint4*>(sOnes);
     for (int i = threadIdx.x; i < C::ONES_BYTES / 16; i += TC_THREADS)
       o[i] = make_uint4(OP16_ONE_PAIR, OP16_ONE_PAIR, OP16_ONE_PAIR, OP16_ONE_PAIR);
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC2_STAGES; ++s) {
+    for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
-    mbar_init(o_done, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 4);
+      mbar_init(&o_done[s], 1);
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -541,8 +540,8 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
   if (warp == 0) {
     // ------------------------------------------------------------------ K/V loader (see v1 for the box geometry)
     for (int j = 0; j < ntiles; ++j) {
-      const int stage = j % TC2_STAGES;
-      if (j >= TC2_STAGES) mbar_wait(&kv_empty[stage], ((j / TC2_STAGES) - 1) & 1);
+      const int stage = j % C::STAGES;
+      if (j >= C::STAGES) mbar_wait(&kv_empty[stage], ((j / C::STAGES) - 1) & 1);
       if (elect_one()) {
         uint8_t* kdst = sKV + stage * C::STAGE;
         uint8_t* vdst = kdst + C::KV_TILE;
@@ -566,31 +565,32 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
     constexpr uint32_t idesc_pv = umma_idesc_op16_bmn(TC_BQ, C::NPV);
     constexpr uint32_t idesc_sum = umma_idesc_op16(TC_BQ, 16);
     auto issue_s = [&](int j) {
-      const int stage = j % TC2_STAGES;
-      mbar_wait(&kv_full[stage], (j / TC2_STAGES) & 1);
+      const int stage = j % C::STAGES;
+      mbar_wait(&kv_full[stage], (j / C::STAGES) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t ka = smem_u32(sKV + stage * C::STAGE);
         const uint32_t qa = smem_u32(sQ);
+        const uint32_t d_tmem = tmem_base + (j & 1) * TC_BKV;
 #pragma unroll
         for (int ks = 0; ks < C::KSTEPS; ++ks) {
           const uint64_t da = umma_desc_sw128(qa + (ks >> 2) * (TC_BQ * 128)) + static_cast<uint64_t>(2 * (ks & 3));
           const uint64_t db = umma_desc_sw128(ka + (ks >> 2) * (TC_BKV * 128)) + static_cast<uint64_t>(2 * (ks & 3));
-          umma_f16(tmem_base, da, db, idesc_s, ks != 0 ? 1u : 0u);
+          umma_f16(d_tmem, da, db, idesc_s, ks != 0 ? 1u : 0u);
         }
-        umma_commit(s_full);
+        umma_commit(&s_full[j & 1]);
       }
       __syncwarp();
     };
     issue_s(0);
     for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(p_full, j & 1);             // P(j) is in shared memory, S is free, O was rescaled if it had to be
+      if (j + 1 < ntiles) issue_s(j + 1);   // S buffer (j+1)&1 was released by p_full(j-1), waited last iteration
+      mbar_wait(&p_full[j & 1], (j >> 1) & 1);   // P(j) is in shared memory and O was rescaled if it had to be
       tc_fence_after();
-      if (j + 1 < ntiles) issue_s(j + 1);   // next S first: the softmax warps wait for it, nobody waits for P V yet
       if (elect_one()) {
-        const int stage = j % TC2_STAGES;
+        const int stage = j % C::STAGES;
         const uint32_t va = smem_u32(sKV + stage * C::STAGE) + C::KV_TILE;
-        const uint32_t pa = smem_u32(sP);
+        const uint32_t pa = smem_u32(sP + (j & 1) * C::P_BYTES);
         const uint32_t acc = j != 0 ? 1u : 0u;
 #pragma unroll
         for (int ks = 0; ks < TC_BKV / 16; ++ks) {
@@ -603,7 +603,7 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         for (int ks = 0; ks < TC_BKV / 16; ++ks)
           umma_f16(tmem_base + C::SUM_COL0, umma_desc_sw128(pa) + static_cast<uint64_t>(2 * ks),
                    umma_desc_sw128(oa) + static_cast<uint64_t>(2 * ks), idesc_sum, (ks != 0) ? 1u : acc);
-        umma_commit(o_done);
+        umma_commit(&o_done[j & 1]);
         umma_commit(&kv_empty[stage]);
       }
       __syncwarp();
@@ -613,17 +613,16 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_addr;
     const uint32_t t_o = tmem_base + lane_addr + C::O_COL0;
     const uint32_t t_sum = tmem_base + lane_addr + C::SUM_COL0;
     float m_used = -INFINITY;
     const float sc = p.scale_log2;
-    uint8_t* prow = sP + row * 128;
 
     for (int j = 0; j < ntiles; ++j) {
       const int nvalid = (j < tiles0) ? (p.n0 - j * TC_BKV) : (n1 - (j - tiles0) * TC_BKV);
-      mbar_wait(s_full, j & 1);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
+      const uint32_t t_s = tmem_base + lane_addr + (j & 1) * TC_BKV;
       uint32_t s0[32], s1[32];
       tmem_ld32(t_s, s0);
       tmem_ld32(t_s + 32, s1);
@@ -641,17 +640,14 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
 #pragma unroll
       for (int k = 8; k < 32; ++k) mxa[k & 7] = fmax3(mxa[k & 7], __uint_as_float(s0[k]), __uint_as_float(s1[k]));
       const float mx = fmaxf(fmax3(mxa[0], mxa[1], mxa[2]), fmax3(fmax3(mxa[3], mxa[4], mxa[5]), mxa[6], mxa[7]));
-      // P V (j-1) has consumed the P buffer and is folded into O once o_done reaches phase j-1 (long since: it was issued
-      // right after S(j)); the wait also orders this thread's TMEM reads / writes of O after those MMAs
-      if (j > 0) {
-        mbar_wait(o_done, (j - 1) & 1);
-        tc_fence_after();
-      }
       // lazy rescale: warp-uniform decision (tcgen05.ld / st are warp-collective); rows that did not need it move too
       const bool need = (mx - m_used) * sc > TC2_TAU;   // true on the first tile (m_used = -inf)
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = fmaxf(m_used, mx);
         if (j > 0) {
+          // every P V issued so far must have landed in O before it is rescaled; P V (j) waits for this warp's p_full
+          mbar_wait(&o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc_fence_after();
           const float f = ex2f((m_used - m_new) * sc);
 #pragma unroll
           for (int c = 0; c < C::NPV / 16; ++c) {
@@ -669,7 +665,10 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         }
         m_used = m_new;
       }
+      // P buffer j&1 was read by P V (j-2)
+      if (j >= 2) mbar_wait(&o_done[j & 1], ((j - 2) >> 1) & 1);
       const float nmsc = -(m_used * sc);
+      uint8_t* prow = sP + (j & 1) * C::P_BYTES + row * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float pv[8];
@@ -695,10 +694,10 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
     }
     // ---- epilogue: O / l
-    mbar_wait(o_done, (ntiles - 1) & 1);
+    mbar_wait(&o_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
     tc_fence_after();
     const uint32_t lsum = tmem_ld1(t_sum);
     tmem_ld_wait();

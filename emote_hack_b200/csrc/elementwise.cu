@@ -95,11 +95,13 @@ __global__ void im2col3x3_kernel(const T* __restrict__ x, int n_img, int H, int 
   }
 }
 
-__global__ void upsample2x_kernel(const float* __restrict__ x, int n_img, int H, int W, int C,
-                                  op16* __restrict__ out) {
+// nearest-neighbour resize to Ho x Wo: source index floor(dst * in / out) (F.interpolate(mode="nearest")); Ho = 2H, Wo = 2W
+// is the x2 upsample of Upsample3D
+__global__ void upsample_nearest_kernel(const float* __restrict__ x, int n_img, int H, int W, int C, int Ho, int Wo,
+                                        op16* __restrict__ out) {
   pdl_prologue();
   const int oct = C >> 3;
-  const int Ho = 2 * H, Wo = 2 * W;
+  const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
   const long long total = (long long)n_img * Ho * Wo * oct;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -108,7 +110,8 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, int n_img, int H,
     const int xo = (int)(r % Wo);
     const int yo = (int)((r / Wo) % Ho);
     const long long img = r / ((long long)Wo * Ho);
-    const uint4 w = load8_as_bf16<float>(x + ((img * H + (yo >> 1)) * W + (xo >> 1)) * C + c8 * 8);
+    const int ys = min((int)floorf((float)yo * sy), H - 1), xs = min((int)floorf((float)xo * sx), W - 1);
+    const uint4 w = load8_as_bf16<float>(x + ((img * H + ys) * W + xs) * C + c8 * 8);
     *reinterpret_cast<uint4*>(out + r * C + c8 * 8) = w;
   }
 }
@@ -319,9 +322,20 @@ extern "C" int emote_upsample2x(const float* x, int32_t n_img, int32_t H, int32_
                                 void* stream) {
   if (!x || !out_bf16 || n_img <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0) return set_error("emote_upsample2x: bad arguments");
   const long long total = (long long)n_img * 4 * H * W * (C / 8);
-  launch_kernel(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM(stream), x, n_img, H, W, C,
-                                                                     reinterpret_cast<op16*>(out_bf16));
+  launch_kernel(upsample_nearest_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM(stream), x, n_img, H, W, C,
+                2 * H, 2 * W, reinterpret_cast<op16*>(out_bf16));
   EMOTE_CHECK_LAUNCH("emote_upsample2x");
+  return 0;
+}
+
+extern "C" int emote_upsample_nearest(const float* x, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t Ho,
+                                      int32_t Wo, void* out_bf16, void* stream) {
+  if (!x || !out_bf16 || n_img <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0 || C <= 0 || C % 8 != 0)
+    return set_error("emote_upsample_nearest: bad arguments (C must be a multiple of 8)");
+  const long long total = (long long)n_img * Ho * Wo * (C / 8);
+  launch_kernel(upsample_nearest_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM(stream), x, n_img, H, W, C, Ho, Wo,
+                reinterpret_cast<op16*>(out_bf16));
+  EMOTE_CHECK_LAUNCH("emote_upsample_nearest");
   return 0;
 }
 

@@ -211,6 +211,15 @@ def upsample2x(x: torch.Tensor, n_img: int, H: int, W: int, Cc: int) -> torch.Te
     return out
 
 
+def upsample_nearest(x: torch.Tensor, n_img: int, H: int, W: int, Cc: int, Ho: int, Wo: int) -> torch.Tensor:
+    """nearest-neighbour resize of tokens-major fp32 [n_img, H, W, C] to Ho x Wo -> op16 conv operand"""
+    _req(x, F32, "upsample_nearest.x")
+    out = torch.empty((n_img * Ho * Wo, Cc), dtype=OP16, device=x.device)
+    check(_lib.load().emote_upsample_nearest(x.data_ptr(), n_img, H, W, Cc, Ho, Wo, out.data_ptr(), _stream()),
+          "emote_upsample_nearest")
+    return out
+
+
 def latent_im2col(lat: torch.Tensor, pre_scale: float = 1.0, pw_weight=None, pw_bias=None) -> torch.Tensor:
     """lat [B, Cl, F, H, W] fp32 (standard NCFHW contiguous) -> bf16 [B*F*H*W, 64]."""
     _req(lat, F32, "latent_im2col.lat")

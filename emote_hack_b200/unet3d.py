@@ -170,12 +170,20 @@ class Upsample3D(nn.Module):
 
     def forward(self, hidden_states, output_size=None):
         assert hidden_states.shape[1] == self.channels
-        if output_size is not None:
-            raise NotImplementedError("Upsample3D: forced output_size is not supported (inputs must be multiples of 8)")
         tok, (b, c, f, h, w) = _tokens(hidden_states)
-        up = ops.upsample2x(tok, b * f, h, w, c)
-        out = self.conv.forward_tokens(up, b * f, 2 * h, 2 * w, stats_rows=ops.stats_rows_for(4 * h * w, 4 * f * h * w))
-        return _untokens(out, b, self.out_channels, f, 2 * h, 2 * w)
+        if output_size is None:
+            ho, wo = 2 * h, 2 * w
+            up = ops.upsample2x(tok, b * f, h, w, c)
+        else:   # forced size (resnet.py:75-76): [f, ho, wo] like F.interpolate(size=...) on the 5-D tensor, or (ho, wo)
+            size = tuple(int(s) for s in output_size)
+            if len(size) == 3:
+                if size[0] != f:
+                    raise NotImplementedError("Upsample3D: output_size must keep the number of frames")
+                size = size[1:]
+            ho, wo = size
+            up = ops.upsample_nearest(tok, b * f, h, w, c, ho, wo)
+        out = self.conv.forward_tokens(up, b * f, ho, wo, stats_rows=ops.stats_rows_for(ho * wo, f * ho * wo))
+        return _untokens(out, b, self.out_channels, f, ho, wo)
 
 
 class Downsample3D(nn.Module):
@@ -1029,13 +1037,19 @@ class UNet3DConditionModel(nn.Module):
         self.config = AttrDict({k: v for k, v in locals().items() if k not in ("self", "__class__")})
         self.sample_size = sample_size
         self.in_channels = in_channels
-        if class_embed_type is not None or num_class_embeds is not None:
-            raise NotImplementedError("UNet3DConditionModel: class embeddings are a cold path (not implemented)")
         time_embed_dim = block_out_channels[0] * 4
         self.conv_in = InflatedConv3d(in_channels, block_out_channels[0], kernel_size=3, padding=(1, 1))
         self.time_proj = Timesteps(block_out_channels[0], flip_sin_to_cos, freq_shift)
         self.time_embedding = TimestepEmbedding(block_out_channels[0], time_embed_dim)
-        self.class_embedding = None
+        # class embedding (unet_controlnet.py:121-128)
+        if class_embed_type is None and num_class_embeds is not None:
+            self.class_embedding = nn.Embedding(num_class_embeds, time_embed_dim)
+        elif class_embed_type == "timestep":
+            self.class_embedding = TimestepEmbedding(block_out_channels[0], time_embed_dim)
+        elif class_embed_type == "identity":
+            self.class_embedding = nn.Identity(time_embed_dim, time_embed_dim)
+        else:
+            self.class_embedding = None
         n = len(down_block_types)
         if isinstance(only_cross_attention, bool):
             only_cross_attention = [only_cross_attention] * n
@@ -1121,8 +1135,8 @@ class UNet3DConditionModel(nn.Module):
             raise EmoteKernelError("emote_hack_b200 modules run on CUDA only (no CPU fallback)")
         if attention_mask is not None:
             raise NotImplementedError("attention_mask is not supported by the CUDA path")
-        if any(s % (2 ** self.num_upsamplers) != 0 for s in sample.shape[-2:]):
-            raise NotImplementedError("sample height/width must be multiples of 2**num_upsamplers")
+        # the up blocks are told the size to produce when the latent is not a multiple of 2**num_upsamplers (:355-364)
+        forward_upsample_size = any(s % (2 ** self.num_upsamplers) != 0 for s in sample.shape[-2:])
         in_dtype = sample.dtype
         sample = sample.float()
         if self.config.center_input_sample:
@@ -1133,6 +1147,18 @@ class UNet3DConditionModel(nn.Module):
             timesteps = torch.tensor([timesteps], dtype=torch.float32, device=sample.device)
         timesteps = timesteps.reshape(-1).to(device=sample.device, dtype=torch.float32).expand(sample.shape[0]).contiguous()
         emb = self.time_embedding(self.time_proj(timesteps))
+        if self.class_embedding is not None:                     # unet_controlnet.py:400-408
+            if class_labels is None:
+                raise ValueError("class_labels should be provided when num_class_embeds > 0")
+            if self.config.class_embed_type == "timestep":
+                cl = class_labels.reshape(-1).to(device=sample.device, dtype=torch.float32).expand(sample.shape[0]).contiguous()
+                class_emb = self.class_embedding(self.time_proj(cl))
+            elif isinstance(self.class_embedding, nn.Embedding):   # a table row per sample: parameter indexing, no arithmetic
+                class_emb = self.class_embedding.weight.detach()[class_labels.reshape(-1).long()].float()
+                class_emb = class_emb.expand(sample.shape[0], -1).contiguous()
+            else:
+                class_emb = class_labels.to(device=sample.device, dtype=torch.float32).expand(sample.shape[0], -1).contiguous()
+            emb = ops.add_f32(emb.contiguous(), class_emb)
         emb._emote_silu_bf16 = ops.silu_bf16(emb)  # shared by the 22 resnets' time_emb_proj
 
         sample = self.conv_in(sample.contiguous())
@@ -1146,11 +1172,14 @@ class UNet3DConditionModel(nn.Module):
         sample = self.mid_block(sample, emb, encoder_hidden_states=encoder_hidden_states)
         if is_controlnet:
             sample = self._add_residual(sample, mid_block_additional_residual)
-        for blk in self.up_blocks:
+        for i, blk in enumerate(self.up_blocks):
             k = len(blk.resnets)
             res, down_res = down_res[-k:], down_res[:-k]
+            upsample_size = None
+            if forward_upsample_size and i != len(self.up_blocks) - 1:
+                upsample_size = down_res[-1].shape[2:]           # [f, h, w] of the skip the next block starts from (:458-460)
             sample = blk(hidden_states=sample, temb=emb, res_hidden_states_tuple=res,
-                         encoder_hidden_states=encoder_hidden_states)
+                         encoder_hidden_states=encoder_hidden_states, upsample_size=upsample_size)
         tok, (b, c, f, h, w) = _tokens(sample)
         g = self.conv_norm_out
         a, _ = ops.group_norm([tok], g.num_groups, f * h * w, b, g.weight, g.bias, g.eps, True)

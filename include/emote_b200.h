@@ -179,6 +179,10 @@ int emote_im2col3x3_bf16(const void* x, int32_t n_img, int32_t H, int32_t W, int
                          void* out_bf16, void* stream);
 /* nearest-neighbour x2 upsample in H and W (Upsample3D, resnet.py:74), fp32 -> bf16 conv operand */
 int emote_upsample2x(const float* x, int32_t n_img, int32_t H, int32_t W, int32_t C, void* out_bf16, void* stream);
+/* nearest-neighbour resize to a forced Ho x Wo (F.interpolate(size=output_size), resnet.py:76: the `upsample_size` the UNet
+ * forwards when the latent size is not a multiple of 2**num_upsamplers, unet_controlnet.py:355-364,453-460) */
+int emote_upsample_nearest(const float* x, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t Ho, int32_t Wo,
+                           void* out_bf16, void* stream);
 /* out_bf16[row, c_offset + c] = bf16(x[row, c]) (pitch C_total) */
 int emote_cast_bf16(const float* x, int64_t rows, int32_t C_src, int32_t c_offset, int32_t C_total, void* out_bf16,
                     void* stream);

@@ -57,6 +57,33 @@ def make_ddim_golden():
     torch.save(out, GOLD / "ddim_reference_steps.pt")
 
 
+def make_cold_branch_golden():
+    """Cold branches of UNet3DConditionModel.forward recorded from the reference: a latent size that is not a multiple of
+    2**num_upsamplers (forced `upsample_size`, unet_controlnet.py:355-364,458-460) and the three class-embedding types
+    (:121-128, 400-408)."""
+    U = ref_shim.load_reference_unet_class()
+    out = {}
+    with torch.no_grad():
+        for tag, extra in (("odd_size", {}), ("class_table", {"num_class_embeds": 4}),
+                           ("class_timestep", {"class_embed_type": "timestep"}), ("class_identity", {"class_embed_type": "identity"})):
+            m = U(**dict(TINY_CFG, **extra)).eval()
+            shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+            out[f"{tag}_keys"] = shapes
+            m.load_state_dict(seeded_unet_state_dict(shapes, seed=4), strict=True)
+            hw = 10 if tag == "odd_size" else 8
+            x, ctx = make_inputs(2, 2, hw, seed=77)
+            kw = {}
+            if tag == "class_table":
+                kw["class_labels"] = torch.tensor([1, 3])
+            elif tag == "class_timestep":
+                kw["class_labels"] = torch.tensor([7.0, 250.0])
+            elif tag == "class_identity":
+                kw["class_labels"] = torch.randn(2, 256, generator=torch.Generator().manual_seed(78))
+            out[tag] = m(x, torch.tensor(301), ctx, **kw).sample.contiguous()
+            out[f"{tag}_labels"] = kw.get("class_labels")
+    torch.save(out, GOLD / "unet3d_tiny_cold_branches.pt")
+
+
 def make_speed_encoder_golden():
     """SpeedEncoder (Net.py:198-258) executed from the reference source: inputs, its own randomly initialised MLP weights
     and outputs."""
@@ -75,6 +102,7 @@ def main():
     GOLD.mkdir(parents=True, exist_ok=True)
     make_ddim_golden()
     make_speed_encoder_golden()
+    make_cold_branch_golden()
     U = ref_shim.load_reference_unet_class()
     RC = ref_shim.load_reference_control_class()
     uniform = ref_shim.load_reference_context_uniform()
@@ -175,5 +203,7 @@ if __name__ == "__main__":
         make_ddim_golden()
     elif sys.argv[1:] == ["speed"]:
         make_speed_encoder_golden()
+    elif sys.argv[1:] == ["cold"]:
+        make_cold_branch_golden()
     else:
         main()

@@ -58,6 +58,7 @@ class UNet3DOracle:
         self.mm_heads = (c.get("motion_module_kwargs") or {}).get("num_attention_heads", 8)
         self.mid_scale = c.get("mid_block_scale_factor", 1)
         self.center = c.get("center_input_sample", False)
+        self.class_embed_type = c.get("class_embed_type")
         self.n_down = n_blocks
         self._collect = None
         # like unet.set_attention_slice (unet_controlnet.py:259-322 -> orig_attention.py:686-727): the score matrix is
@@ -203,18 +204,19 @@ class UNet3DOracle:
     @torch.no_grad()
     def forward(self, sample: Tensor, timestep, encoder_hidden_states: Tensor, banks: Optional[Dict[str, List[Tensor]]] = None,
                 do_classifier_free_guidance: bool = True, down_block_additional_residuals=None,
-                mid_block_additional_residual=None, collect_banks: Optional[Dict[str, List[Tensor]]] = None) -> Tensor:
+                mid_block_additional_residual=None, collect_banks: Optional[Dict[str, List[Tensor]]] = None,
+                class_labels: Optional[Tensor] = None) -> Tensor:
         """`collect_banks` (a dict, filled in place): run as a ReferenceNet WRITER — every BasicTransformerBlock appends
         its LayerNorm1 output under its module name (the caller keeps the mid / up entries, fusion_blocks='midup')."""
         self._collect = collect_banks
         try:
             return self._forward(sample, timestep, encoder_hidden_states, banks, do_classifier_free_guidance,
-                                 down_block_additional_residuals, mid_block_additional_residual)
+                                 down_block_additional_residuals, mid_block_additional_residual, class_labels)
         finally:
             self._collect = None
 
     def _forward(self, sample, timestep, encoder_hidden_states, banks, do_classifier_free_guidance,
-                 down_block_additional_residuals, mid_block_additional_residual) -> Tensor:
+                 down_block_additional_residuals, mid_block_additional_residual, class_labels=None) -> Tensor:
         x = sample.to(self.dtype)
         ctx = encoder_hidden_states.to(self.dtype)
         if self.center:
@@ -223,6 +225,18 @@ class UNet3DOracle:
         t = t.reshape(-1).to(x.device).expand(x.shape[0])
         emb = timestep_embedding(t, self.time_dim, self.flip, self.shift).to(self.dtype)
         emb = self._lin("time_embedding.linear_2", F.silu(self._lin("time_embedding.linear_1", emb)))
+        # class embedding (unet_controlnet.py:400-408): Embedding table / TimestepEmbedding of the projected labels / identity
+        if self._has("class_embedding.weight"):
+            emb = emb + self.sd["class_embedding.weight"][class_labels.reshape(-1).long()]
+        elif self._has("class_embedding.linear_1.weight"):
+            ce = timestep_embedding(class_labels.reshape(-1).to(x.device).expand(x.shape[0]), self.time_dim, self.flip,
+                                    self.shift).to(self.dtype)
+            emb = emb + self._lin("class_embedding.linear_2", F.silu(self._lin("class_embedding.linear_1", ce)))
+        elif self.class_embed_type == "identity":
+            emb = emb + class_labels.to(self.dtype)
+        # the interpolation output size is forced when the latent is not a multiple of 2**num_upsamplers (:355-364, 458-460)
+        n_up = sum(1 for bi in range(self.n_down) if self._has(f"up_blocks.{bi}.upsamplers.0.conv.weight"))
+        force_size = any(s % (2 ** n_up) != 0 for s in x.shape[-2:])
 
         x = self._conv5("conv_in", x)
         skips = [x]
@@ -263,7 +277,10 @@ class UNet3DOracle:
                 if self._has(f"{p}.motion_modules.{li}.temporal_transformer.norm.weight"):
                     x = self._motion(f"{p}.motion_modules.{li}", x)
             if self._has(f"{p}.upsamplers.0.conv.weight"):
-                x = F.interpolate(x, scale_factor=(1.0, 2.0, 2.0), mode="nearest")  # resnet.py:74
+                if force_size and bi != self.n_down - 1:
+                    x = F.interpolate(x, size=skips[-1].shape[2:], mode="nearest")  # resnet.py:76
+                else:
+                    x = F.interpolate(x, scale_factor=(1.0, 2.0, 2.0), mode="nearest")  # resnet.py:74
                 x = self._conv5(f"{p}.upsamplers.0.conv", x)
 
         if not self._has("conv_out.weight"):

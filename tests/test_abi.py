@@ -96,7 +96,7 @@ def test_entry_points_reject_bad_arguments_without_touching_the_gpu():
     assert b"GEGLU" in lib.emote_last_error()
     attn = _lib.EmoteAttnArgs()
     assert lib.emote_attention_tc_bf16(C.byref(attn), None) != 0
-    assert lib.emote_attention_tc_supported(40) == 1 and lib.emote_attention_tc_supported(64) == 0
+    assert lib.emote_attention_tc_supported(40) == 1 and lib.emote_attention_tc_supported(64) == 1 and lib.emote_attention_tc_supported(48) == 0
     assert lib.emote_im2col3x3_s2_pad01(p, 1, 7, 8, 8, p, None) != 0      # odd height
     assert b"even H" in lib.emote_last_error()
     assert lib.emote_upsample2x(p, 1, 4, 4, 12, p, None) != 0             # C % 8 != 0

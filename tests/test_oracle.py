@@ -171,6 +171,19 @@ def test_ddim_oracle_against_live_reference_code():
             assert rel_l2(o.step(eps, t, x), method(types.SimpleNamespace(scheduler=fwd), eps, t, x)[0]) < 1e-6
 
 
+def test_port_cold_branches_match_reference_golden():
+    """forced upsample size (latent not a multiple of 8) and the three class-embedding types, against outputs recorded
+    from the reference UNet3DConditionModel (oracle/make_golden.py cold)"""
+    from oracle.unet3d_port import UNet3DOracle
+    gold = torch.load(GOLD / "unet3d_tiny_cold_branches.pt")
+    for tag, extra in (("odd_size", {}), ("class_table", {"num_class_embeds": 4}),
+                       ("class_timestep", {"class_embed_type": "timestep"}), ("class_identity", {"class_embed_type": "identity"})):
+        o = UNet3DOracle(seeded_unet_state_dict(gold[f"{tag}_keys"], 4), dict(TINY_CFG, **extra))
+        x, ctx = make_inputs(2, 2, 10 if tag == "odd_size" else 8, seed=77)
+        got = o(x, 301, ctx, class_labels=gold[f"{tag}_labels"])
+        assert got.shape == gold[tag].shape and rel_l2(got, gold[tag]) < 1e-5, tag
+
+
 def test_speed_encoder_restatement_pinned_on_reference_class():
     """oracle/ref_audio.speed_encoder_restated against vectors recorded by executing the reference's SpeedEncoder
     (Net.py:198-258, cut out with ast) — and against the live class when /root/reference is present"""

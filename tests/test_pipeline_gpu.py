@@ -42,6 +42,25 @@ def test_cuda_unet_against_reference_golden_vectors():
                  rel_l2(mods["down_blocks.0.attentions.0"](h, encoder_hidden_states=c7).sample, gold["blk_transformer"]), 5e-3)
 
 
+def test_cuda_unet_cold_branches_against_reference_golden_vectors():
+    """forced `upsample_size` (10x10 latent: 10 -> 5 -> 3 -> 2 and back) and the class-embedding variants of
+    UNet3DConditionModel.forward (unet_controlnet.py:121-128, 355-364, 400-408, 458-460) vs the reference's outputs"""
+    from emote_hack_b200.unet3d import UNet3DConditionModel
+    gold = torch.load(GOLD / "unet3d_tiny_cold_branches.pt")
+    for tag, extra in (("odd_size", {}), ("class_table", {"num_class_embeds": 4}),
+                       ("class_timestep", {"class_embed_type": "timestep"}), ("class_identity", {"class_embed_type": "identity"})):
+        m = UNet3DConditionModel(**dict(TINY_CFG, **extra)).eval()
+        m.load_state_dict(seeded_unet_state_dict(gold[f"{tag}_keys"], 4), strict=True)
+        m = m.cuda()
+        x, ctx = make_inputs(2, 2, 10 if tag == "odd_size" else 8, seed=77)
+        labels = gold[f"{tag}_labels"]
+        out = m(x.cuda(), 301, ctx.cuda(), class_labels=None if labels is None else labels.cuda()).sample
+        assert out.shape == gold[tag].shape
+        check_parity(f"golden.cold.{tag}", rel_l2(out, gold[tag]), 2e-2)
+    with pytest.raises(ValueError):
+        m(x.cuda(), 301, ctx.cuda())                       # class embedding configured, no labels
+
+
 @pytest.fixture(scope="module")
 def tiny_vae():
     from emote_hack_b200.vae import AutoencoderKL

@@ -450,7 +450,7 @@ struct Tc2Cfg {
   static constexpr int KSTEPS = (D + 15) / 16;
   static constexpr int NPV = KSTEPS * 16;
   static constexpr int CH = D / 8;
-  static constexpr int STAGES = (D <= 64) ? 3 : 2;       // K/V ring
+  static constexpr int STAGES = (D <= 96) ? 3 : 2;       // K/V ring (head_dim 160: 2 stages of 48 KB fit next to Q and P)
   static constexpr int Q_BYTES = ATOMS * TC_BQ * 128;
   static constexpr int KV_TILE = ATOMS * TC_BKV * 128;
   static constexpr int STAGE = 2 * KV_TILE;
@@ -844,11 +844,13 @@ extern "C" int emote_attention_tc_bf16(const EmoteAttnArgs* a, void* stream_) {
   p.kv1_div = a->kv1_batch_div > 0 ? a->kv1_batch_div : 1;
   p.kv1_first = a->kv1_first_batch;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  // share of the exponentials moved from MUFU.EX2 to the FMA pipe: 0, 1/4 or 1/2 (EMOTE_ATTN_EMU = 0 / 1 / 2, dev knob)
-  static const int emu = [] {
+  // share of the exponentials moved from MUFU.EX2 to the FMA pipe: 0, 1/4 or 1/2 (EMOTE_ATTN_EMU = 0 / 1 / 2, dev knob).
+  // Measured on B200 (v2 kernel, 32 x 8 heads): head_dim 40, N = 4096: 1.64 / 1.55 / 1.50 ms; head_dim 80: 1/4 is best.
+  static const int emu_env = [] {
     const char* e = std::getenv("EMOTE_ATTN_EMU");
-    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : -1;
   }();
+  const int emu = emu_env >= 0 ? emu_env : ((attn_tc_version() == 2 && a->head_dim == 40) ? 2 : 1);
   if (attn_tc_version() == 1) {
     if (a->head_dim == 40) {
       if (emu == 0) return launch_tc<40, 0>(p, a->batch, stream);

@@ -84,6 +84,7 @@ SIGNATURES = {
     "emote_attention_bf16": [C.POINTER(EmoteAttnArgs), _vp],
     "emote_attention_tc_bf16": [C.POINTER(EmoteAttnArgs), _vp],
     "emote_attention_tc_supported": [_i32],
+    "emote_attention_wide_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
     "emote_temporal_attention_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
     "emote_softmax_rows_bf16": [_vp, _i64, _i32, _f32, _vp, _vp],
     "emote_latent_im2col": [_vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp],

@@ -1,451 +1,37 @@
-// tcgen05 flash attention for the spatial self-attention / reference-attention layers (head_dim 40 and 80), where
-// >80% of the attention time of a UNet call is spent (N = 4096 / 1024 keys per image).
+// tcgen05 flash attention for the spatial self-attention / reference-attention layers (head_dim 40 / 80 / 160) and the
+// wav2vec2 encoder (head_dim 64): >80% of the attention time of a UNet call is spent here (N = 4096 / 1024 keys per image).
 //
 //   per CTA: 128 query rows of one (image, head).  Per 64-key tile:
 //     S  = Q K^T          tcgen05.mma 128 x 64 x 16 (x KSTEPS), Q/K K-major 128B-swizzled smem, S in TMEM (fp32)
-//     P  = exp2(S*c - m)  4 softmax warps, one thread per query row (TMEM lane == row: no shuffles), P -> smem (bf16)
-//     PV = P V            tcgen05.mma 128 x NPV x 16 (x4), A = P (K-major), B = V consumed MN-major straight from
-//                         its natural [key][d] layout (no transpose), result in TMEM
-//     O  = O*corr + PV    accumulated in registers by the row's thread (no TMEM read-modify-write of O)
-//   one thread of warp 0 streams K/V tiles with TMA into a 3-stage ring (128B swizzle; zero-fills the tail), warp 1
-//   issues the MMAs, warps 2-5 do the softmax.  S and PV are double buffered in TMEM so the softmax of tile j+1
-//   overlaps P V of tile j.  Two CTAs fit per SM (96 KB smem, 256 TMEM columns each) for latency hiding.
+//     P  = exp2(S*c - m)  4 softmax warps, one thread per query row (TMEM lane == row: no shuffles), P -> smem (16-bit)
+//     O += P V            tcgen05.mma 128 x NPV x 16 (x4) ACCUMULATING in TMEM, A = P (K-major), B = V consumed MN-major
+//                         straight from its natural [key][d] layout (no transpose); row sums from a P x ones MMA
+//   one thread of warp 0 streams K/V tiles with TMA into a ring (128B swizzle; zero-fills the tail), warp 1 issues the
+//   MMAs, warps 2-5 do the softmax.  S and P are double buffered so the softmax of tile j overlaps S(j+1) and P V(j-1).
 //
 // Same semantics as flash_attn_kernel in attention.cu (two key/value segments, per-batch visibility of segment 1,
 // ragged tails); reference arithmetic: orig_attention.py:655-684, mutual_self_attention.py:239-255.
-#include "common.cuh"
-#include "emote_b200.h"
-#include "host_utils.h"
+#include "attention_tc.cuh"
 
 #include <cstdlib>
 
 namespace emote {
 
-struct AttnTcDev {
-  const op16 *q, *k0, *v0, *k1, *v1;
-  op16* out;
-  int heads, d;
-  int nq, n0, n1;
-  long long q_bs, q_rs, kv0_bs, kv0_rs, kv1_bs, kv1_rs, o_bs, o_rs;
-  int kv0_div, kv1_div, kv1_first;
-  float scale_log2;
-};
-
-constexpr int TC_BQ = 128;
-constexpr int TC_BKV = 64;
-constexpr int TC_STAGES = 3;   // K/V ring
-
-constexpr int TC_THREADS = 192;  // warp0 loader, warp1 MMA, warps 2-5 softmax
-
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ float ex2f(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// packed fp32x2 FMA (FFMA2): {d.x, d.y} = {a.x, a.y} * {b, b} + {c, c}
-__device__ __forceinline__ void ffma2_bcast(float& d0, float& d1, float a0, float a1, float b, float c) {
-  unsigned long long aa, bb, cc, dd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dd) : "l"(aa), "l"(bb), "l"(cc));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dd));
-}
-// {d.x, d.y} = {a.x, a.y} * {b, b} + {c.x, c.y}
-__device__ __forceinline__ void ffma2_acc(float& d0, float& d1, float a0, float a1, float b, float c0, float c1) {
-  unsigned long long aa, bb, cc, dd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(c0), "f"(c1));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dd) : "l"(aa), "l"(bb), "l"(cc));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dd));
-}
-// {d.x, d.y} = {a.x, a.y} * {b.x, b.y} + {c, c}
-__device__ __forceinline__ void ffma2_vvb(float& d0, float& d1, float a0, float a1, float b0, float b1, float c) {
-  unsigned long long aa, bb, cc, dd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b0), "f"(b1));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dd) : "l"(aa), "l"(bb), "l"(cc));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dd));
-}
-// 2^x for a pair on the FMA / ALU pipes instead of MUFU.EX2 (the softmax loop is MUFU-bound at head_dim 40: 160 FLOP
-// per exponential).  Cody-Waite: n = round(x) through the 1.5 * 2^23 magic add, f = x - n in [-0.5, 0.5], 2^f by a
-// degree-3 minimax polynomial (max rel. error 7.5e-5, 26x below the bf16 rounding of P), exponent spliced in with one
-// shift-add.  x is clamped at -126 (masked keys arrive as -inf and leave as 2^-126 ~ 0).
-__device__ __forceinline__ void exp2_poly2(float& r0, float& r1, float x0, float x1) {
-  constexpr float MAGIC = 12582912.f;  // 1.5 * 2^23: low mantissa bits of (x + MAGIC) hold round(x)
-  x0 = fmaxf(x0, -126.f);
-  x1 = fmaxf(x1, -126.f);
-  float xf0, xf1, n0, n1, f0, f1, p0, p1;
-  ffma2_bcast(xf0, xf1, x0, x1, 1.0f, MAGIC);
-  ffma2_bcast(n0, n1, xf0, xf1, 1.0f, -MAGIC);
-  ffma2_acc(f0, f1, n0, n1, -1.0f, x0, x1);
-  ffma2_bcast(p0, p1, f0, f1, 0.055171505f, 0.24261077f);
-  ffma2_vvb(p0, p1, p0, p1, f0, f1, 0.69326097f);
-  ffma2_vvb(p0, p1, p0, p1, f0, f1, 0.99992812f);
-  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(xf0) << 23));
-  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(xf1) << 23));
-}
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
-  uint32_t r;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-  return r;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-
-// UMMA smem descriptor, MN-major operand, 128B swizzle: rows = K index (128 B = 64 MN elements each), 8-row groups
-// 1024 B apart (SBO), 64-element MN atoms `lbo_bytes` apart (LBO).
-__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-__host__ __device__ constexpr uint32_t umma_idesc_op16_bmn(int M, int N) {  // A K-major, B MN-major
-  return umma_idesc_op16(M, N) | (1u << 16);
-}
-
-// D = head dim (40 or 80).  ATOMS = 64-element swizzle atoms covering D, KSTEPS = 16-wide MMA k-steps over D,
-// NPV = PV accumulator columns (D rounded up to 16).
-template <int D>
-struct TcCfg {
-  static constexpr int ATOMS = (D + 63) / 64;
-  static constexpr int KSTEPS = (D + 15) / 16;
-  static constexpr int NPV = KSTEPS * 16;
-  static constexpr int CH = D / 8;                       // 16-byte chunks per row that carry data
-  static constexpr int Q_BYTES = ATOMS * TC_BQ * 128;
-  static constexpr int KV_TILE = ATOMS * TC_BKV * 128;   // one K or V tile
-  static constexpr int STAGE = 2 * KV_TILE;
-  static constexpr int P_BYTES = TC_BQ * 128;            // 128 rows x 64 keys bf16
-  static constexpr int ONES_BYTES = 16 * 128;            // 16 x 64 bf16 ones: B operand of the row-sum MMA
-  static constexpr int SMEM = Q_BYTES + TC_STAGES * STAGE + 2 * P_BYTES + ONES_BYTES + 256 + 1024;
-  static constexpr int TMEM_COLS = (2 * TC_BKV + 2 * NPV + 32 <= 256) ? 256 : 512;
-  static constexpr int PV_COL0 = 2 * TC_BKV;
-  static constexpr int SUM_COL0 = PV_COL0 + 2 * NPV;     // 2 x 16 columns: l = P x ones (every column holds the row sum)
-};
-
-// EMU = pairs (of the 4 in every 8-key chunk) whose exponentials run on the FMA pipe (exp2_poly2) instead of MUFU.EX2
-template <int D, int EMU>
-__global__ void __launch_bounds__(TC_THREADS, (D <= 64) ? 2 : 1)
-flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
-                     const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
-                     const AttnTcDev p) {
-  using C = TcCfg<D>;
-  pdl_launch_dependents();
-  extern __shared__ uint8_t tc_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + C::Q_BYTES;
-  uint8_t* sP = sKV + TC_STAGES * C::STAGE;
-  uint8_t* sOnes = sP + 2 * C::P_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + C::ONES_BYTES);
-  uint64_t* kv_full = bars;                  // [STAGES] TMA (expect_tx) -> MMA
-  uint64_t* kv_empty = kv_full + TC_STAGES;  // [STAGES] MMA commit -> loader
-  uint64_t* s_full = kv_empty + TC_STAGES;   // [2] MMA commit -> softmax
-  uint64_t* p_full = s_full + 2;             // [2] softmax (4 warp arrivals) -> MMA
-  uint64_t* o_full = p_full + 2;             // [2] MMA commit -> softmax
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y;
-  const int q0 = blockIdx.x * TC_BQ;
-
-  const int n1 = (p.n1 > 0 && b >= p.kv1_first) ? p.n1 : 0;
-  const int tiles0 = (p.n0 + TC_BKV - 1) / TC_BKV;
-  const int tiles1 = (n1 + TC_BKV - 1) / TC_BKV;
-  const int ntiles = tiles0 + tiles1;
-
-  // ---- one-time setup: zero the operand ring (pad chunks stay zero forever), barriers, TMEM, Q tile
-  {
-    uint4* z = reinterpret_cast<uint4*>(smem);
-    const int n16 = (C::Q_BYTES + TC_STAGES * C::STAGE + 2 * C::P_BYTES) / 16;
-    for (int i = threadIdx.x; i < n16; i += TC_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    uint4* o = reinterpret_cast<uint4*>(sOnes);
-    for (int i = threadIdx.x; i < C::ONES_BYTES / 16; i += TC_THREADS)
-      o[i] = make_uint4(OP16_ONE_PAIR, OP16_ONE_PAIR, OP16_ONE_PAIR, OP16_ONE_PAIR);  // 1.0 pairs
-  }
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 4);   // one arrival per softmax warp
-      mbar_init(&o_full[s], 1);
-    }
-    mbar_fence_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
-  }
-  __syncthreads();
-  pdl_wait();  // smem / barriers / TMEM are ready; q, k, v of earlier kernels may be read from here on
-  {
-    // Q tile: rows q0..q0+127, chunks < D/8; atom = chunk/8; physical 16B slot = (chunk%8) ^ (row%8)
-    const op16* qg = p.q + (long long)b * p.q_bs + (long long)q0 * p.q_rs + h * p.d;
-    const int nvq = p.nq - q0;
-    for (int i = threadIdx.x; i < TC_BQ * C::CH; i += TC_THREADS) {
-      const int r = i / C::CH, c = i - r * C::CH;
-      const uint32_t dst = smem_u32(sQ) + (c >> 3) * (TC_BQ * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4);
-      cp_async16_zfill(dst, qg + (long long)r * p.q_rs + c * 8, r < nvq);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-  }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ K/V loader: one thread, TMA
-    // Each K / V tile is 64 keys x (ATOMS x 64) columns starting at column h*D of the [batch][key][heads*D] view: the
-    // box over-reads up to 64-D%64 columns of the NEXT head (or zero-fill past the row end).  Harmless: the matching Q
-    // columns are zero (QK^T) and the extra P*V columns are never stored.  Rows past the segment end are zero-filled.
-    for (int j = 0; j < ntiles; ++j) {  // warp-uniform loop, one elected lane issues
-      const int stage = j % TC_STAGES;
-      if (j >= TC_STAGES) mbar_wait(&kv_empty[stage], ((j / TC_STAGES) - 1) & 1);
-      if (elect_one()) {
-        uint8_t* kdst = sKV + stage * C::STAGE;
-        uint8_t* vdst = kdst + C::KV_TILE;
-        mbar_expect_tx(&kv_full[stage], C::STAGE);
-        const bool seg0 = j < tiles0;
-        const CUtensorMap* mk = seg0 ? &tmK0 : &tmK1;
-        const CUtensorMap* mv = seg0 ? &tmV0 : &tmV1;
-        const int row = (seg0 ? j : j - tiles0) * TC_BKV;
-        const int bidx = seg0 ? b / p.kv0_div : b / p.kv1_div;
-#pragma unroll
-        for (int a = 0; a < C::ATOMS; ++a) {
-          tma_load_3d(kdst + a * (TC_BKV * 128), mk, &kv_full[stage], h * D + a * 64, row, bidx);
-          tma_load_3d(vdst + a * (TC_BKV * 128), mv, &kv_full[stage], h * D + a * 64, row, bidx);
-        }
-      }
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane)
-    {
-      constexpr uint32_t idesc_s = umma_idesc_op16(TC_BQ, TC_BKV);
-      constexpr uint32_t idesc_pv = umma_idesc_op16_bmn(TC_BQ, C::NPV);
-      constexpr uint32_t idesc_sum = umma_idesc_op16(TC_BQ, 16);
-      auto issue_s = [&](int j) {
-        const int stage = j % TC_STAGES;
-        mbar_wait(&kv_full[stage], (j / TC_STAGES) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t ka = smem_u32(sKV + stage * C::STAGE);
-          const uint32_t qa = smem_u32(sQ);
-          const uint32_t d_tmem = tmem_base + (j & 1) * TC_BKV;
-#pragma unroll
-          for (int ks = 0; ks < C::KSTEPS; ++ks) {
-            const uint64_t da = umma_desc_sw128(qa + (ks >> 2) * (TC_BQ * 128)) + static_cast<uint64_t>(2 * (ks & 3));
-            const uint64_t db = umma_desc_sw128(ka + (ks >> 2) * (TC_BKV * 128)) + static_cast<uint64_t>(2 * (ks & 3));
-            umma_f16(d_tmem, da, db, idesc_s, ks != 0 ? 1u : 0u);
-          }
-          umma_commit(&s_full[j & 1]);
-        }
-        __syncwarp();
-      };
-      issue_s(0);
-      for (int j = 0; j < ntiles; ++j) {
-        if (j + 1 < ntiles) issue_s(j + 1);  // S buffer (j+1)&1 was released by p_full(j-1), waited last iteration
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const int stage = j % TC_STAGES;
-          const uint32_t va = smem_u32(sKV + stage * C::STAGE) + C::KV_TILE;
-          const uint32_t pa = smem_u32(sP + (j & 1) * C::P_BYTES);
-          const uint32_t d_tmem = tmem_base + C::PV_COL0 + (j & 1) * C::NPV;
-#pragma unroll
-          for (int ks = 0; ks < TC_BKV / 16; ++ks) {
-            const uint64_t da = umma_desc_sw128(pa) + static_cast<uint64_t>(2 * ks);
-            // MN-major B: 16 keys = 16 rows of 128 B further down the tile
-            const uint64_t db = umma_desc_sw128_mn(va + ks * 16 * 128, TC_BKV * 128);
-            umma_f16(d_tmem, da, db, idesc_pv, ks != 0 ? 1u : 0u);
-          }
-          // row sums of the bf16 P actually multiplied into V: P x ones (K-major 16 x 64 tile of 1.0)
-          const uint32_t oa = smem_u32(sOnes);
-          const uint32_t s_tmem = tmem_base + C::SUM_COL0 + (j & 1) * 16;
-#pragma unroll
-          for (int ks = 0; ks < TC_BKV / 16; ++ks)
-            umma_f16(s_tmem, umma_desc_sw128(pa) + static_cast<uint64_t>(2 * ks),
-                     umma_desc_sw128(oa) + static_cast<uint64_t>(2 * ks), idesc_sum, ks != 0 ? 1u : 0u);
-          umma_commit(&o_full[j & 1]);
-          umma_commit(&kv_empty[stage]);
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax warps: thread == query row
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;          // row inside the CTA tile == TMEM lane
-    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    float o_acc[C::NPV];
-#pragma unroll
-    for (int i = 0; i < C::NPV; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
-    const float sc = p.scale_log2;
-
-    auto accumulate_pv = [&](int j, float corr) {
-      mbar_wait(&o_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t ta = tmem_base + lane_addr + C::PV_COL0 + (j & 1) * C::NPV;
-      uint32_t r[C::NPV / 16][16];
-#pragma unroll
-      for (int c = 0; c < C::NPV / 16; ++c) tmem_ld16(ta + c * 16, r[c]);
-      const uint32_t rsum = tmem_ld1(tmem_base + lane_addr + C::SUM_COL0 + (j & 1) * 16);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < C::NPV / 16; ++c)
-#pragma unroll
-        for (int k = 0; k < 16; k += 2)
-          ffma2_acc(o_acc[c * 16 + k], o_acc[c * 16 + k + 1], o_acc[c * 16 + k], o_acc[c * 16 + k + 1], corr,
-                    __uint_as_float(r[c][k]), __uint_as_float(r[c][k + 1]));
-      l_run = fmaf(l_run, corr, __uint_as_float(rsum));
-    };
-
-    for (int j = 0; j < ntiles; ++j) {
-      int nvalid = (j < tiles0) ? (p.n0 - j * TC_BKV) : (n1 - (j - tiles0) * TC_BKV);
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t ta = tmem_base + lane_addr + (j & 1) * TC_BKV;
-      uint32_t s0[32], s1[32];
-      tmem_ld32(ta, s0);
-      tmem_ld32(ta + 32, s1);
-      tmem_ld_wait();
-      if (nvalid < TC_BKV) {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          if (k >= nvalid) s0[k] = 0xff800000u;        // -inf
-          if (k + 32 >= nvalid) s1[k] = 0xff800000u;
-        }
-      }
-      // row max: 8 independent chains of 3-input max, then a tree
-      float mxa[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) mxa[k] = fmaxf(__uint_as_float(s0[k]), __uint_as_float(s1[k]));
-#pragma unroll
-      for (int k = 8; k < 32; ++k) mxa[k & 7] = fmax3(mxa[k & 7], __uint_as_float(s0[k]), __uint_as_float(s1[k]));
-      const float mx = fmaxf(fmax3(mxa[0], mxa[1], mxa[2]), fmax3(fmax3(mxa[3], mxa[4], mxa[5]), mxa[6], mxa[7]));
-      const float m_new = fmaxf(m_run, mx);
-      const float corr = (m_run == -INFINITY) ? 0.f : ex2f((m_run - m_new) * sc);
-      const float nmsc = -(m_new * sc);
-      m_run = m_new;
-      uint8_t* prow = sP + (j & 1) * C::P_BYTES + row * 128;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys; the row sum comes back from the tensor core (P x ones)
-        float pv[8];
-#pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-          const int idx = c * 8 + k;
-          const float sa = __uint_as_float(idx < 32 ? s0[idx] : s1[idx - 32]);
-          const float sb = __uint_as_float(idx < 32 ? s0[idx + 1] : s1[idx - 31]);
-          float x0, x1;
-          ffma2_bcast(x0, x1, sa, sb, sc, nmsc);
-          if (k >= 8 - 2 * EMU) {   // compile-time after unrolling
-            exp2_poly2(pv[k], pv[k + 1], x0, x1);
-          } else {
-            pv[k] = ex2f(x0);
-            pv[k + 1] = ex2f(x1);
-          }
-        }
-        uint4 w;
-        w.x = pack_op16x2(pv[0], pv[1]); w.y = pack_op16x2(pv[2], pv[3]);
-        w.z = pack_op16x2(pv[4], pv[5]); w.w = pack_op16x2(pv[6], pv[7]);
-        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = w;
-      }
-      // publish P (generic-proxy smem writes -> async proxy) and release S[j&1]: one arrival per warp
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[j & 1]);
-      // fold in the previous tile's P V while the tensor core works on this one
-      if (j > 0) accumulate_pv(j - 1, corr_prev);
-      corr_prev = corr;
-    }
-    accumulate_pv(ntiles - 1, corr_prev);
-
-    const int qrow = q0 + row;
-    if (qrow < p.nq) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      op16* og = p.out + (long long)b * p.o_bs + (long long)qrow * p.o_rs + h * p.d;
-#pragma unroll
-      for (int c = 0; c < C::CH; ++c) {
-        uint4 w;
-        w.x = pack_op16x2(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
-        w.y = pack_op16x2(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
-        w.z = pack_op16x2(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
-        w.w = pack_op16x2(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
-        *reinterpret_cast<uint4*>(og + c * 8) = w;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// v2: O and the row sums accumulate in TMEM (PV / P x ones MMAs with the accumulate flag) and are rescaled LAZILY.
+// O and the row sums accumulate in TMEM (PV / P x ones MMAs with the accumulate flag) and are rescaled LAZILY.
 //
-// The v1 kernel above folds every tile's P V into per-thread registers (O = O*corr + PV: a TMEM read of the whole PV tile
-// plus D FMAs per row and tile, 48-80 live registers).  Timing shows one CTA needs ~1600 cycles per 64-key tile whatever
-// else runs on the SM: the softmax warp's dependent chain (S load -> max -> 64 exponentials -> P store -> P V fold) is
-// what bounds it, not MUFU (48 % busy) or the tensor pipe (27 %).  Here the softmax thread only produces P: it keeps the
+// The round-1 kernel folded every tile's P V into per-thread registers (O = O*corr + PV: a TMEM read of the whole PV tile
+// plus D FMAs per row and tile, 48-80 live registers, 153 registers per thread).  Timing showed one CTA needs ~1600 cycles
+// per 64-key tile whatever else runs on the SM: the softmax warp's dependent chain (S load -> max -> 64 exponentials ->
+// P store -> P V fold) bounds it, not MUFU (48 % busy) or the tensor pipe (27 %).  Here the softmax thread only produces
+// P (120 registers; head_dim 40, N = 4096, 32 x 8 heads: 1.62 -> 1.51 ms; ncu: issue slots 60 %, XU 34 %, tensor 29 %,
+// ~450 issued instructions per warp and tile — the kernel is issue-bound on the exponentials' scalar work).  It keeps the
 // exponent reference m_used of its row and moves it only when the running maximum has grown by more than 2^8 (log2 units);
 // then — rarely after the first tiles — the thread rescales its own O row and row sum in TMEM (tcgen05.ld -> multiply ->
 // tcgen05.st) before publishing P.  P is therefore bounded by 2^8 instead of 1 (fp32 accumulation; exact after the final
 // division by the equally scaled row sum).  S and P stay double-buffered so S(j+1) is computed while softmax(j) runs.
-constexpr float TC2_TAU = 8.0f;   // lazy-rescale threshold in log2 units: P <= 2^8
-
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      :
-      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 template <int D>
-struct Tc2Cfg {
+struct TcCfg {
   static constexpr int ATOMS = (D + 63) / 64;
   static constexpr int KSTEPS = (D + 15) / 16;
   static constexpr int NPV = KSTEPS * 16;
@@ -465,11 +51,11 @@ struct Tc2Cfg {
 };
 
 template <int D, int EMU>
-__global__ void __launch_bounds__(TC_THREADS, Tc2Cfg<D>::CTAS)
-flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
+__global__ void __launch_bounds__(TC_THREADS, TcCfg<D>::CTAS)
+flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
                       const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
                       const AttnTcDev p) {
-  using C = Tc2Cfg<D>;
+  using C = TcCfg<D>;
   pdl_launch_dependents();
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -538,7 +124,10 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ K/V loader (see v1 for the box geometry)
+    // ------------------------------------------------------------------ K/V loader: one thread, TMA
+    // Each K / V tile is 64 keys x (ATOMS x 64) columns starting at column h*D of the [batch][key][heads*D] view: the
+    // box over-reads up to 64-D%64 columns of the NEXT head (or zero-fill past the row end).  Harmless: the matching Q
+    // columns are zero (QK^T) and the extra P*V columns are never stored.  Rows past the segment end are zero-filled.
     for (int j = 0; j < ntiles; ++j) {
       const int stage = j % C::STAGES;
       if (j >= C::STAGES) mbar_wait(&kv_empty[stage], ((j / C::STAGES) - 1) & 1);
@@ -734,15 +323,6 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
   }
 }
 
-// [batch][key][cols] bf16 view starting at `base` (the k or v pointer, i.e. already offset to its first column)
-static int make_kv_map(CUtensorMap* m, const void* base, int cols, int nkeys, long long row_stride, long long batch_stride,
-                       int nbatch) {
-  uint64_t dims[3] = {(uint64_t)cols, (uint64_t)nkeys, (uint64_t)nbatch};
-  uint64_t strides[2] = {(uint64_t)row_stride * 2, (uint64_t)(nbatch > 1 ? batch_stride : row_stride * nkeys) * 2};
-  uint32_t box[3] = {64, (uint32_t)TC_BKV, 1};
-  return make_tensor_map(m, base, 3, dims, strides, box);
-}
-
 static int make_all_kv_maps(const AttnTcDev& p, int batch, CUtensorMap& mk0, CUtensorMap& mv0, CUtensorMap& mk1,
                             CUtensorMap& mv1) {
   const int cols = p.heads * p.d;
@@ -766,7 +346,7 @@ static int launch_tc(const AttnTcDev& p, int batch, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(flash_attn_tc_kernel<D, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-    if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(flash_attn_tc)", e);
+    if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(flash_attn_tc2)", e);
     configured = true;
   }
   CUtensorMap mk0, mv0, mk1, mv1;
@@ -777,45 +357,18 @@ static int launch_tc(const AttnTcDev& p, int batch, cudaStream_t stream) {
   return 0;
 }
 
-template <int D, int EMU>
-static int launch_tc2(const AttnTcDev& p, int batch, cudaStream_t stream) {
-  using C = Tc2Cfg<D>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(flash_attn_tc2_kernel<D, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-    if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(flash_attn_tc2)", e);
-    configured = true;
-  }
-  CUtensorMap mk0, mv0, mk1, mv1;
-  if (int rc = make_all_kv_maps(p, batch, mk0, mv0, mk1, mv1)) return rc;
-  dim3 grid((p.nq + TC_BQ - 1) / TC_BQ, p.heads, batch);
-  launch_kernel(flash_attn_tc2_kernel<D, EMU>, dim3(grid), dim3(TC_THREADS), C::SMEM, stream, mk0, mv0, mk1, mv1, p);
-  EMOTE_CHECK_LAUNCH("emote_attention_tc_bf16");
-  return 0;
-}
-
 template <int D>
-static int dispatch_tc2(int emu, const AttnTcDev& p, int batch, cudaStream_t stream) {
-  if (emu == 0) return launch_tc2<D, 0>(p, batch, stream);
-  if (emu == 2) return launch_tc2<D, 2>(p, batch, stream);
-  return launch_tc2<D, 1>(p, batch, stream);
+static int dispatch_tc(int emu, const AttnTcDev& p, int batch, cudaStream_t stream) {
+  if (emu == 0) return launch_tc<D, 0>(p, batch, stream);
+  if (emu == 2) return launch_tc<D, 2>(p, batch, stream);
+  return launch_tc<D, 1>(p, batch, stream);
 }
 
 }  // namespace emote
 
 using namespace emote;
 
-// v2 kernel (O in TMEM, lazy rescale): head_dim 40 / 64 / 80 / 160; EMOTE_ATTN_TC=1 selects the v1 kernel (40 / 80 only)
-static int attn_tc_version() {
-  static const int v = [] {
-    const char* e = std::getenv("EMOTE_ATTN_TC");
-    return (e && e[0] == '1') ? 1 : 2;
-  }();
-  return v;
-}
-
 extern "C" int emote_attention_tc_supported(int32_t head_dim) {
-  if (attn_tc_version() == 1) return (head_dim == 40 || head_dim == 80) ? 1 : 0;
   return (head_dim == 40 || head_dim == 64 || head_dim == 80 || head_dim == 160) ? 1 : 0;
 }
 
@@ -845,26 +398,16 @@ extern "C" int emote_attention_tc_bf16(const EmoteAttnArgs* a, void* stream_) {
   p.kv1_first = a->kv1_first_batch;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   // share of the exponentials moved from MUFU.EX2 to the FMA pipe: 0, 1/4 or 1/2 (EMOTE_ATTN_EMU = 0 / 1 / 2, dev knob).
-  // Measured on B200 (v2 kernel, 32 x 8 heads): head_dim 40, N = 4096: 1.64 / 1.55 / 1.50 ms; head_dim 80: 1/4 is best.
+  // Measured on B200 (32 images x 8 heads): head_dim 40, N = 4096: 1.64 / 1.55 / 1.50 ms; head_dim 80: 1/4 is best.
   static const int emu_env = [] {
     const char* e = std::getenv("EMOTE_ATTN_EMU");
     return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : -1;
   }();
-  const int emu = emu_env >= 0 ? emu_env : ((attn_tc_version() == 2 && a->head_dim == 40) ? 2 : 1);
-  if (attn_tc_version() == 1) {
-    if (a->head_dim == 40) {
-      if (emu == 0) return launch_tc<40, 0>(p, a->batch, stream);
-      if (emu == 2) return launch_tc<40, 2>(p, a->batch, stream);
-      return launch_tc<40, 1>(p, a->batch, stream);
-    }
-    if (emu == 0) return launch_tc<80, 0>(p, a->batch, stream);
-    if (emu == 2) return launch_tc<80, 2>(p, a->batch, stream);
-    return launch_tc<80, 1>(p, a->batch, stream);
-  }
+  const int emu = emu_env >= 0 ? emu_env : (a->head_dim == 40 ? 2 : 1);
   switch (a->head_dim) {
-    case 40: return dispatch_tc2<40>(emu, p, a->batch, stream);
-    case 64: return dispatch_tc2<64>(emu, p, a->batch, stream);
-    case 80: return dispatch_tc2<80>(emu, p, a->batch, stream);
-    default: return dispatch_tc2<160>(emu, p, a->batch, stream);
+    case 40: return dispatch_tc<40>(emu, p, a->batch, stream);
+    case 64: return dispatch_tc<64>(emu, p, a->batch, stream);
+    case 80: return dispatch_tc<80>(emu, p, a->batch, stream);
+    default: return dispatch_tc<160>(emu, p, a->batch, stream);
   }
 }

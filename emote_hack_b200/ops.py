@@ -321,6 +321,15 @@ def attention(q: torch.Tensor, k0: torch.Tensor, v0: torch.Tensor, out: torch.Te
     return out
 
 
+def attention_wide(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, batch: int, nq: int, nk: int,
+                   q_strides, kv_strides, o_strides, scale: float):
+    """single 512-wide head (VAE mid block): tcgen05 flash kernel batched over images; *_strides = (batch, row) elements"""
+    check(_lib.load().emote_attention_wide_bf16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, nq, nk, 512,
+                                                q_strides[0], q_strides[1], kv_strides[0], kv_strides[1], o_strides[0],
+                                                o_strides[1], scale, _stream()), "emote_attention_wide_bf16")
+    return out
+
+
 def temporal_attention(qkv: torch.Tensor, B: int, F_: int, HW: int, heads: int, head_dim: int) -> torch.Tensor:
     _req(qkv, OP16, "temporal_attention.qkv")
     out = torch.empty((B * F_ * HW, heads * head_dim), dtype=OP16, device=qkv.device)

@@ -106,28 +106,29 @@ class AttentionBlock(nn.Module):
         if self._pk is None or self._pk["ver"] != ver:
             with torch.no_grad():
                 self._pk = {
-                    "wqk": ops.pack_linear(torch.cat([self.query.weight, self.key.weight], 0)),
-                    "bqk": _f32c(torch.cat([self.query.bias, self.key.bias], 0)),
-                    "wv": ops.pack_linear(self.value.weight), "bv": _f32c(self.value.bias),
+                    "wqkv": ops.pack_linear(torch.cat([self.query.weight, self.key.weight, self.value.weight], 0)),
+                    "bqkv": _f32c(torch.cat([self.query.bias, self.key.bias, self.value.bias], 0)),
                     "wo": ops.pack_linear(self.proj_attn.weight), "bo": _f32c(self.proj_attn.bias), "ver": ver}
         return self._pk
 
     def run(self, tok, n_img, h, w):
+        """GroupNorm -> fused q|k|v GEMM -> flash attention over the h*w positions of every image (one head of `channels`
+        dims, all images in one launch) -> proj_attn + residual.  512 channels (the SD VAE): tcgen05 kernel with the
+        accumulator in TMEM (`emote_attention_wide_bf16`); narrow test networks (<= 160 channels): the generic kernels."""
         c, n = self.channels, h * w
         g, p = self.group_norm, self._packed()
         a, _ = ops.group_norm([tok], g.num_groups, n, n_img, g.weight, g.bias, g.eps, False)
-        qk = ops.gemm(a, p["wqk"], bias=p["bqk"], out_dtype=OP16)  # [n_img*n, 2c]
-        q = qk[:, :c].contiguous().view(n_img, n, c)
-        k = qk[:, c:].contiguous().view(n_img, n, c)
+        qkv = ops.gemm(a, p["wqkv"], bias=p["bqkv"], out_dtype=OP16)      # [n_img*n, 3c]
         attn = torch.empty((n_img * n, c), dtype=OP16, device=tok.device)
-        av = a.view(n_img, n, c)
-        for i in range(n_img):
-            # V^T[c, n] = Wv x_i^T : the operand roles are swapped so the PV GEMM gets a K-major B operand;
-            # the value bias is added after PV (softmax rows sum to 1)
-            vt = ops.gemm(p["wv"], av[i], out_dtype=OP16)             # [c, n]
-            s = ops.gemm(q[i], k[i])                                  # [n, n] fp32 scores
-            pr = ops.softmax_rows(s, c ** -0.5)                       # bf16 probabilities
-            ops.gemm(pr, vt, bias=p["bv"], out_dtype=OP16, out=attn[i * n:(i + 1) * n])
+        q, k, v = qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:]
+        if c == 512:
+            ops.attention_wide(q, k, v, attn, batch=n_img, nq=n, nk=n, q_strides=(n * 3 * c, 3 * c),
+                               kv_strides=(n * 3 * c, 3 * c), o_strides=(n * c, c), scale=c ** -0.5)
+        elif c <= 160 and c % 8 == 0:
+            ops.attention(q, k, v, attn, batch=n_img, heads=1, head_dim=c, nq=n, n0=n, q_strides=(n * 3 * c, 3 * c),
+                          kv0_strides=(n * 3 * c, 3 * c), o_strides=(n * c, c), scale=c ** -0.5)
+        else:
+            raise NotImplementedError(f"AttentionBlock: {c} channels (supported: 512, or <= 160 in steps of 8)")
         return ops.gemm(attn, p["wo"], bias=p["bo"], residual=tok)
 
 

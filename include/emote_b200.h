@@ -148,6 +148,15 @@ int emote_attention_bf16(const EmoteAttnArgs* args, void* stream);
 int emote_attention_tc_bf16(const EmoteAttnArgs* args, void* stream);
 int emote_attention_tc_supported(int32_t head_dim); /* 1 if emote_attention_tc_bf16 handles this head_dim */
 
+/* One wide head (head_dim 512): the mid-block attention of the SD VAE (legacy AttentionBlock, orig_attention.py:253-385,
+ * `vae.decode` / `vae.encode` at EMOAnimationPipeline.py:301,412) as a tcgen05 flash kernel batched over frames — no
+ * [N, N] score matrix, no per-frame loop.  q / k / v: op16 rows of 512 (e.g. views into a fused QKV GEMM output),
+ * row r of image b at base + b*batch_stride + r*row_stride (elements); out likewise. */
+int emote_attention_wide_bf16(const void* q, const void* k, const void* v, void* out, int32_t batch, int32_t nq, int32_t nk,
+                              int32_t head_dim, int64_t q_batch_stride, int64_t q_row_stride, int64_t kv_batch_stride,
+                              int64_t kv_row_stride, int64_t o_batch_stride, int64_t o_row_stride, float scale,
+                              void* stream);
+
 /* Temporal self-attention over the frame axis (VersatileAttention, motion_module.py:275-334): for every
  * (sample b, pixel p, head h) attends over the F frames.  qkv: tokens-major [B, F, HW, 3*heads*head_dim] bf16
  * (q | k | v), out: [B, F, HW, heads*head_dim] bf16.  The (b f) d c <-> (b d) f c rearranges

@@ -488,6 +488,35 @@ def test_errors_are_loud(ops):
         ops.gemm(a.cpu(), w)
 
 
+@pytest.mark.parametrize("batch,nq,nk,ramp", [(2, 4096, 4096, False), (3, 300, 300, False), (1, 64, 64, False),
+                                              (2, 1024, 1024, True), (1, 200, 333, False)])
+def test_attention_wide_512_single_head(ops, batch, nq, nk, ramp):
+    """emote_attention_wide_bf16: the VAE mid-block attention (one 512-dim head, orig_attention.py:360-376) as a tcgen05
+    flash kernel batched over images — fused-QKV strides, ragged tails, and rising scores that force the lazy rescale."""
+    g = _gen(24)
+    C = 512
+    if nq == nk:
+        qkv = torch.randn(batch, nq, 3 * C, device="cuda", generator=g)
+        if ramp:   # keys whose scores rise along the key axis: every tile beats the previous maximum by more than 2^8
+            u = torch.nn.functional.normalize(torch.randn(C, device="cuda", generator=g), dim=0)
+            qkv[..., :C] += 6.0 * u * C ** 0.25
+            qkv[..., C:2 * C] += torch.linspace(0, 40, nk, device="cuda")[None, :, None] * u * C ** 0.25
+        qkv = qkv.to(OP16)
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        qs = kvs = (nq * 3 * C, 3 * C)
+    else:
+        q = torch.randn(batch, nq, C, device="cuda", generator=g).to(OP16)
+        kv = torch.randn(batch, nk, 2 * C, device="cuda", generator=g).to(OP16)
+        k, v = kv[..., :C], kv[..., C:]
+        qs, kvs = (nq * C, C), (nk * 2 * C, 2 * C)
+    out = torch.zeros(batch, nq, C, device="cuda", dtype=OP16)
+    ops.attention_wide(q, k, v, out, batch=batch, nq=nq, nk=nk, q_strides=qs, kv_strides=kvs, o_strides=(nq * C, C),
+                       scale=C ** -0.5)
+    ref = _sdpa_ref(q[:, None].float(), k[:, None].float(), v[:, None].float(), C ** -0.5)[:, 0]
+    assert torch.isfinite(out.float()).all()
+    chk(rel_l2(out, ref), 6e-3)
+
+
 def test_flash_attention_tcgen05_lazy_rescale_with_growing_scores(ops):
     """The tcgen05 kernel keeps O in TMEM and rescales it only when a row's running maximum has grown by more than 2^8:
     keys whose scores rise steadily along the key axis (every tile beats the previous maximum by far more than that) force

@@ -236,6 +236,32 @@ def test_cached_graph_is_rebuilt_after_weight_update(tiny_pipe):
     assert rel_l2(pipe.denoise(lat.clone(), ctx, **kw), before) < 1e-5
 
 
+def test_graphed_single_branch_units_and_bank_refresh(tiny_pipe):
+    """GraphedUNet in the three unit modes (pair / uncond / cond): the captured batch-1 branches reproduce their eager call,
+    read the right bank row, and `refresh` swaps conditioning without a re-capture (what ranks do when a window's CFG
+    branches are dealt to different GPUs)."""
+    from emote_hack_b200 import ops
+    from emote_hack_b200.pipeline import GraphedUNet, _run_unet
+    o, pipe = tiny_pipe
+    m = pipe.unet
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(2, 4, 4, 8, 8, generator=g).cuda()
+    ctx = torch.randn(2, 7, 64, generator=g).cuda()
+    banks = {k: [v.cuda() for v in vs] for k, vs in make_banks(m, 8).items()}
+    banks2 = {k: [v.cuda() for v in vs] for k, vs in make_banks(m, 8, seed=8).items()}
+    t = torch.tensor([441.0], device="cuda")
+    for mode, sl in (("pair", slice(0, 2)), ("uncond", slice(0, 1)), ("cond", slice(1, 2))):
+        gr = GraphedUNet(m, (sl.stop - sl.start, 4, 4, 8, 8), ctx[sl], banks, x.device, mode=mode)
+        for bk in (banks, banks2):
+            gr.refresh(ctx[sl], bk)
+            gr.lat.copy_(x[sl])
+            got = gr.replay(441).clone()
+            use = None if mode == "uncond" else {k: [v[0] if mode == "pair" else v[0][1:2]] for k, v in bk.items()}
+            want = _run_unet(m, mode, x[sl].contiguous(), t, ctx[sl], use)
+            assert rel_l2(got, want) < 1e-5, mode
+    assert all(blk._ref_mode is None for blk in m.modules() if hasattr(blk, "_ref_mode"))
+
+
 def test_denoise_sliding_windows_with_overlap_and_banks(tiny_pipe):
     """24 frames, windows of 8 with overlap 2 (closed loop): visit-count averaging, per-window reference banks"""
     from emote_hack_b200.pipeline import uniform

@@ -261,6 +261,37 @@ def test_state_dict_reload_invalidates_packed_weights(tiny):
     assert rel_l2(m(x.cuda(), 5, ctx.cuda()).sample, out1) < 1e-5
 
 
+def test_reference_import_paths_run_the_cuda_modules():
+    """INTEGRATION.md §1 end to end: with the package's `magicanimate` tree aliased into sys.modules, the reference's own
+    import lines (EMOAnimationPipeline.py:54-56) build the B200 modules and a forward runs on the kernels."""
+    import importlib
+    import sys
+    import emote_hack_b200.magicanimate as b200
+    saved = {k: v for k, v in sys.modules.items() if k == "magicanimate" or k.startswith("magicanimate.")}
+    try:
+        for k in saved:
+            del sys.modules[k]
+        sys.modules["magicanimate"] = b200
+        sys.modules["magicanimate.models"] = b200.models
+        for name in ("unet_controlnet", "unet_3d_blocks", "resnet", "attention", "motion_module", "mutual_self_attention"):
+            sys.modules[f"magicanimate.models.{name}"] = getattr(b200.models, name)
+        UNet = importlib.import_module("magicanimate.models.unet_controlnet").UNet3DConditionModel
+        from magicanimate.models.mutual_self_attention import ReferenceAttentionControl
+        torch.manual_seed(0)
+        m = rerandomise_zero_inits(UNet(**TINY_CFG).eval()).cuda()
+        reader = ReferenceAttentionControl(m, do_classifier_free_guidance=True, mode="read", fusion_blocks="midup", batch_size=1)
+        x, ctx = make_inputs(2, 2, 8)
+        from emote_hack_b200 import _lib
+        n0 = _lib.launch_count()
+        out = m(x.cuda(), torch.tensor(301).cuda(), encoder_hidden_states=ctx.cuda(), return_dict=False)[0]
+        assert out.shape == (2, 4, 2, 8, 8) and torch.isfinite(out).all() and _lib.launch_count() > n0
+        reader.release()
+    finally:
+        for k in [k for k in sys.modules if k == "magicanimate" or k.startswith("magicanimate.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
 def test_cpu_tensors_fail_loudly():
     from emote_hack_b200._lib import EmoteKernelError
     from emote_hack_b200.unet3d import ResnetBlock3D

@@ -32,8 +32,9 @@ struct GemmDev {
   int out_bf16;
   int ldc;
   void* out;
-  double* colstats;  // optional [M / stats_rows][N][2] per-column (sum, sum of squares) of the fp32 output, else null
-  int stats_rows;    // rows per statistics batch (multiple of 128: a tile never straddles two batches)
+  float* colstats;   // optional fused GroupNorm statistics of the fp32 output, else null: one (sum, sum of squares) slot per
+                     // 32-row quarter of a sub-tile and column, [sub-tiles * 4][N][2] fp32, written with plain stores
+  int stats_rows;    // rows per statistics batch (validated on the host: a 32-row quarter never straddles two batches)
 };
 
 
@@ -264,9 +265,9 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
         }
       }
       if (stats) {
-        // this thread summed its 4 rows; fold the 8 row groups of the warp (lanes differing in g), then one lane per
-        // column pair sends the 32-row partial to the fp64 accumulators of the tile's statistics batch (fire-and-forget
-        // reductions: no shared-memory stage, no extra barrier)
+        // this thread summed its 4 rows; fold the 8 row groups of the warp (lanes differing in g) in a fixed order, then
+        // one lane per column pair stores the 32-row partial into the quarter's slot: no atomics, no zero-fill, and the
+        // statistics (hence the whole network) are bit-reproducible from run to run
 #pragma unroll
         for (int off = 4; off < 32; off <<= 1) {
           cs0 += __shfl_xor_sync(0xffffffffu, cs0, off);
@@ -274,10 +275,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
           cs1 += __shfl_xor_sync(0xffffffffu, cs1, off);
           cq1 += __shfl_xor_sync(0xffffffffu, cq1, off);
         }
-        if (g == 0 && first_row >= 0) {
-          double* cs = p.colstats + ((size_t)(first_row / p.stats_rows) * p.N + col) * 2;
-          if (c0ok) { atomicAdd(cs, (double)cs0); atomicAdd(cs + 1, (double)cq0); }
-          if (c1ok) { atomicAdd(cs + 2, (double)cs1); atomicAdd(cs + 3, (double)cq1); }
+        if (g == 0 && first_row >= 0) {   // (the second CTA of the last pair may own a sub-tile that does not exist)
+          float* cs = p.colstats + ((size_t)(row_base / 32 + quarter) * p.N + col) * 2;
+          if (c1ok) *reinterpret_cast<float4*>(cs) = make_float4(cs0, cq0, cs1, cq1);
+          else if (c0ok) *reinterpret_cast<float2*>(cs) = make_float2(cs0, cq0);
         }
       }
     };

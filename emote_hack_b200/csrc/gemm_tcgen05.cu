@@ -377,8 +377,9 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   p.out = out;
   if (a->colstats) {
     if (p.out_bf16 || geglu) return set_error("emote_gemm_bf16: colstats needs a plain fp32 output");
-    if (a->stats_rows <= 0 || a->stats_rows % 128 != 0 || a->M % a->stats_rows != 0)
-      return set_error("emote_gemm_bf16: stats_rows must be a multiple of 128 that divides M");
+    if (a->stats_rows <= 0 || a->stats_rows % 32 != 0 || a->M % a->stats_rows != 0 || a->N % 2 != 0 ||
+        (reinterpret_cast<uintptr_t>(a->colstats) & 15) != 0)
+      return set_error("emote_gemm_bf16: stats_rows must be a multiple of 32 that divides M (even N, 16-byte aligned slots)");
     p.colstats = a->colstats;
     p.stats_rows = a->stats_rows;
   }

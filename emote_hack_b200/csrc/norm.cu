@@ -84,38 +84,47 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const float* __restrict__
 
 // y = x * scale[c] + shift[c] with scale = rstd*gamma, shift = beta - mean*rstd*gamma staged in shared memory per
 // block; blockDim = (octets per pass, rows in parallel); GN_APPLY_U rows per thread are in flight per batch.
-// Group statistics from the per-column statistics a GEMM epilogue accumulated (EmoteGemmArgs.colstats): one warp per
-// (batch, group) sums the group's columns over the `fpb` consecutive statistics batches that form one GN batch.
-__global__ void gn_colstats_reduce_kernel(const double* __restrict__ colstats, int C_src, int c_offset, int cpg, int groups,
-                                          int fpb, int n_batches, double* __restrict__ sums, int overwrite) {
+// Group statistics from the per-quarter column slots a GEMM epilogue stored (EmoteGemmArgs.colstats).
+__global__ void __launch_bounds__(256) gn_colstats_reduce_kernel(const float* __restrict__ slots, int C_src, int c_offset,
+                                                                 int cpg, int groups, int slots_per_batch, int n_batches,
+                                                                 double* __restrict__ sums, int overwrite) {
   pdl_prologue();
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (wid >= n_batches * groups) return;
-  const int batch = wid / groups, g = wid - batch * groups;
+  // one block per (batch, group): thread t walks slots t, t + 256, ... of the batch over the group's columns of this
+  // source, in a fixed order; fp64 from the first addition on; fixed-order tree over the block -> deterministic
+  const int batch = blockIdx.x / groups, g = blockIdx.x - batch * groups;
   int c_lo = g * cpg, c_hi = c_lo + cpg;
   if (c_lo < c_offset) c_lo = c_offset;
   if (c_hi > c_offset + C_src) c_hi = c_offset + C_src;
   const int nc = c_hi - c_lo;
+  double* o = sums + ((long long)batch * groups + g) * 2;
   if (nc <= 0) {
-    if (overwrite && lane < 2) sums[(long long)wid * 2 + lane] = 0.0;
+    if (overwrite && threadIdx.x < 2) o[threadIdx.x] = 0.0;
     return;
   }
   double s = 0.0, q = 0.0;
-  for (int i = lane; i < nc * fpb; i += 32) {
-    const int fr = i / nc, c = c_lo + (i - fr * nc) - c_offset;
-    const double2 v = *reinterpret_cast<const double2*>(colstats + (((long long)batch * fpb + fr) * C_src + c) * 2);
-    s += v.x;
-    q += v.y;
+  const float* base = slots + ((long long)batch * slots_per_batch * C_src + (c_lo - c_offset)) * 2;
+  for (int sl = threadIdx.x; sl < slots_per_batch; sl += blockDim.x) {
+    const float2* row = reinterpret_cast<const float2*>(base + (long long)sl * C_src * 2);
+    for (int c = 0; c < nc; ++c) {
+      const float2 v = __ldg(row + c);
+      s += (double)v.x;
+      q += (double)v.y;
+    }
   }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, off);
-    q += __shfl_xor_sync(0xffffffffu, q, off);
+  __shared__ double rs[256], rq[256];
+  rs[threadIdx.x] = s;
+  rq[threadIdx.x] = q;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      rs[threadIdx.x] += rs[threadIdx.x + off];
+      rq[threadIdx.x] += rq[threadIdx.x + off];
+    }
+    __syncthreads();
   }
-  if (lane == 0) {
-    double* o = sums + (long long)wid * 2;
-    if (overwrite) { o[0] = s; o[1] = q; }
-    else { o[0] += s; o[1] += q; }
+  if (threadIdx.x == 0) {
+    if (overwrite) { o[0] = rs[0]; o[1] = rq[0]; }
+    else { o[0] += rs[0]; o[1] += rq[0]; }
   }
 }
 
@@ -347,17 +356,16 @@ extern "C" int emote_gn_stats(const float* x, int32_t C_src, int32_t c_offset, i
   return 0;
 }
 
-extern "C" int emote_gn_colstats_reduce(const double* colstats, int32_t C_src, int32_t c_offset, int32_t C_total,
-                                        int32_t groups, int32_t stat_batches_per_batch, int32_t n_batches, double* sums,
+extern "C" int emote_gn_colstats_reduce(const float* colstats, int32_t C_src, int32_t c_offset, int32_t C_total,
+                                        int32_t groups, int32_t slots_per_batch, int32_t n_batches, double* sums,
                                         int32_t zero_first, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (!colstats || !sums || stat_batches_per_batch <= 0 || n_batches <= 0)
+  if (!colstats || !sums || slots_per_batch <= 0 || n_batches <= 0)
     return set_error("emote_gn_colstats_reduce: bad arguments");
   if (gn_check(C_src, c_offset, C_total, groups, "emote_gn_colstats_reduce: unsupported channel/group configuration"))
     return EMOTE_ERR_INVALID;
-  const int warps = n_batches * groups;
-  launch_kernel(gn_colstats_reduce_kernel, dim3((warps + 3) / 4), dim3(128), 0, stream, colstats, C_src, c_offset, C_total / groups, groups,
-                                                               stat_batches_per_batch, n_batches, sums, zero_first);
+  launch_kernel(gn_colstats_reduce_kernel, dim3((unsigned)(n_batches * groups)), dim3(256), 0, stream, colstats, C_src,
+                c_offset, C_total / groups, groups, slots_per_batch, n_batches, sums, zero_first);
   EMOTE_CHECK_LAUNCH("emote_gn_colstats_reduce");
   return 0;
 }

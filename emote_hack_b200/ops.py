@@ -137,9 +137,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, row_bias=None, rows_per
     args.pair_mode = pair_mode
     args.tma_store = tma_store
     colstats = None
-    if (stats_rows > 0 and FUSED_GN_STATS and out_dtype == F32 and not geglu and stats_rows % 128 == 0
-            and M % stats_rows == 0):
-        colstats = torch.zeros((M // stats_rows, n_out, 2), dtype=torch.float64, device=a.device)
+    if (stats_rows > 0 and FUSED_GN_STATS and out_dtype == F32 and not geglu and not gelu and stats_rows % 32 == 0
+            and M % stats_rows == 0 and n_out % 2 == 0 and _conv_stats_ok(conv, stats_rows)):
+        # one fp32 (sum, sum of squares) slot per 32-row quarter and column: every slot is written, nothing to clear
+        colstats = torch.empty((-(-M // 128) * 4 if conv is None else _conv_subtiles(conv) * 4, n_out, 2), dtype=F32,
+                               device=a.device)
         args.colstats, args.stats_rows = colstats.data_ptr(), stats_rows
     if out_col:
         if out_col + n_out > out.shape[-1] or (out_col * out.element_size()) % 16 != 0:
@@ -163,12 +165,40 @@ def set_pdl(enabled: bool) -> None:
 
 
 def stats_rows_for(rows_per_frame: int, rows_per_sample: int) -> int:
-    """Finest statistics granularity a 128-row GEMM tile never straddles: per frame, else per sample, else none (0)."""
-    if rows_per_frame % 128 == 0:
+    """Finest statistics granularity a 32-row quarter of a GEMM tile never straddles: per frame, else per sample, else
+    none (0)."""
+    if rows_per_frame % 32 == 0:
         return rows_per_frame
-    if rows_per_sample % 128 == 0:
+    if rows_per_sample % 32 == 0:
         return rows_per_sample
     return 0
+
+
+def _conv_geometry(conv):
+    """(bw, bh, images) of the 128-pixel TMA box of the implicit-GEMM conv and whether it is a 2-D patch (gemm_tcgen05.cu)"""
+    n_img, H, W_, _ = conv
+    bw = math.gcd(W_, 128)
+    bh = math.gcd(H, 128 // bw)
+    bn = 128 // (bw * bh)
+    contiguous = bw == 128 or (bw == W_ and (bn == 1 or bh == H))
+    return bw, bh, bn, not contiguous
+
+
+def _conv_subtiles(conv) -> int:
+    n_img, H, W_, _ = conv
+    bw, bh, bn, patch = _conv_geometry(conv)
+    if not patch:
+        return -(-(n_img * H * W_) // 128)
+    return -(-n_img // bn) * (W_ // bw) * (H // bh)
+
+
+def _conv_stats_ok(conv, stats_rows: int) -> bool:
+    """patch-mode convs: a sub-tile touches `images` whole-image groups, which must not straddle a statistics batch"""
+    if conv is None:
+        return True
+    n_img, H, W_, _ = conv
+    bw, bh, bn, patch = _conv_geometry(conv)
+    return (not patch) or stats_rows % (H * W_ * bn) == 0
 
 
 def conv_tile_ok(H: int, W: int) -> bool:
@@ -249,9 +279,9 @@ def group_norm(sources: Sequence[torch.Tensor], groups: int, rows_per_batch: int
         cs = int(s.shape[-1])
         info = getattr(s, "_emote_colstats", None)
         if (info is not None and FUSED_GN_STATS and info[2] == s._version and rows_per_batch % info[1] == 0
-                and info[0].shape[0] * info[1] == rows and info[0].shape[1] == cs):
-            # statistics were accumulated by the GEMM epilogue that wrote this source
-            check(lib.emote_gn_colstats_reduce(info[0].data_ptr(), cs, off, c_total, groups, rows_per_batch // info[1],
+                and rows_per_batch % 32 == 0 and info[0].shape[0] * 32 >= rows and info[0].shape[1] == cs):
+            # statistics were stored by the GEMM epilogue that wrote this source (32-row slots)
+            check(lib.emote_gn_colstats_reduce(info[0].data_ptr(), cs, off, c_total, groups, rows_per_batch // 32,
                                                n_batches, sums.data_ptr(), 1 if i == 0 else 0, st),
                   "emote_gn_colstats_reduce")
         else:

@@ -76,9 +76,11 @@ typedef struct {
                              3 = auto without the weight-stationary kernel (small-K bf16-output shapes) */
   int32_t tma_store;      /* 0 = auto (staged TMA-store epilogues where they apply), 2 = never, 3 = never the
                              double-buffered residual variant, 4 = double-buffered residual variant for any K */
-  double* colstats;       /* optional fused GroupNorm statistics of the fp32 output: [M / stats_rows][N][2] fp64
-                             (sum, sum of squares per column and statistics batch), ACCUMULATED into (caller zeroes) */
-  int32_t stats_rows;     /* rows per statistics batch; multiple of 128 that divides M */
+  float* colstats;        /* optional fused GroupNorm statistics of the fp32 output: one (sum, sum of squares) fp32 slot per
+                             32-row quarter of a 128-row sub-tile and column, [ceil(M/128)*4][N][2] (conv over 2-D patch
+                             tiles: sub-tile order), every slot written with a plain store: no zero-fill, no atomics,
+                             bit-reproducible.  Slots of statistics batch b: [b*stats_rows/32, (b+1)*stats_rows/32). */
+  int32_t stats_rows;     /* rows per statistics batch; multiple of 32 that divides M */
 } EmoteGemmArgs;
 int emote_gemm_bf16(const void* A, const void* Wt, void* out, const EmoteGemmArgs* args, void* stream);
 
@@ -91,13 +93,12 @@ int emote_gemm_bf16(const void* A, const void* Wt, void* out, const EmoteGemmArg
  * sums: [n_batches, groups, 2] doubles (sum, sum of squares); zeroed by the call when zero_first != 0. */
 int emote_gn_stats(const float* x, int32_t C_src, int32_t c_offset, int32_t C_total, int32_t groups,
                    int64_t rows_per_batch, int32_t n_batches, double* sums, int32_t zero_first, void* stream);
-/* GroupNorm statistics from the per-column statistics accumulated by emote_gemm_bf16 (EmoteGemmArgs.colstats) while it
- * wrote the tensor being normalised: replaces the emote_gn_stats pass over that source (same `sums` layout and
- * concat semantics: c_offset / C_total; zero_first = overwrite instead of accumulate).  `stat_batches_per_batch`
- * consecutive statistics batches of colstats [n][C_src][2] form one GroupNorm batch (e.g. the f frames of a sample for
- * the 5-D GroupNorm of resnet.py:180 when the GEMM kept per-frame statistics). */
-int emote_gn_colstats_reduce(const double* colstats, int32_t C_src, int32_t c_offset, int32_t C_total, int32_t groups,
-                             int32_t stat_batches_per_batch, int32_t n_batches, double* sums, int32_t zero_first,
+/* GroupNorm statistics from the slots emote_gemm_bf16 stored (EmoteGemmArgs.colstats) while it wrote the tensor being
+ * normalised: replaces the emote_gn_stats pass over that source (same `sums` layout and concat semantics: c_offset /
+ * C_total; zero_first = overwrite instead of accumulate).  `slots_per_batch` = rows of one GroupNorm batch / 32 (e.g. the
+ * f frames of a sample for the 5-D GroupNorm of resnet.py:180).  Fixed summation order, fp64: deterministic. */
+int emote_gn_colstats_reduce(const float* colstats, int32_t C_src, int32_t c_offset, int32_t C_total, int32_t groups,
+                             int32_t slots_per_batch, int32_t n_batches, double* sums, int32_t zero_first,
                              void* stream);
 
 /* y = (x-mean)*rstd*gamma+beta [-> SiLU if act_silu]; written as bf16 into out[row, c_offset + c] (pitch C_total).

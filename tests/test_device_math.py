@@ -1,7 +1,7 @@
 """Accuracy claims of the polynomial device functions, checked on the CPU by re-running the SAME fp32 arithmetic in
 numpy with the coefficients parsed out of the CUDA sources (so a typo in a constant fails here, without a GPU):
   common.cuh:gelu_sig          exact GELU in logistic form (GEGLU epilogue),  claimed |abs err| <= 2.6e-5
-  attention_tc.cu:exp2_poly2   2^x on the FMA pipe (softmax of the tcgen05 attention), claimed rel err <= 7.5e-5 (+ fp32)
+  attention_tc.cuh:exp2_poly2   2^x on the FMA pipe (softmax of the tcgen05 attention), claimed rel err <= 7.5e-5 (+ fp32)
 The reference arithmetic they stand in for: F.gelu (erf form, orig_attention.py:825-827) and softmax's exp
 (orig_attention.py:671)."""
 import re
@@ -44,7 +44,7 @@ def test_gelu_sig_polynomial():
 
 
 def test_exp2_poly2_cody_waite():
-    src = (CSRC / "attention_tc.cu").read_text()
+    src = (CSRC / "attention_tc.cuh").read_text()
     c = _floats(src, "__device__ __forceinline__ void exp2_poly2", "r0 = __int_as_float")
     # order: MAGIC, clamp (-126 twice), 1.0, MAGIC ops (1.0, -1.0), c3, c2, c1, c0
     magic = c[0]

@@ -216,12 +216,26 @@ def test_group_norm(ops, srcs, rows_per_batch, n_batches):
     out2, _ = ops.group_norm(xs, 32, rows_per_batch, n_batches, gamma, beta, 1e-6, False)
     ref2 = F.group_norm(xc, 32, gamma, beta, 1e-6).permute(0, 2, 1).reshape(rows, ct)
     chk(rel_l2(out2, ref2), 4e-3)
-def _check_colstats(out, stats_rows):
+def _check_colstats(out, stats_rows, ops=None):
+    """the fused statistics of a GEMM output, folded per statistics batch (all channels as ONE group per column pair is not
+    available from the slots directly, so fold them the way group_norm() does: 2 channels per group) against the output"""
+    from emote_hack_b200 import ops as _ops
     cs, sr, ver = out._emote_colstats
-    assert sr == stats_rows and ver == out._version
-    o = out.double().view(-1, stats_rows, out.shape[1])
-    ref = torch.stack([o.sum(1), (o * o).sum(1)], dim=-1)
-    torch.testing.assert_close(cs, ref, rtol=2e-5, atol=1e-3)
+    assert sr == stats_rows and ver == out._version and cs.dtype == torch.float32
+    M, N = out.shape
+    nb = M // stats_rows
+    G = max(g for g in range(1, 65) if N % g == 0 and (N // g) % 2 == 0)
+    sums = torch.empty((nb, G, 2), dtype=torch.float64, device=out.device)
+    from emote_hack_b200._lib import check, load
+    check(load().emote_gn_colstats_reduce(cs.data_ptr(), N, 0, N, G, stats_rows // 32, nb, sums.data_ptr(), 1,
+                                          _ops._stream()), "emote_gn_colstats_reduce")
+    o = out.double().view(nb, stats_rows, G, N // G)
+    ref = torch.stack([o.sum((1, 3)), (o * o).sum((1, 3))], dim=-1)
+    torch.testing.assert_close(sums, ref, rtol=2e-5, atol=1e-3)
+    again = torch.empty_like(sums)
+    check(load().emote_gn_colstats_reduce(cs.data_ptr(), N, 0, N, G, stats_rows // 32, nb, again.data_ptr(), 1,
+                                          _ops._stream()), "emote_gn_colstats_reduce")
+    assert torch.equal(again, sums)          # fixed summation order
 
 
 @pytest.mark.parametrize("M,N,K,sr,mode", [(1024, 320, 320, 256, "res"), (1024, 320, 320, 128, "plain"),

@@ -260,7 +260,9 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank that dies inside a secondary measurement must not hang the others for ever: collectives time out
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=600))
         dist.all_reduce(torch.zeros(1, device=dev))  # communicator warm-up (reference dist_tools.py:55)
 
     from emote_hack_b200 import _lib, ops
@@ -380,81 +382,84 @@ def run_ours(args):
     # ranks (strong scaling), one all-reduce of the accumulated prediction per DDIM step, frame-sharded decode + one
     # uint8 all-gather.  6 DDIM steps are timed (the other 44 are identical work) after a 1-step warm-up.
     if not args.no_variants:
-        LF, LSTEPS = 240, 6
-        gl = torch.Generator().manual_seed(77)
-        lf_lat = torch.randn(1, 4, LF, LAT, LAT, generator=gl).to(dev)
-        lf_ctx = torch.randn(2, 77, 768, generator=gl).to(dev)
-        shard_pipe = EMOAnimationPipeline(vae, unet, DDIMScheduler(), rank=rank, world_size=world)
-        kw = dict(num_inference_steps=DDIM_STEPS, guidance_scale=GUIDANCE, context_frames=FRAMES, context_overlap=4)
-        shard_pipe.denoise(lf_lat.clone(), lf_ctx, num_actual_inference_steps=1, **kw)      # captures the step graphs
-        sync_all()
-        e0.record()
-        got = shard_pipe.denoise(lf_lat.clone(), lf_ctx, num_actual_inference_steps=LSTEPS, **kw)
-        e1.record()
-        sync_all()
-        step_ms = max_over_ranks(e0.elapsed_time(e1)) / LSTEPS
-        e0.record()
-        shard_pipe.decode_latents_device(got, want_u8=True, shard=True)
-        e1.record()
-        sync_all()
-        dec_ms = max_over_ranks(e0.elapsed_time(e1))
-        lf = {"frames": LF, "windows": 20, "units": 40, "units_per_rank": [sum(2 if m == "pair" else 1 for _, m in
-                                                                               plan_units(20, r, world)) for r in range(world)],
-              "ms_per_ddim_step": round(step_ms, 2), "decode_240_frames_ms": round(dec_ms, 1),
-              "value": round(LF / ((DDIM_STEPS * step_ms + dec_ms) / 1000.0), 4), "unit": UNIT, "scaling": "strong",
-              "timed_ddim_steps": LSTEPS,
-              "what": "BASELINE configs[4]: 512x512, 240 frames, sliding 16-frame windows (overlap 4); value = 240 / (50 x "
-                      "measured step time + measured sharded decode); collectives: one fp32 all-reduce of noise_pred "
-                      "[2,4,240,64,64] (31.5 MB) per step + one uint8 all-gather of the frames"}
-        if world > 1:
-            # sharded == single-GPU: every rank also runs the un-sharded loop (2 steps) and compares its own result
-            one = EMOAnimationPipeline(vae, unet, DDIMScheduler(), rank=0, world_size=1)
-            want = one.denoise(lf_lat.clone(), lf_ctx, num_actual_inference_steps=2, **kw)
-            have = shard_pipe.denoise(lf_lat.clone(), lf_ctx, num_actual_inference_steps=2, **kw)
-            rel = ((have - want).norm() / want.norm()).reshape(1).double()
-            dist.all_reduce(rel, op=dist.ReduceOp.MAX)
-            lf["sharded_vs_single_gpu_rel_l2_max_over_ranks"] = float(rel.item())
-            # the same 6 steps un-sharded on this rank alone -> speed-up measured inside one run
-            torch.cuda.synchronize()
+        try:
+            LF, LSTEPS = 240, 6
+            gl = torch.Generator().manual_seed(77)
+            lf_lat = torch.randn(1, 4, LF, LAT, LAT, generator=gl).to(dev)
+            lf_ctx = torch.randn(2, 77, 768, generator=gl).to(dev)
+            shard_pipe = EMOAnimationPipeline(vae, unet, DDIMScheduler(), rank=rank, world_size=world)
+            kw = dict(num_inference_steps=DDIM_STEPS, guidance_scale=GUIDANCE, context_frames=FRAMES, context_overlap=4)
+            shard_pipe.denoise(lf_lat.clone(), lf_ctx, num_actual_inference_steps=1, **kw)      # captures the step graphs
+            sync_all()
             e0.record()
-            one.denoise(lf_lat.clone(), lf_ctx, num_actual_inference_steps=LSTEPS, **kw)
+            got = shard_pipe.denoise(lf_lat.clone(), lf_ctx, num_actual_inference_steps=LSTEPS, **kw)
             e1.record()
-            torch.cuda.synchronize()
-            single_ms = max_over_ranks(e0.elapsed_time(e1)) / LSTEPS
-            lf["single_gpu_ms_per_ddim_step"] = round(single_ms, 2)
-            lf["step_speedup_vs_single_gpu"] = round(single_ms / step_ms, 3)
-        variants["longform_240f"] = lf
-        pipe._graphs.clear(); shard_pipe._graphs.clear()
-        torch.cuda.empty_cache()
+            sync_all()
+            step_ms = max_over_ranks(e0.elapsed_time(e1)) / LSTEPS
+            e0.record()
+            shard_pipe.decode_latents_device(got, want_u8=True, shard=True)
+            e1.record()
+            sync_all()
+            dec_ms = max_over_ranks(e0.elapsed_time(e1))
+            lf = {"frames": LF, "windows": 20, "units": 40, "units_per_rank": [sum(2 if m == "pair" else 1 for _, m in
+                                                                                   plan_units(20, r, world)) for r in range(world)],
+                  "ms_per_ddim_step": round(step_ms, 2), "decode_240_frames_ms": round(dec_ms, 1),
+                  "value": round(LF / ((DDIM_STEPS * step_ms + dec_ms) / 1000.0), 4), "unit": UNIT, "scaling": "strong",
+                  "timed_ddim_steps": LSTEPS,
+                  "what": "BASELINE configs[4]: 512x512, 240 frames, sliding 16-frame windows (overlap 4); value = 240 / (50 x "
+                          "measured step time + measured sharded decode); collectives: one fp32 all-reduce of noise_pred "
+                          "[2,4,240,64,64] (31.5 MB) per step + one uint8 all-gather of the frames"}
+            if world > 1:
+                # sharded == single-GPU: every rank also runs the un-sharded loop (2 steps) and compares its own result
+                one = EMOAnimationPipeline(vae, unet, DDIMScheduler(), rank=0, world_size=1)
+                want = one.denoise(lf_lat.clone(), lf_ctx, num_actual_inference_steps=2, **kw)
+                have = shard_pipe.denoise(lf_lat.clone(), lf_ctx, num_actual_inference_steps=2, **kw)
+                rel = ((have - want).norm() / want.norm()).reshape(1).double()
+                dist.all_reduce(rel, op=dist.ReduceOp.MAX)
+                lf["sharded_vs_single_gpu_rel_l2_max_over_ranks"] = float(rel.item())
+                # the same 6 steps un-sharded on this rank alone -> speed-up measured inside one run
+                torch.cuda.synchronize()
+                e0.record()
+                one.denoise(lf_lat.clone(), lf_ctx, num_actual_inference_steps=LSTEPS, **kw)
+                e1.record()
+                torch.cuda.synchronize()
+                single_ms = max_over_ranks(e0.elapsed_time(e1)) / LSTEPS
+                lf["single_gpu_ms_per_ddim_step"] = round(single_ms, 2)
+                lf["step_speedup_vs_single_gpu"] = round(single_ms / step_ms, 3)
+            variants["longform_240f"] = lf
+            pipe._graphs.clear(); shard_pipe._graphs.clear()
+            torch.cuda.empty_cache()
 
-        # ---- variant: BASELINE config #4 — 768x768 (latent 96x96), 16 frames, one sample (CFG pair) per rank, weak scaling
-        L4, S4 = 96, 3
-        g4 = torch.Generator().manual_seed(99 + rank)
-        lat4 = torch.randn(1, 4, FRAMES, L4, L4, generator=g4).to(dev)
-        ctx4 = torch.randn(2, 77, 768, generator=g4).to(dev)
-        kw4 = dict(num_inference_steps=DDIM_STEPS, guidance_scale=GUIDANCE, context_frames=FRAMES)
-        pipe.denoise(lat4.clone(), ctx4, num_actual_inference_steps=1, **kw4)
-        sync_all()
-        e0.record()
-        out4 = pipe.denoise(lat4.clone(), ctx4, num_actual_inference_steps=S4, **kw4)
-        e1.record()
-        sync_all()
-        step4 = max_over_ranks(e0.elapsed_time(e1)) / S4
-        vae.decode_video(out4, want_u8=True, frame_chunk=8)
-        sync_all()
-        e0.record()
-        vae.decode_video(out4, want_u8=True, frame_chunk=8)
-        e1.record()
-        sync_all()
-        dec4 = max_over_ranks(e0.elapsed_time(e1))
-        variants["cfg4_768"] = {
-            "ms_per_ddim_step": round(step4, 2), "decode_16_frames_ms": round(dec4, 1), "timed_ddim_steps": S4,
-            "value": round(world * FRAMES / ((DDIM_STEPS * step4 + dec4) / 1000.0), 4), "unit": UNIT, "scaling": "weak",
-            "what": "BASELINE configs[3]: 768x768, 16 frames, one sample [2,4,16,96,96] per GPU (90.4 TFLOP per UNet call); "
-                    "value = N x 16 / (50 x measured step time + measured decode)"}
-        pipe._graphs.clear()
-        del out4
-        torch.cuda.empty_cache()
+            # ---- variant: BASELINE config #4 — 768x768 (latent 96x96), 16 frames, one sample (CFG pair) per rank, weak scaling
+            L4, S4 = 96, 3
+            g4 = torch.Generator().manual_seed(99 + rank)
+            lat4 = torch.randn(1, 4, FRAMES, L4, L4, generator=g4).to(dev)
+            ctx4 = torch.randn(2, 77, 768, generator=g4).to(dev)
+            kw4 = dict(num_inference_steps=DDIM_STEPS, guidance_scale=GUIDANCE, context_frames=FRAMES)
+            pipe.denoise(lat4.clone(), ctx4, num_actual_inference_steps=1, **kw4)
+            sync_all()
+            e0.record()
+            out4 = pipe.denoise(lat4.clone(), ctx4, num_actual_inference_steps=S4, **kw4)
+            e1.record()
+            sync_all()
+            step4 = max_over_ranks(e0.elapsed_time(e1)) / S4
+            vae.decode_video(out4, want_u8=True, frame_chunk=8)
+            sync_all()
+            e0.record()
+            vae.decode_video(out4, want_u8=True, frame_chunk=8)
+            e1.record()
+            sync_all()
+            dec4 = max_over_ranks(e0.elapsed_time(e1))
+            variants["cfg4_768"] = {
+                "ms_per_ddim_step": round(step4, 2), "decode_16_frames_ms": round(dec4, 1), "timed_ddim_steps": S4,
+                "value": round(world * FRAMES / ((DDIM_STEPS * step4 + dec4) / 1000.0), 4), "unit": UNIT, "scaling": "weak",
+                "what": "BASELINE configs[3]: 768x768, 16 frames, one sample [2,4,16,96,96] per GPU (90.4 TFLOP per UNet call); "
+                        "value = N x 16 / (50 x measured step time + measured decode)"}
+            pipe._graphs.clear()
+            del out4
+            torch.cuda.empty_cache()
+        except Exception as exc:   # secondary measurements never take the headline line down with them
+            variants["error"] = repr(exc)[:400]
 
     # ---- roofline pass (untimed): every launch of one UNet call bracketed by CUDA events on the launching stream
     roof, roof_classes, breakdown = None, None, None
@@ -532,8 +537,11 @@ def run_ours(args):
         }
         emit(line)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:
+            pass
     return 0
 
 

@@ -70,12 +70,13 @@ class ResnetBlock2D(nn.Module):
         g1, g2 = self.norm1, self.norm2
         raw_needed = self.conv_shortcut is not None
         a1, raw = ops.group_norm([tok], g1.num_groups, h * w, n_img, g1.weight, g1.bias, g1.eps, True, want_raw=raw_needed)
-        h1 = self.conv1.run(a1, n_img, h, w)
+        sr = ops.stats_rows_for(h * w, h * w)   # per-image GroupNorm statistics ride on the conv epilogues
+        h1 = self.conv1.run(a1, n_img, h, w, stats_rows=sr)
         a2, _ = ops.group_norm([h1], g2.num_groups, h * w, n_img, g2.weight, g2.bias, g2.eps, True)
         if raw_needed:
             res = self.conv_shortcut.run(raw, n_img, h, w)
-            return self.conv2.run(a2, n_img, h, w, residual=res, out=res)
-        return self.conv2.run(a2, n_img, h, w, residual=tok)
+            return self.conv2.run(a2, n_img, h, w, residual=res, out=res, stats_rows=sr)
+        return self.conv2.run(a2, n_img, h, w, residual=tok, stats_rows=sr)
 
 
 class AttentionBlock(nn.Module):
@@ -129,7 +130,7 @@ class AttentionBlock(nn.Module):
                           kv0_strides=(n * 3 * c, 3 * c), o_strides=(n * c, c), scale=c ** -0.5)
         else:
             raise NotImplementedError(f"AttentionBlock: {c} channels (supported: 512, or <= 160 in steps of 8)")
-        return ops.gemm(attn, p["wo"], bias=p["bo"], residual=tok)
+        return ops.gemm(attn, p["wo"], bias=p["bo"], residual=tok, stats_rows=ops.stats_rows_for(n, n))
 
 
 class _Up(nn.Module):
@@ -268,7 +269,7 @@ class AutoencoderKL(nn.Module):
         cols = ops.latent_im2col(z.float().contiguous().view(n, cl, 1, h, w), pre_scale,
                                  _f32c(pq.weight).view(cl, cl), _f32c(pq.bias))
         wp, b = d.conv_in.packed()
-        x = ops.gemm(cols, wp, bias=b)
+        x = ops.gemm(cols, wp, bias=b, stats_rows=ops.stats_rows_for(h * w, h * w))
         x = d.mid_block.resnets[0].run(x, n, h, w)
         x = d.mid_block.attentions[0].run(x, n, h, w)
         x = d.mid_block.resnets[1].run(x, n, h, w)
@@ -279,7 +280,7 @@ class AutoencoderKL(nn.Module):
                 c = x.shape[1]
                 up = ops.upsample2x(x, n, h, w, c)
                 h, w = 2 * h, 2 * w
-                x = blk.upsamplers[0].conv.run(up, n, h, w)
+                x = blk.upsamplers[0].conv.run(up, n, h, w, stats_rows=ops.stats_rows_for(h * w, h * w))
         g = d.conv_norm_out
         a, _ = ops.group_norm([x], g.num_groups, h * w, n, g.weight, g.bias, g.eps, True)
         out = torch.empty((n * h * w, 4), dtype=F32, device=x.device)
@@ -299,7 +300,7 @@ class AutoencoderKL(nn.Module):
             raise ValueError(f"image height/width must be multiples of {2 ** n_down}")
         cols = ops.latent_im2col(x.float().contiguous().view(n, ci, 1, h, w))
         wp, b = e.conv_in.packed()
-        t = ops.gemm(cols, wp, bias=b)
+        t = ops.gemm(cols, wp, bias=b, stats_rows=ops.stats_rows_for(h * w, h * w))
         for blk in e.down_blocks:
             for r in blk.resnets:
                 t = r.run(t, n, h, w)
@@ -307,8 +308,8 @@ class AutoencoderKL(nn.Module):
                 conv = blk.downsamplers[0].conv
                 c = t.shape[1]
                 wp, b = conv.packed()
-                t = ops.gemm(ops.im2col_s2_pad01(t, n, h, w, c), wp, bias=b)
                 h, w = h // 2, w // 2
+                t = ops.gemm(ops.im2col_s2_pad01(t, n, 2 * h, 2 * w, c), wp, bias=b, stats_rows=ops.stats_rows_for(h * w, h * w))
         t = e.mid_block.resnets[0].run(t, n, h, w)
         t = e.mid_block.attentions[0].run(t, n, h, w)
         t = e.mid_block.resnets[1].run(t, n, h, w)

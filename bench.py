@@ -277,7 +277,7 @@ def run_ours(args):
         unet = UNet3DConditionModel(**cfg).eval()
         vae = AutoencoderKL().eval()
     rerandomise_zero_inits(unet)
-    pipe = EMOAnimationPipeline(vae, unet, DDIMScheduler(), rank=rank, world_size=1)  # one sample per rank
+    pipe = EMOAnimationPipeline(vae, unet, DDIMScheduler(), rank=0, world_size=1)  # one sample per rank: every rank is a 1-rank pipeline
 
     g = torch.Generator().manual_seed(1234 + rank)
     host_lat = torch.randn(1, 4, FRAMES, LAT, LAT, generator=g).pin_memory()

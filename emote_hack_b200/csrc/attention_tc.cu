@@ -56,7 +56,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
                       const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
                       const AttnTcDev p) {
   using C = TcCfg<D>;
-  pdl_launch_dependents();
+  pdl_launch_early();
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -148,6 +148,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
       }
       __syncwarp();
     }
+    pdl_launch_late();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = umma_idesc_op16(TC_BQ, TC_BKV);

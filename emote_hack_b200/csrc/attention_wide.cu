@@ -42,7 +42,7 @@ template <int EMU>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 flash_attn_wide_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                        const AttnWideDev p) {
-  pdl_launch_dependents();
+  pdl_launch_early();
   extern __shared__ uint8_t wide_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wide_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -132,6 +132,7 @@ flash_attn_wide_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_con
       }
       __syncwarp();
     }
+    pdl_launch_late();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = umma_idesc_op16(TC_BQ, TC_BKV);

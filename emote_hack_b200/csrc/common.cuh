@@ -63,6 +63,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // preceding grid has completed and its writes are visible).  Both are no-ops for launches without the attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Heavy (persistent / multi-stage) kernels: EMOTE_PDL_LATE moves their trigger from the first instruction to the point
+// where the CTA's producer warp has issued its last operand load, so that the dependent grid's CTAs only start to
+// arrive while this grid drains (their set-up overlaps the tail instead of competing with the main loop).
+#ifdef EMOTE_PDL_LATE
+__device__ __forceinline__ void pdl_launch_early() {}
+__device__ __forceinline__ void pdl_launch_late() { pdl_launch_dependents(); }
+#else
+__device__ __forceinline__ void pdl_launch_early() { pdl_launch_dependents(); }
+__device__ __forceinline__ void pdl_launch_late() {}
+#endif
 __device__ __forceinline__ void pdl_prologue() {
   pdl_launch_dependents();
   pdl_wait();

@@ -99,7 +99,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                           const GemmDev p) {
   using S = Gemm2Smem<BN, OUT_MODE>;
   constexpr bool TMA_OUT = OUT_MODE != 0;
-  pdl_launch_dependents();
+  pdl_launch_early();
   extern __shared__ uint8_t smem_raw2[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_out = smem + S::STAGES * S::STAGE_BYTES;
@@ -186,6 +186,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         }
       }
     }
+    pdl_launch_late();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer: one elected lane of the LEADER
     // CTA's warp 1 (warp-uniform loop)

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_bres_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, const GemmDev p, const int slots) {
   using S = BresSmem<BN, KB_MAX>;
-  pdl_launch_dependents();
+  pdl_launch_early();
   extern __shared__ uint8_t smem_raw_bres[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_bres) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;                         // resident weight panel: KB_MAX blocks of [BN rows][64 k] (128B swizzle)
@@ -103,6 +103,7 @@ gemm_bres_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
       }
     }
+    pdl_launch_late();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_op16(BM, BN);

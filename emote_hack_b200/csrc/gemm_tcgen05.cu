@@ -47,7 +47,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   constexpr bool TMA_OUT = OUT_MODE != 0;
   constexpr int EMODE = OUT_MODE == 3 ? 2 : OUT_MODE;   // epilogue flavour
   constexpr int NBUF = OUT_MODE == 3 ? 2 : 1;           // staging buffers
-  pdl_launch_dependents();
+  pdl_launch_early();
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024 B alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -131,6 +131,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
       }
     }
+    pdl_launch_late();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one
     // elected lane issues)

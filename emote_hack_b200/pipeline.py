@@ -305,6 +305,8 @@ def plan_units(n_windows: int, rank: int, world_size: int, shard: str = "units")
     one batch-2 call.  240 frames = 20 windows = 40 units -> 5 per rank on 8 GPUs (ideal 8x); one 16-frame clip = 2 units
     (<= 2x).  shard="windows": the reference's split, whole windows round-robin — `global_context[rank::world_size]`
     (EMOAnimationPipeline.py:757), 3,3,3,3,2,2,2,2 windows at 240 frames (<= 6.67x)."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} is not in [0, world_size = {world_size})")
     if shard == "windows":
         return [(w, "pair") for w in range(rank, n_windows, world_size)]
     if shard != "units":
@@ -348,6 +350,8 @@ class EMOAnimationPipeline:
         self.text_encoder, self.audio_encoder, self.speed_encoder = text_encoder, audio_encoder, speed_encoder
         self.appearance_encoder = appearance_encoder
         self.vae_scale_factor = 8
+        if world_size < 1 or not 0 <= rank < world_size:
+            raise ValueError(f"rank {rank} is not in [0, world_size = {world_size})")
         self.rank, self.world_size, self.process_group = rank, world_size, process_group
         self._graphs: "Dict[tuple, object]" = {}
         self.last_speed_embeddings = None

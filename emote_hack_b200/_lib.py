@@ -105,6 +105,7 @@ SIGNATURES = {
     "emote_scatter_add_frames": [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, _vp],
     "emote_fill_f32": [_vp, _f32, _i64, _vp],
     "emote_vae_postprocess": [_vp, _i32, _i32, _i32, _vp, _vp, _vp],
+    "emote_video_grid_u8": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
 }
 INTROSPECTION = {
     "emote_last_error": (C.c_char_p, []),

@@ -267,7 +267,39 @@ __global__ void vae_post_kernel(const float* __restrict__ tok, int n_img, int HW
     float v = tok[(img * HW + p) * ld + c] * 0.5f + 0.5f;
     v = fminf(fmaxf(v, 0.f), 1.f);
     if (of) of[i] = v;
-    if (ou) ou[i] = (uint8_t)(v * 255.0f + 0.5f);
+    if (ou) ou[i] = (uint8_t)(v * 255.0f);   // truncation, like `(x * 255).numpy().astype(np.uint8)` (magicanimate/utils/util.py:28)
+  }
+}
+
+// videos [b, c, t, h, w] fp32 -> uint8 [t, Hg, Wg, 3]: torchvision.utils.make_grid (nrow images per row, `pad` black pixels
+// around each; a single sample is returned without padding; one channel is replicated to three), optional
+// (x + 1) / 2, then the truncating uint8 cast — the frame loop of save_videos_grid (magicanimate/utils/util.py:21-30).
+__global__ void video_grid_kernel(const float* __restrict__ v, int b, int c, int t, int h, int w, int xmaps, int pad,
+                                  int Hg, int Wg, int rescale, uint8_t* __restrict__ out) {
+  pdl_prologue();
+  const long long total = (long long)t * Hg * Wg;
+  const int cell_h = h + pad, cell_w = w + pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int gx = (int)(i % Wg);
+    const int gy = (int)((i / Wg) % Hg);
+    const int f = (int)(i / ((long long)Wg * Hg));
+    int k = -1, py = 0, px = 0;
+    if (b == 1) {
+      k = 0; py = gy; px = gx;
+    } else {
+      const int cy = gy / cell_h, cx = gx / cell_w;
+      py = gy - cy * cell_h - pad;
+      px = gx - cx * cell_w - pad;
+      if (py >= 0 && px >= 0 && cx < xmaps && cy * xmaps + cx < b) k = cy * xmaps + cx;
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float x = 0.f;
+      if (k >= 0) x = v[((((long long)k * c + (c == 1 ? 0 : ch)) * t + f) * h + py) * w + px];
+      if (rescale) x = (x + 1.0f) / 2.0f;
+      out[i * 3 + ch] = (uint8_t)(int)(x * 255.0f);   // numpy's float -> uint8 cast: truncate, low 8 bits
+    }
   }
 }
 
@@ -460,5 +492,19 @@ extern "C" int emote_vae_postprocess(const float* tok, int32_t n_img, int32_t HW
   if (!tok || n_img <= 0 || HW <= 0 || ld < 3 || (!out_f32 && !out_u8)) return set_error("emote_vae_postprocess: bad arguments");
   launch_kernel(vae_post_kernel, dim3(grid_for((long long)n_img * 3 * HW, 256)), dim3(256), 0, STREAM(stream), tok, n_img, HW, ld, out_f32, out_u8);
   EMOTE_CHECK_LAUNCH("emote_vae_postprocess");
+  return 0;
+}
+
+extern "C" int emote_video_grid_u8(const float* videos, int32_t b, int32_t c, int32_t t, int32_t h, int32_t w, int32_t nrow,
+                                   int32_t padding, int32_t rescale, uint8_t* out, void* stream) {
+  if (!videos || !out || b <= 0 || (c != 1 && c != 3) || t <= 0 || h <= 0 || w <= 0 || nrow <= 0 || padding < 0)
+    return set_error("emote_video_grid_u8: bad arguments (channels must be 1 or 3)");
+  const int xmaps = nrow < b ? nrow : b;
+  const int ymaps = (b + xmaps - 1) / xmaps;
+  const int Hg = b == 1 ? h : (h + padding) * ymaps + padding;
+  const int Wg = b == 1 ? w : (w + padding) * xmaps + padding;
+  launch_kernel(video_grid_kernel, dim3(grid_for((long long)t * Hg * Wg, 256)), dim3(256), 0, STREAM(stream), videos, b, c, t,
+                h, w, xmaps, padding, Hg, Wg, rescale, out);
+  EMOTE_CHECK_LAUNCH("emote_video_grid_u8");
   return 0;
 }

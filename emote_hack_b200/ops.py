@@ -511,6 +511,21 @@ def vae_postprocess(tok: torch.Tensor, n_img: int, H: int, W: int, want_f32: boo
     return of, ou
 
 
+def video_grid_u8(videos: torch.Tensor, nrow: int = 6, padding: int = 2, rescale: bool = False) -> torch.Tensor:
+    """videos [b, c, t, h, w] fp32 -> uint8 [t, Hg, Wg, 3] frames (make_grid + truncating cast, utils/util.py:21-30)."""
+    _req(videos, F32, "video_grid_u8.videos")
+    if videos.dim() != 5 or videos.shape[1] not in (1, 3):
+        raise _lib.EmoteKernelError("video_grid_u8: videos must be [b, 1|3, t, h, w]")
+    b, c, t, h, w = videos.shape
+    xmaps = min(nrow, b)
+    ymaps = -(-b // xmaps)
+    hg, wg = (h, w) if b == 1 else ((h + padding) * ymaps + padding, (w + padding) * xmaps + padding)
+    out = torch.empty((t, hg, wg, 3), dtype=torch.uint8, device=videos.device)
+    check(_lib.load().emote_video_grid_u8(videos.data_ptr(), b, c, t, h, w, nrow, padding, int(bool(rescale)), out.data_ptr(),
+                                          _stream()), "emote_video_grid_u8")
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- audio front-end
 def wave_stats(wave: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
     _req(wave, F32, "wave_stats.wave")

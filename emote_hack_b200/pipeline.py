@@ -398,6 +398,25 @@ class EMOAnimationPipeline:
         mean = self.vae.encode(x)["latent_dist"].mean
         return (mean * self.vae.config.scaling_factor).to(dtype)
 
+    # -- EMOAnimationPipeline.py:479-512 ---------------------------------------------------------------------------
+    def interpolate_latents(self, latents: torch.Tensor, interpolation_factor: int, device=None) -> torch.Tensor:
+        """Insert `interpolation_factor - 1` blended frames between neighbouring latent frames with the method chosen by
+        `magicanimate.utils.util.set_tensor_interpolation_method` (linear / slerp).  The reference fixes the factor to 1
+        (:825), a no-op; larger factors are a cold path kept for API parity (a handful of tiny element-wise ops)."""
+        if interpolation_factor < 2:
+            return latents
+        from .magicanimate.utils.util import get_tensor_interpolation_method, linear
+        blend = get_tensor_interpolation_method() or linear
+        k, f = int(interpolation_factor), latents.shape[2]
+        out = latents.new_zeros((latents.shape[0], latents.shape[1], (f - 1) * k + 1) + tuple(latents.shape[3:]))
+        for j in range(f - 1):
+            v0, v1 = latents[:, :, j], latents[:, :, j + 1]
+            out[:, :, j * k] = v0
+            for r in range(1, k):
+                out[:, :, j * k + r] = blend(v0, v1, r / k)
+        out[:, :, (f - 1) * k] = latents[:, :, f - 1]
+        return out
+
     # -- EMOAnimationPipeline.py:379-400 ---------------------------------------------------------------------------
     @torch.no_grad()
     def next_step(self, model_output: torch.Tensor, timestep: int, x: torch.Tensor, eta: float = 0.0, verbose: bool = False):

@@ -235,9 +235,15 @@ int emote_scatter_add_frames(const float* src, float* dst, const int32_t* frame_
 /* p[0..n) = value (timestep scalar of a captured UNet step, accumulator clears) */
 int emote_fill_f32(float* p, float value, int64_t n, void* stream);
 /* decoded frames: tokens-major [n,H*W,ld>=3] fp32 -> clamp(x/2+0.5,0,1) as fp32 [n,3,H,W] and/or uint8 [n,3,H,W]
- * (EMOAnimationPipeline.py:304) */
+ * (EMOAnimationPipeline.py:304); the uint8 copy uses the truncating cast of the reference's writer (utils/util.py:28) */
 int emote_vae_postprocess(const float* tok, int32_t n_img, int32_t HW, int32_t ld, float* out_f32, uint8_t* out_u8,
                           void* stream);
+/* frames for the video writer — the loop of save_videos_grid (magicanimate/utils/util.py:21-30): videos [b,c,t,h,w]
+ * fp32 (c = 1 or 3) -> uint8 [t, Hg, Wg, 3] with torchvision.utils.make_grid's layout per frame (nrow samples per row,
+ * `padding` zero pixels around each; b == 1: no padding, Hg = h, Wg = w; else Hg = (h+padding)*ceil(b/min(nrow,b))+padding,
+ * Wg = (w+padding)*min(nrow,b)+padding), optional (x+1)/2, then numpy's truncating float->uint8 cast. */
+int emote_video_grid_u8(const float* videos, int32_t b, int32_t c, int32_t t, int32_t h, int32_t w, int32_t nrow,
+                        int32_t padding, int32_t rescale, uint8_t* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ audio front-end
  * wav2vec2-base forward behind `Wav2VecFeatureExtractor` (Net.py:607-667 -> transformers Wav2Vec2Model).

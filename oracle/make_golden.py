@@ -98,10 +98,59 @@ def make_speed_encoder_golden():
                 "centers": list(enc.bucket_centers), "radii": list(enc.bucket_radii)}, GOLD / "speed_encoder.pt")
 
 
+VIDEO_GRID_CASES = [  # (b, c, t, h, w, n_rows, rescale)
+    (3, 3, 2, 5, 7, 2, False), (1, 3, 3, 6, 4, 6, False), (7, 3, 1, 4, 4, 6, True), (2, 1, 2, 3, 5, 6, False),
+    (4, 3, 2, 8, 8, 4, True)]
+
+
+def make_video_grid_golden():
+    """Frames `save_videos_grid` (magicanimate/utils/util.py:21-33) hands to its writer, and `linear` / `slerp`
+    (:125-141), from the untouched reference file.  `imageio` is absent here: a stand-in module records the arguments of
+    `mimsave` (it performs no arithmetic)."""
+    import importlib.util
+    import tempfile
+    import types
+    rec = {}
+    fake = types.ModuleType("imageio")
+    fake.mimsave = lambda path, frames, fps=None, **kw: rec.update(frames=frames, fps=fps)
+    had = sys.modules.get("imageio")
+    sys.modules["imageio"] = fake
+    try:
+        spec = importlib.util.spec_from_file_location("_ref_util", "/root/reference/magicanimate/utils/util.py")
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        out = {"cases": []}
+        for i, (b, c, t, h, w, n_rows, rescale) in enumerate(VIDEO_GRID_CASES):
+            v = torch.rand(b, c, t, h, w, generator=torch.Generator().manual_seed(900 + i))
+            if rescale:
+                v = v * 2 - 1
+            with tempfile.TemporaryDirectory() as d:
+                ref.save_videos_grid(v.clone(), f"{d}/x/y.mp4", rescale=rescale, n_rows=n_rows, fps=25)
+            frames = torch.from_numpy(__import__("numpy").stack(rec["frames"]))
+            if frames.dim() == 3:
+                frames = frames[..., None]
+            out["cases"].append({"shape": (b, c, t, h, w), "n_rows": n_rows, "rescale": rescale, "seed": 900 + i,
+                                 "frames": frames, "fps": rec["fps"]})
+        g = torch.Generator().manual_seed(950)
+        v0, v1 = torch.randn(2, 4, 6, 6, generator=g), torch.randn(2, 4, 6, 6, generator=g)
+        out["interp"] = {"v0": v0, "v1": v1, "t": [0.25, 0.5, 0.8],
+                         "linear": [ref.linear(v0, v1, t) for t in (0.25, 0.5, 0.8)],
+                         "slerp": [ref.slerp(v0, v1, t) for t in (0.25, 0.5, 0.8)],
+                         "slerp_parallel": ref.slerp(v0, v0 * 1.5 + 1e-4 * v1, 0.3)}
+        torch.save(out, GOLD / "video_grid.pt")
+        print("video grid golden:", [tuple(c["frames"].shape) for c in out["cases"]])
+    finally:
+        if had is None:
+            sys.modules.pop("imageio", None)
+        else:
+            sys.modules["imageio"] = had
+
+
 def main():
     GOLD.mkdir(parents=True, exist_ok=True)
     make_ddim_golden()
     make_speed_encoder_golden()
+    make_video_grid_golden()
     make_cold_branch_golden()
     U = ref_shim.load_reference_unet_class()
     RC = ref_shim.load_reference_control_class()
@@ -205,5 +254,7 @@ if __name__ == "__main__":
         make_speed_encoder_golden()
     elif sys.argv[1:] == ["cold"]:
         make_cold_branch_golden()
+    elif sys.argv[1:] == ["util"]:
+        make_video_grid_golden()
     else:
         main()

@@ -34,8 +34,9 @@ with torch.cuda.graph(g):
 torch.cuda.synchronize()
 g.replay(); torch.cuda.synchronize()
 print("graph vs eager rel diff", ((out - ref).norm() / ref.norm()).item())
-e0.record()
-for _ in range(5):
-    g.replay()
-e1.record(); torch.cuda.synchronize()
-print(f"graph replay: device {e0.elapsed_time(e1)/5:.2f} ms/call")
+for rep in range(3):
+    e0.record()
+    for _ in range(20):
+        g.replay()
+    e1.record(); torch.cuda.synchronize()
+    print(f"graph replay: device {e0.elapsed_time(e1)/20:.3f} ms/call")

@@ -483,13 +483,42 @@ def test_cfg_ddim_step(ops):
     assert rel_l2(out, ref) < 1e-5
 
 
+def test_video_grid_frames_match_reference_writer_input(ops, tmp_path):
+    """emote_video_grid_u8 / save_videos_grid: byte-exact against the frames the reference's save_videos_grid
+    (utils/util.py:21-33) handed to imageio (tests/golden/video_grid.pt), and against the numpy oracle on a 512 x 512 clip"""
+    from pathlib import Path
+    import numpy as np
+    from emote_hack_b200.magicanimate.utils import util
+    from oracle import video_grid
+    gold = torch.load(Path(__file__).parent / "golden" / "video_grid.pt")
+    for case in gold["cases"]:
+        v = torch.rand(*case["shape"], generator=torch.Generator().manual_seed(case["seed"]))
+        v = v * 2 - 1 if case["rescale"] else v
+        got = util.video_frames_u8(v.cuda(), case["rescale"], case["n_rows"])
+        assert got.shape == case["frames"].shape and torch.equal(got.cpu(), case["frames"]), case["shape"]
+    v = torch.rand(2, 3, 4, 512, 512, generator=torch.Generator().manual_seed(5))
+    v[0, 0, 0, 0, :4] = torch.tensor([1.0, 0.0, 254.999 / 255, 1e-9])
+    got = util.video_frames_u8(v.cuda(), False, 6).cpu().numpy()
+    assert np.array_equal(got, video_grid.video_frames_u8(v.numpy(), False, 6))
+    assert util.save_videos_grid(v.cuda(), str(tmp_path / "out" / "clip.npy")) in ("numpy", "imageio")
+    back = util.video2images(str(tmp_path / "out" / "clip.npy"), step=1, length=8)
+    assert len(back) == 4 and np.array_equal(np.stack(back), got)
+    util.save_images_grid(v[:, :, :1].cuda(), str(tmp_path / "grid.png"))
+    from PIL import Image
+    png = np.asarray(Image.open(tmp_path / "grid.png"))
+    assert np.array_equal(png, video_grid.video_frames_u8(v[:, :, :1].numpy(), False, 8)[0])
+    with pytest.raises(Exception):
+        ops.video_grid_u8(torch.zeros(1, 2, 1, 4, 4, device="cuda"))
+
+
 def test_vae_postprocess(ops):
     g = _gen(17)
     tok = torch.randn(2 * 64, 4, device="cuda", generator=g)
     of, ou = ops.vae_postprocess(tok, 2, 8, 8, want_f32=True, want_u8=True)
     ref = (tok[:, :3].view(2, 64, 3).permute(0, 2, 1).reshape(2, 3, 8, 8) / 2 + 0.5).clamp(0, 1)
     assert torch.allclose(of, ref, atol=1e-6)
-    assert (ou.float() - ref * 255).abs().max() <= 0.5 + 1e-3
+    assert torch.equal(ou, (of * 255).to(torch.uint8))   # the reference's truncating cast (utils/util.py:28)
+    assert (ou.float() - ref * 255).abs().max() <= 1.0 + 1e-3
 
 
 def test_errors_are_loud(ops):

@@ -310,3 +310,60 @@ def test_vae_oracle_shapes():
     sd2 = {k.replace(".query.", ".to_q.").replace(".key.", ".to_k.").replace(".value.", ".to_v.").replace(".proj_attn.", ".to_out.0."): v
            for k, v in sd.items()}
     assert torch.equal(VAEDecoderOracle(sd2).decode_latents(lat), v)
+
+
+def _video_case_input(case):
+    v = torch.rand(*case["shape"], generator=torch.Generator().manual_seed(case["seed"]))
+    return v * 2 - 1 if case["rescale"] else v
+
+
+def test_video_grid_restatement_pinned_on_reference_frames():
+    """oracle/video_grid.py against the frames the reference's save_videos_grid (utils/util.py:21-33) handed to its writer,
+    and against torchvision.make_grid itself"""
+    import torchvision
+    from oracle import video_grid
+    gold = torch.load(GOLD / "video_grid.pt")
+    for case in gold["cases"]:
+        v = _video_case_input(case)
+        got = video_grid.video_frames_u8(v.numpy(), case["rescale"], case["n_rows"])
+        assert got.shape == tuple(case["frames"].shape) and np.array_equal(got, case["frames"].numpy()), case["shape"]
+        assert case["fps"] == 25
+        tv = torchvision.utils.make_grid(v[:, :, 0], nrow=case["n_rows"]).numpy()
+        assert np.array_equal(video_grid.make_grid(v[:, :, 0].numpy(), case["n_rows"]), tv)
+    it = gold["interp"]
+    for i, t in enumerate(it["t"]):
+        assert np.allclose(video_grid.linear(it["v0"].numpy(), it["v1"].numpy(), t), it["linear"][i].numpy(), atol=1e-6)
+        assert np.allclose(video_grid.slerp(it["v0"].numpy(), it["v1"].numpy(), t), it["slerp"][i].numpy(), atol=1e-5)
+
+
+def test_latent_interpolation_helpers_and_frame_files(tmp_path):
+    """host side of the frames -> file step: linear / slerp (utils/util.py:125-141) against the reference's outputs,
+    `interpolate_latents` (EMOAnimationPipeline.py:479-512) against a direct loop, and the writer / reader pair"""
+    from emote_hack_b200.magicanimate.utils import util
+    from emote_hack_b200.pipeline import EMOAnimationPipeline
+    it = torch.load(GOLD / "video_grid.pt")["interp"]
+    for i, t in enumerate(it["t"]):
+        assert torch.allclose(util.linear(it["v0"], it["v1"], t), it["linear"][i], atol=1e-6)
+        assert torch.allclose(util.slerp(it["v0"], it["v1"], t), it["slerp"][i], atol=1e-5)
+    assert torch.allclose(util.slerp(it["v0"], it["v0"] * 1.5 + 1e-4 * it["v1"], 0.3), it["slerp_parallel"], atol=1e-6)
+
+    pipe = EMOAnimationPipeline.__new__(EMOAnimationPipeline)   # interpolate_latents uses no state
+    lat = torch.randn(1, 4, 3, 2, 2, generator=torch.Generator().manual_seed(3))
+    assert pipe.interpolate_latents(lat, 1) is lat              # the reference's fixed factor (:825): no-op
+    for is_slerp in (False, True):
+        util.set_tensor_interpolation_method(is_slerp)
+        out = pipe.interpolate_latents(lat, 3)
+        assert out.shape == (1, 4, 7, 2, 2)
+        fn = util.slerp if is_slerp else util.linear
+        assert torch.equal(out[:, :, 0], lat[:, :, 0]) and torch.equal(out[:, :, 3], lat[:, :, 1]) and torch.equal(out[:, :, 6], lat[:, :, 2])
+        assert torch.allclose(out[:, :, 4], fn(lat[:, :, 1], lat[:, :, 2], 1 / 3), atol=1e-6)
+    util.set_tensor_interpolation_method(False)
+
+    frames = (np.random.default_rng(0).random((5, 16, 24, 3)) * 255).astype(np.uint8)
+    for name in ("a/clip.npy", "clip.gif", "clip.avi"):
+        util.images2video(list(frames), str(tmp_path / name), fps=8)
+        assert (tmp_path / name).stat().st_size > 0
+    back = util.video2images(str(tmp_path / "a/clip.npy"), step=2, length=2, start=1)
+    assert len(back) == 2 and np.array_equal(back[0], frames[1]) and np.array_equal(back[1], frames[3])
+    avi = util.video2images(str(tmp_path / "clip.avi"), step=1, length=16)
+    assert len(avi) == 5 and avi[0].shape == (16, 24, 3)      # MJPG is lossy: only the geometry is checked

@@ -6,7 +6,7 @@ import torch
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from emote_hack_b200 import ops
-BF16 = torch.bfloat16
+BF16 = ops.OP16   # operand type of the loaded build
 TS = int(os.environ.get('TMA_STORE', '0'))
 PM = int(os.environ.get('PAIR', '0'))
 ops.FORCE_BLOCK_N = int(os.environ.get('BLOCK_N', '0'))

@@ -177,7 +177,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
               if (c1ok) { const float2 r2 = *reinterpret_cast<const float2*>(rp); v0 = r2.x; v1 = r2.y; }
               else if (c0ok) v0 = rp[0];
             }
-            if (OUT_MODE != 2 && has_rb) {   // (mode 2 folds the tile's per-sample bias into the column bias below)
+            if (has_rb) {
               const float* bp = p.row_bias + (size_t)(row / p.rows_per_group) * p.N + col;
               if (c1ok) { const float2 r2 = *reinterpret_cast<const float2*>(bp); v0 += r2.x; v1 += r2.y; }
               else if (c0ok) v0 += bp[0];
@@ -237,7 +237,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
           const int lr = quarter * 32 + g + 8 * i, lc = (c_first + ci) * 8 + 2 * t;
           sp = reinterpret_cast<float*>(stage_) + (lc >> 5) * (BM * 32) + lr * 32 +
                ((((lc & 31) >> 2) ^ (lr & 7)) << 2) + (lc & 3);
-          if (!HAS_ADD && p.residual) {   // residual tile TMA-loaded into the staging boxes (HAS_ADD: it came through registers)
+          if (p.residual) {
             const float2 r2 = *reinterpret_cast<const float2*>(sp);
             v0 += r2.x; v1 += r2.y;
           }

@@ -192,7 +192,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // as soon as the bulk store that last used them has been read; the epilogue warps wait on res_full[buf] before
     // touching them.  Mode 2 has one buffer (load of tile i+1 after the store of tile i); mode 3 has two (the load of
     // tile i+2 follows the store of tile i, so the residual of tile i+1 is already resident when its epilogue starts).
-    const bool res_tma = EMODE == 2 && !HAS_ADD && p.residual != nullptr;
+    const bool res_tma = EMODE == 2 && p.residual != nullptr;
     uint32_t rphase[2] = {0, 0};
     constexpr int NBOX = BN / 32;
     auto load_residual = [&](int tile, int buf) {
@@ -324,7 +324,6 @@ static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   if constexpr (BN == 128) {
     if (out_mode == 3) return launch_gemm<BN, 16, false, 3>(tmA, tmB, tmC, tmR, p, stream);
   }
-  if (out_mode == 5) return launch_gemm<BN, 8, true, 2>(tmA, tmB, tmC, tmR, p, stream);
   if (out_mode >= 2) return launch_gemm<BN, 16, false, 2>(tmA, tmB, tmC, tmR, p, stream);
   if (!p.geglu && (p.residual != nullptr || p.row_bias != nullptr))
     return launch_gemm<BN, 8, true, 0>(tmA, tmB, tmC, tmR, p, stream);
@@ -454,9 +453,6 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
       out_mode = p.patch ? 0 : 1;   // patch mode: 16-bit outputs leave through the register path
     } else if (mode2_ok && !patch_rowbias_per_row && (a->K <= 4096 || want3)) {
       out_mode = want3 ? 3 : 2;
-      // experimental (tma_store == 5): residual prefetched through registers before the accumulator wait, result staged
-      // and bulk-stored — the staging buffer no longer carries the residual, so nothing waits for a TMA load
-      if (a->tma_store == 5 && !use_pair && p.residual) out_mode = 5;
     }
   }
   if (out_mode == 1) {

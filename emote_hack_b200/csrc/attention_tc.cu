@@ -258,7 +258,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
       // P buffer j&1 was read by P V (j-2)
       if (j >= 2) mbar_wait(&o_done[j & 1], ((j - 2) >> 1) & 1);
       const float nmsc = -(m_used * sc);
-      uint8_t* prow = sP + (j & 1) * C::P_BYTES + row * 128;
+      // row r of the P tile is 128 B; its 16-byte chunk c lives at chunk c ^ (r & 7) (128B swizzle): one XOR per store
+      const uint32_t prow = (smem_u32(sP) + (j & 1) * C::P_BYTES + row * 128) ^ ((row & 7) << 4);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float pv[8];
@@ -276,10 +277,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
             pv[k + 1] = ex2f(x1);
           }
         }
-        uint4 w;
-        w.x = pack_op16x2(pv[0], pv[1]); w.y = pack_op16x2(pv[2], pv[3]);
-        w.z = pack_op16x2(pv[4], pv[5]); w.w = pack_op16x2(pv[6], pv[7]);
-        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = w;
+        sts128(prow ^ (c << 4), pack_op16x2(pv[0], pv[1]), pack_op16x2(pv[2], pv[3]), pack_op16x2(pv[4], pv[5]),
+               pack_op16x2(pv[6], pv[7]));
       }
       fence_proxy_async();
       tc_fence_before();

@@ -24,6 +24,10 @@ constexpr int TC_STAGES = 3;   // K/V ring
 
 constexpr int TC_THREADS = 192;  // warp0 loader, warp1 MMA, warps 2-5 softmax
 
+// 16-byte store through the shared window (32-bit address: no generic-address arithmetic in the P-tile loop)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");

@@ -93,18 +93,23 @@ struct Gemm2Smem {
 };
 
 template <int BN, int EPI_WARPS, bool HAS_ADD, int OUT_MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS + (OUT_MODE == 2 ? 32 : 0), 1)
 gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                           const GemmDev p) {
   using S = Gemm2Smem<BN, OUT_MODE>;
   constexpr bool TMA_OUT = OUT_MODE != 0;
+  constexpr bool SPLIT = OUT_MODE == 2;     // store warp (warp 2) + column halves: see gemm_tcgen05.cu
+  constexpr int FIRST_EPI = SPLIT ? 3 : 2;
+  constexpr int NBOX = BN / 32;
+  constexpr int NB_A = (NBOX + 1) / 2;
   pdl_launch_early();
   extern __shared__ uint8_t smem_raw2[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_out = smem + S::STAGES * S::STAGE_BYTES;
   uint8_t* bar_base = smem + S::STAGES * S::STAGE_BYTES + S::OUT_BYTES;
-  uint64_t* res_full = reinterpret_cast<uint64_t*>(bar_base + 192);  // per CTA: residual boxes landed (mode 2)
+  uint64_t* res_full = reinterpret_cast<uint64_t*>(bar_base + 192);  // [2] per CTA, mode 2: column half i of the staging buffer is armed
+  uint64_t* half_done = reinterpret_cast<uint64_t*>(bar_base + 208); // [2] per CTA, mode 2: the epilogue warps finished column half i
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);   // used in the leader: bytes of BOTH CTAs
   uint64_t* empty_bar = full_bar + S::STAGES;                    // per CTA, multicast commit
   uint64_t* tmem_full = empty_bar + S::STAGES;                   // per CTA, multicast commit
@@ -127,7 +132,10 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 2 * EPI_WARPS);
     }
-    mbar_init(res_full, 1);
+    mbar_init(&res_full[0], 1);
+    mbar_init(&res_full[1], 1);
+    mbar_init(&half_done[0], EPI_WARPS);
+    mbar_init(&half_done[1], EPI_WARPS);
     mbar_fence_init();
   }
   cluster_sync_all();  // barriers of both CTAs are initialised before anyone signals across the pair
@@ -228,6 +236,95 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         }
       }
     }
+  } else if (SPLIT && warp == 2) {
+    // ------------------------------------------------------------------ mode 2: store warp of this CTA (one lane)
+    if (lane == 0) {
+      const bool has_res = p.residual != nullptr;
+      auto row_base_of = [&](int tile) { return (tile / p.tiles_n) * (2 * BM) + static_cast<int>(rank) * BM; };
+      auto arm = [&](int tile, int h) {
+        const int tn = tile % p.tiles_n;
+        const int b0 = h ? NB_A : 0, b1 = h ? NBOX : NB_A;
+        int nb = 0;
+        for (int b = b0; b < b1; ++b) nb += (tn * BN + b * 32 < p.N) ? 1 : 0;
+        if (!has_res || nb == 0) {
+          mbar_arrive(&res_full[h]);
+          return;
+        }
+        mbar_expect_tx(&res_full[h], static_cast<uint32_t>(nb) * (BM * 128));
+        for (int b = b0; b < b0 + nb; ++b)
+          tile_box_load(p, stage_out + b * (BM * 128), &tmR, &res_full[h], tn * BN + b * 32, row_base_of(tile));
+      };
+      auto prefetch = [&](int tile) {
+        if (!has_res || tile >= num_tiles) return;
+        const int ntn = tile % p.tiles_n;
+        for (int b = 0; b < NBOX; ++b)
+          if (ntn * BN + b * 32 < p.N) tile_box_prefetch(p, &tmR, ntn * BN + b * 32, row_base_of(tile));
+      };
+      if (pair < num_tiles) {
+        arm(pair, 0);
+        arm(pair, 1);
+      }
+      uint32_t dphase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int tn = tile % p.tiles_n;
+        const int row_base = row_base_of(tile);
+        const bool rows_ok = p.patch ? (row_base / BM < p.subtiles) : (row_base < p.M);   // the second CTA of the last pair may own no valid rows
+        const int nxt = tile + num_pairs;
+        prefetch(nxt);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&half_done[h], dphase);
+          const int b0 = h ? NB_A : 0, b1 = h ? NBOX : NB_A;
+          for (int b = b0; b < b1; ++b)
+            if (rows_ok && tn * BN + b * 32 < p.N)
+              tile_box_store(p, &tmC, stage_out + b * (BM * 128), tn * BN + b * 32, row_base);
+          bulk_commit();
+          if (nxt < num_tiles) {
+            bulk_wait_read0();
+            arm(nxt, h);
+          }
+        }
+        dphase ^= 1;
+      }
+      bulk_wait0();
+    }
+  } else if (SPLIT) {
+    // ------------------------------------------------------------------ mode 2: epilogue warps, two column halves per tile
+    const int quarter = warp & 3;
+    const int part = (warp - FIRST_EPI) >> 2;
+    constexpr int COLS_A = NB_A * 32;
+    int as = 0;
+    uint32_t aphase = 0, rphase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int tm = tile / p.tiles_n;
+      const int tn = tile - tm * p.tiles_n;
+      const int row_base = tm * (2 * BM) + static_cast<int>(rank) * BM;
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
+      mbar_wait(&res_full[0], rphase);
+      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, 2, 0, COLS_A>(p, tbase, row_base, tn * BN, tn, quarter, part, lane, stage_out,
+                                                               [&]() {
+                                                                 mbar_wait(&tmem_full[as], aphase);
+                                                                 tc_fence_after();
+                                                               });
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&half_done[0]);
+      mbar_wait(&res_full[1], rphase);
+      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, 2, COLS_A, BN - COLS_A>(p, tbase, row_base, tn * BN, tn, quarter, part, lane,
+                                                                         stage_out, []() {});
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(mapa_shared(&tmem_empty[as], 0));
+        mbar_arrive(&half_done[1]);
+      }
+      rphase ^= 1;
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
   } else {
     // ------------------------------------------------------------------ epilogue warps (each CTA drains its 128 rows)
     const int ew = warp - 2;
@@ -240,16 +337,30 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const bool res_tma = OUT_MODE == 2 && p.residual != nullptr;
     uint32_t rphase = 0;
     constexpr int NBOX = BN / 32;
-    auto load_residual = [&](int tile) {
+    auto load_residual = [&](int tile, bool after_store) {   // after_store: one bulk group per box was just committed
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
       const int rb = tm * (2 * BM) + static_cast<int>(rank) * BM;
       int nb = 0;
       for (int b = 0; b < NBOX; ++b) nb += (tn * BN + b * 32 < p.N) ? 1 : 0;
       mbar_expect_tx(res_full, static_cast<uint32_t>(nb) * (BM * 128));
-      for (int b = 0; b < nb; ++b) tile_box_load(p, stage_out + b * (BM * 128), &tmR, res_full, tn * BN + b * 32, rb);
+#pragma unroll
+      for (int b = 0; b < NBOX; ++b) {
+        if (after_store) bulk_wait_read_n(NBOX - 1 - b);
+        if (b < nb) tile_box_load(p, stage_out + b * (BM * 128), &tmR, res_full, tn * BN + b * 32, rb);
+      }
     };
-    if (res_tma && threadIdx.x == 64 && pair < num_tiles) load_residual(pair);
+    auto prefetch_residual = [&](int tile) {   // L2 prefetch of a later tile's residual boxes (see gemm_tcgen05.cu)
+      if (tile >= num_tiles) return;
+      const int ntm = tile / p.tiles_n, ntn = tile - ntm * p.tiles_n;
+      const int nrb = ntm * (2 * BM) + static_cast<int>(rank) * BM;
+      for (int b = 0; b < NBOX; ++b)
+        if (ntn * BN + b * 32 < p.N) tile_box_prefetch(p, &tmR, ntn * BN + b * 32, nrb);
+    };
+    if (res_tma && threadIdx.x == 64 && pair < num_tiles) {
+      load_residual(pair, false);
+      for (int k = 1; k < p.res_pf; ++k) prefetch_residual(pair + k * num_pairs);
+    }
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
@@ -257,12 +368,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
       if constexpr (TMA_OUT) {
         if (res_tma) {
-          if (threadIdx.x == 64 && tile + num_pairs < num_tiles) {  // next tile's residual -> L2 (see gemm_tcgen05.cu)
-            const int nt = tile + num_pairs, ntm = nt / p.tiles_n, ntn = nt - ntm * p.tiles_n;
-            const int nrb = ntm * (2 * BM) + static_cast<int>(rank) * BM;
-            for (int b = 0; b < NBOX; ++b)
-              if (ntn * BN + b * 32 < p.N) tile_box_prefetch(p, &tmR, ntn * BN + b * 32, nrb);
-          }
+          if (threadIdx.x == 64) prefetch_residual(tile + p.res_pf * num_pairs);
           mbar_wait(res_full, rphase);
           rphase ^= 1;
         } else if (!first_tile) {
@@ -283,19 +389,19 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         fence_proxy_async_smem();
         named_bar_sync(1, EPI_WARPS * 32);
         if (threadIdx.x == 64) {
-          if (p.patch ? (row_base / BM < p.subtiles) : (row_base < p.M)) {   // the second CTA of the last pair may own no valid rows
-            if constexpr (OUT_MODE == 1) {
-              store_bf16_boxes<BN>(&tmC, stage_out, p, tn, row_base);
-            } else {
-              for (int b = 0; b < NBOX; ++b)
-                if (tn * BN + b * 32 < p.N) tile_box_store(p, &tmC, stage_out + b * (BM * 128), tn * BN + b * 32, row_base);
+          const bool rows_ok = p.patch ? (row_base / BM < p.subtiles) : (row_base < p.M);   // the second CTA of the last pair may own no valid rows
+          if constexpr (OUT_MODE == 1) {
+            if (rows_ok) store_bf16_boxes<BN>(&tmC, stage_out, p, tn, row_base);
+            bulk_commit();
+          } else {
+#pragma unroll
+            for (int b = 0; b < NBOX; ++b) {   // one bulk group per box (possibly empty)
+              if (rows_ok && tn * BN + b * 32 < p.N)
+                tile_box_store(p, &tmC, stage_out + b * (BM * 128), tn * BN + b * 32, row_base);
+              bulk_commit();
             }
           }
-          bulk_commit();
-          if (res_tma && tile + num_pairs < num_tiles) {
-            bulk_wait_read0();
-            load_residual(tile + num_pairs);
-          }
+          if (res_tma && tile + num_pairs < num_tiles) load_residual(tile + num_pairs, true);
         }
       }
       if (++as == 2) {
@@ -340,7 +446,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   }
   const int max_pairs = g2_num_sms / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  launch_kernel(gemm2_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, OUT_MODE>, dim3(2 * pairs), dim3(64 + 32 * EPI_WARPS), S::TOTAL, stream, tmA, tmB, tmC, tmR, p);
+  launch_kernel(gemm2_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, OUT_MODE>, dim3(2 * pairs), dim3(64 + 32 * EPI_WARPS + (OUT_MODE == 2 ? 32 : 0)), S::TOTAL, stream, tmA, tmB, tmC, tmR, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error_cuda("gemm2 launch", e);
   count_launch();

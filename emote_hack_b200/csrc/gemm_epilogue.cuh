@@ -35,6 +35,7 @@ struct GemmDev {
   float* colstats;   // optional fused GroupNorm statistics of the fp32 output, else null: one (sum, sum of squares) slot per
                      // 32-row quarter of a sub-tile and column, [sub-tiles * 4][N][2] fp32, written with plain stores
   int stats_rows;    // rows per statistics batch (validated on the host: a 32-row quarter never straddles two batches)
+  int res_pf;        // modes 2/3: how many tiles ahead of the staging-buffer load the fp32 residual is prefetched into L2 (>= 1)
 };
 
 
@@ -135,7 +136,9 @@ __device__ __forceinline__ void store_bf16_boxes(const CUtensorMap* tmC, const u
 // OUT_MODE 2: fp32 results; `stage` holds BN/32 boxes of [128 rows][32 floats] in the TMA 128-byte swizzle.  When
 //             p.residual is set the caller has TMA-loaded the fp32 residual tile into the same boxes: the epilogue
 //             adds in place and the caller bulk-stores the boxes (the residual stream never touches the LSU path).
-template <int BN, int EPI_WARPS, bool HAS_ADD, int OUT_MODE, class WaitFull>
+// COL0 / NCOLS (multiples of 32; linear epilogue only): restrict the call to tile columns [COL0, COL0 + NCOLS) — the split
+// mode-2 pipeline finishes and stores a tile in two column halves.
+template <int BN, int EPI_WARPS, bool HAS_ADD, int OUT_MODE, int COL0 = 0, int NCOLS = BN, class WaitFull>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tbase, int row_base, int n0, int tn,
                                                    int quarter, int part, int lane, void* stage_, WaitFull wait_full) {
   constexpr bool TMA_OUT = OUT_MODE == 1;
@@ -152,10 +155,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, uint32_t tb
   const int first_row = tile_global_row(p, row_base, 0);   // selects the tile's bias group / statistics batch
 
   if (!p.geglu) {
-    constexpr int NCT = BN / 8;                     // 8-column chunks in the tile
+    constexpr int NCT = NCOLS / 8;                  // 8-column chunks in the (sub-)tile
     constexpr int NCH = NCT / NP;                   // contiguous chunks per warp
     static_assert(NCT % NP == 0, "tile columns must split evenly over the warps of a lane quarter");
-    const int c_first = part * NCH;
+    const int c_first = COL0 / 8 + part * NCH;
     size_t ooff[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) ooff[i] = (size_t)(rok[i] ? rows[i] : 0) * p.ldc;

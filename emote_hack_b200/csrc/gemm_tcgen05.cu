@@ -22,6 +22,10 @@ namespace emote {
 //            registers BEFORE waiting for the accumulator, so ~80 KB/SM of residual reads overlap the main loop;
 //   plain / GEGLU: 16 epilogue warps (4 per TMEM lane quarter) to hide TMEM and issue latency.
 constexpr int gemm_threads(int epi_warps) { return 64 + 32 * epi_warps; }
+// mode 2 (fp32 result staged for TMA stores, residual staged in by TMA) adds warp 2 = store warp: it bulk-stores each column
+// half of a finished tile and re-arms that half of the staging buffer (next tile's residual boxes) while the epilogue warps
+// work on the other half, so nobody waits for a whole-tile store -> reload round trip.
+constexpr int gemm_threads_mode(int epi_warps, int out_mode) { return gemm_threads(epi_warps) + (out_mode == 2 ? 32 : 0); }
 
 template <int BN, int OUT_MODE = 0>
 struct GemmSmem {
@@ -39,7 +43,7 @@ struct GemmSmem {
 };
 
 template <int BN, int EPI_WARPS, bool HAS_ADD, int OUT_MODE>
-__global__ void __launch_bounds__(gemm_threads(EPI_WARPS), 1)
+__global__ void __launch_bounds__(gemm_threads_mode(EPI_WARPS, OUT_MODE), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                          const GemmDev p) {
@@ -47,6 +51,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   constexpr bool TMA_OUT = OUT_MODE != 0;
   constexpr int EMODE = OUT_MODE == 3 ? 2 : OUT_MODE;   // epilogue flavour
   constexpr int NBUF = OUT_MODE == 3 ? 2 : 1;           // staging buffers
+  constexpr bool SPLIT = OUT_MODE == 2;                 // store warp + column halves (see gemm_threads_mode)
+  constexpr int FIRST_EPI = SPLIT ? 3 : 2;              // first epilogue warp
+  constexpr int NBOX = BN / 32;                         // fp32 staging boxes of [128 rows][32 columns] per tile
+  constexpr int NB_A = (NBOX + 1) / 2;                  // boxes in column half 0 (3 of 5 at BN = 160)
   pdl_launch_early();
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024 B alignment.
@@ -58,7 +66,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* tmem_full = empty_bar + S::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint64_t* res_full = reinterpret_cast<uint64_t*>(bar_base + 192);  // [2] modes 2/3: residual boxes landed in staging buffer i
+  uint64_t* res_full = reinterpret_cast<uint64_t*>(bar_base + 192);  // [2] mode 3: residual boxes landed in staging buffer i;
+                                                                     //     mode 2: column half i of the buffer is armed
+  uint64_t* half_done = reinterpret_cast<uint64_t*>(bar_base + 208); // [2] mode 2: the epilogue warps finished column half i
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -76,6 +86,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     mbar_init(&res_full[0], 1);
     mbar_init(&res_full[1], 1);
+    mbar_init(&half_done[0], EPI_WARPS);
+    mbar_init(&half_done[1], EPI_WARPS);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -175,6 +187,96 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
       }
     }
+  } else if (SPLIT && warp == 2) {
+    // ------------------------------------------------------------------ mode 2: store warp (one lane)
+    // Column half h of the staging buffer = boxes [h ? NB_A : 0, h ? NBOX : NB_A).  res_full[h] completes when half h is
+    // armed for the next tile: its residual boxes have landed (arrive.expect_tx + TMA loads), or — no residual / no
+    // valid box — the previous store has been read (plain arrive).  half_done[h] completes when all epilogue warps have
+    // finished half h (their staging writes fenced for the async proxy).
+    if (lane == 0) {
+      const bool has_res = p.residual != nullptr;
+      auto arm = [&](int tile, int h) {
+        const int tm = tile / p.tiles_n;
+        const int tn = tile - tm * p.tiles_n;
+        const int b0 = h ? NB_A : 0, b1 = h ? NBOX : NB_A;
+        int nb = 0;
+        for (int b = b0; b < b1; ++b) nb += (tn * BN + b * 32 < p.N) ? 1 : 0;
+        if (!has_res || nb == 0) {
+          mbar_arrive(&res_full[h]);
+          return;
+        }
+        mbar_expect_tx(&res_full[h], static_cast<uint32_t>(nb) * (BM * 128));
+        for (int b = b0; b < b0 + nb; ++b)
+          tile_box_load(p, stage_out + b * (BM * 128), &tmR, &res_full[h], tn * BN + b * 32, tm * BM);
+      };
+      auto prefetch = [&](int tile) {   // residual boxes of a later tile -> L2
+        if (!has_res || tile >= num_tiles) return;
+        const int ntm = tile / p.tiles_n, ntn = tile - ntm * p.tiles_n;
+        for (int b = 0; b < NBOX; ++b)
+          if (ntn * BN + b * 32 < p.N) tile_box_prefetch(p, &tmR, ntn * BN + b * 32, ntm * BM);
+      };
+      if (static_cast<int>(blockIdx.x) < num_tiles) {
+        arm(blockIdx.x, 0);
+        arm(blockIdx.x, 1);
+      }
+      uint32_t dphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / p.tiles_n;
+        const int tn = tile - tm * p.tiles_n;
+        const int nxt = tile + static_cast<int>(gridDim.x);
+        prefetch(nxt);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&half_done[h], dphase);
+          const int b0 = h ? NB_A : 0, b1 = h ? NBOX : NB_A;
+          for (int b = b0; b < b1; ++b)
+            if (tn * BN + b * 32 < p.N) tile_box_store(p, &tmC, stage_out + b * (BM * 128), tn * BN + b * 32, tm * BM);
+          bulk_commit();
+          if (nxt < num_tiles) {
+            bulk_wait_read0();   // the boxes of this half (and anything older) have been read: they may be overwritten
+            arm(nxt, h);
+          }
+        }
+        dphase ^= 1;
+      }
+      bulk_wait0();
+    }
+  } else if (SPLIT) {
+    // ------------------------------------------------------------------ mode 2: epilogue warps, two column halves per tile
+    const int quarter = warp & 3;
+    const int part = (warp - FIRST_EPI) >> 2;
+    constexpr int COLS_A = NB_A * 32;
+    int as = 0;
+    uint32_t aphase = 0, rphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile / p.tiles_n;
+      const int tn = tile - tm * p.tiles_n;
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
+      mbar_wait(&res_full[0], rphase);
+      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, 2, 0, COLS_A>(p, tbase, tm * BM, tn * BN, tn, quarter, part, lane, stage_out,
+                                                               [&]() {
+                                                                 mbar_wait(&tmem_full[as], aphase);
+                                                                 tc_fence_after();
+                                                               });
+      fence_proxy_async_smem();   // staging writes -> visible to the TMA (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&half_done[0]);
+      mbar_wait(&res_full[1], rphase);
+      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, 2, COLS_A, BN - COLS_A>(p, tbase, tm * BM, tn * BN, tn, quarter, part, lane,
+                                                                         stage_out, []() {});
+      tc_fence_before();          // release the accumulator stage back to the MMA warp
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tmem_empty[as]);
+        mbar_arrive(&half_done[1]);
+      }
+      rphase ^= 1;
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
   } else {
     // ------------------------------------------------------------------ epilogue warps (TMEM -> regs -> global)
     // EPI_WARPS warps: warp w may touch TMEM lanes 32*(w%4)..+31; the warps of a lane quarter take the 8-column
@@ -195,18 +297,33 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const bool res_tma = EMODE == 2 && p.residual != nullptr;
     uint32_t rphase[2] = {0, 0};
     constexpr int NBOX = BN / 32;
-    auto load_residual = [&](int tile, int buf) {
+    // `after_store`: the buffer's boxes were just bulk-stored, one group per box — box b is reloaded as soon as ITS store
+    // has been read instead of after the whole tile's
+    auto load_residual = [&](int tile, int buf, bool after_store) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
       int nb = 0;
       for (int b = 0; b < NBOX; ++b) nb += (tn * BN + b * 32 < p.N) ? 1 : 0;
       mbar_expect_tx(&res_full[buf], static_cast<uint32_t>(nb) * (BM * 128));
-      for (int b = 0; b < nb; ++b)
-        tile_box_load(p, stage_out + buf * S::OUT_BUF + b * (BM * 128), &tmR, &res_full[buf], tn * BN + b * 32, tm * BM);
+#pragma unroll
+      for (int b = 0; b < NBOX; ++b) {
+        if (after_store) bulk_wait_read_n(NBOX - 1 - b);
+        if (b < nb)
+          tile_box_load(p, stage_out + buf * S::OUT_BUF + b * (BM * 128), &tmR, &res_full[buf], tn * BN + b * 32, tm * BM);
+      }
+    };
+    // L2 prefetch of the residual boxes of a later tile: the staging buffers are (re)loaded from L2, and HBM keeps streaming
+    // while the CTAs sit in the add / store phases (all CTAs run those phases in lockstep)
+    auto prefetch_residual = [&](int tile) {
+      if (tile >= num_tiles) return;
+      const int ntm = tile / p.tiles_n, ntn = tile - ntm * p.tiles_n;
+      for (int b = 0; b < NBOX; ++b)
+        if (ntn * BN + b * 32 < p.N) tile_box_prefetch(p, &tmR, ntn * BN + b * 32, ntm * BM);
     };
     if (res_tma && threadIdx.x == 64) {
       for (int k = 0; k < NBUF; ++k)
-        if (static_cast<int>(blockIdx.x + k * gridDim.x) < num_tiles) load_residual(blockIdx.x + k * gridDim.x, k);
+        if (static_cast<int>(blockIdx.x + k * gridDim.x) < num_tiles) load_residual(blockIdx.x + k * gridDim.x, k, false);
+      for (int k = NBUF; k < NBUF + p.res_pf - 1; ++k) prefetch_residual(blockIdx.x + k * gridDim.x);
     }
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -217,13 +334,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
       if constexpr (TMA_OUT) {
         if (res_tma) {
-          if (NBUF == 1 && threadIdx.x == 64 && tile + static_cast<int>(gridDim.x) < num_tiles) {
-            // single staging buffer: the next tile's residual can only be loaded after this tile's store; have it
-            // waiting in L2 by then
-            const int nt = tile + gridDim.x, ntm = nt / p.tiles_n, ntn = nt - ntm * p.tiles_n;
-            for (int b = 0; b < NBOX; ++b)
-              if (ntn * BN + b * 32 < p.N) tile_box_prefetch(p, &tmR, ntn * BN + b * 32, ntm * BM);
-          }
+          // a staging buffer can only be reloaded after its tile's store: have that residual waiting in L2 by then
+          if (threadIdx.x == 64) prefetch_residual(tile + (NBUF - 1 + p.res_pf) * static_cast<int>(gridDim.x));
           mbar_wait(&res_full[buf], rphase[buf]);
           rphase[buf] ^= 1;
         } else if (!first_tile) {  // the previous tile's bulk store must have read the staging buffer before it is rewritten
@@ -247,16 +359,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (threadIdx.x == 64) {
           if constexpr (EMODE == 1) {
             store_bf16_boxes<BN>(&tmC, stage_buf, p, tn, tm * BM);
+            bulk_commit();
           } else {
-            for (int b = 0; b < NBOX; ++b)
+#pragma unroll
+            for (int b = 0; b < NBOX; ++b) {   // one bulk group per box (empty for boxes past N)
               if (tn * BN + b * 32 < p.N) tile_box_store(p, &tmC, stage_buf + b * (BM * 128), tn * BN + b * 32, tm * BM);
+              bulk_commit();
+            }
           }
-          bulk_commit();
           const int nxt = tile + NBUF * static_cast<int>(gridDim.x);
-          if (res_tma && nxt < num_tiles) {
-            bulk_wait_read0();
-            load_residual(nxt, buf);
-          }
+          if (res_tma && nxt < num_tiles) load_residual(nxt, buf, true);
         }
       }
       if (++as == 2) {
@@ -285,6 +397,15 @@ int launch_gemm_bres(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                      cudaStream_t stream);
 bool gemm_skinny_applicable(const EmoteGemmArgs* a);                                                    // gemm_skinny.cu
 int launch_gemm_skinny(const void* A, const void* Wt, void* out, const EmoteGemmArgs* a, cudaStream_t stream);
+static int residual_prefetch_distance() {
+  static int d = 0;
+  if (d == 0) {
+    const char* e = std::getenv("EMOTE_RES_PF");   // dev knob
+    d = e ? atoi(e) : 2;
+    if (d < 1 || d > 8) d = 2;
+  }
+  return d;
+}
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -311,7 +432,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   p.tiles_n = (p.N + BN - 1) / BN;
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  launch_kernel(gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, OUT_MODE>, dim3(grid), dim3(gemm_threads(EPI_WARPS)), S::TOTAL, stream, tmA, tmB, tmC, tmR, p);
+  launch_kernel(gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, OUT_MODE>, dim3(grid), dim3(gemm_threads_mode(EPI_WARPS, OUT_MODE)), S::TOTAL, stream, tmA, tmB, tmC, tmR, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error_cuda("gemm launch", e);
   count_launch();
@@ -348,13 +469,13 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   if (act_gelu && (a->row_bias || a->colstats)) return set_error("emote_gemm_bf16: the GELU epilogue takes no row_bias / colstats");
   if (geglu && (a->N % 2 != 0 || a->out_dtype != EMOTE_DT_OP16 || a->residual || a->row_bias))
     return set_error("emote_gemm_bf16: GEGLU epilogue needs even N, bf16 output, no residual/row_bias");
-  // Double-buffered residual staging (mode 3, 128-column tiles, single CTA): the HBM-bound 1x1 GEMMs with an fp32
-  // residual at the 320-channel level (K <= 320: 97 -> 79 us; slower than mode 2 from K = 640 on; tma_store == 4 forces it).
+  // Double-buffered residual staging (mode 3, 128-column tiles, single CTA) is only kept for A/B runs (tma_store == 4):
+  // it beat the old whole-tile mode 2 at K <= 320 (97 -> 79 us) but loses to mode 2 with the store warp and column
+  // halves (73 us), and it was always slower from K = 640 on.
   const bool mode2_ok = a->tma_store != 2 && a->out_dtype == EMOTE_DT_F32 && !geglu &&
                         (!a->row_bias || (a->rows_per_group > 0 && a->rows_per_group % 128 == 0)) &&
                         (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0;
-  const bool want3 = mode2_ok && !conv && a->residual && a->pair_mode != 1 && a->block_n != 160 && a->tma_store != 3 &&
-                     (a->K <= 320 || a->tma_store == 4);
+  const bool want3 = mode2_ok && !conv && a->residual && a->pair_mode != 1 && a->block_n != 160 && a->tma_store == 4;
   const int bn = want3 ? 128 : (a->block_n ? a->block_n : ((a->N % 160 == 0) ? 160 : 128));
   if (bn != 128 && bn != 160) return set_error("emote_gemm_bf16: block_n must be 128 or 160");
   if (geglu && a->N % bn != 0) return set_error("emote_gemm_bf16: GEGLU needs N % block_n == 0");
@@ -370,6 +491,7 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   p.bias = a->bias; p.row_bias = a->row_bias;
   p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
   p.residual = a->residual; p.ldr = a->ldr;
+  p.res_pf = residual_prefetch_distance();
   p.out_scale = a->out_scale;
   p.geglu = geglu ? 1 : 0;
   p.act_gelu = act_gelu ? 1 : 0;

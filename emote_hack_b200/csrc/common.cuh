@@ -157,16 +157,6 @@ __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-// at most n (0..4) of the most recent bulk groups may still be reading their shared-memory source
-__device__ __forceinline__ void bulk_wait_read_n(int n) {
-  switch (n) {
-    case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
-    case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
-    case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
-    case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
-    default: asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); break;
-  }
-}
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

@@ -333,45 +333,13 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     int as = 0;
     uint32_t aphase = 0;
     bool first_tile = true;
-    // mode 2 with a residual: see gemm_tcgen05.cu (each CTA of the pair stages the residual of its own 128 rows)
-    const bool res_tma = OUT_MODE == 2 && p.residual != nullptr;
-    uint32_t rphase = 0;
-    constexpr int NBOX = BN / 32;
-    auto load_residual = [&](int tile, bool after_store) {   // after_store: one bulk group per box was just committed
-      const int tm = tile / p.tiles_n;
-      const int tn = tile - tm * p.tiles_n;
-      const int rb = tm * (2 * BM) + static_cast<int>(rank) * BM;
-      int nb = 0;
-      for (int b = 0; b < NBOX; ++b) nb += (tn * BN + b * 32 < p.N) ? 1 : 0;
-      mbar_expect_tx(res_full, static_cast<uint32_t>(nb) * (BM * 128));
-#pragma unroll
-      for (int b = 0; b < NBOX; ++b) {
-        if (after_store) bulk_wait_read_n(NBOX - 1 - b);
-        if (b < nb) tile_box_load(p, stage_out + b * (BM * 128), &tmR, res_full, tn * BN + b * 32, rb);
-      }
-    };
-    auto prefetch_residual = [&](int tile) {   // L2 prefetch of a later tile's residual boxes (see gemm_tcgen05.cu)
-      if (tile >= num_tiles) return;
-      const int ntm = tile / p.tiles_n, ntn = tile - ntm * p.tiles_n;
-      const int nrb = ntm * (2 * BM) + static_cast<int>(rank) * BM;
-      for (int b = 0; b < NBOX; ++b)
-        if (ntn * BN + b * 32 < p.N) tile_box_prefetch(p, &tmR, ntn * BN + b * 32, nrb);
-    };
-    if (res_tma && threadIdx.x == 64 && pair < num_tiles) {
-      load_residual(pair, false);
-      for (int k = 1; k < p.res_pf; ++k) prefetch_residual(pair + k * num_pairs);
-    }
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
       const int row_base = tm * (2 * BM) + static_cast<int>(rank) * BM;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
       if constexpr (TMA_OUT) {
-        if (res_tma) {
-          if (threadIdx.x == 64) prefetch_residual(tile + p.res_pf * num_pairs);
-          mbar_wait(res_full, rphase);
-          rphase ^= 1;
-        } else if (!first_tile) {
+        if (!first_tile) {   // the previous tile's bulk store must have read the staging buffer before it is rewritten
           if (threadIdx.x == 64) bulk_wait_read0();
           named_bar_sync(2, EPI_WARPS * 32);
         }
@@ -385,23 +353,13 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(&tmem_empty[as], 0));
-      if constexpr (TMA_OUT) {
+      if constexpr (TMA_OUT) {   // mode 1: the staged 16-bit tile leaves through one bulk tensor store
         fence_proxy_async_smem();
         named_bar_sync(1, EPI_WARPS * 32);
         if (threadIdx.x == 64) {
-          const bool rows_ok = p.patch ? (row_base / BM < p.subtiles) : (row_base < p.M);   // the second CTA of the last pair may own no valid rows
-          if constexpr (OUT_MODE == 1) {
-            if (rows_ok) store_bf16_boxes<BN>(&tmC, stage_out, p, tn, row_base);
-            bulk_commit();
-          } else {
-#pragma unroll
-            for (int b = 0; b < NBOX; ++b) {   // one bulk group per box (possibly empty)
-              if (rows_ok && tn * BN + b * 32 < p.N)
-                tile_box_store(p, &tmC, stage_out + b * (BM * 128), tn * BN + b * 32, row_base);
-              bulk_commit();
-            }
-          }
-          if (res_tma && tile + num_pairs < num_tiles) load_residual(tile + num_pairs, true);
+          // the second CTA of the last pair may own no valid rows
+          if (p.patch ? (row_base / BM < p.subtiles) : (row_base < p.M)) store_bf16_boxes<BN>(&tmC, stage_out, p, tn, row_base);
+          bulk_commit();
         }
       }
       if (++as == 2) {

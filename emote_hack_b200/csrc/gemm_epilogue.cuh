@@ -35,7 +35,6 @@ struct GemmDev {
   float* colstats;   // optional fused GroupNorm statistics of the fp32 output, else null: one (sum, sum of squares) slot per
                      // 32-row quarter of a sub-tile and column, [sub-tiles * 4][N][2] fp32, written with plain stores
   int stats_rows;    // rows per statistics batch (validated on the host: a 32-row quarter never straddles two batches)
-  int res_pf;        // modes 2/3: how many tiles ahead of the staging-buffer load the fp32 residual is prefetched into L2 (>= 1)
 };
 
 

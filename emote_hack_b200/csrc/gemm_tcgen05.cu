@@ -32,11 +32,9 @@ struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = OUT_MODE == 3 ? 3 : ((BN <= 128) ? 6 : (BN <= 160 ? 5 : 4)) - (OUT_MODE == 2 ? 1 : 0);
+  static constexpr int STAGES = ((BN <= 128) ? 6 : (BN <= 160 ? 5 : 4)) - (OUT_MODE == 2 ? 1 : 0);
   // output tile staged for the TMA store: bf16 (mode 1) or fp32 residual-in / result-out boxes (mode 2)
-  // mode 3 = mode 2 with TWO staging buffers (residual of tile i+1 lands while tile i is finished and stored)
-  static constexpr int OUT_BUF = OUT_MODE == 1 ? BM * BN * 2 : (OUT_MODE >= 2 ? BM * BN * 4 : 0);
-  static constexpr int OUT_BYTES = OUT_BUF * (OUT_MODE == 3 ? 2 : 1);
+  static constexpr int OUT_BYTES = OUT_MODE == 1 ? BM * BN * 2 : (OUT_MODE == 2 ? BM * BN * 4 : 0);
   static constexpr int BAR_BYTES = 256;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024 /*align slack*/;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
@@ -49,8 +47,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                          const GemmDev p) {
   using S = GemmSmem<BN, OUT_MODE>;
   constexpr bool TMA_OUT = OUT_MODE != 0;
-  constexpr int EMODE = OUT_MODE == 3 ? 2 : OUT_MODE;   // epilogue flavour
-  constexpr int NBUF = OUT_MODE == 3 ? 2 : 1;           // staging buffers
   constexpr bool SPLIT = OUT_MODE == 2;                 // store warp + column halves (see gemm_threads_mode)
   constexpr int FIRST_EPI = SPLIT ? 3 : 2;              // first epilogue warp
   constexpr int NBOX = BN / 32;                         // fp32 staging boxes of [128 rows][32 columns] per tile
@@ -66,8 +62,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* tmem_full = empty_bar + S::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint64_t* res_full = reinterpret_cast<uint64_t*>(bar_base + 192);  // [2] mode 3: residual boxes landed in staging buffer i;
-                                                                     //     mode 2: column half i of the buffer is armed
+  uint64_t* res_full = reinterpret_cast<uint64_t*>(bar_base + 192);  // [2] mode 2: column half i of the staging buffer is armed
   uint64_t* half_done = reinterpret_cast<uint64_t*>(bar_base + 208); // [2] mode 2: the epilogue warps finished column half i
 
   const int warp = threadIdx.x >> 5;
@@ -290,85 +285,32 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     int as = 0;
     uint32_t aphase = 0;
     bool first_tile = true;
-    // modes 2/3 with a residual: thread 64 TMA-loads the fp32 residual tile of an upcoming tile into the staging boxes
-    // as soon as the bulk store that last used them has been read; the epilogue warps wait on res_full[buf] before
-    // touching them.  Mode 2 has one buffer (load of tile i+1 after the store of tile i); mode 3 has two (the load of
-    // tile i+2 follows the store of tile i, so the residual of tile i+1 is already resident when its epilogue starts).
-    const bool res_tma = EMODE == 2 && p.residual != nullptr;
-    uint32_t rphase[2] = {0, 0};
-    constexpr int NBOX = BN / 32;
-    // `after_store`: the buffer's boxes were just bulk-stored, one group per box — box b is reloaded as soon as ITS store
-    // has been read instead of after the whole tile's
-    auto load_residual = [&](int tile, int buf, bool after_store) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
-      int nb = 0;
-      for (int b = 0; b < NBOX; ++b) nb += (tn * BN + b * 32 < p.N) ? 1 : 0;
-      mbar_expect_tx(&res_full[buf], static_cast<uint32_t>(nb) * (BM * 128));
-#pragma unroll
-      for (int b = 0; b < NBOX; ++b) {
-        if (after_store) bulk_wait_read_n(NBOX - 1 - b);
-        if (b < nb)
-          tile_box_load(p, stage_out + buf * S::OUT_BUF + b * (BM * 128), &tmR, &res_full[buf], tn * BN + b * 32, tm * BM);
-      }
-    };
-    // L2 prefetch of the residual boxes of a later tile: the staging buffers are (re)loaded from L2, and HBM keeps streaming
-    // while the CTAs sit in the add / store phases (all CTAs run those phases in lockstep)
-    auto prefetch_residual = [&](int tile) {
-      if (tile >= num_tiles) return;
-      const int ntm = tile / p.tiles_n, ntn = tile - ntm * p.tiles_n;
-      for (int b = 0; b < NBOX; ++b)
-        if (ntn * BN + b * 32 < p.N) tile_box_prefetch(p, &tmR, ntn * BN + b * 32, ntm * BM);
-    };
-    if (res_tma && threadIdx.x == 64) {
-      for (int k = 0; k < NBUF; ++k)
-        if (static_cast<int>(blockIdx.x + k * gridDim.x) < num_tiles) load_residual(blockIdx.x + k * gridDim.x, k, false);
-      for (int k = NBUF; k < NBUF + p.res_pf - 1; ++k) prefetch_residual(blockIdx.x + k * gridDim.x);
-    }
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int tm = tile / p.tiles_n;
-      const int tn = tile - tm * p.tiles_n;
-      const int buf = (NBUF == 2) ? (it & 1) : 0;
-      uint8_t* stage_buf = stage_out + buf * S::OUT_BUF;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
       if constexpr (TMA_OUT) {
-        if (res_tma) {
-          // a staging buffer can only be reloaded after its tile's store: have that residual waiting in L2 by then
-          if (threadIdx.x == 64) prefetch_residual(tile + (NBUF - 1 + p.res_pf) * static_cast<int>(gridDim.x));
-          mbar_wait(&res_full[buf], rphase[buf]);
-          rphase[buf] ^= 1;
-        } else if (!first_tile) {  // the previous tile's bulk store must have read the staging buffer before it is rewritten
+        if (!first_tile) {  // the previous tile's bulk store must have read the staging buffer before it is rewritten
           if (threadIdx.x == 64) bulk_wait_read0();
           named_bar_sync(2, EPI_WARPS * 32);
         }
         first_tile = false;
       }
-      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, EMODE>(p, tbase, tm * BM, tn * BN, tn, quarter, part, lane, stage_buf,
-                                                        [&]() {
-                                                          mbar_wait(&tmem_full[as], aphase);
-                                                          tc_fence_after();
-                                                        });
+      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, OUT_MODE>(p, tbase, tm * BM, tn * BN, tn, quarter, part, lane, stage_out,
+                                                           [&]() {
+                                                             mbar_wait(&tmem_full[as], aphase);
+                                                             tc_fence_after();
+                                                           });
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
-      if constexpr (TMA_OUT) {
+      if constexpr (TMA_OUT) {   // mode 1: the staged 16-bit tile leaves through one bulk tensor store
         fence_proxy_async_smem();                 // staging writes -> visible to the TMA (async proxy)
         named_bar_sync(1, EPI_WARPS * 32);
         if (threadIdx.x == 64) {
-          if constexpr (EMODE == 1) {
-            store_bf16_boxes<BN>(&tmC, stage_buf, p, tn, tm * BM);
-            bulk_commit();
-          } else {
-#pragma unroll
-            for (int b = 0; b < NBOX; ++b) {   // one bulk group per box (empty for boxes past N)
-              if (tn * BN + b * 32 < p.N) tile_box_store(p, &tmC, stage_buf + b * (BM * 128), tn * BN + b * 32, tm * BM);
-              bulk_commit();
-            }
-          }
-          const int nxt = tile + NBUF * static_cast<int>(gridDim.x);
-          if (res_tma && nxt < num_tiles) load_residual(nxt, buf, true);
+          store_bf16_boxes<BN>(&tmC, stage_out, p, tn, tm * BM);
+          bulk_commit();
         }
       }
       if (++as == 2) {
@@ -397,15 +339,6 @@ int launch_gemm_bres(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                      cudaStream_t stream);
 bool gemm_skinny_applicable(const EmoteGemmArgs* a);                                                    // gemm_skinny.cu
 int launch_gemm_skinny(const void* A, const void* Wt, void* out, const EmoteGemmArgs* a, cudaStream_t stream);
-static int residual_prefetch_distance() {
-  static int d = 0;
-  if (d == 0) {
-    const char* e = std::getenv("EMOTE_RES_PF");   // dev knob
-    d = e ? atoi(e) : 2;
-    if (d < 1 || d > 8) d = 2;
-  }
-  return d;
-}
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -442,9 +375,6 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 template <int BN>
 static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                          int out_mode, GemmDev& p, cudaStream_t stream) {
-  if constexpr (BN == 128) {
-    if (out_mode == 3) return launch_gemm<BN, 16, false, 3>(tmA, tmB, tmC, tmR, p, stream);
-  }
   if (out_mode >= 2) return launch_gemm<BN, 16, false, 2>(tmA, tmB, tmC, tmR, p, stream);
   if (!p.geglu && (p.residual != nullptr || p.row_bias != nullptr))
     return launch_gemm<BN, 8, true, 0>(tmA, tmB, tmC, tmR, p, stream);
@@ -469,14 +399,10 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   if (act_gelu && (a->row_bias || a->colstats)) return set_error("emote_gemm_bf16: the GELU epilogue takes no row_bias / colstats");
   if (geglu && (a->N % 2 != 0 || a->out_dtype != EMOTE_DT_OP16 || a->residual || a->row_bias))
     return set_error("emote_gemm_bf16: GEGLU epilogue needs even N, bf16 output, no residual/row_bias");
-  // Double-buffered residual staging (mode 3, 128-column tiles, single CTA) is only kept for A/B runs (tma_store == 4):
-  // it beat the old whole-tile mode 2 at K <= 320 (97 -> 79 us) but loses to mode 2 with the store warp and column
-  // halves (73 us), and it was always slower from K = 640 on.
   const bool mode2_ok = a->tma_store != 2 && a->out_dtype == EMOTE_DT_F32 && !geglu &&
                         (!a->row_bias || (a->rows_per_group > 0 && a->rows_per_group % 128 == 0)) &&
                         (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0;
-  const bool want3 = mode2_ok && !conv && a->residual && a->pair_mode != 1 && a->block_n != 160 && a->tma_store == 4;
-  const int bn = want3 ? 128 : (a->block_n ? a->block_n : ((a->N % 160 == 0) ? 160 : 128));
+  const int bn = a->block_n ? a->block_n : ((a->N % 160 == 0) ? 160 : 128);
   if (bn != 128 && bn != 160) return set_error("emote_gemm_bf16: block_n must be 128 or 160");
   if (geglu && a->N % bn != 0) return set_error("emote_gemm_bf16: GEGLU needs N % block_n == 0");
   if ((a->out_dtype == EMOTE_DT_OP16 && a->ldc % 8 != 0) || (a->out_dtype == EMOTE_DT_F32 && a->ldc % 4 != 0))
@@ -491,7 +417,6 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   p.bias = a->bias; p.row_bias = a->row_bias;
   p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
   p.residual = a->residual; p.ldr = a->ldr;
-  p.res_pf = residual_prefetch_distance();
   p.out_scale = a->out_scale;
   p.geglu = geglu ? 1 : 0;
   p.act_gelu = act_gelu ? 1 : 0;
@@ -556,7 +481,7 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   bool use_pair = (conv || a->K >= 1024) && a->M >= 256 && pair_tiles >= 64;
   if (p.patch && p.subtiles < 2) use_pair = false;
   if (a->pair_mode == 1) use_pair = true;
-  if (a->pair_mode == 2 || want3) use_pair = false;
+  if (a->pair_mode == 2) use_pair = false;
   {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t strides[1] = {(uint64_t)a->K * 2};
@@ -573,8 +498,8 @@ extern "C" int emote_gemm_bf16(const void* A, const void* Wt, void* out, const E
   if (a->tma_store != 2) {
     if (p.out_bf16 && !(p.residual || p.row_bias)) {
       out_mode = p.patch ? 0 : 1;   // patch mode: 16-bit outputs leave through the register path
-    } else if (mode2_ok && !patch_rowbias_per_row && (a->K <= 4096 || want3)) {
-      out_mode = want3 ? 3 : 2;
+    } else if (mode2_ok && !patch_rowbias_per_row && a->K <= 4096) {
+      out_mode = 2;
     }
   }
   if (out_mode == 1) {

@@ -74,8 +74,7 @@ typedef struct {
   int32_t block_n;        /* 0 = auto (160 if N % 160 == 0 else 128) */
   int32_t pair_mode;      /* 0 = auto, 1 = force CTA pairs (cta_group::2, 256-row tiles), 2 = force single CTA,
                              3 = auto without the weight-stationary kernel (small-K bf16-output shapes) */
-  int32_t tma_store;      /* 0 = auto (staged TMA-store epilogues where they apply), 2 = never, 3 = never the
-                             double-buffered residual variant, 4 = double-buffered residual variant for any K */
+  int32_t tma_store;      /* 0 = auto (staged TMA-store epilogues where they apply), 2 = never (register path; dev / A-B runs) */
   float* colstats;        /* optional fused GroupNorm statistics of the fp32 output: one (sum, sum of squares) fp32 slot per
                              32-row quarter of a 128-row sub-tile and column, [ceil(M/128)*4][N][2] (conv over 2-D patch
                              tiles: sub-tile order), every slot written with a plain store: no zero-fill, no atomics,

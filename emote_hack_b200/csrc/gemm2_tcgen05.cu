@@ -332,20 +332,23 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const int part = ew >> 2;
     int as = 0;
     uint32_t aphase = 0;
-    bool first_tile = true;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+    const bool two_buf = TMA_OUT && p.geglu != 0;   // GEGLU: two half-width staging buffers (see gemm_tcgen05.cu)
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
       const int row_base = tm * (2 * BM) + static_cast<int>(rank) * BM;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
+      uint8_t* stage_buf = stage_out + ((two_buf && (it & 1)) ? BM * (BN / 2) * 2 : 0);
       if constexpr (TMA_OUT) {
-        if (!first_tile) {   // the previous tile's bulk store must have read the staging buffer before it is rewritten
-          if (threadIdx.x == 64) bulk_wait_read0();
+        if (it > (two_buf ? 1 : 0)) {   // the bulk store that last used this buffer must have read it before it is rewritten
+          if (threadIdx.x == 64) {
+            if (two_buf) bulk_wait_read1(); else bulk_wait_read0();
+          }
           named_bar_sync(2, EPI_WARPS * 32);
         }
-        first_tile = false;
       }
-      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, OUT_MODE>(p, tbase, row_base, tn * BN, tn, quarter, part, lane, stage_out,
+      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, OUT_MODE>(p, tbase, row_base, tn * BN, tn, quarter, part, lane, stage_buf,
                                                            [&]() {
                                                              mbar_wait(&tmem_full[as], aphase);
                                                              tc_fence_after();
@@ -358,7 +361,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         named_bar_sync(1, EPI_WARPS * 32);
         if (threadIdx.x == 64) {
           // the second CTA of the last pair may own no valid rows
-          if (p.patch ? (row_base / BM < p.subtiles) : (row_base < p.M)) store_bf16_boxes<BN>(&tmC, stage_out, p, tn, row_base);
+          if (p.patch ? (row_base / BM < p.subtiles) : (row_base < p.M)) store_bf16_boxes<BN>(&tmC, stage_buf, p, tn, row_base);
           bulk_commit();
         }
       }

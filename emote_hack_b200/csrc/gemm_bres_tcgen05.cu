@@ -150,15 +150,20 @@ gemm_bres_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int part = ew >> 2;
     int as = 0;
     uint32_t aphase = 0;
-    bool first_tile = true;
-    for (int tm = slot; tm < p.tiles_m; tm += slots) {
+    // GEGLU tiles are half as wide (BN/2 outputs): the staging area holds two of them, so tile i is written while the
+    // bulk store of tile i-1 is still reading its buffer (only the store of tile i-2 has to be done)
+    const bool two_buf = p.geglu != 0;
+    int it = 0;
+    for (int tm = slot; tm < p.tiles_m; tm += slots, ++it) {
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
-      if (!first_tile) {  // the previous tile's bulk store must have read the staging buffer before it is rewritten
-        if (threadIdx.x == 64) bulk_wait_read0();
+      uint8_t* stage_buf = stage_out + ((two_buf && (it & 1)) ? BM * (BN / 2) * 2 : 0);
+      if (it > (two_buf ? 1 : 0)) {  // the bulk store that last used this buffer must have read it before it is rewritten
+        if (threadIdx.x == 64) {
+          if (two_buf) bulk_wait_read1(); else bulk_wait_read0();
+        }
         named_bar_sync(2, EPI_WARPS * 32);
       }
-      first_tile = false;
-      gemm_epilogue_tile<BN, EPI_WARPS, false, 1>(p, tbase, tm * BM, n0, tn, quarter, part, lane, stage_out, [&]() {
+      gemm_epilogue_tile<BN, EPI_WARPS, false, 1>(p, tbase, tm * BM, n0, tn, quarter, part, lane, stage_buf, [&]() {
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
       });
@@ -168,7 +173,7 @@ gemm_bres_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       fence_proxy_async_smem();
       named_bar_sync(1, EPI_WARPS * 32);
       if (threadIdx.x == 64) {
-        store_bf16_boxes<BN>(&tmC, stage_out, p, tn, tm * BM);
+        store_bf16_boxes<BN>(&tmC, stage_buf, p, tn, tm * BM);
         bulk_commit();
       }
       if (++as == 2) {

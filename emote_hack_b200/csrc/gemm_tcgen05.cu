@@ -284,19 +284,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int part = ew >> 2;
     int as = 0;
     uint32_t aphase = 0;
-    bool first_tile = true;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // mode 1, GEGLU: tiles are half as wide (BN/2 outputs), the staging area holds two of them — tile i is written while
+    // the bulk store of tile i-1 is still reading its buffer (only the store of tile i-2 has to be done)
+    const bool two_buf = TMA_OUT && p.geglu != 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BN);
+      uint8_t* stage_buf = stage_out + ((two_buf && (it & 1)) ? BM * (BN / 2) * 2 : 0);
       if constexpr (TMA_OUT) {
-        if (!first_tile) {  // the previous tile's bulk store must have read the staging buffer before it is rewritten
-          if (threadIdx.x == 64) bulk_wait_read0();
+        if (it > (two_buf ? 1 : 0)) {  // the bulk store that last used this buffer must have read it before it is rewritten
+          if (threadIdx.x == 64) {
+            if (two_buf) bulk_wait_read1(); else bulk_wait_read0();
+          }
           named_bar_sync(2, EPI_WARPS * 32);
         }
-        first_tile = false;
       }
-      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, OUT_MODE>(p, tbase, tm * BM, tn * BN, tn, quarter, part, lane, stage_out,
+      gemm_epilogue_tile<BN, EPI_WARPS, HAS_ADD, OUT_MODE>(p, tbase, tm * BM, tn * BN, tn, quarter, part, lane, stage_buf,
                                                            [&]() {
                                                              mbar_wait(&tmem_full[as], aphase);
                                                              tc_fence_after();
@@ -309,7 +314,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         fence_proxy_async_smem();                 // staging writes -> visible to the TMA (async proxy)
         named_bar_sync(1, EPI_WARPS * 32);
         if (threadIdx.x == 64) {
-          store_bf16_boxes<BN>(&tmC, stage_out, p, tn, tm * BM);
+          store_bf16_boxes<BN>(&tmC, stage_buf, p, tn, tm * BM);
           bulk_commit();
         }
       }

@@ -1,5 +1,5 @@
-"""Dev tool: time the tcgen05 attention kernel (EMOTE_ATTN_TC=1 selects the v1 kernel, EMOTE_ATTN_EMU the exp split)
-against the mma.sync kernel on the UNet's self-attention shapes."""
+"""Dev tool: time the tcgen05 attention kernel (EMOTE_ATTN_EMU = exp split) against the mma.sync kernel on the UNet's
+self-attention shapes."""
 import os
 import sys
 from pathlib import Path
@@ -8,7 +8,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from emote_hack_b200 import _lib, ops
 OP16 = ops.OP16
-print(f"operand={_lib.OPERAND} EMOTE_ATTN_TC={os.environ.get('EMOTE_ATTN_TC', '2')} EMOTE_ATTN_EMU={os.environ.get('EMOTE_ATTN_EMU', '1')}")
+print(f"operand={_lib.OPERAND} EMOTE_ATTN_EMU={os.environ.get('EMOTE_ATTN_EMU', 'default')}")
 shapes = [(32, 8, 40, 4096, 0), (32, 8, 80, 1024, 0), (32, 8, 160, 256, 0), (32, 8, 40, 4096, 4096), (1, 12, 64, 499, 0)]
 for (batch, heads, d, n, n1) in shapes:
     C = heads * d

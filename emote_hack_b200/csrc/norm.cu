@@ -85,16 +85,12 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const float* __restrict__
 // y = x * scale[c] + shift[c] with scale = rstd*gamma, shift = beta - mean*rstd*gamma staged in shared memory per
 // block; blockDim = (octets per pass, rows in parallel); GN_APPLY_U rows per thread are in flight per batch.
 // Group statistics from the per-quarter column slots a GEMM epilogue stored (EmoteGemmArgs.colstats).
-constexpr int GN_RED_THREADS = 1024, GN_RED_U = 8;
-__global__ void __launch_bounds__(GN_RED_THREADS) gn_colstats_reduce_kernel(const float* __restrict__ slots, int C_src,
-                                                                           int c_offset, int cpg, int groups,
-                                                                           int slots_per_batch, int n_batches,
-                                                                           double* __restrict__ sums, int overwrite) {
+__global__ void __launch_bounds__(256) gn_colstats_reduce_kernel(const float* __restrict__ slots, int C_src, int c_offset,
+                                                                 int cpg, int groups, int slots_per_batch, int n_batches,
+                                                                 double* __restrict__ sums, int overwrite) {
   pdl_prologue();
-  // one block per (batch, group).  The group's (sum, sum of squares) pairs of this source — `nc` consecutive float2 per
-  // slot — are walked as one flat index so that neighbouring threads read neighbouring pairs; every thread keeps
-  // GN_RED_U independent loads in flight (the slots sit in L2: the walk is latency-, not bandwidth-bound), adds in fp64
-  // in a fixed order, and a fixed-order tree folds the block -> bit-reproducible.
+  // one block per (batch, group): thread t walks slots t, t + 256, ... of the batch over the group's columns of this
+  // source, in a fixed order; fp64 from the first addition on; fixed-order tree over the block -> deterministic
   const int batch = blockIdx.x / groups, g = blockIdx.x - batch * groups;
   int c_lo = g * cpg, c_hi = c_lo + cpg;
   if (c_lo < c_offset) c_lo = c_offset;
@@ -106,30 +102,20 @@ __global__ void __launch_bounds__(GN_RED_THREADS) gn_colstats_reduce_kernel(cons
     return;
   }
   double s = 0.0, q = 0.0;
-  const float2* base = reinterpret_cast<const float2*>(slots) + (long long)batch * slots_per_batch * C_src + (c_lo - c_offset);
-  const int total = slots_per_batch * nc;
-  for (int i0 = threadIdx.x; i0 < total; i0 += GN_RED_THREADS * GN_RED_U) {
-    float2 v[GN_RED_U];
-#pragma unroll
-    for (int u = 0; u < GN_RED_U; ++u) {
-      const int i = i0 + u * GN_RED_THREADS;
-      v[u] = make_float2(0.f, 0.f);
-      if (i < total) {
-        const int sl = i / nc;
-        v[u] = __ldg(base + (long long)sl * C_src + (i - sl * nc));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < GN_RED_U; ++u) {
-      s += (double)v[u].x;
-      q += (double)v[u].y;
+  const float* base = slots + ((long long)batch * slots_per_batch * C_src + (c_lo - c_offset)) * 2;
+  for (int sl = threadIdx.x; sl < slots_per_batch; sl += blockDim.x) {
+    const float2* row = reinterpret_cast<const float2*>(base + (long long)sl * C_src * 2);
+    for (int c = 0; c < nc; ++c) {
+      const float2 v = __ldg(row + c);
+      s += (double)v.x;
+      q += (double)v.y;
     }
   }
-  __shared__ double rs[GN_RED_THREADS], rq[GN_RED_THREADS];
+  __shared__ double rs[256], rq[256];
   rs[threadIdx.x] = s;
   rq[threadIdx.x] = q;
   __syncthreads();
-  for (int off = GN_RED_THREADS / 2; off > 0; off >>= 1) {
+  for (int off = 128; off > 0; off >>= 1) {
     if (threadIdx.x < off) {
       rs[threadIdx.x] += rs[threadIdx.x + off];
       rq[threadIdx.x] += rq[threadIdx.x + off];
@@ -378,7 +364,7 @@ extern "C" int emote_gn_colstats_reduce(const float* colstats, int32_t C_src, in
     return set_error("emote_gn_colstats_reduce: bad arguments");
   if (gn_check(C_src, c_offset, C_total, groups, "emote_gn_colstats_reduce: unsupported channel/group configuration"))
     return EMOTE_ERR_INVALID;
-  launch_kernel(gn_colstats_reduce_kernel, dim3((unsigned)(n_batches * groups)), dim3(GN_RED_THREADS), 0, stream, colstats, C_src,
+  launch_kernel(gn_colstats_reduce_kernel, dim3((unsigned)(n_batches * groups)), dim3(256), 0, stream, colstats, C_src,
                 c_offset, C_total / groups, groups, slots_per_batch, n_batches, sums, zero_first);
   EMOTE_CHECK_LAUNCH("emote_gn_colstats_reduce");
   return 0;

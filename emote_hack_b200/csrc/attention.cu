@@ -598,11 +598,12 @@ static int launch_flash(const AttnDev& p, int batch, cudaStream_t stream) {
   constexpr int MT = (DP <= 80) ? 2 : 1;
   constexpr int BQ = 64 * MT;
   constexpr int SMEM = (BQ + 4 * 64) * (DP + 8) * 2;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  int dev__ = 0;
+  if (configured.pending(&dev__)) {
     cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<DP, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(flash_attn)", e);
-    configured = true;
+    configured.done(dev__);
   }
   dim3 grid((p.nq + BQ - 1) / BQ, p.heads, batch);
   launch_kernel(flash_attn_kernel<DP, MT>, dim3(grid), dim3(FA_THREADS), SMEM, stream, p);
@@ -613,12 +614,13 @@ static int launch_flash(const AttnDev& p, int batch, cudaStream_t stream) {
 template <int DP, int NK16>
 static int launch_short_kv(const AttnDev& p, int batch, cudaStream_t stream) {
   constexpr int SMEM = (2 * NK16 * 16 + 2 * 64) * (DP + 8) * 2;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  int dev__ = 0;
+  if (configured.pending(&dev__)) {
     cudaError_t e =
         cudaFuncSetAttribute(short_kv_attn_kernel<DP, NK16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(short_kv_attn)", e);
-    configured = true;
+    configured.done(dev__);
   }
   const int n_qtiles = (p.nq + 63) / 64;
   // ~4 CTAs per SM worth of work items, each streaming several query tiles over one resident K/V
@@ -644,12 +646,13 @@ template <int DP, int FP>
 static int launch_temporal(const op16* qkv, op16* out, int B, int F, int HW, int heads, int d,
                            float scale_log2, cudaStream_t stream) {
   constexpr int SMEM = TA_WARPS * 3 * FP * (DP + 8) * 2;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  int dev__ = 0;
+  if (configured.pending(&dev__)) {
     cudaError_t e =
         cudaFuncSetAttribute(temporal_attn_kernel<DP, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(temporal_attn)", e);
-    configured = true;
+    configured.done(dev__);
   }
   const int hgroups = (heads + TA_WARPS - 1) / TA_WARPS;
   const long long blocks = (long long)B * HW * hgroups;

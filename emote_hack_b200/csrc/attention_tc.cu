@@ -343,11 +343,12 @@ static int make_all_kv_maps(const AttnTcDev& p, int batch, CUtensorMap& mk0, CUt
 template <int D, int EMU>
 static int launch_tc(const AttnTcDev& p, int batch, cudaStream_t stream) {
   using C = TcCfg<D>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  int dev__ = 0;
+  if (configured.pending(&dev__)) {
     cudaError_t e = cudaFuncSetAttribute(flash_attn_tc_kernel<D, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(flash_attn_tc2)", e);
-    configured = true;
+    configured.done(dev__);
   }
   CUtensorMap mk0, mv0, mk1, mv1;
   if (int rc = make_all_kv_maps(p, batch, mk0, mv0, mk1, mv1)) return rc;

@@ -318,11 +318,12 @@ extern "C" int emote_attention_wide_bf16(const void* q, const void* k, const voi
   const int64_t strides[] = {q_batch_stride, q_row_stride, kv_batch_stride, kv_row_stride, o_batch_stride, o_row_stride};
   for (int64_t s : strides)
     if (s % 8 != 0) return set_error("emote_attention_wide_bf16: strides must keep rows 16-byte aligned");
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  int dev__ = 0;
+  if (configured.pending(&dev__)) {
     cudaError_t e = cudaFuncSetAttribute(flash_attn_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM);
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(flash_attn_wide)", e);
-    configured = true;
+    configured.done(dev__);
   }
   CUtensorMap mk, mv;
   if (int rc = make_kv_map(&mk, k, W_D, nk, kv_row_stride, kv_batch_stride, batch)) return rc;

@@ -207,12 +207,13 @@ int launch_gemm_bres(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                      cudaStream_t stream) {
   constexpr int BN = 160, KB_MAX = 5, EPI = 16;
   using S = BresSmem<BN, KB_MAX>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  int dev__ = 0;
+  if (configured.pending(&dev__)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bres_tcgen05_kernel<BN, KB_MAX, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(gemm_bres)", e);
-    configured = true;
+    configured.done(dev__);
   }
   p.tiles_m = (p.M + BM - 1) / BM;
   p.tiles_n = (p.N + BN - 1) / BN;

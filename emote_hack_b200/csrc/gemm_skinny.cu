@@ -80,11 +80,12 @@ int launch_gemm_skinny(const void* A, const void* Wt, void* out, const EmoteGemm
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(Wt) & 15))
     return set_error("emote_gemm_bf16(skinny): operands must be 16-byte aligned");
   const size_t smem = (size_t)a->M * a->K * 2;
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
+  static PerDeviceOnce configured;
+  int dev__ = 0;
+  if (smem > 48 * 1024 && configured.pending(&dev__)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(gemm_skinny)", e);
-    configured = 96 * 1024;
+    configured.done(dev__);
   }
   int blocks = (a->N + SK_WARPS - 1) / SK_WARPS;
   if (blocks > 148 * 4) blocks = 148 * 4;

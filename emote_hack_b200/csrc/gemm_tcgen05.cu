@@ -359,12 +359,13 @@ template <int BN, int EPI_WARPS, bool HAS_ADD, int OUT_MODE>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                        GemmDev& p, cudaStream_t stream) {
   using S = GemmSmem<BN, OUT_MODE>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  int dev__ = 0;
+  if (configured.pending(&dev__)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI_WARPS, HAS_ADD, OUT_MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(gemm)", e);
-    configured = true;
+    configured.done(dev__);
   }
   p.tiles_m = p.patch ? p.subtiles : (p.M + BM - 1) / BM;
   p.tiles_n = (p.N + BN - 1) / BN;

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <utility>
 
 namespace emote {
@@ -38,6 +39,18 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
+
+// cudaFuncSetAttribute applies to the device that is current when it is called: a launcher remembers, per device
+// ordinal, whether it has raised its kernel's dynamic shared-memory limit there.  Two threads racing through pending()
+// both configure — the call is idempotent.
+struct PerDeviceOnce {
+  std::atomic<uint64_t> mask{0};
+  bool pending(int* dev) {
+    if (cudaGetDevice(dev) != cudaSuccess) *dev = 0;
+    return !((mask.load(std::memory_order_acquire) >> (*dev & 63)) & 1ull);
+  }
+  void done(int dev) { mask.fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
 
 #define EMOTE_CHECK_LAUNCH(name)                                   \
   do {                                                             \

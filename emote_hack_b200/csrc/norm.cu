@@ -8,6 +8,8 @@
 #include "emote_b200.h"
 #include "host_utils.h"
 
+#include <cstdlib>
+
 namespace emote {
 
 constexpr int GN_MAX_PASS = 4;
@@ -128,6 +130,70 @@ __global__ void __launch_bounds__(256) gn_colstats_reduce_kernel(const float* __
   }
 }
 
+// Same result slots, flat walk: the (slot, column) pairs of one (batch, group) are numbered e = slot * nc + column and
+// thread t takes e = t, t + NT, ...; eight independent loads are in flight per thread before the first fp64 addition, so a
+// 2048-slot batch costs 3 rounds of memory latency with NT = 1024 (the per-slot walk above: one round per slot and column
+// batch, ~24).  Fixed mapping + fixed-order warp / block folds -> deterministic.
+template <int NT>
+__global__ void __launch_bounds__(NT) gn_colstats_reduce_flat_kernel(const float* __restrict__ slots, int C_src,
+                                                                     int c_offset, int cpg, int groups,
+                                                                     int slots_per_batch, double* __restrict__ sums,
+                                                                     int overwrite) {
+  pdl_prologue();
+  const int batch = blockIdx.x / groups, g = blockIdx.x - batch * groups;
+  int c_lo = g * cpg, c_hi = c_lo + cpg;
+  if (c_lo < c_offset) c_lo = c_offset;
+  if (c_hi > c_offset + C_src) c_hi = c_offset + C_src;
+  const int nc = c_hi - c_lo;
+  double* o = sums + ((long long)batch * groups + g) * 2;
+  if (nc <= 0) {
+    if (overwrite && threadIdx.x < 2) o[threadIdx.x] = 0.0;
+    return;
+  }
+  const float2* base =
+      reinterpret_cast<const float2*>(slots) + ((long long)batch * slots_per_batch * C_src + (c_lo - c_offset));
+  const int total = slots_per_batch * nc;   // < 2^30 (checked by the launcher): 32-bit index arithmetic
+  double s = 0.0, q = 0.0;
+  for (int e0 = threadIdx.x; e0 < total; e0 += 8 * NT) {
+    // branch-free: out-of-range elements re-read the last valid one and are masked after all eight loads were issued
+    // (a guarded load makes the compiler convert each value right behind its load, serialising the latencies)
+    float2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = min(e0 + u * NT, total - 1);
+      const int sl = e / nc;
+      v[u] = __ldg(base + (long long)sl * C_src + (e - sl * nc));
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool ok = e0 + u * NT < total;
+      s += ok ? (double)v[u].x : 0.0;
+      q += ok ? (double)v[u].y : 0.0;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_down_sync(0xffffffffu, s, off);
+    q += __shfl_down_sync(0xffffffffu, q, off);
+  }
+  __shared__ double ws[NT / 32], wq[NT / 32];
+  if ((threadIdx.x & 31) == 0) {
+    ws[threadIdx.x >> 5] = s;
+    wq[threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0.0, Q = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) {
+      S += ws[w];
+      Q += wq[w];
+    }
+    if (overwrite) { o[0] = S; o[1] = Q; }
+    else { o[0] += S; o[1] += Q; }
+  }
+}
+
 constexpr int GN_APPLY_U = 4;  // rows per thread in flight
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, int C_src, int c_offset, int C_total,
                                                        int cpg, int groups, long long rows_per_batch, int rows_per_block,
@@ -141,21 +207,27 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   float* s_shift = gn_smem + C_src;
   const int batch = blockIdx.y;
   {
+    // mean / rstd once per group (fp64 divide + square root), then one fp32 multiply-add pair per channel
+    __shared__ float g_mean[GN_MAX_GROUPS], g_rstd[GN_MAX_GROUPS];
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int nthr = blockDim.x * blockDim.y;
     const double cnt = (double)rows_per_batch * (double)cpg;
-    for (int c = tid; c < C_src; c += nthr) {
-      const int ct = c_offset + c;
-      const int g = ct / cpg;
+    for (int g = tid; g < groups; g += nthr) {
       const double sm = sums[((long long)batch * groups + g) * 2];
       const double sq = sums[((long long)batch * groups + g) * 2 + 1];
       const double mean = sm / cnt;
       double var = sq / cnt - mean * mean;
       if (var < 0.0) var = 0.0;
-      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-      const float sc = rstd * gamma[ct];
+      g_mean[g] = (float)mean;
+      g_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    for (int c = tid; c < C_src; c += nthr) {
+      const int ct = c_offset + c;
+      const int g = ct / cpg;
+      const float sc = g_rstd[g] * gamma[ct];
       s_scale[c] = sc;
-      s_shift[c] = beta[ct] - (float)mean * sc;
+      s_shift[c] = beta[ct] - g_mean[g] * sc;
     }
     __syncthreads();
   }
@@ -364,8 +436,23 @@ extern "C" int emote_gn_colstats_reduce(const float* colstats, int32_t C_src, in
     return set_error("emote_gn_colstats_reduce: bad arguments");
   if (gn_check(C_src, c_offset, C_total, groups, "emote_gn_colstats_reduce: unsupported channel/group configuration"))
     return EMOTE_ERR_INVALID;
-  launch_kernel(gn_colstats_reduce_kernel, dim3((unsigned)(n_batches * groups)), dim3(256), 0, stream, colstats, C_src,
-                c_offset, C_total / groups, groups, slots_per_batch, n_batches, sums, zero_first);
+  // EMOTE_GN_REDUCE=slots selects the per-slot walk (the round-2 kernel) for A/B timing
+  static const bool per_slot_walk = [] {
+    const char* e = getenv("EMOTE_GN_REDUCE");
+    return e && e[0] == 's';
+  }();
+  const dim3 grid((unsigned)(n_batches * groups));
+  const int cpg = C_total / groups;
+  const long long per_group = (long long)slots_per_batch * cpg;   // (slot, column) pairs one block folds
+  if (per_slot_walk || per_group >= (1LL << 30))
+    launch_kernel(gn_colstats_reduce_kernel, grid, dim3(256), 0, stream, colstats, C_src, c_offset, cpg, groups,
+                  slots_per_batch, n_batches, sums, zero_first);
+  else if (per_group > 8 * 512)
+    launch_kernel(gn_colstats_reduce_flat_kernel<1024>, grid, dim3(1024), 0, stream, colstats, C_src, c_offset, cpg,
+                  groups, slots_per_batch, sums, zero_first);
+  else
+    launch_kernel(gn_colstats_reduce_flat_kernel<256>, grid, dim3(256), 0, stream, colstats, C_src, c_offset, cpg, groups,
+                  slots_per_batch, sums, zero_first);
   EMOTE_CHECK_LAUNCH("emote_gn_colstats_reduce");
   return 0;
 }

@@ -290,6 +290,37 @@ def test_group_norm_from_fused_statistics(ops):
         assert rel_l2(a, b) < 1e-3
 
 
+@pytest.mark.parametrize("C_src,c_off,C_total,groups,slots,nb", [
+    (320, 0, 320, 32, 2048, 2),      # 64x64x16-frame level of the UNet: 20480 (slot, column) pairs per block (1024 threads)
+    (320, 640, 960, 32, 2048, 2),    # second source of a channel concat: groups straddle / miss the source
+    (1280, 0, 1280, 32, 32, 2),      # 8x8 level: 1280 pairs per block (256 threads)
+    (128, 0, 128, 32, 8192, 3),      # VAE decoder, one 512x512 frame per statistics batch
+    (64, 0, 64, 32, 5, 7)])          # fewer pairs than threads
+def test_gn_colstats_reduce_on_synthetic_slots(ops, C_src, c_off, C_total, groups, slots, nb):
+    """emote_gn_colstats_reduce alone: random per-quarter slots -> (sum, sum of squares) per (batch, group) in fp64, in
+    overwrite and in accumulate mode (the second source of a concatenated GroupNorm input), deterministic."""
+    from emote_hack_b200._lib import check, load
+    from emote_hack_b200 import ops as _ops
+    g = _gen(31)
+    cs = torch.randn(nb, slots, C_src, 2, device="cuda", generator=g) * 3 + 1
+    cpg = C_total // groups
+    ref = torch.zeros(nb, groups, 2, dtype=torch.float64, device="cuda")
+    col = cs.double().sum(1)                                  # [nb, C_src, 2]
+    for c in range(C_src):
+        ref[:, (c_off + c) // cpg] += col[:, c]
+    seed = torch.randn(nb, groups, 2, device="cuda", generator=g).double()
+    for overwrite in (1, 0):
+        sums = seed.clone()
+        check(load().emote_gn_colstats_reduce(cs.data_ptr(), C_src, c_off, C_total, groups, slots, nb, sums.data_ptr(),
+                                              overwrite, _ops._stream()), "emote_gn_colstats_reduce")
+        # overwrite: groups without a column of this source become 0; accumulate: they are left alone
+        torch.testing.assert_close(sums, ref if overwrite else ref + seed, rtol=1e-12, atol=1e-9)
+        again = seed.clone()
+        check(load().emote_gn_colstats_reduce(cs.data_ptr(), C_src, c_off, C_total, groups, slots, nb, again.data_ptr(),
+                                              overwrite, _ops._stream()), "emote_gn_colstats_reduce")
+        assert torch.equal(again, sums)
+
+
 @pytest.mark.parametrize("C", [64, 320, 1280])
 def test_layer_norm(ops, C):
     g = _gen(9)

@@ -113,6 +113,7 @@ INTROSPECTION = {
     "emote_abi_version": (C.c_int, []),
     "emote_operand_dtype": (C.c_int, []),
     "emote_set_pdl": (None, [C.c_int]),
+    "emote_set_tuning": (C.c_int, [C.c_char_p, C.c_int32]),
 }
 
 _lib = None

@@ -42,6 +42,17 @@ bool pdl_enabled() {
 }
 void set_pdl(int enabled) { g_pdl.store(enabled ? 1 : 0, std::memory_order_relaxed); }
 
+static std::atomic<int> g_gn_reduce{-1};
+int gn_reduce_mode() {
+  int v = g_gn_reduce.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = std::getenv("EMOTE_GN_REDUCE");
+    v = (e && e[0] == 's') ? 0 : 1;
+    g_gn_reduce.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -100,3 +111,10 @@ extern "C" int emote_operand_dtype(void) {
 #endif
 }
 extern "C" void emote_set_pdl(int enabled) { emote::set_pdl(enabled); }
+extern "C" int emote_set_tuning(const char* key, int32_t value) {
+  if (key && std::strcmp(key, "gn_reduce") == 0) {
+    emote::g_gn_reduce.store(value ? 1 : 0, std::memory_order_relaxed);
+    return 0;
+  }
+  return emote::set_error("emote_set_tuning: unknown key");
+}

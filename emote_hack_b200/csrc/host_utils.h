@@ -24,6 +24,8 @@ int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t
 // enabled (EMOTE_PDL=1 or emote_set_pdl(1); off by default — it measured slower on the UNet step graph); the kernels
 // gate their global-memory accesses with griddepcontrol.wait, a no-op for ordinary launches.
 bool pdl_enabled();
+// emote_set_tuning("gn_reduce", v): 1 = flat fold (default; EMOTE_GN_REDUCE=slots in the environment starts with 0)
+int gn_reduce_mode();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                  Args&&... args) {

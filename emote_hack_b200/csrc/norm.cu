@@ -8,8 +8,6 @@
 #include "emote_b200.h"
 #include "host_utils.h"
 
-#include <cstdlib>
-
 namespace emote {
 
 constexpr int GN_MAX_PASS = 4;
@@ -436,11 +434,8 @@ extern "C" int emote_gn_colstats_reduce(const float* colstats, int32_t C_src, in
     return set_error("emote_gn_colstats_reduce: bad arguments");
   if (gn_check(C_src, c_offset, C_total, groups, "emote_gn_colstats_reduce: unsupported channel/group configuration"))
     return EMOTE_ERR_INVALID;
-  // EMOTE_GN_REDUCE=slots selects the per-slot walk (the round-2 kernel) for A/B timing
-  static const bool per_slot_walk = [] {
-    const char* e = getenv("EMOTE_GN_REDUCE");
-    return e && e[0] == 's';
-  }();
+  // emote_set_tuning("gn_reduce", 0) / EMOTE_GN_REDUCE=slots selects the per-slot walk for A/B timing
+  const bool per_slot_walk = gn_reduce_mode() == 0;
   const dim3 grid((unsigned)(n_batches * groups));
   const int cpg = C_total / groups;
   const long long per_group = (long long)slots_per_batch * cpg;   // (slot, column) pairs one block folds

@@ -164,6 +164,11 @@ def set_pdl(enabled: bool) -> None:
     _lib.load().emote_set_pdl(1 if enabled else 0)
 
 
+def set_tuning(key: str, value: int) -> None:
+    """Measurement knobs of the library (`emote_set_tuning`): "gn_reduce" 1 = flat statistics fold (default), 0 = per-slot walk."""
+    check(_lib.load().emote_set_tuning(key.encode(), int(value)), "emote_set_tuning")
+
+
 def stats_rows_for(rows_per_frame: int, rows_per_sample: int) -> int:
     """Finest statistics granularity a 32-row quarter of a GEMM tile never straddles: per frame, else per sample, else
     none (0)."""

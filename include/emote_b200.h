@@ -46,6 +46,10 @@ int emote_abi_version(void);
 /* Programmatic dependent launch of the library's kernels (default off; EMOTE_PDL=1 in the environment enables it):
  * each kernel's set-up may overlap the tail of the previous one; results are unaffected. */
 void emote_set_pdl(int enabled);
+/* Measurement knobs (A/B timing of kernel variants inside one process; results are the same up to fp64 summation order).
+ * key "gn_reduce": 1 = flat fold of the GroupNorm statistic slots (default), 0 = the per-slot walk.  Returns 0, or
+ * EMOTE_ERR_INVALID for an unknown key. */
+int emote_set_tuning(const char* key, int32_t value);
 
 /* ------------------------------------------------------------------------------------------------ GEMM / conv
  * out[M,N] = epilogue(A[M,K] x Wt[N,K]^T), bf16 operands, fp32 accumulation on tcgen05 tensor cores.

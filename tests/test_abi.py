@@ -104,3 +104,12 @@ def test_entry_points_reject_bad_arguments_without_touching_the_gpu():
     assert b"multiple of 64" in lib.emote_last_error()
     with __import__("pytest").raises(_lib.EmoteKernelError):
         _lib.check(1, "emote_layernorm")
+
+
+def test_tuning_knob_accepts_known_keys_only():
+    from emote_hack_b200 import _lib
+    lib = _lib.load()
+    assert lib.emote_set_tuning(b"gn_reduce", 0) == 0 and lib.emote_set_tuning(b"gn_reduce", 1) == 0
+    assert lib.emote_set_tuning(b"no_such_knob", 1) != 0
+    assert b"unknown key" in lib.emote_last_error()
+    assert lib.emote_set_tuning(None, 1) != 0

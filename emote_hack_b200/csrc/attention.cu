@@ -452,9 +452,9 @@ __global__ void __launch_bounds__(FA_THREADS) short_kv_attn_kernel(const AttnDev
 }
 
 // --------------------------------------------------------------------------- temporal attention
-constexpr int TA_WARPS = 4;
-
-template <int DP, int FP>
+// TA_WARPS heads of one (sample, pixel) per block: 4 by default, 8 (a whole 8-head row per block) through the
+// "temporal_warps" knob
+template <int DP, int FP, int TA_WARPS>
 __global__ void __launch_bounds__(TA_WARPS * 32) temporal_attn_kernel(const op16* __restrict__ qkv,
                                                                         op16* __restrict__ out, int F, int HW,
                                                                         int heads, int d, float scale_log2) {
@@ -642,23 +642,34 @@ static int dispatch_short_kv(const AttnDev& p, int batch, cudaStream_t stream) {
   return launch_short_kv<DP, 8>(p, batch, stream);
 }
 
-template <int DP, int FP>
-static int launch_temporal(const op16* qkv, op16* out, int B, int F, int HW, int heads, int d,
-                           float scale_log2, cudaStream_t stream) {
+template <int DP, int FP, int TA_WARPS>
+static int launch_temporal_w(const op16* qkv, op16* out, int B, int F, int HW, int heads, int d,
+                             float scale_log2, cudaStream_t stream) {
   constexpr int SMEM = TA_WARPS * 3 * FP * (DP + 8) * 2;
   static PerDeviceOnce configured;
   int dev__ = 0;
   if (configured.pending(&dev__)) {
-    cudaError_t e =
-        cudaFuncSetAttribute(temporal_attn_kernel<DP, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(temporal_attn_kernel<DP, FP, TA_WARPS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(temporal_attn)", e);
     configured.done(dev__);
   }
   const int hgroups = (heads + TA_WARPS - 1) / TA_WARPS;
   const long long blocks = (long long)B * HW * hgroups;
-  launch_kernel(temporal_attn_kernel<DP, FP>, dim3((unsigned)blocks), dim3(TA_WARPS * 32), SMEM, stream, qkv, out, F, HW, heads, d, scale_log2);
+  launch_kernel(temporal_attn_kernel<DP, FP, TA_WARPS>, dim3((unsigned)blocks), dim3(TA_WARPS * 32), SMEM, stream, qkv,
+                out, F, HW, heads, d, scale_log2);
   EMOTE_CHECK_LAUNCH("emote_temporal_attention_bf16");
   return 0;
+}
+
+template <int DP, int FP>
+static int launch_temporal(const op16* qkv, op16* out, int B, int F, int HW, int heads, int d,
+                           float scale_log2, cudaStream_t stream) {
+  if constexpr (8 * 3 * FP * (DP + 8) * 2 <= 200 * 1024) {   // eight heads' Q / K / V must fit one block's shared memory
+    if (tuning(TUNE_TEMPORAL_WARPS, 4) == 8 && heads > 4)
+      return launch_temporal_w<DP, FP, 8>(qkv, out, B, F, HW, heads, d, scale_log2, stream);
+  }
+  return launch_temporal_w<DP, FP, 4>(qkv, out, B, F, HW, heads, d, scale_log2, stream);
 }
 
 }  // namespace emote

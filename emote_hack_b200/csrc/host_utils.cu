@@ -42,15 +42,25 @@ bool pdl_enabled() {
 }
 void set_pdl(int enabled) { g_pdl.store(enabled ? 1 : 0, std::memory_order_relaxed); }
 
-static std::atomic<int> g_gn_reduce{-1};
-int gn_reduce_mode() {
-  int v = g_gn_reduce.load(std::memory_order_relaxed);
-  if (v < 0) {
+// measurement knobs (emote_set_tuning): value < 0 = library default
+static const char* const g_tuning_keys[TUNE_COUNT] = {"gn_reduce", "gn_apply_blocks", "ln_warps", "temporal_warps"};
+static std::atomic<int> g_tuning[TUNE_COUNT] = {{-1}, {-1}, {-1}, {-1}};
+int tuning(int id, int dflt) {
+  int v = g_tuning[id].load(std::memory_order_relaxed);
+  if (id == TUNE_GN_REDUCE && v < 0) {
     const char* e = std::getenv("EMOTE_GN_REDUCE");
     v = (e && e[0] == 's') ? 0 : 1;
-    g_gn_reduce.store(v, std::memory_order_relaxed);
+    g_tuning[id].store(v, std::memory_order_relaxed);
   }
-  return v;
+  return v < 0 ? dflt : v;
+}
+int set_tuning(const char* key, int value) {
+  for (int i = 0; i < TUNE_COUNT; ++i)
+    if (key && std::strcmp(key, g_tuning_keys[i]) == 0) {
+      g_tuning[i].store(value, std::memory_order_relaxed);
+      return 0;
+    }
+  return set_error("emote_set_tuning: unknown key");
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -111,10 +121,4 @@ extern "C" int emote_operand_dtype(void) {
 #endif
 }
 extern "C" void emote_set_pdl(int enabled) { emote::set_pdl(enabled); }
-extern "C" int emote_set_tuning(const char* key, int32_t value) {
-  if (key && std::strcmp(key, "gn_reduce") == 0) {
-    emote::g_gn_reduce.store(value ? 1 : 0, std::memory_order_relaxed);
-    return 0;
-  }
-  return emote::set_error("emote_set_tuning: unknown key");
-}
+extern "C" int emote_set_tuning(const char* key, int32_t value) { return emote::set_tuning(key, value); }

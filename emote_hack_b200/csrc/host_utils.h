@@ -24,8 +24,11 @@ int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t
 // enabled (EMOTE_PDL=1 or emote_set_pdl(1); off by default — it measured slower on the UNet step graph); the kernels
 // gate their global-memory accesses with griddepcontrol.wait, a no-op for ordinary launches.
 bool pdl_enabled();
-// emote_set_tuning("gn_reduce", v): 1 = flat fold (default; EMOTE_GN_REDUCE=slots in the environment starts with 0)
-int gn_reduce_mode();
+// emote_set_tuning knobs: launch-geometry / variant choices that can be switched inside one process for A/B timing.
+// tuning(id, dflt) returns the library default until a value >= 0 was set.
+enum { TUNE_GN_REDUCE = 0, TUNE_GN_APPLY_BLOCKS, TUNE_LN_WARPS, TUNE_TEMPORAL_WARPS, TUNE_COUNT };
+int tuning(int id, int dflt);
+int set_tuning(const char* key, int value);
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                  Args&&... args) {

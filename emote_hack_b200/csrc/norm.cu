@@ -286,7 +286,7 @@ constexpr int LN_MAX_V = 32;  // float2 per lane -> C <= 2048
 // One warp per row, NV float2 per lane (C = 64*NV).  NV is a template parameter so the row lives in exactly
 // 2*NV registers (occupancy) and all loads of a row are issued back to back (bytes in flight).
 template <int NV>
-__global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict__ x, long long M, int C_rt,
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long M, int C_rt,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, const float* __restrict__ pe, int pe_rows_per_frame,
                                                         int pe_frames, op16* __restrict__ out,
@@ -435,7 +435,7 @@ extern "C" int emote_gn_colstats_reduce(const float* colstats, int32_t C_src, in
   if (gn_check(C_src, c_offset, C_total, groups, "emote_gn_colstats_reduce: unsupported channel/group configuration"))
     return EMOTE_ERR_INVALID;
   // emote_set_tuning("gn_reduce", 0) / EMOTE_GN_REDUCE=slots selects the per-slot walk for A/B timing
-  const bool per_slot_walk = gn_reduce_mode() == 0;
+  const bool per_slot_walk = tuning(TUNE_GN_REDUCE, 1) == 0;
   const dim3 grid((unsigned)(n_batches * groups));
   const int cpg = C_total / groups;
   const long long per_group = (long long)slots_per_batch * cpg;   // (slot, column) pairs one block folds
@@ -466,9 +466,13 @@ extern "C" int emote_gn_apply(const float* x, int32_t C_src, int32_t c_offset, i
   int by = 256 / bx;
   if (by < 1) by = 1;
   const long long total_rows = rows_per_batch * (long long)n_batches;
-  long long k = total_rows / ((long long)GN_APPLY_U * by * 2368);
+  // rows per block: aim at ~16 blocks per SM (2368) on large tensors, one load batch per block on small ones
+  int target_blocks = tuning(TUNE_GN_APPLY_BLOCKS, 2368);
+  if (target_blocks < 1) target_blocks = 2368;
+  long long k = total_rows / ((long long)GN_APPLY_U * by * target_blocks);
   if (k < 1) k = 1;
-  if (k > 4) k = 4;
+  const int kmax = tuning(TUNE_GN_APPLY_BLOCKS, 0) > 0 ? 8 : 4;   // the knob also lifts the cap for the sweep
+  if (k > kmax) k = kmax;
   const int rows_per_block = (int)(GN_APPLY_U * by * k);
   const long long chunks = (rows_per_batch + rows_per_block - 1) / rows_per_block;
   dim3 grid((unsigned)chunks, (unsigned)n_batches), block(bx, by);
@@ -488,7 +492,8 @@ static int layernorm_impl(const float* x, int64_t M, int32_t C, const float* gam
   if (!x || !gamma || !beta || (!out_bf16 && !out_f32) || M <= 0) return set_error("emote_layernorm: bad arguments");
   if (C % 64 != 0 || C > 64 * LN_MAX_V) return set_error("emote_layernorm: C must be a multiple of 64 and <= 2048");
   if (pe && (pe_rows_per_frame <= 0 || pe_frames <= 0)) return set_error("emote_layernorm: bad positional table dims");
-  const int warps = 4;
+  int warps = tuning(TUNE_LN_WARPS, 4);
+  if (warps < 1 || warps > 8) warps = 4;
   const long long blocks = (M + warps - 1) / warps;
   op16* o = reinterpret_cast<op16*>(out_bf16);
 #define EMOTE_LN(NVV) launch_kernel(layernorm_kernel<NVV>, dim3((unsigned)blocks), dim3(warps * 32), 0, stream, \

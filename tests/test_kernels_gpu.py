@@ -400,6 +400,46 @@ def test_temporal_attention(ops, heads, d, F_, HW):
     ref = _sdpa_ref(sp(qkv[..., :C]), sp(qkv[..., C:2 * C]), sp(qkv[..., 2 * C:]), d ** -0.5)
     ref = ref.permute(0, 2, 1, 3).reshape(B, HW, F_, C).permute(0, 2, 1, 3)
     chk(rel_l2(out, ref), 6e-3)
+def test_tuning_knobs_change_launch_geometry_not_results(ops):
+    """emote_set_tuning: heads per temporal-attention block, rows per LayerNorm block, gn_apply block count — the same bits
+    under every setting (the statistics-fold knob changes the fp64 summation order and is compared by value in
+    test_gn_colstats_reduce_on_synthetic_slots)."""
+    from emote_hack_b200._lib import check, load
+    g = _gen(33)
+    B, F_, HW, heads, d = 2, 16, 64, 8, 40
+    C = heads * d
+    qkv = torch.randn(B * F_ * HW, 3 * C, device="cuda", generator=g).to(OP16)
+    x = torch.randn(1000, 1280, device="cuda", generator=g) * 2 + 1
+    gamma, beta = torch.randn(1280, device="cuda", generator=g), torch.randn(1280, device="cuda", generator=g)
+    pe = torch.randn(24, 1280, device="cuda", generator=g)
+    xs = x.view(4, 250, 32, 40).double()
+    sums = torch.stack([xs.sum((1, 3)), (xs * xs).sum((1, 3))], dim=-1).contiguous()
+
+    def gn_apply():
+        out = torch.empty(1000, 1280, dtype=OP16, device="cuda")
+        check(load().emote_gn_apply(x.data_ptr(), 1280, 0, 1280, 32, 250, 4, sums.data_ptr(), gamma.data_ptr(),
+                                    beta.data_ptr(), 1e-5, 1, out.data_ptr(), None, ops._stream()), "emote_gn_apply")
+        return out
+
+    try:
+        ref_t = ops.temporal_attention(qkv, B, F_, HW, heads, d)
+        ref_l = ops.layer_norm(x, gamma, beta, pe=pe, rows_per_frame=10, frames=20)
+        ref_g = gn_apply()
+        want = F.silu(F.group_norm(x.view(4, 250, 1280).permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1)
+        chk(rel_l2(ref_g, want.reshape(1000, 1280)), 4e-3)
+        ops.set_tuning("temporal_warps", 8)
+        assert torch.equal(ops.temporal_attention(qkv, B, F_, HW, heads, d), ref_t)
+        for w in (1, 2, 8):
+            ops.set_tuning("ln_warps", w)
+            assert torch.equal(ops.layer_norm(x, gamma, beta, pe=pe, rows_per_frame=10, frames=20), ref_l)
+        for tb in (1, 37, 296):
+            ops.set_tuning("gn_apply_blocks", tb)
+            assert torch.equal(gn_apply(), ref_g)
+    finally:
+        for k in ("temporal_warps", "ln_warps", "gn_apply_blocks"):
+            ops.set_tuning(k, -1)
+
+
 def test_softmax_rows(ops):
     g = _gen(13)
     s = torch.randn(300, 4096, device="cuda", generator=g) * 4

@@ -464,8 +464,16 @@ def run_ours(args):
     # ---- roofline pass (untimed): every launch of one UNet call bracketed by CUDA events on the launching stream
     roof, roof_classes, breakdown = None, None, None
     if rank == 0:
-        with ops.KernelProfiler() as prof:
-            unet(lat_dev.expand(2, -1, -1, -1, -1).contiguous(), 981, ctx_dev)
+        # three profiled calls, per-launch median: one pass right after the timed loop is at the mercy of a single
+        # power-cap excursion (the same launch sequence every time, so the records line up one to one)
+        x_roof = lat_dev.expand(2, -1, -1, -1, -1).contiguous()
+        passes = []
+        for _ in range(3):
+            with ops.KernelProfiler() as prof:
+                unet(x_roof, 981, ctx_dev)
+            passes.append(prof.times)
+        if len({tuple(n for n, _, _ in p_) for p_ in passes}) == 1:
+            prof.times = [(rec[0][0], sorted(r[1] for r in rec)[1], rec[0][2]) for rec in zip(*passes)]
         peaks = measured_peaks()
         tf = prof.gemm_flops / 1e12
         achieved = tf / (prof.gemm_ms / 1e3)
@@ -476,7 +484,7 @@ def run_ours(args):
                 "dram__bytes_write.sum, mean over the GEMM launches of one UNet call; profiles/*_unet_call_dram_traffic.json)",
                 "peak_source": peaks["source"],
                 "note": f"{tf:.2f} algorithmic TFLOP (2*M*N*K of the reference's conv/linear ops) in {n_gemm} launches "
-                        f"of one UNet call, {prof.gemm_ms:.2f} ms total; timed per launch with CUDA events in an eager pass "
+                        f"of one UNet call, {prof.gemm_ms:.2f} ms total; timed per launch with CUDA events, per-launch median of three eager passes "
                         "(the clip loop replays the same launches from a CUDA graph)"}
         roof_classes = _roofline_classes(prof, peaks)
         total = sum(ms_ for _, ms_, _ in prof.times)

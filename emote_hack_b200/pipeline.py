@@ -536,7 +536,11 @@ class EMOAnimationPipeline:
             if writer_ctx.shape[0] != 2:
                 raise ValueError("the ReferenceNet writer needs a [2, n, d] context (pass appearance_context)")
         if not guidance_scale > 1.0:
-            raise NotImplementedError("the fused sampler implements the classifier-free-guidance path the reference runs")
+            # the reference's own no-CFG path cannot run either: `pred_uc, pred_c = pred.chunk(2)` on a batch-1 prediction
+            # and `control.chunk(2)` (EMOAnimationPipeline.py:651,787) fail to unpack, and its average over overlapping
+            # windows (`noise_pred / counter`, :813) only happens inside the CFG branch
+            raise NotImplementedError("guidance_scale <= 1: the fused sampler implements the classifier-free-guidance path "
+                                      "(the only one the reference pipeline can execute)")
         if latents.dim() != 5 or latents.shape[0] != 1:
             raise ValueError("denoise() handles one sample [1, c, f, h, w] per call (run samples on different ranks / sequentially)")
         dev = latents.device

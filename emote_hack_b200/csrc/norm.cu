@@ -82,9 +82,8 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const float* __restrict__
   }
 }
 
-// y = x * scale[c] + shift[c] with scale = rstd*gamma, shift = beta - mean*rstd*gamma staged in shared memory per
-// block; blockDim = (octets per pass, rows in parallel); GN_APPLY_U rows per thread are in flight per batch.
-// Group statistics from the per-quarter column slots a GEMM epilogue stored (EmoteGemmArgs.colstats).
+// Group statistics from the per-quarter column slots a GEMM epilogue stored (EmoteGemmArgs.colstats): the per-slot walk
+// (kept as the A/B partner of the flat fold below and for > 2^30 pairs per group).
 __global__ void __launch_bounds__(256) gn_colstats_reduce_kernel(const float* __restrict__ slots, int C_src, int c_offset,
                                                                  int cpg, int groups, int slots_per_batch, int n_batches,
                                                                  double* __restrict__ sums, int overwrite) {
@@ -192,6 +191,8 @@ __global__ void __launch_bounds__(NT) gn_colstats_reduce_flat_kernel(const float
   }
 }
 
+// y = x * scale[c] + shift[c] with scale = rstd*gamma, shift = beta - mean*rstd*gamma staged in shared memory per
+// block; blockDim = (octets per pass, rows in parallel); GN_APPLY_U rows per thread are in flight per batch.
 constexpr int GN_APPLY_U = 4;  // rows per thread in flight
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, int C_src, int c_offset, int C_total,
                                                        int cpg, int groups, long long rows_per_batch, int rows_per_block,
